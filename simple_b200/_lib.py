@@ -1,0 +1,96 @@
+"""ctypes binding of the C ABI declared in include/simple_b200.h (built in-tree as csrc/libsimple_b200.so).
+
+No CPU fallback: `lib()` raises if the shared library is missing or cannot be loaded.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, 'csrc')
+_SO = os.path.join(_CSRC, 'libsimple_b200.so')
+_LIB = None
+
+SB_MAX_TAPS = 16
+
+
+def build(verbose=False, force=False):
+    """Compile every CUDA source for sm_100a into csrc/libsimple_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = sorted(glob.glob(os.path.join(_CSRC, '*.cu')))
+    deps = srcs + glob.glob(os.path.join(_CSRC, '*.cuh')) + [os.path.join(_HERE, '..', 'include', 'simple_b200.h')]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
+        return _SO
+    cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+           '--use_fast_math', '-shared', '-Xcompiler', '-fPIC', '-o', _SO] + srcs
+    if verbose:
+        cmd.insert(1, '-Xptxas')
+        cmd.insert(2, '-v')
+    subprocess.run(cmd, check=True, cwd=_CSRC)
+    return _SO
+
+
+class TapGemmArgs(ctypes.Structure):
+    _fields_ = [
+        ('a', ctypes.c_void_p), ('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('C', ctypes.c_int),
+        ('Ho', ctypes.c_int), ('Wo', ctypes.c_int),
+        ('bw', ctypes.c_int), ('bh', ctypes.c_int), ('bb', ctypes.c_int),
+        ('ntaps', ctypes.c_int), ('tap_dy', ctypes.c_int * SB_MAX_TAPS), ('tap_dx', ctypes.c_int * SB_MAX_TAPS),
+        ('w', ctypes.c_void_p), ('N', ctypes.c_int), ('ldw', ctypes.c_int),
+        ('out', ctypes.c_void_p), ('out_f32', ctypes.c_int), ('ldo', ctypes.c_int),
+        ('bias', ctypes.c_void_p), ('relu', ctypes.c_int), ('splits', ctypes.c_int), ('accumulate', ctypes.c_int),
+    ]
+
+
+class TapWgradArgs(ctypes.Structure):
+    _fields_ = [
+        ('a', ctypes.c_void_p), ('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('C', ctypes.c_int),
+        ('dy', ctypes.c_void_p), ('Ho', ctypes.c_int), ('Wo', ctypes.c_int), ('N', ctypes.c_int),
+        ('bw', ctypes.c_int), ('bh', ctypes.c_int), ('bb', ctypes.c_int),
+        ('ntaps', ctypes.c_int), ('tap_dy', ctypes.c_int * SB_MAX_TAPS), ('tap_dx', ctypes.c_int * SB_MAX_TAPS),
+        ('dw', ctypes.c_void_p), ('ldw', ctypes.c_int), ('splits', ctypes.c_int),
+    ]
+
+
+def lib():
+    """Load the CUDA library; raise loudly if it is not there (the product has no fallback path)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_SO):
+        raise RuntimeError(
+            f'simple_b200: CUDA extension {_SO} is missing. Build it with `python -c "import __graft_entry__ as g; '
+            f'g.build()"` (needs nvcc). There is no CPU or PyTorch fallback.')
+    L = ctypes.CDLL(_SO)
+    L.sb_init.argtypes = [ctypes.c_int]
+    L.sb_init.restype = ctypes.c_int
+    L.sb_launch_count.restype = ctypes.c_longlong
+    L.sb_version.restype = ctypes.c_char_p
+    for name in dir(_Sigs):
+        if name.startswith('sb_'):
+            fn = getattr(L, name)
+            fn.argtypes = getattr(_Sigs, name)
+            fn.restype = ctypes.c_int
+    _LIB = L
+    return L
+
+
+_p, _i, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+
+
+class _Sigs:
+    sb_tap_gemm = [ctypes.POINTER(TapGemmArgs), _p]
+    sb_tap_wgrad = [ctypes.POINTER(TapWgradArgs), _p]
+
+
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f'simple_b200: {what} failed with code {rc}')
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,488 @@
+// Implicit-GEMM convolution ("tap GEMM") and its weight gradient on the sm_100a tensor cores.
+//
+//   forward / dgrad:  out[b,y,x,n] (+)= sum_t sum_c A[b, y+dy_t, x+dx_t, c] * Wp[n, t*C + c]
+//   wgrad:            dw[n, t*C + c] += sum_{b,y,x} dY[b,y,x,n] * A[b, y+dy_t, x+dx_t, c]
+//
+// Warp-specialised, one output tile per CTA:  warp 0 = TMA producer (4-D box loads of the NHWC activation, shifted by
+// the tap, zero-filled outside the image; 2-D loads of the packed weights), warp 1 = tcgen05.mma issuer (single
+// elected thread, accumulators in TMEM), warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> global store or red.add).
+// Shared-memory operand tiles are 128-byte-swizzled rows of 64 bf16, the layout TMA writes and UMMA reads.
+// Reference call sites replaced: simple/next_frame_predictor.py:225,229,245-246,137-139,45,266-268,275.
+#include "common.cuh"
+#include "../../include/simple_b200.h"
+
+namespace sb {
+
+long long g_launches = 0;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int load_driver_entry() {
+  if (g_encode) return SB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return SB_ERR_DRIVER;
+  g_encode = (EncodeTiledFn)fn;
+  return SB_OK;
+}
+
+// NHWC bf16 tensor [B,H,W,C] -> 4-D map (C, W, H, B), box (64, bw, bh, bb), 128B swizzle, zero OOB fill.
+static int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int bw, int bh, int bb) {
+  if (((uintptr_t)ptr & 15) || (C % 8)) return SB_ERR_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
+}
+// bf16 matrix [rows, ld] (K contiguous) -> 2-D map (K, rows), box (64, box_rows).
+static int make_map_2d(CUtensorMap* m, const void* ptr, int rows, int k, int ld, int box_rows) {
+  if (((uintptr_t)ptr & 15) || (ld % 8)) return SB_ERR_ARG;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
+}
+
+struct TapGemmDev {
+  int B, Ho, Wo;
+  int bw, bh, bb, rows;
+  int tiles_x, tiles_y;
+  int C, kchunks, ntaps;
+  int tap_dy[SB_MAX_TAPS], tap_dx[SB_MAX_TAPS];
+  int N, splits;
+  void* out;
+  int out_f32, ldo;
+  const float* bias;
+  int relu, atomic;
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+    tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ TapGemmDev p) {
+  constexpr int B_BYTES = BN * 128;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kATileBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+  const int n0 = blockIdx.y * BN;
+  const int KT = p.ntaps * p.kchunks;
+  const int k_begin = (int)((long long)KT * blockIdx.z / p.splits);
+  const int k_end = (int)((long long)KT * (blockIdx.z + 1) / p.splits);
+  const int nk = k_end - k_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)B_BYTES;
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int kk = k_begin + i;
+        const int t = kk / p.kchunks;
+        const int c0 = (kk - t * p.kchunks) * 64;
+        mbar_expect_tx(&full[s], tx_bytes);
+        tma_load_4d(sA + s * kATileBytes, &tmA, &full[s], c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b0);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], t * p.C + c0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
+        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const int xl = r % p.bw, yl = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
+    const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
+    const bool valid = (r < p.rows) && (x < p.Wo) && (y < p.Ho) && (b < p.B);
+    const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (!valid) continue;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      const int nb = n0 + c;
+      if (p.atomic) {
+        float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (nb + j < p.N) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (nb + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (nb + j < p.N) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0);
+              pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2);
+              pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmDev& p, dim3 grid,
+                           cudaStream_t stream) {
+  constexpr int smem = STAGES * (kATileBytes + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tap_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  tap_gemm_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad: D[m = dY channel (128/tile), n = A channel (BN/tile)] += sum over a 64-pixel box; both operands MN-major.
+// ------------------------------------------------------------------------------------------------------------------
+struct TapWgradDev {
+  int tiles_x, tiles_y, tiles_b;
+  int bw, bh, bb;
+  int C, N, ntaps, c_tiles, m_tiles;
+  int tap_dy[SB_MAX_TAPS], tap_dx[SB_MAX_TAPS];
+  float* dw;
+  int ldw, splits;
+};
+constexpr int kWgRows = 64;                   // pixels per stage (K of the contraction)
+constexpr int kWgChunkBytes = kWgRows * 128;  // 64 pixels x 64 channels bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+    tap_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ TapWgradDev p) {
+  constexpr int NCH = BN / 64;
+  constexpr int DY_BYTES = 2 * kWgChunkBytes;
+  constexpr int A_BYTES = NCH * kWgChunkBytes;
+  constexpr int TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sDY = smem;
+  uint8_t* sA = smem + STAGES * DY_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + STAGES * A_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int w = blockIdx.x;
+  const int ct = w % p.c_tiles;
+  w /= p.c_tiles;
+  const int t = w % p.ntaps;
+  const int mtile = w / p.ntaps;
+  const int m0 = mtile * 128, c0 = ct * BN;
+  const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
+  const int pt_begin = (int)((long long)PT * blockIdx.y / p.splits);
+  const int pt_end = (int)((long long)PT * (blockIdx.y + 1) / p.splits);
+  const int nk = pt_end - pt_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmDY);
+      tma_prefetch_desc(&tmA);
+      const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int pt = pt_begin + i;
+        const int x0 = (pt % p.tiles_x) * p.bw;
+        const int y0 = ((pt / p.tiles_x) % p.tiles_y) * p.bh;
+        const int b0 = (pt / (p.tiles_x * p.tiles_y)) * p.bb;
+        mbar_expect_tx(&full[s], (uint32_t)(DY_BYTES + A_BYTES));
+        tma_load_4d(sDY + s * DY_BYTES, &tmDY, &full[s], m0, x0, y0, b0);
+        tma_load_4d(sDY + s * DY_BYTES + kWgChunkBytes, &tmDY, &full[s], m0 + 64, x0, y0, b0);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+          tma_load_4d(sA + s * A_BYTES + j * kWgChunkBytes, &tmA, &full[s], c0 + j * 64, x0 + dx, y0 + dy, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      for (int i = 0; i < nk; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(sDY + s * DY_BYTES);
+        const uint32_t b_addr = smem_u32(sA + s * A_BYTES);
+#pragma unroll
+        for (int k = 0; k < kWgRows / 16; ++k) {
+          // MN-major, SW128: LBO = byte stride between 64-channel chunks, SBO = byte stride between 8-pixel groups
+          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
+          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 16 * 128, kWgChunkBytes, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int lg = warp & 3;
+    const int m = m0 + lg * 32 + lane;
+    const bool valid = m < p.N;
+    float* orow = p.dw + (long long)m * p.ldw + (long long)t * p.C + c0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (c0 + c >= p.C) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (!valid) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (c0 + c + j < p.C)
+          red_add_v4(orow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_tap_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmA, const TapWgradDev& p, dim3 grid,
+                            cudaStream_t stream) {
+  constexpr int smem = STAGES * (2 + BN / 64) * kWgChunkBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tap_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  tap_wgrad_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmDY, tmA, p);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !a->a || !a->w || !a->out) return SB_ERR_ARG;
+  if (a->ntaps < 1 || a->ntaps > SB_MAX_TAPS) return SB_ERR_ARG;
+  const int rows = a->bw * a->bh * a->bb;
+  if (rows < 1 || rows > 128 || a->bw > 256 || a->bh > 256 || a->bb > 256) return SB_ERR_ARG;
+  if (a->N % 8 || a->N < 8) return SB_ERR_ARG;
+  const bool atomic = a->splits > 1 || a->accumulate;
+  if (atomic && !a->out_f32) return SB_ERR_ARG;
+  if (a->ldo % (a->out_f32 ? 4 : 8)) return SB_ERR_ARG;
+  if (a->ldw < a->ntaps * a->C) return SB_ERR_ARG;
+  int rc = load_driver_entry();
+  if (rc) return rc;
+  TapGemmDev p;
+  p.B = a->B; p.Ho = a->Ho; p.Wo = a->Wo;
+  p.bw = a->bw; p.bh = a->bh; p.bb = a->bb; p.rows = rows;
+  p.tiles_x = (a->Wo + a->bw - 1) / a->bw;
+  p.tiles_y = (a->Ho + a->bh - 1) / a->bh;
+  const int tiles_b = (a->B + a->bb - 1) / a->bb;
+  p.C = a->C; p.kchunks = (a->C + 63) / 64; p.ntaps = a->ntaps;
+  for (int i = 0; i < SB_MAX_TAPS; ++i) {
+    p.tap_dy[i] = i < a->ntaps ? a->tap_dy[i] : 0;
+    p.tap_dx[i] = i < a->ntaps ? a->tap_dx[i] : 0;
+  }
+  p.N = a->N;
+  const int KT = p.ntaps * p.kchunks;
+  p.splits = a->splits < 1 ? 1 : (a->splits > KT ? KT : a->splits);
+  p.out = a->out; p.out_f32 = a->out_f32; p.ldo = a->ldo;
+  p.bias = a->bias; p.relu = a->relu; p.atomic = atomic ? 1 : 0;
+
+  // N tile: 256 when it divides N (fewer A re-reads), else 192 / 128 / 96
+  int BN;
+  if (a->N % 256 == 0) BN = 256;
+  else if (a->N % 192 == 0) BN = 192;
+  else if (a->N % 128 == 0) BN = 128;
+  else if (a->N <= 96) BN = 96;
+  else BN = 128;
+  CUtensorMap tmA, tmB;
+  rc = make_map_nhwc(&tmA, a->a, a->B, a->H, a->W, a->C, a->bw, a->bh, a->bb);
+  if (rc) return rc;
+  rc = make_map_2d(&tmB, a->w, a->N, a->ntaps * a->C, a->ldw, BN);
+  if (rc) return rc;
+  dim3 grid(p.tiles_x * p.tiles_y * tiles_b, (a->N + BN - 1) / BN, p.splits);
+  switch (BN) {
+    case 256: return launch_tap_gemm<256, 4>(tmA, tmB, p, grid, stream);
+    case 192: return launch_tap_gemm<192, 5>(tmA, tmB, p, grid, stream);
+    case 128: return launch_tap_gemm<128, 3>(tmA, tmB, p, grid, stream);
+    default: return launch_tap_gemm<96, 3>(tmA, tmB, p, grid, stream);
+  }
+}
+
+extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !a->a || !a->dy || !a->dw) return SB_ERR_ARG;
+  if (a->ntaps < 1 || a->ntaps > SB_MAX_TAPS) return SB_ERR_ARG;
+  if (a->bw * a->bh * a->bb != kWgRows) return SB_ERR_ARG;
+  if (a->ldw % 4 || a->ldw < a->ntaps * a->C || a->C % 8 || a->N % 8) return SB_ERR_ARG;
+  int rc = load_driver_entry();
+  if (rc) return rc;
+  TapWgradDev p;
+  p.bw = a->bw; p.bh = a->bh; p.bb = a->bb;
+  p.tiles_x = (a->Wo + a->bw - 1) / a->bw;
+  p.tiles_y = (a->Ho + a->bh - 1) / a->bh;
+  p.tiles_b = (a->B + a->bb - 1) / a->bb;
+  p.C = a->C; p.N = a->N; p.ntaps = a->ntaps;
+  for (int i = 0; i < SB_MAX_TAPS; ++i) {
+    p.tap_dy[i] = i < a->ntaps ? a->tap_dy[i] : 0;
+    p.tap_dx[i] = i < a->ntaps ? a->tap_dx[i] : 0;
+  }
+  p.dw = a->dw; p.ldw = a->ldw;
+  const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
+  p.splits = a->splits < 1 ? 1 : (a->splits > PT ? PT : a->splits);
+  int BN;
+  if (a->C > 128) BN = 256;
+  else if (a->C > 64) BN = 128;
+  else BN = 64;
+  p.c_tiles = (a->C + BN - 1) / BN;
+  p.m_tiles = (a->N + 127) / 128;
+  CUtensorMap tmDY, tmA;
+  rc = make_map_nhwc(&tmDY, a->dy, a->B, a->Ho, a->Wo, a->N, a->bw, a->bh, a->bb);
+  if (rc) return rc;
+  rc = make_map_nhwc(&tmA, a->a, a->B, a->H, a->W, a->C, a->bw, a->bh, a->bb);
+  if (rc) return rc;
+  dim3 grid(p.m_tiles * p.ntaps * p.c_tiles, p.splits, 1);
+  switch (BN) {
+    case 256: return launch_tap_wgrad<256, 4>(tmDY, tmA, p, grid, stream);
+    case 128: return launch_tap_wgrad<128, 6>(tmDY, tmA, p, grid, stream);
+    default: return launch_tap_wgrad<64, 6>(tmDY, tmA, p, grid, stream);
+  }
+}
+
+extern "C" int sb_init(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SB_ERR_CUDA;
+  if (prop.major != 10) return SB_ERR_ARCH;
+  return load_driver_entry();
+}
+extern "C" long long sb_launch_count(void) { return sb::g_launches; }
+extern "C" const char* sb_version(void) { return "simple_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,82 @@
+"""tcgen05 tap-GEMM / wgrad kernels vs a plain PyTorch fp32 reference of the same contraction (bf16 inputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+@pytest.mark.parametrize('M,K,N', [(300, 256, 128), (128, 64, 96), (1000, 384, 192), (517, 512, 256), (64, 1024, 768)])
+def test_plain_gemm(M, K, N):
+    from simple_b200.gemm import tap_gemm
+    torch.manual_seed(0)
+    a = torch.randn(1, 1, M, K, device=_dev()).bfloat16()
+    w = torch.randn(N, K, device=_dev()).bfloat16()
+    bias = torch.randn(N, device=_dev())
+    out = tap_gemm(a, w, [(0, 0)], 1, M, bias=bias, relu=True, out_dtype=torch.float32)
+    ref = F.relu(a.float().reshape(M, K) @ w.float().t() + bias)
+    torch.cuda.synchronize()
+    assert torch.allclose(out.reshape(M, N), ref, rtol=1e-3, atol=1e-2), float((out.reshape(M, N) - ref).abs().max())
+    out16 = tap_gemm(a, w, [(0, 0)], 1, M, bias=bias, relu=False)
+    ref16 = (a.float().reshape(M, K) @ w.float().t() + bias)
+    assert torch.allclose(out16.float().reshape(M, N), ref16, rtol=1e-2, atol=1e-1)
+
+
+@pytest.mark.parametrize('splits', [1, 3])
+def test_conv3x3(splits):
+    from simple_b200.gemm import tap_gemm
+    torch.manual_seed(1)
+    B, H, W, C, N = 3, 13, 10, 128, 256
+    x = torch.randn(B, H, W, C, device=_dev()).bfloat16()
+    wt = (torch.randn(N, C, 3, 3, device=_dev()) * 0.05).bfloat16()
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = tap_gemm(x, wp, taps, H, W, splits=splits, out_dtype=torch.float32)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref, rtol=1e-3, atol=1e-2), float((out - ref).abs().max())
+
+
+def test_conv4x4s2_via_s2d():
+    """4x4 stride-2 pad-1 conv == 2x2 stride-1 taps over the padded space-to-depth input."""
+    from simple_b200.gemm import tap_gemm
+    torch.manual_seed(2)
+    B, H, W, C, N = 2, 105, 80, 96, 192
+    Ho, Wo = 52, 40
+    x = torch.randn(B, C, H, W, device=_dev()).bfloat16()
+    wt = (torch.randn(N, C, 4, 4, device=_dev()) * 0.05).bfloat16()
+    xp = F.pad(x, (1, 1, 1, 1))  # [B,C,107,82]
+    H2, W2 = Ho + 1, Wo + 1
+    xp = xp[:, :, :2 * H2, :2 * W2]
+    s2d = xp.reshape(B, C, H2, 2, W2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, H2, W2, 4 * C).contiguous()
+    # packed weights [N, (dy,dx),(py,px),c] with ky = 2dy+py
+    wp = wt.reshape(N, C, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(N, 16 * C).contiguous()  # o,dy,dx,py,px,c
+    taps = [(dy, dx) for dy in range(2) for dx in range(2)]
+    out = tap_gemm(s2d, wp, taps, Ho, Wo, out_dtype=torch.float32)
+    ref = F.conv2d(x.float(), wt.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref, rtol=1e-3, atol=2e-2), float((out - ref).abs().max())
+
+
+@pytest.mark.parametrize('C,N,splits', [(128, 256, 1), (64, 96, 2), (384, 192, 3)])
+def test_wgrad(C, N, splits):
+    from simple_b200.gemm import tap_wgrad
+    torch.manual_seed(3)
+    B, H, W = 5, 13, 10
+    x = torch.randn(B, H, W, C, device=_dev()).bfloat16()
+    dy = torch.randn(B, H, W, N, device=_dev()).bfloat16()
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    dw = torch.zeros(N, 9 * C, device=_dev())
+    tap_wgrad(x, dy, taps, dw, splits=splits)
+    xn = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wref = torch.zeros(N, C, 3, 3, device=_dev(), requires_grad=True)
+    y = F.conv2d(xn, wref, padding=1)
+    (g,) = torch.autograd.grad(y, wref, dy.float().permute(0, 3, 1, 2))
+    ref = g.permute(0, 2, 3, 1).reshape(N, 9 * C)
+    torch.cuda.synchronize()
+    err = float((dw - ref).abs().max())
+    assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), err
