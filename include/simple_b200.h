@@ -80,6 +80,78 @@ typedef struct {
 } sb_tap_wgrad_args;
 int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused per-pixel 256-way softmax cross-entropy, clipped loss, gradient and argmax decode (one HBM pass).
+ * logits: bf16 [B*HW, 768], channel = colour*256 + value (colour-major permutation of the reference's
+ * value*3+colour, applied when the logits weights are packed).  target: u8 [B,3,HW] (reference NCHW order).
+ * dlogits (may alias logits) = (softmax - onehot) * [ce > clip] * gscale; loss_sum += sum max(ce, clip);
+ * dbias[768] += column sums of dlogits; argmax_out: u8 [B,3,HW] (first index on ties, like torch.argmax).
+ * dlogits == NULL selects the decode-only (rollout) variant.
+ * Replaces: simple/trainer.py:130,134-137 and simple/subproc_vec_env.py:428 (K14).
+ * --------------------------------------------------------------------------------------------------------- */
+int sb_pixel_ce(const void* logits, const uint8_t* target, int B, int HW, float clip, float gscale, void* dlogits,
+                uint8_t* argmax_out, double* loss_sum, float* dbias, sb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused elementwise stage between two tap GEMMs ("prep"), its statistics and its backward.
+ * A view is a bf16 tensor holding a logical [B,H,W,C] activation: kind 0 = plain NHWC; kind 1 = padded
+ * space-to-depth [B,H2,W2,s*s*C] with element (b,y2,x2,(py*s+px)*C+c) = logical (b, s*y2+py-pad, s*x2+px-pad, c).
+ * forward:  z = [relu](in) + add;  x = InstanceNorm(z; sums,gamma,beta) + Ta;  out1 = x;
+ *           x = dropout(x; p) + Tb;  out2 = x * sc[b,c] + sh[b,c]
+ * Replaces: nn.InstanceNorm2d, F.dropout, timing-signal adds, skip adds, ActionInjector at
+ *   simple/next_frame_predictor.py:317,320-326,343-350 and simple/utils.py:98-105 (K3,K4,K7,K8).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* p;
+  int kind, s, pad, H2, W2;
+} sb_view;
+typedef struct {
+  int B, H, W, C;          /* logical dims; C % 8 == 0 */
+  sb_view in;              /* main input */
+  const void* add;         /* optional plain bf16 [B,H,W,C] */
+  int relu_in;
+  const float* sums;       /* [B,C,2] from sb_stats, or NULL: no InstanceNorm */
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* Ta;         /* fp32 [H,W,C] or NULL */
+  void* out1;              /* optional plain bf16 */
+  float p;                 /* dropout probability */
+  unsigned long long seed; /* Philox key */
+  unsigned int stream_id;  /* Philox stream (one per dropout site) */
+  const uint8_t* keep;     /* optional explicit keep mask u8 [B,H,W,C] ("randomness as input" parity mode) */
+  const float* Tb;
+  const float* sc;         /* fp32 [B,C] or NULL */
+  const float* sh;
+  sb_view out2;
+  /* backward */
+  sb_view g2;              /* grad wrt out2 (layout of out2) */
+  const void* g1;          /* grad wrt out1 (plain) or NULL */
+  float* bsums;            /* [B,C,4]: sum gx, sum gx*xhat, sum g2*xd (d sc), sum g2 (d sh); caller zeroes */
+  sb_view d_main;          /* grad wrt in (layout of in), masked by in>0 when relu_in */
+  void* d_add;             /* grad wrt add (plain) or NULL */
+} sb_prep_args;
+int sb_stats(const sb_prep_args* args, float* sums /* [B,C,2], caller zeroes */, sb_stream_t stream);
+int sb_prep(const sb_prep_args* args, sb_stream_t stream);
+int sb_prep_bwd_reduce(const sb_prep_args* args, sb_stream_t stream);
+int sb_prep_bwd_apply(const sb_prep_args* args, sb_stream_t stream);
+
+/* standardize_frame (simple/utils.py:122-126): in fp32 [B,C,P] -> (x-mean)/max(std_unbiased, 1/sqrt(P)) written to
+ * dst_bf16[(b*P+i)*ld + coff + c] and/or out_f32 [B,C,P] (may alias `in`: the reference standardises targets in place). */
+int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
+                   sb_stream_t stream);
+
+/* conv-GRU blend of the recurrent state (simple/next_frame_predictor.py:298-303) and its backward.
+ * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld. */
+int sb_gru_blend(const void* G, const float* s_old, float* s_new, void* xs, int xs_ld, long long npix,
+                 sb_stream_t stream);
+int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs_ld, void* dG, long long npix,
+                     sb_stream_t stream);
+
+/* fp32 (O,I,KH,KW) master weight -> bf16 GEMM operands (see DESIGN.md "weight packing"). */
+int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
+                 const int* operm, void* fwd, void* tr, sb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,24 @@ class TapWgradArgs(ctypes.Structure):
     ]
 
 
+class SbView(ctypes.Structure):
+    _fields_ = [('p', ctypes.c_void_p), ('kind', ctypes.c_int), ('s', ctypes.c_int), ('pad', ctypes.c_int),
+                ('H2', ctypes.c_int), ('W2', ctypes.c_int)]
+
+
+class PrepArgs(ctypes.Structure):
+    _fields_ = [
+        ('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('C', ctypes.c_int),
+        ('inp', SbView), ('add', ctypes.c_void_p), ('relu_in', ctypes.c_int),
+        ('sums', ctypes.c_void_p), ('eps', ctypes.c_float), ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p),
+        ('Ta', ctypes.c_void_p), ('out1', ctypes.c_void_p),
+        ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('stream_id', ctypes.c_uint),
+        ('keep', ctypes.c_void_p), ('Tb', ctypes.c_void_p), ('sc', ctypes.c_void_p), ('sh', ctypes.c_void_p),
+        ('out2', SbView), ('g2', SbView), ('g1', ctypes.c_void_p), ('bsums', ctypes.c_void_p),
+        ('d_main', SbView), ('d_add', ctypes.c_void_p),
+    ]
+
+
 def lib():
     """Load the CUDA library; raise loudly if it is not there (the product has no fallback path)."""
     global _LIB
@@ -81,6 +99,15 @@ _p, _i, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlo
 class _Sigs:
     sb_tap_gemm = [ctypes.POINTER(TapGemmArgs), _p]
     sb_tap_wgrad = [ctypes.POINTER(TapWgradArgs), _p]
+    sb_pixel_ce = [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p]
+    sb_stats = [ctypes.POINTER(PrepArgs), _p, _p]
+    sb_prep = [ctypes.POINTER(PrepArgs), _p]
+    sb_prep_bwd_reduce = [ctypes.POINTER(PrepArgs), _p]
+    sb_prep_bwd_apply = [ctypes.POINTER(PrepArgs), _p]
+    sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p]
+    sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
+    sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]
+    sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
 
 
 EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version'] + [n for n in dir(_Sigs) if n.startswith('sb_')]

@@ -1,0 +1,635 @@
+// Fused elementwise / reduction kernels around the tap GEMMs (HBM-bound; vectorised 16-byte accesses, NHWC bf16).
+//
+//  * sb_standardize      simple/utils.py:122-126 (+ loops next_frame_predictor.py:307,333-334)
+//  * sb_stats            per-(b,c) sums for InstanceNorm2d (next_frame_predictor.py:247,269,49) and spatial means (:339,352)
+//  * sb_prep             InstanceNorm apply + timing add + skip save + dropout + timing add + ActionInjector
+//                        + layout change (plain <-> padded space-to-depth)  (next_frame_predictor.py:320-326,343-350)
+//  * sb_prep_bwd_*       the matching backward
+//  * sb_gru_blend[_bwd]  next_frame_predictor.py:298-303
+//  * sb_pack_conv        fp32 (O,I,kh,kw) master weights -> bf16 K-major GEMM operands
+#include "common.cuh"
+#include "../../include/simple_b200.h"
+
+namespace sb {
+extern long long g_launches;
+
+struct __align__(16) BF8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void bf8_to_f(const BF8& b, float* f) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 t = __bfloat1622float2(b.v[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ BF8 f_to_bf8(const float* f) {
+  BF8 b;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b.v[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return b;
+}
+__device__ __forceinline__ void ld8f(const float* p, float* f) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// A bf16 tensor holding a logical [B,H,W,C] activation, either plain NHWC or padded space-to-depth:
+//   s2d element (b, y2, x2, (py*s+px)*C + c) = logical (b, s*y2+py-pad, s*x2+px-pad, c)
+struct View {
+  void* p;
+  int kind;  // 0 plain, 1 s2d
+  int s, pad, H2, W2;
+};
+__device__ __forceinline__ long long view_off(const View& v, int H, int W, int C, int b, int y, int x, int c) {
+  if (v.kind == 0) return (((long long)b * H + y) * W + x) * C + c;
+  const int yp = y + v.pad, xp = x + v.pad;
+  const int y2 = yp / v.s, x2 = xp / v.s;
+  const int ph = (yp - y2 * v.s) * v.s + (xp - x2 * v.s);
+  return ((((long long)b * v.H2 + y2) * v.W2 + x2) * (v.s * v.s) + ph) * C + c;
+}
+
+struct PrepParams {
+  int B, H, W, C;
+  View in;                  // main input
+  const __nv_bfloat16* add; // optional plain [B,H,W,C], added to main (skip connection)
+  int relu_in;              // forward: apply ReLU to main first;  backward: mask d_main by (main > 0)
+  const float* sums;        // [B,C,2] raw sum / sum of squares of (main+add), or NULL (no InstanceNorm)
+  float eps;
+  const float* gamma;
+  const float* beta;
+  const float* Ta;          // [H,W,C] or NULL
+  __nv_bfloat16* out1;      // optional plain [B,H,W,C]: value after Ta (skip / h)
+  float p;                  // dropout probability (0 = none)
+  unsigned long long seed;
+  unsigned int stream_id;
+  const uint8_t* keep;      // parity mode: explicit keep mask, uint8 [B,H,W,C]
+  const float* Tb;          // [H,W,C] or NULL
+  const float* sc;          // [B,C] or NULL: x = x*sc + sh  (ActionInjector with sc = sigmoid(dense1(a)), sh = dense2(a))
+  const float* sh;
+  View out2;
+  // backward only
+  View g2;                  // grad wrt out2 (same layout as out2)
+  const __nv_bfloat16* g1;  // grad wrt out1 (plain) or NULL
+  float* bsums;             // [B,C,4]: sum gx, sum gx*xhat, sum g2*xd, sum g2
+  View d_main;              // grad wrt main (same layout as in)
+  __nv_bfloat16* d_add;     // grad wrt add (plain) or NULL
+};
+
+// keep decisions for 8 consecutive channels from one Philox call (16 random bits each)
+__device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, long long elem_index, bool* k) {
+  if (q.keep) {
+    const uint2 m = *reinterpret_cast<const uint2*>(q.keep + elem_index);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      k[j] = ((m.x >> (8 * j)) & 0xff) != 0;
+      k[4 + j] = ((m.y >> (8 * j)) & 0xff) != 0;
+    }
+    return;
+  }
+  const uint4 r = philox4x32(make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), q.stream_id, 0u),
+                             make_uint2((uint32_t)q.seed, (uint32_t)(q.seed >> 32)));
+  const uint32_t thr = (uint32_t)(q.p * 65536.0f);
+  k[0] = (r.x & 0xffff) >= thr; k[1] = (r.x >> 16) >= thr;
+  k[2] = (r.y & 0xffff) >= thr; k[3] = (r.y >> 16) >= thr;
+  k[4] = (r.z & 0xffff) >= thr; k[5] = (r.z >> 16) >= thr;
+  k[6] = (r.w & 0xffff) >= thr; k[7] = (r.w >> 16) >= thr;
+}
+
+// value of (main [+relu] + add) for 8 channels; also returns raw main
+__device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x, int c, float* z, float* mainv,
+                                       bool fwd_relu) {
+  const BF8 m = *reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) +
+                                              view_off(q.in, q.H, q.W, q.C, b, y, x, c));
+  bf8_to_f(m, mainv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) z[j] = (fwd_relu && q.relu_in) ? fmaxf(mainv[j], 0.f) : mainv[j];
+  if (q.add) {
+    float a[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(q.add + (((long long)b * q.H + y) * q.W + x) * q.C + c), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] += a[j];
+  }
+}
+
+// forward chain up to the value before the injector (xd); xhat / xn optionally returned
+__device__ __forceinline__ void fwd_chain(const PrepParams& q, int b, int y, int x, int c, const float* z, float* xhat,
+                                          float* xn, float* xd, bool* k) {
+  const float invP = 1.0f / (float)(q.H * q.W);
+  const long long pix = ((long long)b * q.H + y) * q.W + x;
+  float g[8], bt[8];
+  if (q.sums) {
+    ld8f(q.gamma + c, g);
+    ld8f(q.beta + c, bt);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = z[j];
+    if (q.sums) {
+      const float s1 = q.sums[((long long)b * q.C + c + j) * 2], s2 = q.sums[((long long)b * q.C + c + j) * 2 + 1];
+      const float mean = s1 * invP;
+      const float var = fmaxf(s2 * invP - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + q.eps);
+      xhat[j] = (v - mean) * rstd;
+      v = xhat[j] * g[j] + bt[j];
+    } else {
+      xhat[j] = v;
+    }
+    xn[j] = v;
+  }
+  if (q.Ta) {
+    float t[8];
+    ld8f(q.Ta + ((long long)y * q.W + x) * q.C + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xn[j] += t[j];
+  }
+  if (q.p > 0.f) {
+    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, k);
+    const float inv_keep = 1.0f / (1.0f - q.p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xd[j] = k[j] ? xn[j] * inv_keep : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xd[j] = xn[j];
+      k[j] = true;
+    }
+  }
+  if (q.Tb) {
+    float t[8];
+    ld8f(q.Tb + ((long long)y * q.W + x) * q.C + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xd[j] += t[j];
+  }
+}
+
+// iteration space: logical pixels, extended to the padded extent of `ext` when it is an s2d view
+__device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y0, int* ny, int* x0, int* nx) {
+  if (ext.kind == 0) {
+    *y0 = 0; *ny = H; *x0 = 0; *nx = W;
+  } else {
+    *y0 = -ext.pad; *ny = ext.s * ext.H2; *x0 = -ext.pad; *nx = ext.s * ext.W2;
+  }
+}
+
+__global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ PrepParams q) {
+  int y0, ny, x0, nx;
+  iter_space(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
+  const int CV = q.C / 8;
+  const long long total = (long long)q.B * ny * nx * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
+    const int xx = (int)(r % nx) + x0;
+    r /= nx;
+    const int yy = (int)(r % ny) + y0;
+    const int b = (int)(r / ny);
+    const int c = cv * 8;
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy, xx, c);
+    if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
+      *reinterpret_cast<uint4*>(o2) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float z[8], mainv[8], xhat[8], xn[8], xd[8];
+    bool k[8];
+    load_z(q, b, yy, xx, c, z, mainv, true);
+    fwd_chain(q, b, yy, xx, c, z, xhat, xn, xd, k);
+    if (q.out1) *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(xn);
+    if (q.sc) {
+      float s[8], h[8];
+      ld8f(q.sc + (long long)b * q.C + c, s);
+      ld8f(q.sh + (long long)b * q.C + c, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * s[j] + h[j];
+    }
+    *reinterpret_cast<BF8*>(o2) = f_to_bf8(xd);
+  }
+}
+
+// gradient wrt the normalised value (gx) for 8 channels, plus g2
+__device__ __forceinline__ void bwd_gx(const PrepParams& q, int b, int y, int x, int c, const bool* k, float* g2,
+                                       float* gx) {
+  bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) +
+                                         view_off(q.g2, q.H, q.W, q.C, b, y, x, c)),
+           g2);
+  float s[8];
+  if (q.sc) ld8f(q.sc + (long long)b * q.C + c, s);
+  const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = q.sc ? g2[j] * s[j] : g2[j];
+    gx[j] = k[j] ? v * inv_keep : 0.f;
+  }
+  if (q.g1) {
+    float t[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(q.g1 + (((long long)b * q.H + y) * q.W + x) * q.C + c), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gx[j] += t[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-(b,c) reductions over pixels.  MODE 0: sum z, sum z^2 (2 values).  MODE 1: backward sums (4 values).
+// grid = (slabs, B); block = CV * PL threads (thread = one 8-channel vector x one pixel lane)
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL,
+                                                        int pix_per_slab) {
+  constexpr int NV = MODE == 0 ? 2 : 4;
+  extern __shared__ float sm[];
+  const int CV = q.C / 8;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int b = blockIdx.y;
+  const int c = cv * 8;
+  const int P = q.H * q.W;
+  const int p_begin = blockIdx.x * pix_per_slab;
+  const int p_end = min(P, p_begin + pix_per_slab);
+  float acc[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
+  if (pl < PL) {
+    for (int pix = p_begin + pl; pix < p_end; pix += PL) {
+      const int y = pix / q.W, x = pix - y * q.W;
+      float z[8], mainv[8];
+      load_z(q, b, y, x, c, z, mainv, true);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += z[j];
+          acc[1][j] += z[j] * z[j];
+        }
+      } else {
+        float xhat[8], xn[8], xd[8], g2[8], gx[8];
+        bool k[8];
+        fwd_chain(q, b, y, x, c, z, xhat, xn, xd, k);
+        bwd_gx(q, b, y, x, c, k, g2, gx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += gx[j];
+          acc[1][j] += gx[j] * xhat[j];
+          acc[2][j] += g2[j] * xd[j];
+          acc[3][j] += g2[j];
+        }
+      }
+    }
+  }
+  // reduce over pixel lanes through shared memory: sm[pl][cv][v][j]
+  float* mine = sm + ((size_t)pl * CV + cv) * (NV * 8);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * NV * 8; i += blockDim.x) {
+    const int cvv = i / (NV * 8), rem = i % (NV * 8);
+    const int v = rem / 8, j = rem % 8;
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += sm[((size_t)l * CV + cvv) * (NV * 8) + rem];
+    atomicAdd(out + ((long long)b * q.C + cvv * 8 + j) * NV + v, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) prep_bwd_apply_kernel(const __grid_constant__ PrepParams q) {
+  int y0, ny, x0, nx;
+  iter_space(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
+  const int CV = q.C / 8;
+  const float invP = 1.0f / (float)(q.H * q.W);
+  const long long total = (long long)q.B * ny * nx * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long r = i / CV;
+    const int xx = (int)(r % nx) + x0;
+    r /= nx;
+    const int yy = (int)(r % ny) + y0;
+    const int b = (int)(r / ny);
+    const int c = cv * 8;
+    __nv_bfloat16* dm = reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy, xx, c);
+    if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
+      *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    float z[8], mainv[8], xhat[8], xn[8], xd[8], g2[8], gx[8], dz[8];
+    bool k[8];
+    load_z(q, b, yy, xx, c, z, mainv, true);
+    fwd_chain(q, b, yy, xx, c, z, xhat, xn, xd, k);
+    bwd_gx(q, b, yy, xx, c, k, g2, gx);
+    if (q.sums) {
+      float g[8];
+      ld8f(q.gamma + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long sb_ = ((long long)b * q.C + c + j);
+        const float s1 = q.sums[sb_ * 2], s2 = q.sums[sb_ * 2 + 1];
+        const float mean = s1 * invP;
+        const float var = fmaxf(s2 * invP - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + q.eps);
+        const float m1 = q.bsums[sb_ * 4] * invP, m2 = q.bsums[sb_ * 4 + 1] * invP;
+        dz[j] = rstd * g[j] * (gx[j] - m1 - xhat[j] * m2);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = gx[j];
+    }
+    if (q.d_add) *reinterpret_cast<BF8*>(q.d_add + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(dz);
+    if (q.relu_in) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dz[j] = mainv[j] > 0.f ? dz[j] : 0.f;
+    }
+    *reinterpret_cast<BF8*>(dm) = f_to_bf8(dz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// standardize_frame: one block per (b, channel); the H*W plane is staged in shared memory (read HBM once)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    standardize_kernel(const float* __restrict__ in, int C, int P, __nv_bfloat16* dst, int ld, int coff,
+                       float* out_f32) {
+  extern __shared__ float plane[];
+  __shared__ float red[8];
+  __shared__ float s_mean, s_scale;
+  const int bc = blockIdx.x;
+  const int b = bc / C, c = bc - b * C;
+  const float* src = in + (long long)bc * P;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float v = src[i];
+    plane[i] = v;
+    s += v;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    s_mean = t / (float)P;
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  float v2 = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float d = plane[i] - mean;
+    v2 += d * d;
+  }
+  v2 = warp_sum(v2);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float var = t / (float)(P - 1);  // unbiased (torch.var default)
+    s_scale = 1.0f / fmaxf(__fsqrt_rn(var), rsqrtf((float)P));
+  }
+  __syncthreads();
+  const float inv = s_scale;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float v = (plane[i] - mean) * inv;
+    if (dst) dst[((long long)b * P + i) * ld + coff + c] = __float2bfloat16_rn(v);
+    if (out_f32) out_f32[(long long)bc * P + i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv-GRU blend of the recurrent state (next_frame_predictor.py:298-303)
+//   G bf16 [NPIX, 128] = gate conv output (0..63 gate, 64..127 candidate); state fp32 [NPIX, 64]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    gru_blend_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ s_old, float* s_new,
+                     __nv_bfloat16* xs, int xs_ld, long long npix) {
+  const long long total = npix * 8;  // 8 vectors of 8 channels
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i >> 3;
+    const int c = (int)(i & 7) * 8;
+    float g[8], cand[8], s[8], o[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + c), g);
+    bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + 64 + c), cand);
+    ld8f(s_old + pix * 64 + c, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.0f / (1.0f + __expf(-g[j]));
+      const float tc = tanhf(cand[j]);
+      o[j] = s[j] * sg + tc * (1.0f - sg);
+    }
+    *reinterpret_cast<float4*>(s_new + pix * 64 + c) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(s_new + pix * 64 + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<BF8*>(xs + pix * xs_ld + c) = f_to_bf8(o);
+  }
+}
+
+// dG from d(state_new): d/dgate = sg*(1-sg)*(s - tanh(c)),  d/dcand = (1-sg)*(1-tanh(c)^2).  s_old carries no grad.
+__global__ void __launch_bounds__(256)
+    gru_blend_bwd_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ s_old,
+                         const __nv_bfloat16* __restrict__ dxs, int dxs_ld, __nv_bfloat16* dG, long long npix) {
+  const long long total = npix * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i >> 3;
+    const int c = (int)(i & 7) * 8;
+    float g[8], cand[8], s[8], d[8], dg[8], dc[8];
+    bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + c), g);
+    bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + 64 + c), cand);
+    ld8f(s_old + pix * 64 + c, s);
+    bf8_to_f(*reinterpret_cast<const BF8*>(dxs + pix * dxs_ld + c), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.0f / (1.0f + __expf(-g[j]));
+      const float tc = tanhf(cand[j]);
+      dg[j] = d[j] * sg * (1.0f - sg) * (s[j] - tc);
+      dc[j] = d[j] * (1.0f - sg) * (1.0f - tc * tc);
+    }
+    *reinterpret_cast<BF8*>(dG + pix * 128 + c) = f_to_bf8(dg);
+    *reinterpret_cast<BF8*>(dG + pix * 128 + 64 + c) = f_to_bf8(dc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing.  W fp32 [O, I, KH, KW] (Conv2d layout; a ConvTranspose2d weight [in,out,kh,kw] is passed as-is with
+// O=in, I=out).  s = space-to-depth factor (stride), taps T = (KH/s)*(KW/s), phases PH = s*s, ky = s*dy + py.
+//   fwd[operm(o), (t*PH + ph)*Ipad + iperm(i)] = W[o,i,ky,kx]        (bf16, [Opad, T*PH*Ipad])
+//   tr [ph*Ipad + iperm(i), t*Opad + operm(o)] = W[o,i,ky,kx]        (bf16, [PH*Ipad, T*Opad])
+// Both destinations are zero-filled by the caller once (padding never changes).
+// ---------------------------------------------------------------------------------------------------------------
+struct PackParams {
+  const float* w;
+  int O, I, KH, KW, s;
+  int Ipad, Opad;
+  const int* iperm;
+  const int* operm;
+  __nv_bfloat16* fwd;
+  __nv_bfloat16* tr;
+};
+__global__ void __launch_bounds__(256) pack_conv_kernel(const __grid_constant__ PackParams q) {
+  const int KK = q.KH * q.KW;
+  const long long total = (long long)q.O * q.I * KK;
+  const int TW = q.KW / q.s, PH = q.s * q.s, T = (q.KH / q.s) * TW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // idx enumerates (o, k, i) with i fastest so that the fwd writes are coalesced
+    const int i = (int)(idx % q.I);
+    long long r = idx / q.I;
+    const int kk = (int)(r % KK);
+    const int o = (int)(r / KK);
+    const int ky = kk / q.KW, kx = kk - ky * q.KW;
+    const int dy = ky / q.s, py = ky - dy * q.s, dx = kx / q.s, px = kx - dx * q.s;
+    const int t = dy * TW + dx, ph = py * q.s + px;
+    const float v = q.w[((long long)o * q.I + i) * KK + kk];
+    const int oo = q.operm ? q.operm[o] : o;
+    const int ii = q.iperm ? q.iperm[i] : i;
+    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+    if (q.fwd) q.fwd[(long long)oo * ((long long)T * PH * q.Ipad) + ((long long)t * PH + ph) * q.Ipad + ii] = bv;
+    if (q.tr) q.tr[((long long)ph * q.Ipad + ii) * ((long long)T * q.Opad) + (long long)t * q.Opad + oo] = bv;
+  }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------
+static View mk_view(const sb_view* v) {
+  View r;
+  r.p = v->p; r.kind = v->kind; r.s = v->s; r.pad = v->pad; r.H2 = v->H2; r.W2 = v->W2;
+  return r;
+}
+static int fill(PrepParams& q, const sb_prep_args* a) {
+  if (!a || a->C % 8 || a->C < 8 || a->C / 8 > 256) return SB_ERR_ARG;
+  q.B = a->B; q.H = a->H; q.W = a->W; q.C = a->C;
+  q.in = mk_view(&a->in);
+  q.add = (const __nv_bfloat16*)a->add;
+  q.relu_in = a->relu_in;
+  q.sums = a->sums; q.eps = a->eps; q.gamma = a->gamma; q.beta = a->beta;
+  q.Ta = a->Ta; q.out1 = (__nv_bfloat16*)a->out1;
+  q.p = a->p; q.seed = a->seed; q.stream_id = a->stream_id; q.keep = a->keep;
+  q.Tb = a->Tb; q.sc = a->sc; q.sh = a->sh;
+  q.out2 = mk_view(&a->out2);
+  q.g2 = mk_view(&a->g2);
+  q.g1 = (const __nv_bfloat16*)a->g1;
+  q.bsums = a->bsums;
+  q.d_main = mk_view(&a->d_main);
+  q.d_add = (__nv_bfloat16*)a->d_add;
+  if (q.sums && (!q.gamma || !q.beta)) return SB_ERR_ARG;
+  if ((q.sc == nullptr) != (q.sh == nullptr)) return SB_ERR_ARG;
+  return SB_OK;
+}
+static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* threads) {
+  const int CV = q.C / 8;
+  *PL = 256 / CV < 1 ? 1 : 256 / CV;
+  *threads = CV * (*PL);
+  const int P = q.H * q.W;
+  int want = (148 * 4 + q.B - 1) / q.B;  // ~4 CTAs per SM over the whole grid
+  if (want < 1) want = 1;
+  int per = (P + want - 1) / want;
+  if (per < *PL) per = *PL;
+  *pps = per;
+  *slabs = (P + per - 1) / per;
+}
+
+extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) {
+  PrepParams q;
+  int rc = fill(q, a);
+  if (rc || !sums || !q.in.p) return SB_ERR_ARG;
+  q.sums = nullptr;
+  int PL, slabs, pps, threads;
+  reduce_cfg(q, &PL, &slabs, &pps, &threads);
+  const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
+  reduce_bc_kernel<0><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
+  PrepParams q;
+  int rc = fill(q, a);
+  if (rc || !q.in.p || !q.out2.p) return SB_ERR_ARG;
+  int y0, ny, x0, nx;
+  if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
+  (void)y0; (void)x0;
+  prep_fwd_kernel<<<grid_for((long long)q.B * ny * nx * (q.C / 8)), 256, 0, (cudaStream_t)stream>>>(q);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
+  PrepParams q;
+  int rc = fill(q, a);
+  if (rc || !q.in.p || !q.g2.p || !q.bsums) return SB_ERR_ARG;
+  int PL, slabs, pps, threads;
+  reduce_cfg(q, &PL, &slabs, &pps, &threads);
+  const size_t smem = (size_t)threads * 4 * 8 * sizeof(float);
+  reduce_bc_kernel<1><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
+  PrepParams q;
+  int rc = fill(q, a);
+  if (rc || !q.in.p || !q.g2.p || !q.d_main.p || (q.sums && !q.bsums)) return SB_ERR_ARG;
+  int ny, nx;
+  if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
+  prep_bwd_apply_kernel<<<grid_for((long long)q.B * ny * nx * (q.C / 8)), 256, 0, (cudaStream_t)stream>>>(q);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
+                              sb_stream_t stream) {
+  if (!in || B < 1 || C < 1 || P < 2 || P * sizeof(float) > 200 * 1024) return SB_ERR_ARG;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(standardize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  standardize_kernel<<<B * C, 256, P * sizeof(float), (cudaStream_t)stream>>>(in, C, P, (__nv_bfloat16*)dst_bf16, ld,
+                                                                              coff, out_f32);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_gru_blend(const void* G, const float* s_old, float* s_new, void* xs, int xs_ld, long long npix,
+                            sb_stream_t stream) {
+  if (!G || !s_old || !s_new || !xs || xs_ld % 8) return SB_ERR_ARG;
+  gru_blend_kernel<<<grid_for(npix * 8), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)G, s_old, s_new,
+                                                                         (__nv_bfloat16*)xs, xs_ld, npix);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs_ld, void* dG,
+                                long long npix, sb_stream_t stream) {
+  if (!G || !s_old || !dxs || !dG || dxs_ld % 8) return SB_ERR_ARG;
+  gru_blend_bwd_kernel<<<grid_for(npix * 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)G, s_old, (const __nv_bfloat16*)dxs, dxs_ld, (__nv_bfloat16*)dG, npix);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
+                            const int* operm, void* fwd, void* tr, sb_stream_t stream) {
+  if (!w || s < 1 || KH % s || KW % s || Ipad < I || Opad < O || (!fwd && !tr)) return SB_ERR_ARG;
+  PackParams q;
+  q.w = w; q.O = O; q.I = I; q.KH = KH; q.KW = KW; q.s = s; q.Ipad = Ipad; q.Opad = Opad;
+  q.iperm = iperm; q.operm = operm; q.fwd = (__nv_bfloat16*)fwd; q.tr = (__nv_bfloat16*)tr;
+  pack_conv_kernel<<<grid_for((long long)O * I * KH * KW), 256, 0, (cudaStream_t)stream>>>(q);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

@@ -1,0 +1,580 @@
+"""B200-native NextFramePredictor (drop-in for simple/next_frame_predictor.py of the reference).
+
+Same constructor, same 120 parameters / state_dict keys and tensor layouts, same forward signature:
+    forward(x [B,12,H,W] f32 in [0,1], action [B,n] or [B,1,n] one-hot, target [B,3,H,W] or None, epsilon)
+        -> (logits [B,256,3,H,W], reward_pred [B,3], value_pred [B])
+The arithmetic runs in the CUDA kernels of simple_b200/csrc (tcgen05 tap GEMMs + fused elementwise stages) on
+NHWC bf16 activations; parameters stay fp32 in the reference layout and are re-packed to bf16 GEMM operands.
+Only the default architecture flags are supported (no multi-backend dispatch); anything else raises.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ConvSpec, PackedWeight, PrepSpec, fused_prep, plain, s2d_in, s2d_out, tap_conv
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers (same attribute names and creation order as the reference => identical init + state_dict)
+# ---------------------------------------------------------------------------------------------------------------
+class ActionInjector(nn.Module):  # simple/utils.py:91-96
+    def __init__(self, n_action, size):
+        super().__init__()
+        self.dense1 = nn.Linear(n_action, size)
+        self.dense2 = nn.Linear(n_action, size)
+
+    def scale_shift(self, action):
+        """sigmoid(dense1(a)), dense2(a) as [B,C] (the broadcast over H,W happens inside the fused kernels)."""
+        a = action.reshape(action.shape[0], -1)
+        return torch.sigmoid(self.dense1(a)), self.dense2(a)
+
+
+class MeanAttention(nn.Module):  # simple/utils.py:72-88
+    def __init__(self, in_size, out_size):
+        super().__init__()
+        self.input_embedding = nn.Conv2d(in_size, 4, 1)
+        self.dense = nn.Linear(5 * in_size, out_size)
+
+    def forward(self, x):  # x: contiguous NCHW fp32
+        b, c = x.shape[0], x.shape[1]
+        m = x.mean(dim=(2, 3))
+        a = F.conv2d(x, self.input_embedding.weight, self.input_embedding.bias).contiguous()
+        s = F.softmax(a.reshape(b, -1, 4), dim=1)  # reference quirk: groups are (flat index) mod 4
+        s = s.reshape(b, 1, 4, x.shape[2], x.shape[3])
+        am = (x.unsqueeze(2) * s).mean(dim=(3, 4))
+        l = torch.cat((am, m.unsqueeze(-1)), dim=-1).reshape(b, 5 * c)
+        return self.dense(l)
+
+
+class RewardEstimator(nn.Module):  # next_frame_predictor.py:11-24
+    def __init__(self, config, input_size):
+        super().__init__()
+        self.dense1 = nn.Linear(input_size, 128)
+        self.dense2 = nn.Linear(128, 3)
+
+    def forward(self, x):
+        return self.dense2(F.relu(self.dense1(x)))
+
+
+class ValueEstimator(nn.Module):  # :27-34
+    def __init__(self, input_size):
+        super().__init__()
+        self.dense = nn.Linear(input_size, 1)
+
+
+class MiddleNetwork(nn.Module):  # :37-50
+    def __init__(self, config, filters):
+        super().__init__()
+        layers = []
+        for i in range(config.hidden_layers):
+            layers.append(nn.Conv2d(filters, filters, 3, padding=1))
+            layers.append(None if i == 0 else nn.InstanceNorm2d(filters, affine=True, eps=1e-6))
+        self.middle_network = nn.ModuleList(layers)
+
+
+class BitsPredictor(nn.Module):  # :66-121
+    def __init__(self, config, input_size, state_size, total_number_bits, bits_at_once=8):
+        super().__init__()
+        self.config = config
+        self.total_number_bits = total_number_bits
+        self.bits_at_once = bits_at_once
+        self.dense1 = nn.Linear(input_size, state_size)
+        self.dense2 = nn.Linear(input_size, state_size)
+        self.dense3 = nn.Linear(input_size, state_size)
+        self.dense4 = nn.Linear(2 ** bits_at_once, state_size)
+        self.dense5 = nn.Linear(state_size, 2 ** bits_at_once)
+        self.lstm = nn.LSTMCell(state_size, state_size)
+
+    def _cell(self, x, h, c):
+        gates = F.linear(x, self.lstm.weight_ih, self.lstm.bias_ih) + F.linear(h, self.lstm.weight_hh, self.lstm.bias_hh)
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        return torch.sigmoid(o) * torch.tanh(c), c
+
+    def forward(self, x, rand, target_bits=None):
+        """x: [B,4608] (C,H,W order).  Teacher-forced loss when target_bits is given, else sampled bits in {-1,+1}."""
+        n = self.total_number_bits // self.bits_at_once
+        first = self.dense1(x)
+        h = self.dense2(x)
+        c = self.dense3(x)
+        if target_bits is not None:
+            tb = target_bits.reshape(-1, n, self.bits_at_once).clamp(min=0.)
+            w = (2 ** torch.arange(self.bits_at_once, device=x.device)).float()
+            tints = (tb * w).sum(-1).long()  # LSB first, on device (the reference round-trips through the host)
+            emb = self.dense4(F.one_hot(tints, 2 ** self.bits_at_once).float())
+            emb = emb * (rand.keep_mask(emb.shape, 0.1) / 0.9)
+            tin = torch.cat((first.unsqueeze(1), emb), dim=1)
+            outs = []
+            for i in range(n):
+                h, c = self._cell(tin[:, i, :], h, c)
+                outs.append(h)
+            outs = torch.stack(outs, dim=1)
+            outs = outs * (rand.keep_mask(outs.shape, 0.1) / 0.9)
+            pred = self.dense5(outs)
+            loss = F.cross_entropy(pred.permute(0, 2, 1), tints)
+            return pred, loss / self.config.rollout_length
+        samples = []
+        inp = first
+        with torch.no_grad():  # integer outputs: nothing to differentiate
+            for i in range(n):
+                h, c = self._cell(inp, h, c)
+                logits = self.dense5(h)
+                # multinomial(exp(logits), 1) == argmax(exp(logits) / Exp(1) noise)
+                s = torch.argmax(torch.exp(logits) / rand.exponential(logits.shape), dim=-1)
+                samples.append(s)
+                inp = self.dense4.weight.t()[s] + self.dense4.bias  # dense4(one_hot(s))
+            ints = torch.stack(samples, dim=1)
+            shifts = torch.arange(self.bits_at_once, device=x.device)
+            bits = ((ints.unsqueeze(-1) >> shifts) & 1).float().reshape(-1, self.total_number_bits)
+        return 2 * bits - 1, 0.0
+
+
+class StochasticModel(nn.Module):  # :124-206
+    def __init__(self, config, layer_shape, n_action):
+        super().__init__()
+        self.config = config
+        channels = config.frame_shape[0] * (int(config.stacking) + 1)
+        filters = [128, 512]
+        self.lstm_loss = None
+        self.get_lstm_loss()
+        self.input_embedding = nn.Conv2d(channels, config.hidden_size, 1)
+        self.conv1 = nn.Conv2d(config.hidden_size, filters[0], 8, 4, padding=2)
+        self.conv2 = nn.Conv2d(filters[0], filters[1], 8, 4, padding=2)
+        self.dense1 = nn.Linear(2 * 2 * channels, config.bottleneck_bits)
+        self.dense2 = nn.Linear(config.bottleneck_bits, layer_shape[0])
+        self.dense3 = nn.Linear(config.bottleneck_bits, layer_shape[0])
+        self.action_injector = ActionInjector(n_action, config.hidden_size)
+        self.mean_attentions = nn.ModuleList([MeanAttention(f, 2 * channels) for f in filters])
+        self.bits_predictor = BitsPredictor(config, layer_shape[0] * layer_shape[1] * layer_shape[2],
+                                            config.latent_state_size, config.bottleneck_bits)
+
+    def add_bits(self, layer, bits):
+        z_mul = torch.sigmoid(self.dense2(bits))[:, :, None, None]
+        z_add = self.dense3(bits)[:, :, None, None]
+        return layer * z_mul + z_add
+
+    def get_lstm_loss(self, reset=True):
+        res = self.lstm_loss
+        if reset:
+            dev = res.device if isinstance(res, torch.Tensor) else None
+            self.lstm_loss = torch.tensor(0., device=dev)
+        return res
+
+
+def timing_signal_nhwc(C, H, W, min_timescale=1.0, max_timescale=1.0e4):
+    """simple/utils.py:129-154 as an NHWC fp32 table [H,W,C] (channels: sin(h w), cos(h w), sin(w w), cos(w w))."""
+    nts = C // 4
+    inc = math.log(float(max_timescale) / float(min_timescale)) / (nts - 1)
+    inv = min_timescale * torch.exp(torch.arange(nts, dtype=torch.float32) * -torch.tensor(inc, dtype=torch.float32))
+    t = torch.zeros(H, W, C)
+    ph = torch.arange(H, dtype=torch.float32).unsqueeze(1) * inv.unsqueeze(0)
+    pw = torch.arange(W, dtype=torch.float32).unsqueeze(1) * inv.unsqueeze(0)
+    t[:, :, 0 * nts:1 * nts] = torch.sin(ph)[:, None, :]
+    t[:, :, 1 * nts:2 * nts] = torch.cos(ph)[:, None, :]
+    t[:, :, 2 * nts:3 * nts] = torch.sin(pw)[None, :, :]
+    t[:, :, 3 * nts:4 * nts] = torch.cos(pw)[None, :, :]
+    return t.contiguous()
+
+
+class DeviceRand:
+    """Fast-path randomness for the small latent tensors (torch's CUDA generator); the big dropout masks are Philox
+    streams generated inside the fused kernels from (seed, stream_id, element index)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def keep_mask(self, shape, p):
+        return (torch.rand(shape, device=self.device) >= p).float()
+
+    def big_keep_mask(self, shape, p):
+        return None  # generated in-kernel
+
+    def uniform(self, shape):
+        return torch.rand(shape, device=self.device)
+
+    def exponential(self, shape):
+        return torch.empty(shape, device=self.device).exponential_(1)
+
+    def truncnorm(self, shape):
+        # truncated normal on [-2,2] sigma, sigma = 0.2, by inverse CDF (the reference calls scipy on the host)
+        lo, hi = 0.5 * (1 + math.erf(-2 / math.sqrt(2))), 0.5 * (1 + math.erf(2 / math.sqrt(2)))
+        u = torch.rand(shape, device=self.device) * (hi - lo) + lo
+        return 0.2 * math.sqrt(2) * torch.erfinv(2 * u - 1)
+
+
+class InjectedRand:
+    """Parity mode ("randomness as input"): replays an explicit list of draws recorded from the oracle, in the
+    reference's draw order.  Keep masks arrive as NCHW 0/1 floats."""
+
+    def __init__(self, log, device):
+        self.log = [(k, t.to(device)) for k, t in log]
+        self.pos = 0
+        self.device = device
+        self.seed = 0
+
+    def _next(self, kind, shape):
+        k, t = self.log[self.pos]
+        self.pos += 1
+        assert k == kind and tuple(t.shape) == tuple(shape), (k, kind, tuple(t.shape), tuple(shape))
+        return t
+
+    def keep_mask(self, shape, p):
+        return self._next('keep', shape)
+
+    def big_keep_mask(self, shape, p):
+        m = self._next('keep', shape)  # [B,C,H,W] -> u8 NHWC
+        return m.permute(0, 2, 3, 1).contiguous().to(torch.uint8)
+
+    def uniform(self, shape):
+        return self._next('uniform', shape)
+
+    def exponential(self, shape):
+        return self._next('exp', shape)
+
+    def truncnorm(self, shape):
+        return self._next('truncnorm', shape)
+
+
+def mix(x1, x2, eps, rand):
+    """simple/utils.py:157-163 -- x2 where rand < eps."""
+    mask = (rand.uniform(x1.shape) < eps).float()
+    return (1 - mask) * x1 + mask * x2
+
+
+class NextFramePredictor(nn.Module):
+
+    def __init__(self, config, n_action):
+        super().__init__()
+        self.config = config
+        c = config
+        if (tuple(c.frame_shape) != (3, 105, 80) or int(c.stacking) != 4 or c.hidden_size != 96 or c.compress_steps != 5
+                or c.filter_double_steps != 3 or c.hidden_layers != 2 or c.recurrent_state_size != 64
+                or c.bottleneck_bits != 128 or c.latent_state_size != 128 or not c.stack_internal_states
+                or not c.use_stochastic_model):
+            raise ValueError('simple_b200.NextFramePredictor supports the default architecture flags only')
+        self.n_action = n_action
+        filters = c.hidden_size
+        channels = c.frame_shape[0] * int(c.stacking) + c.recurrent_state_size
+        self.gate = nn.Conv2d(channels, 2 * c.recurrent_state_size, 3, padding=1)
+        self.input_embedding = nn.Conv2d(channels, c.hidden_size, 1)
+        nn.init.normal_(self.input_embedding.bias, std=0.01)
+        down = []
+        shape = [filters, c.frame_shape[1], c.frame_shape[2]]
+        self._enc_shapes = [list(shape)]
+        for i in range(c.compress_steps):
+            in_filters = filters
+            if i < c.filter_double_steps:
+                filters *= 2
+            shape = [filters, shape[1] // 2, shape[2] // 2]
+            self._enc_shapes.append(list(shape))
+            down.append(nn.Conv2d(in_filters, filters, 4, stride=2, padding=1))
+            down.append(nn.InstanceNorm2d(filters, affine=True, eps=1e-6))
+        self.downscale_layers = nn.ModuleList(down)
+        middle_shape = shape
+        up = []
+        inj = [ActionInjector(n_action, filters)]
+        self._dec_shapes = []
+        for i in range(c.compress_steps):
+            inj.append(ActionInjector(n_action, filters))
+            in_filters = filters
+            if i >= c.compress_steps - c.filter_double_steps:
+                filters //= 2
+            tgt = self._enc_shapes[-i - 2]
+            op = (tgt[1] - shape[1] * 2, tgt[2] - shape[2] * 2)
+            assert op[0] in (0, 1) and op[1] in (0, 1)
+            shape = [filters, tgt[1], tgt[2]]
+            self._dec_shapes.append(list(shape))
+            up.append(nn.ConvTranspose2d(in_filters, filters, 4, stride=2, padding=1, output_padding=op))
+            up.append(nn.InstanceNorm2d(filters, affine=True, eps=1e-6))
+        self.upscale_layers = nn.ModuleList(up)
+        self.action_injectors = nn.ModuleList(inj)
+        self.logits = nn.Conv2d(c.hidden_size, 256 * c.frame_shape[0], 1)
+        self.middle_network = MiddleNetwork(c, middle_shape[0])
+        self.reward_estimator = RewardEstimator(c, middle_shape[0] + filters)
+        self.value_estimator = ValueEstimator(middle_shape[0] * middle_shape[1] * middle_shape[2])
+        self.stochastic_model = StochasticModel(c, middle_shape, n_action)
+
+        self._state = None        # fp32 [B,H,W,64] recurrent state (detached)
+        self._xs_prev = None      # bf16 [B,H,W,128]: previous step's (state | x_start | 0) operand of the gate conv
+        self._plan = None
+        self._packed = None
+        self._auto_repack = True
+        self.parity_rand = None   # set to an InjectedRand to run with explicit randomness
+        self.last_aux = {}
+
+    # ------------------------------------------------------------------ reference surface
+    def init_internal_states(self, batch_size):
+        dev = self.logits.weight.device
+        H, W = self.config.frame_shape[1:]
+        self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
+        self._xs_prev = None
+
+    @property
+    def internal_states(self):
+        return None if self._state is None else self._state.permute(0, 3, 1, 2)
+
+    @property
+    def last_x_start(self):
+        return None if self._xs_prev is None else self._xs_prev[..., 64:76].float().permute(0, 3, 1, 2)
+
+    def load_state_dict(self, *a, **kw):
+        r = super().load_state_dict(*a, **kw)
+        self._packed = None
+        return r
+
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        self._packed = None
+        self._plan = None
+        return r
+
+    # ------------------------------------------------------------------ static plan (layouts, specs, timing tables)
+    def _build_plan(self, dev):
+        c = self.config
+        H, W = c.frame_shape[1:]
+        P = {}
+        taps22 = [(dy, dx) for dy in range(2) for dx in range(2)]
+        taps33 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+        # timing tables (next_frame_predictor.py:234,241,270): index 0, encoder 1..5, decoder 6..10
+        es, ds = self._enc_shapes, self._dec_shapes
+        tshapes = [es[0]] + [es[i] for i in range(5)] + [ds[i] for i in range(5)]
+        P['timing'] = [timing_signal_nhwc(s[0], s[1], s[2]).to(dev) for s in tshapes]
+        P['stoch_timing'] = timing_signal_nhwc(c.hidden_size, H, W).to(dev)
+        # gate 3x3 on XS (state 0..63 | x_start 64..75 | zero pad to 128), no dgrad (inputs are detached / data)
+        P['gate'] = ConvSpec('gate', H, W, 128, H, W, 128, taps33, relu=False, need_dgrad=False)
+        P['embed'] = ConvSpec('embed', H, W, 128, H, W, 96, [(0, 0)], relu=False)
+        P['down'], P['down_lay'] = [], []
+        for i in range(5):
+            Ci, Hi, Wi = es[i]
+            Co, Ho, Wo = es[i + 1]
+            lay = s2d_in(Hi, Wi, Ci, 4, 2, 1)
+            P['down_lay'].append(lay)
+            P['down'].append(ConvSpec(f'down{i}', lay.H2, lay.W2, 4 * Ci, Ho, Wo, Co, taps22, relu=True))
+        P['mid'] = [ConvSpec(f'mid{i}', 3, 2, 768, 3, 2, 768, taps33, relu=True, bwd_mask=(i == 0)) for i in range(2)]
+        P['up'], P['up_lay'] = [], []
+        shape = es[5]
+        for i in range(5):
+            Ci, Hi, Wi = shape
+            Co, Ho, Wo = ds[i]
+            lay = s2d_out(Hi, Wi, Ho, Wo, Co)
+            P['up_lay'].append(lay)
+            P['up'].append(ConvSpec(f'up{i}', Hi, Wi, Ci, Hi + 1, Wi + 1, 4 * Co, [(-dy, -dx) for dy, dx in taps22],
+                                    relu=True, transposed=True, bias_tile=4))
+            shape = ds[i]
+        P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False)
+        # posterior encoder of the stochastic model (train only)
+        P['s_embed'] = ConvSpec('s_embed', H, W, 64, H, W, 96, [(0, 0)], relu=False, need_dgrad=False)
+        l1 = s2d_in(H, W, 96, 8, 4, 2)
+        P['s_lay1'] = l1
+        P['s_conv1'] = ConvSpec('s_conv1', l1.H2, l1.W2, 16 * 96, 26, 20, 128, taps22, relu=False)
+        l2 = s2d_in(26, 20, 128, 8, 4, 2)
+        P['s_lay2'] = l2
+        P['s_conv2'] = ConvSpec('s_conv2', l2.H2, l2.W2, 16 * 128, 6, 5, 512, taps22, relu=False)
+        # fused elementwise stages
+        T = P['timing']
+        drop = c.dropout
+        P['prep_enc'] = []
+        for i in range(5):
+            Ci, Hi, Wi = es[i]
+            P['prep_enc'].append(PrepSpec(Hi, Wi, Ci, plain(Hi, Wi, Ci), P['down_lay'][i], relu_in=(i > 0), norm=(i > 0),
+                                          Ta=T[0] if i == 0 else None, want_out1=True, p=drop, stream_id=1 + i,
+                                          Tb=T[i + 1]))
+        P['prep_x5'] = PrepSpec(3, 2, 768, plain(3, 2, 768), plain(3, 2, 768), relu_in=True, norm=True)
+        rd = c.residual_dropout
+        P['prep_m0'] = PrepSpec(3, 2, 768, plain(3, 2, 768), plain(3, 2, 768), p=rd, stream_id=10)
+        P['prep_m1'] = PrepSpec(3, 2, 768, plain(3, 2, 768), plain(3, 2, 768), relu_in=True, p=rd, stream_id=11)
+        P['prep_dec'] = [PrepSpec(3, 2, 768, plain(3, 2, 768), plain(3, 2, 768), relu_in=True, norm=True, p=drop,
+                                  stream_id=20, inject=True)]
+        for i in range(1, 5):
+            Co, Ho, Wo = ds[i - 1]
+            P['prep_dec'].append(PrepSpec(Ho, Wo, Co, P['up_lay'][i - 1], plain(Ho, Wo, Co), relu_in=True, norm=True,
+                                          Ta=T[5 + i], p=drop, stream_id=20 + i, inject=True))
+        P['prep_final'] = PrepSpec(H, W, 96, P['up_lay'][4], plain(H, W, 96), relu_in=True, norm=True, Ta=T[10])
+        P['prep_s0'] = PrepSpec(H, W, 96, plain(H, W, 96), l1, Ta=P['stoch_timing'], inject=True)
+        P['prep_s1'] = PrepSpec(26, 20, 128, plain(26, 20, 128), l2, relu_in=True)
+        P['tmean10'] = T[10].mean(dim=(0, 1))
+        return P
+
+    def _build_packed(self):
+        c = self.config
+        sm = self.stochastic_model
+        pk = {}
+        # gate input order is (state 64, x_start 12) == XS order; pad K 76 -> 128
+        pk['gate'] = PackedWeight(self.gate.weight, 1, Ipad=128)
+        # input_embedding input order is (x_start 12, state 64): permute to XS order
+        perm = [64 + i for i in range(12)] + list(range(64))
+        pk['embed'] = PackedWeight(self.input_embedding.weight, 1, Ipad=128, iperm=perm)
+        for i in range(5):
+            pk[f'down{i}'] = PackedWeight(self.downscale_layers[2 * i].weight, 2)
+            pk[f'up{i}'] = PackedWeight(self.upscale_layers[2 * i].weight, 2)
+        for i in range(2):
+            pk[f'mid{i}'] = PackedWeight(self.middle_network.middle_network[2 * i].weight, 1)
+        # logits: output channel v*3+colour -> colour*256+v so that a softmax group is contiguous
+        operm = [(o % 3) * 256 + o // 3 for o in range(768)]
+        pk['logits'] = PackedWeight(self.logits.weight, 1, operm=operm)
+        pk['s_embed'] = PackedWeight(sm.input_embedding.weight, 1, Ipad=64)
+        pk['s_conv1'] = PackedWeight(sm.conv1.weight, 4)
+        pk['s_conv2'] = PackedWeight(sm.conv2.weight, 4)
+        self._logit_perm = torch.tensor(operm, device=self.logits.weight.device)
+        return pk
+
+    def _weights(self):
+        return {'gate': self.gate, 'embed': self.input_embedding, 'logits': self.logits,
+                's_embed': self.stochastic_model.input_embedding, 's_conv1': self.stochastic_model.conv1,
+                's_conv2': self.stochastic_model.conv2,
+                **{f'down{i}': self.downscale_layers[2 * i] for i in range(5)},
+                **{f'up{i}': self.upscale_layers[2 * i] for i in range(5)},
+                **{f'mid{i}': self.middle_network.middle_network[2 * i] for i in range(2)}}
+
+    def repack(self, names=None):
+        """Refresh the bf16 GEMM operands from the fp32 master weights (after an optimiser step / load)."""
+        if self._packed is None:
+            self._packed = self._build_packed()
+            return
+        mods = self._weights()
+        for k in (names or self._packed.keys()):
+            self._packed[k].pack(mods[k].weight)
+
+    def _conv(self, name, spec, a, need_weight_grad=True):
+        m = self._weights_cache[name]
+        return tap_conv(spec, a, m.weight, m.bias, self._packed[name])
+
+    # ------------------------------------------------------------------ forward
+    def _trunk(self, x, action, target, epsilon, rand):
+        c = self.config
+        P = self._plan
+        dev = x.device
+        B = x.shape[0]
+        H, W = c.frame_shape[1:]
+        seed = rand.seed
+        training = self.training and target is not None
+        aux = self.last_aux = {}
+
+        def keep(spec_shape_nchw, p):
+            return rand.big_keep_mask(spec_shape_nchw, p)
+
+        # ---- standardise + recurrent state (K5, K6)
+        xs = torch.zeros(B, H, W, 128, device=dev, dtype=torch.bfloat16)
+        ops.standardize(x.contiguous().float(), dst=xs, coff=64)
+        if self._state is None or self._state.shape[0] != B:
+            self.init_internal_states(B)
+        if self._xs_prev is not None:
+            G = self._conv('gate', P['gate'], self._xs_prev)
+            xs, s_new = ops.GruBlend.apply(G, self._state, xs)
+            self._state = s_new
+        self._xs_prev = xs.detach()
+        e = self._conv('embed', P['embed'], xs)
+        # ---- encoder (K1, K3, K4, K8)
+        skips = []
+        main = e
+        for i in range(5):
+            sp = P['prep_enc'][i]
+            nrm = self.downscale_layers[2 * i - 1] if i > 0 else None
+            km = keep((B, sp.C, sp.H, sp.W), sp.p)
+            skip, A = fused_prep(sp, main, gamma=nrm.weight if nrm is not None else None,
+                                 beta=nrm.bias if nrm is not None else None, seed=seed, keep=km)
+            skips.append(skip)
+            main = self._conv(f'down{i}', P['down'][i], A)
+        nrm = self.downscale_layers[9]
+        _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias)
+        # ---- bottleneck heads and latent (tiny tensors; fp32, NCHW semantics of the reference)
+        h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
+        value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
+                              self.value_estimator.dense.bias).squeeze(-1)
+        sc0, sh0 = self.action_injectors[0].scale_shift(action)
+        h = h * sc0[:, :, None, None] + sh0[:, :, None, None]
+        if target is not None:
+            ps = torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+            ops.standardize(target, dst=ps, coff=12, out_f32=target)  # in place, like the reference (:332-334)
+        sm = self.stochastic_model
+        if training:
+            ps[..., :12] = xs.detach()[..., 64:76]
+            h = self._posterior(h, ps, action, epsilon, rand, aux)
+        else:
+            bits, _ = sm.bits_predictor(h.reshape(B, -1), rand)
+            aux['bits'] = bits
+            h = sm.add_bits(h, bits)
+        x_mid = h.mean(dim=(2, 3))
+        hm = h.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        # ---- middle network (:52-63)
+        mn = self.middle_network.middle_network
+        sp = P['prep_m0']
+        _, A = fused_prep(sp, hm, seed=seed, keep=keep((B, 768, 3, 2), sp.p))
+        y1 = self._conv('mid0', P['mid'][0], A)
+        sp = P['prep_m1']
+        _, A = fused_prep(sp, y1, seed=seed, keep=keep((B, 768, 3, 2), sp.p))
+        y2 = self._conv('mid1', P['mid'][1], A)
+        # ---- decoder (K2, K3, K4, K7, K8)
+        main, add, nrm = y2, y1, mn[3]
+        for i in range(5):
+            sp = P['prep_dec'][i]
+            sc, sh = self.action_injectors[i + 1].scale_shift(action)
+            km = keep((B, sp.C, sp.H, sp.W), sp.p)
+            _, A = fused_prep(sp, main, add=add, gamma=nrm.weight, beta=nrm.bias, sc=sc, sh=sh, seed=seed, keep=km)
+            main = self._conv(f'up{i}', P['up'][i], A)
+            add = skips[4 - i]
+            nrm = self.upscale_layers[2 * i + 1]
+        _, hf = fused_prep(P['prep_final'], main, add=add, gamma=nrm.weight, beta=nrm.bias)
+        # x_fin = mean_hw(IN(z)*gamma + beta + timing) == beta + mean_hw(timing): the normalised part has zero mean
+        x_fin = (nrm.bias + P['tmean10']).unsqueeze(0).expand(B, -1)
+        reward_pred = self.reward_estimator(torch.cat((x_mid, x_fin), dim=1))
+        logits = self._conv('logits', P['logits'], hf)  # bf16 [B,H,W,768], channel = colour*256 + value
+        return logits, reward_pred, value_pred
+
+    def _posterior(self, layer, ps, action, epsilon, rand, aux):
+        """StochasticModel.forward, training branch (next_frame_predictor.py:162-197)."""
+        c = self.config
+        P = self._plan
+        sm = self.stochastic_model
+        B = layer.shape[0]
+        e = self._conv('s_embed', P['s_embed'], ps)
+        sc, sh = sm.action_injector.scale_shift(action)
+        _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh)
+        c1 = self._conv('s_conv1', P['s_conv1'], A)  # [B,26,20,128], pre-ReLU
+        x1 = sm.mean_attentions[0](c1.float().permute(0, 3, 1, 2).contiguous())
+        _, A = fused_prep(P['prep_s1'], c1)
+        c2 = self._conv('s_conv2', P['s_conv2'], A)  # [B,6,5,512]
+        x2 = sm.mean_attentions[1](c2.float().permute(0, 3, 1, 2).contiguous())
+        x = sm.dense1(torch.cat((x1, x2), dim=-1))
+        aux['posterior_pre'] = x
+        bits_clean = (2 * (0 < x).float()).detach() - 1
+        x = torch.tanh(x + rand.truncnorm(x.shape))
+        bits = x + (2 * (0 < x).float() - 1 - x).detach()
+        noise = 2 * (c.bottleneck_noise < rand.uniform(x.shape)).float() - 1
+        bits = bits * noise
+        bits = mix(bits, x, 1 - epsilon, rand)
+        flat = layer.reshape(B, -1)
+        _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean)
+        sm.lstm_loss = sm.lstm_loss.to(lstm_loss.device) + lstm_loss
+        bits_pred, _ = sm.bits_predictor(flat, rand)
+        aux['bits_pred'] = bits_pred
+        bits_pred = bits_clean + (bits_pred - bits_clean).detach()
+        bits = mix(bits_pred, bits, 1 - (1 - epsilon) * c.latent_rnn_max_sampling, rand)
+        aux['bits'] = bits
+        res = sm.add_bits(layer, bits)
+        return mix(res, layer, 1 - (1 - epsilon) * c.latent_use_max_probability, rand)
+
+    def forward_internal(self, x, action, target=None, epsilon=0):
+        """Runs the network and returns the INTERNAL logits (bf16 [B,H,W,768], colour-major) + reward + value."""
+        dev = x.device
+        if dev.type != 'cuda':
+            raise RuntimeError('simple_b200.NextFramePredictor runs on CUDA (sm_100a) only; there is no CPU fallback')
+        if self._plan is None:
+            self._plan = self._build_plan(dev)
+        if self._packed is None:
+            self._packed = self._build_packed()
+        elif self._auto_repack:
+            self.repack()
+        self._weights_cache = self._weights()
+        rand = self.parity_rand if self.parity_rand is not None else DeviceRand(dev)
+        return self._trunk(x, action, target, epsilon, rand)
+
+    def forward(self, x, action, target=None, epsilon=0):
+        logits, reward_pred, value_pred = self.forward_internal(x, action, target, epsilon)
+        B, H, W, _ = logits.shape
+        ref = logits.reshape(B, H, W, 3, 256).permute(0, 4, 3, 1, 2).float()
+        return ref, reward_pred, value_pred

@@ -1,0 +1,414 @@
+"""Host-side operators of the world-model hot path: thin autograd wrappers over the C-ABI CUDA kernels.
+
+Every function here launches hand-written sm_100a kernels through `simple_b200._lib`; nothing falls back to ATen for
+the arithmetic (torch is used for allocation, streams and the autograd tape only).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .gemm import tap_gemm, tap_wgrad
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# layouts
+# ---------------------------------------------------------------------------------------------------------------
+class Lay:
+    """Physical layout of a logical [B,H,W,C] bf16 activation: plain NHWC (s=1) or padded space-to-depth."""
+
+    def __init__(self, H, W, C, s=1, pad=0, H2=None, W2=None):
+        self.H, self.W, self.C, self.s, self.pad = H, W, C, s, pad
+        self.kind = 0 if s == 1 else 1
+        self.H2 = H2 if H2 is not None else H
+        self.W2 = W2 if W2 is not None else W
+
+    def shape(self, B):
+        if self.kind == 0:
+            return (B, self.H, self.W, self.C)
+        return (B, self.H2, self.W2, self.s * self.s * self.C)
+
+    def view(self, t):
+        v = _lib.SbView()
+        v.p = t.data_ptr() if t is not None else None
+        v.kind, v.s, v.pad, v.H2, v.W2 = self.kind, self.s, self.pad, self.H2, self.W2
+        return v
+
+    def to_nchw(self, t):
+        """Debug/test helper: physical tensor -> logical [B,C,H,W] fp32."""
+        B = t.shape[0]
+        if self.kind == 0:
+            return t.float().permute(0, 3, 1, 2)
+        s = self.s
+        x = t.float().reshape(B, self.H2, self.W2, s, s, self.C).permute(0, 5, 1, 3, 2, 4)
+        x = x.reshape(B, self.C, self.H2 * s, self.W2 * s)
+        return x[:, :, self.pad:self.pad + self.H, self.pad:self.pad + self.W]
+
+
+def plain(H, W, C):
+    return Lay(H, W, C)
+
+
+def s2d_in(H, W, C, k, s, pad):
+    """Layout consumed by a k x k / stride s / padding pad convolution expressed as (k/s)^2 stride-1 taps."""
+    Ho = (H + 2 * pad - k) // s + 1
+    Wo = (W + 2 * pad - k) // s + 1
+    return Lay(H, W, C, s=s, pad=pad, H2=Ho + k // s - 1, W2=Wo + k // s - 1)
+
+
+def s2d_out(Hin, Win, Hout, Wout, C):
+    """Layout produced by a 4x4 / stride 2 / padding 1 transposed convolution run as 4 taps: N = (phase, C)."""
+    return Lay(Hout, Wout, C, s=2, pad=1, H2=Hin + 1, W2=Win + 1)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raw kernel wrappers
+# ---------------------------------------------------------------------------------------------------------------
+class PrepSpec:
+    """Static description of one fused elementwise stage (see sb_prep in include/simple_b200.h)."""
+
+    def __init__(self, H, W, C, lay_in, lay_out, relu_in=False, norm=False, Ta=None, want_out1=False, p=0.0,
+                 stream_id=0, Tb=None, inject=False, eps=1e-6):
+        self.H, self.W, self.C = H, W, C
+        self.lay_in, self.lay_out = lay_in, lay_out
+        self.relu_in, self.norm, self.Ta, self.want_out1 = relu_in, norm, Ta, want_out1
+        self.p, self.stream_id, self.Tb, self.inject, self.eps = p, stream_id, Tb, inject, eps
+
+
+def _prep_args(spec, B, main, add, sums, gamma, beta, sc, sh, out1, out2, seed, keep):
+    a = _lib.PrepArgs()
+    a.B, a.H, a.W, a.C = B, spec.H, spec.W, spec.C
+    a.inp = spec.lay_in.view(main)
+    a.add = _ptr(add)
+    a.relu_in = int(spec.relu_in)
+    a.sums = _ptr(sums)
+    a.eps = spec.eps
+    a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+    a.Ta = _ptr(spec.Ta)
+    a.out1 = _ptr(out1)
+    a.p = float(spec.p)
+    a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    a.stream_id = spec.stream_id
+    a.keep = _ptr(keep)
+    a.Tb = _ptr(spec.Tb)
+    a.sc, a.sh = _ptr(sc), _ptr(sh)
+    a.out2 = spec.lay_out.view(out2)
+    return a
+
+
+def stats_raw(spec, main, add=None):
+    """Per-(b,c) raw sums [B,C,2] (sum, sum of squares) of relu?(main)+add over the logical H x W pixels."""
+    B = main.shape[0]
+    sums = torch.zeros(B, spec.C, 2, device=main.device, dtype=torch.float32)
+    a = _prep_args(spec, B, main, add, None, None, None, None, None, None, None, 0, None)
+    _lib.check(_lib.lib().sb_stats(ctypes.byref(a), sums.data_ptr(), _lib.stream_ptr()), 'sb_stats')
+    return sums
+
+
+class FusedPrep(torch.autograd.Function):
+    """z = relu?(main)+add; x = IN(z)*gamma+beta + Ta; out1 = x; out2 = (dropout(x)+Tb)*sc + sh, with layout change."""
+
+    @staticmethod
+    def forward(ctx, spec, main, add, gamma, beta, sc, sh, seed, keep):
+        B = main.shape[0]
+        dev = main.device
+        sums = stats_raw(spec, main, add) if spec.norm else None
+        gamma_f = gamma.detach().float().contiguous() if gamma is not None else None
+        beta_f = beta.detach().float().contiguous() if beta is not None else None
+        sc_f = sc.detach().float().contiguous() if sc is not None else None
+        sh_f = sh.detach().float().contiguous() if sh is not None else None
+        out1 = torch.empty((B, spec.H, spec.W, spec.C), device=dev, dtype=torch.bfloat16) if spec.want_out1 else None
+        out2 = torch.empty(spec.lay_out.shape(B), device=dev, dtype=torch.bfloat16)
+        a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, out1, out2, seed, keep)
+        _lib.check(_lib.lib().sb_prep(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep')
+        ctx.spec, ctx.seed = spec, seed
+        ctx.save_for_backward(main, add, sums, gamma_f, beta_f, sc_f, sh_f, keep)
+        ctx.has = (add is not None, gamma is not None, sc is not None)
+        if out1 is None:
+            out1 = torch.empty(0, device=dev, dtype=torch.bfloat16)
+            ctx.mark_non_differentiable(out1)
+        return out1, out2
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        spec = ctx.spec
+        main, add, sums, gamma_f, beta_f, sc_f, sh_f, keep = ctx.saved_tensors
+        B = main.shape[0]
+        dev = main.device
+        has_add, has_norm, has_inj = ctx.has
+        if g2 is None:
+            g2 = torch.zeros(spec.lay_out.shape(B), device=dev, dtype=torch.bfloat16)
+        g2 = g2.contiguous()
+        if not spec.want_out1:
+            g1 = None
+        if g1 is not None:
+            g1 = g1.contiguous()
+        a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, None, None, ctx.seed, keep)
+        a.g2 = spec.lay_out.view(g2)
+        a.g1 = _ptr(g1)
+        bsums = None
+        if has_norm or has_inj:
+            bsums = torch.zeros(B, spec.C, 4, device=dev, dtype=torch.float32)
+            a.bsums = bsums.data_ptr()
+            _lib.check(_lib.lib().sb_prep_bwd_reduce(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_reduce')
+        d_main = torch.empty_like(main)
+        d_add = torch.empty_like(add) if has_add else None
+        a.d_main = spec.lay_in.view(d_main)
+        a.d_add = _ptr(d_add)
+        _lib.check(_lib.lib().sb_prep_bwd_apply(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_apply')
+        dgamma = bsums[:, :, 1].sum(0) if has_norm else None
+        dbeta = bsums[:, :, 0].sum(0) if has_norm else None
+        dsc = bsums[:, :, 2].contiguous() if has_inj else None
+        dsh = bsums[:, :, 3].contiguous() if has_inj else None
+        return None, d_main, d_add, dgamma, dbeta, dsc, dsh, None, None
+
+
+def fused_prep(spec, main, add=None, gamma=None, beta=None, sc=None, sh=None, seed=0, keep=None):
+    out1, out2 = FusedPrep.apply(spec, main, add, gamma, beta, sc, sh, seed, keep)
+    return (out1 if spec.want_out1 else None), out2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# convolution as tap GEMM
+# ---------------------------------------------------------------------------------------------------------------
+class ConvSpec:
+    """Static description of one convolution lowered to tap GEMMs.
+
+    fwd:   y[B,Ho,Wo,N]      = taps(a [B,Ha,Wa,Ca]; w_fwd [N, T*Ca])         (+bias, relu)
+    dgrad: da[B,Ha,Wa,Ca]    = taps^-(dy; w_tr [Ca, T*N])
+    wgrad: dw_packed[N,T*Ca] = sum_pix dy (x) a_shifted
+    For a Conv2d: w_fwd = pack.fwd, w_tr = pack.tr;  for a ConvTranspose2d the roles are swapped (see sb_pack_conv).
+    """
+
+    def __init__(self, name, Ha, Wa, Ca, Ho, Wo, N, taps, relu, transposed=False, need_dgrad=True, bias_tile=1,
+                 bwd_mask=False):
+        self.name = name
+        self.Ha, self.Wa, self.Ca, self.Ho, self.Wo, self.N = Ha, Wa, Ca, Ho, Wo, N
+        self.taps, self.relu, self.transposed = taps, relu, transposed
+        self.need_dgrad, self.bias_tile = need_dgrad, bias_tile
+        # bwd_mask: apply the ReLU mask inside backward (incoming gradients normally arrive already masked by the
+        # fused elementwise stage that consumed the output; a residual branch bypasses that stage)
+        self.bwd_mask = bwd_mask
+        self.neg_taps = [(-dy, -dx) for dy, dx in taps]
+
+
+class PackedWeight:
+    """bf16 GEMM operands of one conv-like parameter plus the index maps to (un)pack gradients."""
+
+    def __init__(self, weight, s, Ipad=None, Opad=None, iperm=None, operm=None):
+        O, I, KH, KW = weight.shape
+        self.O, self.I, self.KH, self.KW, self.s = O, I, KH, KW, s
+        self.Ipad, self.Opad = Ipad or I, Opad or O
+        self.T, self.PH = (KH // s) * (KW // s), s * s
+        dev = weight.device
+        self.iperm = torch.tensor(iperm, dtype=torch.int32, device=dev) if iperm is not None else None
+        self.operm = torch.tensor(operm, dtype=torch.int32, device=dev) if operm is not None else None
+        self.fwd = torch.zeros(self.Opad, self.T * self.PH * self.Ipad, device=dev, dtype=torch.bfloat16)
+        self.tr = torch.zeros(self.PH * self.Ipad, self.T * self.Opad, device=dev, dtype=torch.bfloat16)
+        # gather index: reference (o,i,ky,kx) -> column-major position in the packed "fwd" layout
+        o = torch.arange(O, device=dev).view(O, 1, 1, 1)
+        i = torch.arange(I, device=dev).view(1, I, 1, 1)
+        ky = torch.arange(KH, device=dev).view(1, 1, KH, 1)
+        kx = torch.arange(KW, device=dev).view(1, 1, 1, KW)
+        t = (ky // s) * (KW // s) + (kx // s)
+        ph = (ky % s) * s + (kx % s)
+        oo = self.operm.long()[o] if self.operm is not None else o
+        ii = self.iperm.long()[i] if self.iperm is not None else i
+        self.gather = (oo * (self.T * self.PH * self.Ipad) + (t * self.PH + ph) * self.Ipad + ii).reshape(-1)
+        self.pack(weight)
+
+    def pack(self, weight):
+        w = weight.detach()
+        assert w.dtype == torch.float32 and w.is_contiguous()
+        _lib.check(_lib.lib().sb_pack_conv(w.data_ptr(), self.O, self.I, self.KH, self.KW, self.s, self.Ipad,
+                                           self.Opad, _ptr(self.iperm), _ptr(self.operm), self.fwd.data_ptr(),
+                                           self.tr.data_ptr(), _lib.stream_ptr()), 'sb_pack_conv')
+
+    def unpack_grad(self, g_packed):
+        """fp32 gradient in packed 'fwd' layout -> reference layout [O,I,KH,KW]."""
+        return g_packed.reshape(-1)[self.gather].reshape(self.O, self.I, self.KH, self.KW)
+
+
+def colsum(t2d):
+    """Column sums of a bf16 [rows, C] matrix (bias gradients) via the per-(b,c) reduction kernel."""
+    rows, C = t2d.shape
+    spec = PrepSpec(1, rows, C, plain(1, rows, C), plain(1, rows, C))
+    return stats_raw(spec, t2d.reshape(1, 1, rows, C))[0, :, 0]
+
+
+class TapConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, a, weight, bias, pw):
+        w_op = pw.tr if spec.transposed else pw.fwd
+        bias_f = None
+        if bias is not None:
+            bias_f = bias.detach().float()
+            if pw.operm is not None:  # output channels are stored permuted: physical[operm[o]] = reference[o]
+                bp = torch.empty_like(bias_f)
+                bp[pw.operm.long()] = bias_f
+                bias_f = bp
+            if spec.bias_tile > 1:
+                bias_f = bias_f.repeat(spec.bias_tile)
+            bias_f = bias_f.contiguous()
+        B = a.shape[0]
+        splits = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
+        if splits > 1:
+            acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits)
+            y = _bias_act(acc, bias_f, spec.relu)
+        else:
+            y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu)
+        ctx.spec, ctx.pw = spec, pw
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(a, y if spec.bwd_mask else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec, pw = ctx.spec, ctx.pw
+        a, y = ctx.saved_tensors
+        if y is not None:
+            dy = dy * (y > 0)
+        dy = dy.contiguous()
+        B = a.shape[0]
+        da = None
+        if spec.need_dgrad and ctx.needs_input_grad[1]:
+            w_op = pw.fwd if spec.transposed else pw.tr
+            splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
+            if splits > 1:
+                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits).bfloat16()
+            else:
+                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca)
+        T = len(spec.taps)
+        if spec.transposed:
+            # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
+            dwp = torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
+            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=_wgrad_splits(B, spec.Ha, spec.Wa, spec.Ca, spec.N, T))
+        else:
+            dwp = torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
+            tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T))
+        dweight = pw.unpack_grad(dwp)
+        dbias = None
+        if ctx.has_bias:
+            dbias = colsum(dy.reshape(-1, spec.N))
+            if spec.bias_tile > 1:
+                dbias = dbias.reshape(spec.bias_tile, -1).sum(0)
+            if pw.operm is not None:
+                dbias = dbias[pw.operm.long()]
+        return None, da, dweight, dbias, None
+
+
+def auto_splits(B, Ho, Wo, N, KT):
+    """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed."""
+    from .gemm import choose_box
+    bw, bh, bb = choose_box(Wo, Ho, B)
+    m_tiles = -(-Wo // bw) * -(-Ho // bh) * -(-B // bb)
+    BN = 256 if N % 256 == 0 else 192 if N % 192 == 0 else 128 if N % 128 == 0 else 96 if N <= 96 else 128
+    ctas = m_tiles * -(-N // BN)
+    if ctas >= 100:
+        return 1
+    return int(max(1, min(KT, -(-296 // ctas), 32)))
+
+
+def _wgrad_splits(B, Ho, Wo, M, Ccols, T):
+    """Pixel-split factor so that the wgrad grid has roughly two waves of CTAs."""
+    BN = 256 if Ccols > 128 else (128 if Ccols > 64 else 64)
+    ctas = -(-M // 128) * T * -(-Ccols // BN)
+    ptiles = max(1, (B * Ho * Wo) // 64)
+    want = max(1, (2 * 148) // ctas)
+    return int(min(want, ptiles))
+
+
+def _bias_act(acc, bias, relu):
+    """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16."""
+    y = acc
+    if bias is not None:
+        y = y + bias
+    if relu:
+        y = torch.relu(y)
+    return y.bfloat16()
+
+
+def tap_conv(spec, a, weight, bias, pw):
+    return TapConv.apply(spec, a, weight, bias, pw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# recurrent state blend, standardisation, loss
+# ---------------------------------------------------------------------------------------------------------------
+class GruBlend(torch.autograd.Function):
+    """xs_state (bf16, written into xs[..., :64]) = s*sigmoid(g) + tanh(c)*(1-sigmoid(g)); returns the new fp32 state."""
+
+    @staticmethod
+    def forward(ctx, G, s_old, xs):
+        npix = G.numel() // 128
+        s_new = torch.empty_like(s_old)
+        _lib.check(_lib.lib().sb_gru_blend(G.data_ptr(), s_old.data_ptr(), s_new.data_ptr(), xs.data_ptr(),
+                                           xs.shape[-1], npix, _lib.stream_ptr()), 'sb_gru_blend')
+        ctx.save_for_backward(G, s_old)
+        ctx.mark_dirty(xs)
+        ctx.mark_non_differentiable(s_new)
+        return xs, s_new
+
+    @staticmethod
+    def backward(ctx, dxs, _):
+        G, s_old = ctx.saved_tensors
+        npix = G.numel() // 128
+        dxs = dxs.contiguous()
+        dG = torch.empty_like(G)
+        _lib.check(_lib.lib().sb_gru_blend_bwd(G.data_ptr(), s_old.data_ptr(), dxs.data_ptr(), dxs.shape[-1],
+                                               dG.data_ptr(), npix, _lib.stream_ptr()), 'sb_gru_blend_bwd')
+        return dG, None, None
+
+
+def standardize(x, dst=None, coff=0, out_f32=None):
+    """x fp32 [B,C,H,W] -> standardised; writes bf16 into dst[..., coff:coff+C] (NHWC) and/or fp32 `out_f32` (NCHW)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, C, H, W = x.shape
+    _lib.check(_lib.lib().sb_standardize(x.data_ptr(), B, C, H * W, _ptr(dst), dst.shape[-1] if dst is not None else 0,
+                                         coff, _ptr(out_f32), _lib.stream_ptr()), 'sb_standardize')
+
+
+class PixelCE(torch.autograd.Function):
+    """Clipped per-pixel CE (simple/trainer.py:134-137) on colour-major bf16 logits [B,H,W,768]; the gradient is
+    produced in the same pass and overwrites the logits buffer."""
+
+    @staticmethod
+    def forward(ctx, logits, target_u8, clip, want_argmax, unit_grad):
+        B, H, W, _ = logits.shape
+        HW = H * W
+        loss_sum = torch.zeros(1, device=logits.device, dtype=torch.float64)
+        dbias = torch.zeros(768, device=logits.device, dtype=torch.float32)
+        amax = torch.empty(B, 3, H, W, device=logits.device, dtype=torch.uint8) if want_argmax else None
+        n = float(B * 3 * HW)
+        dl = logits.detach()
+        _lib.check(_lib.lib().sb_pixel_ce(dl.data_ptr(), target_u8.data_ptr(), B, HW, clip, 1.0 / n, dl.data_ptr(),
+                                          _ptr(amax), loss_sum.data_ptr(), dbias.data_ptr(), _lib.stream_ptr()),
+                   'sb_pixel_ce')
+        ctx.save_for_backward(dl)
+        ctx.unit_grad = unit_grad
+        loss = (loss_sum / n - clip).float().reshape(())
+        if amax is None:
+            amax = torch.empty(0, device=logits.device, dtype=torch.uint8)
+        ctx.mark_non_differentiable(amax)
+        return loss, amax
+
+    @staticmethod
+    def backward(ctx, gloss, _):
+        (dl,) = ctx.saved_tensors
+        # the training loss enters the total with weight 1 (trainer.py:141); honour other weights generically
+        if ctx.unit_grad:  # caller guarantees d(total)/d(loss) == 1: skip a full pass over the gradient
+            return dl, None, None, None, None
+        return dl * gloss.to(dl.dtype), None, None, None, None
+
+
+def pixel_argmax(logits):
+    """argmax decode of colour-major bf16 logits [B,H,W,768] -> u8 [B,3,H,W] (subproc_vec_env.py:428)."""
+    B, H, W, _ = logits.shape
+    amax = torch.empty(B, 3, H, W, device=logits.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().sb_pixel_ce(logits.data_ptr(), None, B, H * W, 0.0, 0.0, None, amax.data_ptr(), None, None,
+                                      _lib.stream_ptr()), 'sb_pixel_ce')
+    return amax

@@ -1,0 +1,340 @@
+"""Per-kernel parity: every fused CUDA operator vs a plain PyTorch fp32 reference of the same op (same bf16 inputs),
+and vs the numpy/float64 oracle where one exists."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+# ------------------------------------------------------------------------------------------------ pixel CE (K14)
+@pytest.mark.parametrize('B,HW', [(1, 64), (2, 8400), (3, 1000)])
+def test_pixel_ce_vs_oracle(B, HW):
+    from oracle.wm_oracle import pixel_ce_np
+    from simple_b200 import ops
+    torch.manual_seed(0)
+    H, W = HW // 8 if HW % 8 == 0 else HW, 8 if HW % 8 == 0 else 1
+    logits = (torch.randn(B, H, W, 768, device=DEV) * 3).bfloat16()
+    # force exact ties so that the first-index rule is exercised
+    logits[:, :, :, 5] = logits[:, :, :, 200]
+    target = torch.randint(0, 256, (B, 3, H, W), device=DEV, dtype=torch.uint8)
+    # make some pixels confidently right so that the 0.03 clip is active
+    t0 = target[0, 0].long()
+    logits[0, :, :, :256].scatter_(2, t0.unsqueeze(-1), 30.0)
+    ref_in = logits.float().cpu().numpy().reshape(B, H * W, 3, 256)
+    lg = logits.clone()
+    loss, amax = ops.PixelCE.apply(lg.requires_grad_(True), target, 0.03, True, True)
+    torch.cuda.synchronize()
+    dl = lg.detach().float().cpu().numpy().reshape(B, H * W, 3, 256)
+    tg = target.cpu().numpy().reshape(B, 3, H * W)
+    rows = np.concatenate([ref_in[:, :, g, :].reshape(-1, 256) for g in range(3)])
+    tgt = np.concatenate([tg[:, g, :].reshape(-1) for g in range(3)])
+    oloss, odl, oarg = pixel_ce_np(rows, tgt, 0.03)
+    assert abs(float(loss) - oloss) < 1e-3 * max(1.0, abs(oloss)), (float(loss), oloss)
+    got_dl = np.concatenate([dl[:, :, g, :].reshape(-1, 256) for g in range(3)])
+    scale = np.abs(odl).max()
+    assert np.abs(got_dl - odl).max() <= 1e-2 * scale, np.abs(got_dl - odl).max() / scale
+    got_arg = np.concatenate([amax.cpu().numpy().reshape(B, 3, H * W)[:, g, :].reshape(-1) for g in range(3)])
+    assert np.array_equal(got_arg, oarg)  # bit-exact, first index on ties
+    # decode-only variant
+    am2 = ops.pixel_argmax(logits)
+    assert torch.equal(am2, amax)
+
+
+def test_standardize_vs_oracle():
+    from oracle.wm_oracle import standardize_frame
+    from simple_b200 import ops
+    torch.manual_seed(1)
+    x = torch.rand(3, 12, 105, 80)
+    x[1, 3] = 0.25  # constant plane: exercises the 1/sqrt(P) floor
+    ref = torch.stack([standardize_frame(f) for f in x])
+    xs = torch.zeros(3, 105, 80, 128, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(3, 12, 105, 80, device=DEV)
+    ops.standardize(x.to(DEV), dst=xs, coff=64, out_f32=out)
+    assert torch.allclose(out.cpu(), ref, atol=2e-5, rtol=1e-5)
+    got = xs[..., 64:76].float().permute(0, 3, 1, 2).cpu()
+    assert torch.allclose(got, ref, atol=2e-2, rtol=1e-2)
+    assert float(xs[..., :64].abs().max()) == 0 and float(xs[..., 76:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------------ fused prep
+def _prep_reference(spec, main_nchw, add_nchw, gamma, beta, sc, sh, keep_nchw, relu_in):
+    z = F.relu(main_nchw) if relu_in else main_nchw
+    if add_nchw is not None:
+        z = z + add_nchw
+    x = z
+    if gamma is not None:
+        x = F.instance_norm(z, weight=gamma, bias=beta, eps=1e-6)
+    if spec.Ta is not None:
+        x = x + spec.Ta.permute(2, 0, 1)
+    out1 = x
+    if spec.p > 0:
+        x = x * (keep_nchw / (1 - spec.p))
+    if spec.Tb is not None:
+        x = x + spec.Tb.permute(2, 0, 1)
+    if sc is not None:
+        x = x * sc[:, :, None, None] + sh[:, :, None, None]
+    return out1, x
+
+
+@pytest.mark.parametrize('case', ['enc0', 'enc', 'dec', 'final', 's2d4'])
+def test_fused_prep_fwd_bwd(case):
+    from simple_b200 import ops
+    from simple_b200.ops import PrepSpec, plain, s2d_in, s2d_out
+    torch.manual_seed(2)
+    B = 3
+    if case == 'enc0':
+        H, W, C = 21, 16, 96
+        Ta, Tb = torch.randn(H, W, C, device=DEV), torch.randn(H, W, C, device=DEV)
+        spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 4, 2, 1), Ta=Ta, want_out1=True, p=0.15, Tb=Tb)
+        norm = inj = add = False
+    elif case == 'enc':
+        H, W, C = 13, 10, 192
+        Tb = torch.randn(H, W, C, device=DEV)
+        spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 4, 2, 1), relu_in=True, norm=True, want_out1=True,
+                        p=0.15, Tb=Tb)
+        norm, inj, add = True, False, False
+    elif case == 'dec':
+        H, W, C = 13, 10, 96  # output of a convT from 6x5 with output_padding (1,0)
+        Ta = torch.randn(H, W, C, device=DEV)
+        spec = PrepSpec(H, W, C, s2d_out(6, 5, H, W, C), plain(H, W, C), relu_in=True, norm=True, Ta=Ta, p=0.15,
+                        inject=True)
+        norm, inj, add = True, True, True
+    elif case == 'final':
+        H, W, C = 7, 6, 96
+        Ta = torch.randn(H, W, C, device=DEV)
+        spec = PrepSpec(H, W, C, s2d_out(3, 3, H, W, C), plain(H, W, C), relu_in=True, norm=True, Ta=Ta)
+        norm, inj, add = True, False, True
+    else:
+        H, W, C = 26, 20, 128
+        spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 8, 4, 2), relu_in=True)
+        norm = inj = add = False
+    main_l = (torch.randn(B, C, H, W, device=DEV)).bfloat16().float()
+    # physical main tensor in the input layout (random garbage in the padding positions of s2d-phase inputs)
+    lay = spec.lay_in
+    if lay.kind == 0:
+        main_p = main_l.permute(0, 2, 3, 1).contiguous().bfloat16()
+    else:
+        s = lay.s
+        full = torch.randn(B, C, lay.H2 * s, lay.W2 * s, device=DEV)
+        full[:, :, lay.pad:lay.pad + H, lay.pad:lay.pad + W] = main_l
+        main_p = full.reshape(B, C, lay.H2, s, lay.W2, s).permute(0, 2, 4, 3, 5, 1).reshape(lay.shape(B))
+        main_p = main_p.contiguous().bfloat16()
+    add_l = torch.randn(B, C, H, W, device=DEV).bfloat16().float() if add else None
+    add_p = add_l.permute(0, 2, 3, 1).contiguous().bfloat16() if add else None
+    gamma = (torch.rand(C, device=DEV) + 0.5) if norm else None
+    beta = torch.randn(C, device=DEV) if norm else None
+    sc = torch.rand(B, C, device=DEV) if inj else None
+    sh = torch.randn(B, C, device=DEV) if inj else None
+    keep_l = (torch.rand(B, C, H, W, device=DEV) > 0.15).float() if spec.p > 0 else None
+    keep_p = keep_l.permute(0, 2, 3, 1).contiguous().to(torch.uint8) if keep_l is not None else None
+
+    leaves = [t for t in (main_p, add_p, gamma, beta, sc, sh) if t is not None]
+    for t in leaves:
+        t.requires_grad_(True)
+    out1, out2 = ops.fused_prep(spec, main_p, add=add_p, gamma=gamma, beta=beta, sc=sc, sh=sh, seed=0, keep=keep_p)
+    # reference
+    rl = [t.detach().clone().requires_grad_(True) for t in (main_l, ) + tuple(
+        t for t in (add_l, gamma, beta, sc, sh) if t is not None)]
+    it = iter(rl)
+    r_main = next(it)
+    r_add = next(it) if add else None
+    r_gamma = next(it) if norm else None
+    r_beta = next(it) if norm else None
+    r_sc = next(it) if inj else None
+    r_sh = next(it) if inj else None
+    ro1, ro2 = _prep_reference(spec, r_main, r_add, r_gamma, r_beta, r_sc, r_sh, keep_l, spec.relu_in)
+    got2 = spec.lay_out.to_nchw(out2)
+    assert rel(got2, ro2) < 1.5e-2, rel(got2, ro2)
+    if spec.lay_out.kind == 1:  # padding of the s2d output must be exactly zero
+        lo = spec.lay_out
+        full = out2.float().reshape(B, lo.H2, lo.W2, lo.s, lo.s, C).permute(0, 5, 1, 3, 2, 4).reshape(
+            B, C, lo.H2 * lo.s, lo.W2 * lo.s).clone()
+        full[:, :, lo.pad:lo.pad + H, lo.pad:lo.pad + W] = 0
+        assert float(full.abs().max()) == 0
+    if spec.want_out1:
+        assert rel(out1.float().permute(0, 3, 1, 2), ro1) < 1.5e-2
+    # backward
+    g2_l = torch.randn_like(ro2).bfloat16().float()
+    g1_l = torch.randn_like(ro1).bfloat16().float() if spec.want_out1 else None
+    lo = spec.lay_out
+    if lo.kind == 0:
+        g2_p = g2_l.permute(0, 2, 3, 1).contiguous().bfloat16()
+    else:
+        s = lo.s
+        full = torch.zeros(B, C, lo.H2 * s, lo.W2 * s, device=DEV)
+        full[:, :, lo.pad:lo.pad + H, lo.pad:lo.pad + W] = g2_l
+        g2_p = full.reshape(B, C, lo.H2, s, lo.W2, s).permute(0, 2, 4, 3, 5, 1).reshape(lo.shape(B)).contiguous().bfloat16()
+    if spec.want_out1:
+        torch.autograd.backward([out1, out2], [g1_l.permute(0, 2, 3, 1).contiguous().bfloat16(), g2_p])
+        torch.autograd.backward([ro1, ro2], [g1_l, g2_l])
+    else:
+        out2.backward(g2_p)
+        ro2.backward(g2_l)
+    gm = spec.lay_in.to_nchw(main_p.grad)
+    assert rel(gm, r_main.grad) < 2e-2, rel(gm, r_main.grad)
+    if spec.lay_in.kind == 1:  # gradient at the padding positions of an s2d-phase input must be zero
+        li = spec.lay_in
+        full = main_p.grad.float().reshape(B, li.H2, li.W2, li.s, li.s, C).permute(0, 5, 1, 3, 2, 4).reshape(
+            B, C, li.H2 * li.s, li.W2 * li.s).clone()
+        full[:, :, li.pad:li.pad + H, li.pad:li.pad + W] = 0
+        assert float(full.abs().max()) == 0
+    if add:
+        assert rel(add_p.grad.float().permute(0, 3, 1, 2), r_add.grad) < 2e-2
+    if norm:
+        assert rel(gamma.grad, r_gamma.grad) < 2e-2, rel(gamma.grad, r_gamma.grad)
+        assert rel(beta.grad, r_beta.grad) < 2e-2
+    if inj:
+        assert rel(sc.grad, r_sc.grad) < 2e-2
+        assert rel(sh.grad, r_sh.grad) < 2e-2
+
+
+def test_philox_dropout_rate_and_replay():
+    from simple_b200 import ops
+    from simple_b200.ops import PrepSpec, plain
+    H, W, C, B = 52, 40, 192, 4
+    spec = PrepSpec(H, W, C, plain(H, W, C), plain(H, W, C), p=0.15, stream_id=3)
+    x = torch.ones(B, H, W, C, device=DEV, dtype=torch.bfloat16).requires_grad_(True)
+    _, y = ops.fused_prep(spec, x, seed=1234)
+    frac = float((y == 0).float().mean())
+    assert abs(frac - 0.15) < 5e-3, frac
+    assert abs(float(y.float().max()) - 1 / 0.85) < 1e-2
+    y.backward(torch.ones_like(y))
+    # the backward regenerates the same mask from (seed, stream, index)
+    assert torch.equal((x.grad == 0), (y == 0))
+    _, y2 = ops.fused_prep(spec, x.detach(), seed=1235)
+    assert not torch.equal(y2 == 0, y == 0)
+
+
+# ------------------------------------------------------------------------------------------------ conv layers
+def _check_conv(kind):
+    from simple_b200 import ops
+    from simple_b200.ops import ConvSpec, PackedWeight, s2d_in, s2d_out
+    torch.manual_seed(3)
+    B = 3
+    taps22 = [(dy, dx) for dy in range(2) for dx in range(2)]
+    if kind == 'down':
+        Ci, Co, H, W = 96, 192, 21, 16
+        w = (torch.randn(Co, Ci, 4, 4, device=DEV) * 0.05).requires_grad_(True)
+        lay = s2d_in(H, W, Ci, 4, 2, 1)
+        Ho, Wo = H // 2, W // 2
+        spec = ConvSpec('t', lay.H2, lay.W2, 4 * Ci, Ho, Wo, Co, taps22, relu=False)
+        pw = PackedWeight(w, 2)
+        fref = lambda x, w_, b_: F.conv2d(x, w_, b_, stride=2, padding=1)
+        lay_out = ops.plain(Ho, Wo, Co)
+    elif kind == 's4':
+        Ci, Co, H, W = 32, 128, 26, 20
+        w = (torch.randn(Co, Ci, 8, 8, device=DEV) * 0.05).requires_grad_(True)
+        lay = s2d_in(H, W, Ci, 8, 4, 2)
+        Ho, Wo = 6, 5
+        spec = ConvSpec('t', lay.H2, lay.W2, 16 * Ci, Ho, Wo, Co, taps22, relu=False)
+        pw = PackedWeight(w, 4)
+        fref = lambda x, w_, b_: F.conv2d(x, w_, b_, stride=4, padding=2)
+        lay_out = ops.plain(Ho, Wo, Co)
+    elif kind == 'up':
+        Ci, Co, H, W = 128, 96, 6, 5
+        Ho, Wo = 13, 10  # output_padding (1, 0)
+        w = (torch.randn(Ci, Co, 4, 4, device=DEV) * 0.05).requires_grad_(True)
+        lay = ops.plain(H, W, Ci)
+        spec = ConvSpec('t', H, W, Ci, H + 1, W + 1, 4 * Co, [(-dy, -dx) for dy, dx in taps22], relu=False,
+                        transposed=True, bias_tile=4)
+        pw = PackedWeight(w, 2)
+        fref = lambda x, w_, b_: F.conv_transpose2d(x, w_, b_, stride=2, padding=1, output_padding=(1, 0))
+        lay_out = s2d_out(H, W, Ho, Wo, Co)
+    elif kind == 'c3':
+        Ci, Co, H, W = 76, 128, 9, 7
+        w = (torch.randn(Co, Ci, 3, 3, device=DEV) * 0.05).requires_grad_(True)
+        lay = ops.plain(H, W, 128)
+        Ho, Wo = H, W
+        spec = ConvSpec('t', H, W, 128, H, W, Co, [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)], relu=False)
+        pw = PackedWeight(w, 1, Ipad=128)
+        fref = lambda x, w_, b_: F.conv2d(x, w_, b_, padding=1)
+        lay_out = ops.plain(Ho, Wo, Co)
+    else:  # 1x1 with permuted outputs and inputs (logits / input_embedding style)
+        Ci, Co, H, W = 96, 768, 9, 8
+        w = (torch.randn(Co, Ci, 1, 1, device=DEV) * 0.05).requires_grad_(True)
+        lay = ops.plain(H, W, Ci)
+        Ho, Wo = H, W
+        spec = ConvSpec('t', H, W, Ci, H, W, Co, [(0, 0)], relu=False)
+        operm = [(o % 3) * 256 + o // 3 for o in range(768)]
+        pw = PackedWeight(w, 1, operm=operm)
+        fref = lambda x, w_, b_: F.conv2d(x, w_, b_)
+        lay_out = ops.plain(Ho, Wo, Co)
+    Cl = lay.C if kind != 'c3' else Ci
+    x_l = torch.randn(B, Cl, lay.H, lay.W, device=DEV).bfloat16().float()
+    bias = torch.randn(w.shape[1] if kind == 'up' else w.shape[0], device=DEV).requires_grad_(True)
+    # physical input
+    if lay.kind == 0:
+        xp = x_l.permute(0, 2, 3, 1)
+        if kind == 'c3':
+            xp = F.pad(xp, (0, 128 - Ci))
+        x_p = xp.contiguous().bfloat16()
+    else:
+        s = lay.s
+        full = torch.zeros(B, Cl, lay.H2 * s, lay.W2 * s, device=DEV)
+        full[:, :, lay.pad:lay.pad + lay.H, lay.pad:lay.pad + lay.W] = x_l
+        x_p = full.reshape(B, Cl, lay.H2, s, lay.W2, s).permute(0, 2, 4, 3, 5, 1).reshape(lay.shape(B)).contiguous().bfloat16()
+    x_p.requires_grad_(True)
+    y = ops.tap_conv(spec, x_p, w, bias, pw)
+    xr = x_l.clone().requires_grad_(True)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    br = bias.detach().clone().requires_grad_(True)
+    yr = fref(xr, wr, br)
+    got = lay_out.to_nchw(y)
+    if kind == '1x1':
+        got = got[:, torch.tensor(operm, device=DEV)]  # physical channel operm[o] holds reference channel o
+    assert rel(got, yr) < 1e-2, rel(got, yr)
+    # backward with a gradient that is zero outside the valid region (as the fused stages produce it)
+    g_l = torch.randn_like(yr).bfloat16().float()
+    if lay_out.kind == 0:
+        gl = g_l
+        if kind == '1x1':
+            gp_l = torch.empty_like(g_l)
+            gp_l[:, torch.tensor(operm, device=DEV)] = g_l
+            gl = gp_l
+        g_p = gl.permute(0, 2, 3, 1).contiguous().bfloat16()
+    else:
+        lo = lay_out
+        full = torch.zeros(B, lo.C, lo.H2 * 2, lo.W2 * 2, device=DEV)
+        full[:, :, 1:1 + lo.H, 1:1 + lo.W] = g_l
+        g_p = full.reshape(B, lo.C, lo.H2, 2, lo.W2, 2).permute(0, 2, 4, 3, 5, 1).reshape(lo.shape(B)).contiguous().bfloat16()
+    y.backward(g_p)
+    yr.backward(g_l)
+    gx = lay.to_nchw(x_p.grad)
+    if kind == 'c3':
+        gx = gx[:, :Ci]
+    assert rel(gx, xr.grad) < 1.5e-2, rel(gx, xr.grad)
+    assert rel(w.grad, wr.grad) < 1.5e-2, rel(w.grad, wr.grad)
+    assert rel(bias.grad, br.grad) < 1.5e-2, rel(bias.grad, br.grad)
+
+
+@pytest.mark.parametrize('kind', ['down', 's4', 'up', 'c3', '1x1'])
+def test_conv_layer_fwd_bwd(kind):
+    _check_conv(kind)
+
+
+def test_gru_blend():
+    from simple_b200 import ops
+    torch.manual_seed(4)
+    B, H, W = 2, 9, 8
+    G = torch.randn(B, H, W, 128, device=DEV).bfloat16().requires_grad_(True)
+    s_old = torch.randn(B, H, W, 64, device=DEV)
+    xs = torch.zeros(B, H, W, 128, device=DEV, dtype=torch.bfloat16)
+    xs[..., 64:76] = 1.0
+    xs2, s_new = ops.GruBlend.apply(G, s_old, xs)
+    Gr = G.detach().float().requires_grad_(True)
+    g, c = Gr[..., :64], Gr[..., 64:]
+    ref = s_old * torch.sigmoid(g) + torch.tanh(c) * (1 - torch.sigmoid(g))
+    assert torch.allclose(s_new, ref, atol=1e-4, rtol=1e-4)
+    assert rel(xs2[..., :64], ref) < 1e-2
+    assert float((xs2[..., 64:76] - 1).abs().max()) == 0
+    gout = torch.randn(B, H, W, 128, device=DEV).bfloat16()
+    xs2.backward(gout)
+    ref.backward(gout[..., :64].float())
+    assert rel(G.grad, Gr.grad) < 1.5e-2
