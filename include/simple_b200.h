@@ -70,7 +70,7 @@ typedef struct {
   int B, H, W, C;
   const void* dy;     /* bf16 [B,Ho,Wo,N] */
   int Ho, Wo, N;
-  int bw, bh, bb;     /* pixel box, bw*bh*bb == 128 exactly (may overhang; TMA zero-fills) */
+  int bw, bh, bb;     /* pixel box, bw*bh*bb == 64 exactly (may overhang; TMA zero-fills) */
   int ntaps;
   int tap_dy[SB_MAX_TAPS];
   int tap_dx[SB_MAX_TAPS];
@@ -110,6 +110,8 @@ typedef struct {
   sb_view in;              /* main input */
   const void* add;         /* optional plain bf16 [B,H,W,C] */
   int relu_in;
+  int in_f32;              /* main input is fp32 (outputs and gradients stay bf16) */
+  int add_f32;             /* `add` is fp32 */
   const float* sums;       /* [B,C,2] from sb_stats, or NULL: no InstanceNorm */
   float eps;
   const float* gamma;
@@ -151,6 +153,35 @@ int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs
 /* fp32 (O,I,KH,KW) master weight -> bf16 GEMM operands (see DESIGN.md "weight packing"). */
 int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
                  const int* operm, void* fwd, void* tr, sb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Multi-tensor fused clip_grad_norm_ + Adafactor (fairseq defaults: eps=(1e-30,1e-3), clip_threshold=1,
+ * decay_rate=-0.8, relative_step, scale_parameter, no momentum, no weight decay).
+ * Replaces: simple/trainer.py:148 and simple/adafactor.py:113-212 (K16, K17).
+ * Descriptors and block maps live in DEVICE memory (built by the host wrapper each step; one small H2D copy).
+ *   sb_grad_sumsq:      block_map[i] = (tensor, first 4096-element chunk); *total += sum g^2  (caller zeroes total)
+ *   sb_adafactor_conv:  4-D weights (O,I,KH,KW) of one kernel size; block_map[i] = (tensor, first patch), 128 patches
+ *                       per block; pass 1 updates row/col states and acc[0]=sum u^2, acc[1]=sum p^2 (caller zeroes
+ *                       acc), pass 2 applies the update.  g is scaled by min(1, max_norm/(sqrt(total)+1e-6)).
+ *   sb_adafactor_small: 1-D (cols==0, state in `row`) and 2-D tensors, one CTA per descriptor.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* p;        /* parameter, fp32, reference layout */
+  const float* g;  /* gradient */
+  float* row;      /* exp_avg_sq_row  (or exp_avg_sq for 1-D) */
+  float* col;      /* exp_avg_sq_col */
+  float* acc;      /* 2 floats: sum u^2, sum p^2 (RMS state) */
+  long long n;     /* elements */
+  int rows, cols;  /* 2-D: shape; 1-D: cols = 0; 4-D: unused */
+  float beta2t;    /* 1 - step^-0.8 */
+  float rel_step;  /* min(1e-2, 1/sqrt(step)) */
+} sb_tensor_desc;
+int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
+                  sb_stream_t stream);
+int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
+                      const float* total_sumsq, float max_norm, int pass, sb_stream_t stream);
+int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
+                       const float* total_sumsq, float max_norm, sb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -340,6 +340,8 @@ def forward(p, cfg, state, x, action, target=None, epsilon=0, rand=None, trainin
                      stride=2, padding=1)
         h = F.relu(h)
         h = instance_norm(h, p[f'downscale_layers.{2 * i + 1}.weight'], p[f'downscale_layers.{2 * i + 1}.bias'])
+    aux['skips'] = inputs
+    aux['x5'] = h
     value_pred = F.linear(torch.flatten(h, start_dim=1), p['value_estimator.dense.weight'],
                           p['value_estimator.dense.bias']).squeeze(-1)
     h = action_injector(p, 'action_injectors.0', h, action)

@@ -60,7 +60,7 @@ class SbView(ctypes.Structure):
 class PrepArgs(ctypes.Structure):
     _fields_ = [
         ('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('C', ctypes.c_int),
-        ('inp', SbView), ('add', ctypes.c_void_p), ('relu_in', ctypes.c_int),
+        ('inp', SbView), ('add', ctypes.c_void_p), ('relu_in', ctypes.c_int), ('in_f32', ctypes.c_int), ('add_f32', ctypes.c_int),
         ('sums', ctypes.c_void_p), ('eps', ctypes.c_float), ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p),
         ('Ta', ctypes.c_void_p), ('out1', ctypes.c_void_p),
         ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('stream_id', ctypes.c_uint),
@@ -108,6 +108,9 @@ class _Sigs:
     sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
     sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
+    sb_grad_sumsq = [_p, _p, _i, _p, _p]
+    sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]
+    sb_adafactor_small = [_p, _i, _i, _p, _f, _p]
 
 
 EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version'] + [n for n in dir(_Sigs) if n.startswith('sb_')]

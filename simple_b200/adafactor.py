@@ -1,0 +1,162 @@
+"""Adafactor (drop-in for simple/adafactor.py of the reference, used with all defaults at simple/trainer.py:22).
+
+Same constructor / `zero_grad()` / `step()` surface and the same per-parameter state keys (`step`,
+`exp_avg_sq_row`, `exp_avg_sq_col` or `exp_avg_sq`, `RMS`), but the whole update -- including the preceding
+`clip_grad_norm_` when `step(max_grad_norm=...)` is used -- runs in three fused multi-tensor CUDA kernels
+(csrc/adafactor.cu) with no host synchronisation.  Only the defaults the reference uses are implemented; any other
+hyper-parameter raises (there is no slow path).
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DESC = np.dtype([('p', np.uint64), ('g', np.uint64), ('row', np.uint64), ('col', np.uint64), ('acc', np.uint64),
+                  ('n', np.int64), ('rows', np.int32), ('cols', np.int32), ('beta2t', np.float32),
+                  ('rel_step', np.float32)])
+assert _DESC.itemsize == 64
+
+
+class Adafactor(torch.optim.Optimizer):
+
+    def __init__(self, params, lr=None, eps=(1e-30, 1e-3), clip_threshold=1.0, decay_rate=-0.8, beta1=None,
+                 weight_decay=0.0, scale_parameter=True, relative_step=True, warmup_init=False):
+        if lr is not None and relative_step:
+            raise ValueError('Cannot combine manual lr and relative_step options')
+        if warmup_init and not relative_step:
+            raise ValueError('warmup_init requires relative_step=True')
+        if (lr is not None or tuple(eps) != (1e-30, 1e-3) or clip_threshold != 1.0 or decay_rate != -0.8
+                or beta1 is not None or weight_decay != 0.0 or not scale_parameter or not relative_step or warmup_init):
+            raise ValueError('simple_b200.Adafactor implements the defaults used by the reference only')
+        defaults = dict(lr=lr, eps=eps, clip_threshold=clip_threshold, decay_rate=decay_rate, beta1=beta1,
+                        weight_decay=weight_decay, scale_parameter=scale_parameter, relative_step=relative_step,
+                        warmup_init=warmup_init)
+        super().__init__(params, defaults)
+        self._cache = {}
+        self.grad_norm_sq = None  # device scalar: squared global gradient norm of the last step (before clipping)
+
+    def _init_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st['step'] = 0
+            if p.dim() >= 2:
+                st['exp_avg_sq_row'] = torch.zeros(p.shape[:-1], device=p.device, dtype=torch.float32)
+                st['exp_avg_sq_col'] = torch.zeros(p.shape[:-2] + p.shape[-1:], device=p.device, dtype=torch.float32)
+            else:
+                st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32)
+            st['RMS'] = 0
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm=None, grads=None):
+        """One optimisation step.  `max_grad_norm` fuses torch.nn.utils.clip_grad_norm_(params, max_grad_norm) in
+        front (simple/trainer.py:148); `grads` optionally maps parameters to externally held gradient tensors
+        (e.g. views of an all-reduced flat buffer) instead of `p.grad`."""
+        loss = closure() if closure is not None else None
+        active = []
+        for group in self.param_groups:
+            for p in group['params']:
+                g = grads.get(p) if grads is not None else p.grad
+                if g is None:
+                    continue  # adafactor.py:125-126 -- e.g. gate.* on the first step of a rollout window
+                if not p.is_cuda:
+                    raise RuntimeError('simple_b200.Adafactor runs on CUDA only; there is no CPU fallback')
+                if p.dtype != torch.float32 or g.dtype != torch.float32 or p.dim() not in (1, 2, 4):
+                    raise RuntimeError('unsupported parameter for the fused Adafactor')
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                    if grads is None:
+                        p.grad = g
+                assert p.is_contiguous()
+                active.append((p, g))
+        if not active:
+            return loss
+        dev = active[0][0].device
+        n = len(active)
+        descs = np.zeros(n, dtype=_DESC)
+        acc = torch.zeros(n, 2, device=dev, dtype=torch.float32)
+        total = torch.zeros(1, device=dev, dtype=torch.float32)
+        for i, (p, g) in enumerate(active):
+            st = self._init_state(p)
+            st['step'] += 1
+            t = st['step']
+            d = descs[i]
+            d['p'], d['g'] = p.data_ptr(), g.data_ptr()
+            if p.dim() >= 2:
+                d['row'], d['col'] = st['exp_avg_sq_row'].data_ptr(), st['exp_avg_sq_col'].data_ptr()
+            else:
+                d['row'] = st['exp_avg_sq'].data_ptr()
+            d['acc'] = acc.data_ptr() + 8 * i
+            d['n'] = p.numel()
+            d['rows'], d['cols'] = (p.shape[0], p.shape[1]) if p.dim() == 2 else (0, 0)
+            d['beta2t'] = 1.0 - math.pow(t, -0.8)
+            d['rel_step'] = min(1e-2, 1.0 / math.sqrt(t))
+            st['RMS'] = _LazyRMS(acc, i, p.numel())
+        key = tuple(id(p) for p, _ in active)
+        maps = self._cache.get(key)
+        if maps is None:
+            maps = self._build_maps(active, dev)
+            self._cache = {key: maps}
+        descs_dev = torch.from_numpy(descs.view(np.uint8)).to(dev, non_blocking=True)
+        L = _lib.lib()
+        s = _lib.stream_ptr()
+        mn = float(max_grad_norm) if max_grad_norm is not None else 0.0
+        _lib.check(L.sb_grad_sumsq(descs_dev.data_ptr(), maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
+                                   total.data_ptr(), s), 'sb_grad_sumsq')
+        for (kh, kw), (idx, bm) in maps['conv'].items():
+            sub = descs_dev.view(n, 64)[idx].contiguous()
+            for pas in (1, 2):
+                _lib.check(L.sb_adafactor_conv(sub.data_ptr(), bm.data_ptr(), bm.shape[0], kh, kw, total.data_ptr(), mn,
+                                               pas, s), 'sb_adafactor_conv')
+        if maps['small'] is not None:
+            idx, rc = maps['small']
+            sub = descs_dev.view(n, 64)[idx].contiguous()
+            _lib.check(L.sb_adafactor_small(sub.data_ptr(), idx.numel(), rc, total.data_ptr(), mn, s),
+                       'sb_adafactor_small')
+        self.grad_norm_sq = total
+        self._keep = (descs_dev, acc)
+        return loss
+
+    @staticmethod
+    def _build_maps(active, dev):
+        sumsq = []
+        conv = {}
+        small = []
+        rc = 1
+        for i, (p, _) in enumerate(active):
+            nchunks = -(-p.numel() // 4096)
+            sumsq += [(i, c) for c in range(nchunks)]
+            if p.dim() == 4:
+                conv.setdefault((p.shape[2], p.shape[3]), []).append(i)
+            else:
+                small.append(i)
+                if p.dim() == 2:
+                    rc = max(rc, p.shape[0] + p.shape[1])
+        maps = {'sumsq': torch.tensor(sumsq, dtype=torch.int32, device=dev), 'conv': {}, 'small': None}
+        for k, idxs in conv.items():
+            bm = []
+            for local, i in enumerate(idxs):
+                npatch = active[i][0].numel() // (k[0] * k[1])
+                bm += [(local, b * 128) for b in range(-(-npatch // 128))]
+            maps['conv'][k] = (torch.tensor(idxs, dtype=torch.long, device=dev),
+                               torch.tensor(bm, dtype=torch.int32, device=dev))
+        if small:
+            maps['small'] = (torch.tensor(small, dtype=torch.long, device=dev), rc)
+        return maps
+
+
+class _LazyRMS:
+    """state['RMS'] of the reference is a 0-d tensor; here it is derived on demand from the device accumulators so
+    that the optimiser never synchronises the host."""
+
+    def __init__(self, acc, i, n):
+        self.acc, self.i, self.n = acc, i, n
+
+    def tensor(self):
+        return torch.sqrt(self.acc[self.i, 1] / self.n)
+
+    def __float__(self):
+        return float(self.tensor())

@@ -1,0 +1,260 @@
+// Multi-tensor fused clip_grad_norm_ + Adafactor (fairseq defaults) -- K16/K17 of SURVEY 2.3.
+// Replaces simple/trainer.py:148 (clip_grad_norm_) and simple/adafactor.py:113-212 (~1800 ATen launches + 120 host
+// syncs per step in the reference) by three launches with no host synchronisation:
+//   1. sb_grad_sumsq        : sum g^2 over every gradient                     -> clip coefficient (device scalar)
+//   2. sb_adafactor_conv    : 4-D weights (O,I,kh,kw).  The factored second moment of fairseq's Adafactor reduces
+//                             over kw (row state (O,I,kh)) and kh (col state (O,I,kw)): everything is local to one
+//                             (o,i) patch, one thread per patch; pass 1 updates the state and accumulates
+//                             sum u^2 / sum p^2, pass 2 applies p -= lr * u / max(1, RMS(u)).
+//   3. sb_adafactor_small   : 1-D / 2-D tensors, one CTA per tensor (block-local reductions).
+// HBM-bound: ~12 B/param minimum (read p, g; write p) + state; see DESIGN.md.
+#include "common.cuh"
+#include "../../include/simple_b200.h"
+
+namespace sb {
+extern long long g_launches;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+__device__ __forceinline__ float clip_coef(const float* total_sumsq, float max_norm) {
+  if (max_norm <= 0.f) return 1.0f;
+  const float c = max_norm / (__fsqrt_rn(*total_sumsq) + 1e-6f);
+  return fminf(c, 1.0f);
+}
+
+// ---- 1. global gradient norm ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const int2* __restrict__ block_map, float* total) {
+  __shared__ float red[8];
+  const int2 bm = block_map[blockIdx.x];  // (tensor, first element)
+  const sb_tensor_desc d = descs[bm.x];
+  const long long begin = (long long)bm.y * 4096;
+  const long long end = begin + 4096 < d.n ? begin + 4096 : d.n;
+  float s = 0.f;
+  for (long long i = begin + threadIdx.x; i < end; i += 256) {
+    const float g = d.g[i];
+    s += g * g;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(total, s);
+}
+
+// ---- 2. conv-type weights ---------------------------------------------------------------------------------------
+template <int KH, int KW, int PASS>
+__global__ void __launch_bounds__(128)
+    adafactor_conv_kernel(const sb_tensor_desc* __restrict__ descs, const int2* __restrict__ block_map,
+                          const float* __restrict__ total_sumsq, float max_norm) {
+  constexpr int KK = KH * KW;
+  __shared__ float red[8];
+  const int2 bm = block_map[blockIdx.x];  // (tensor, first patch)
+  const sb_tensor_desc d = descs[bm.x];
+  const long long patch = (long long)bm.y + threadIdx.x;
+  const long long npatch = d.n / KK;
+  const float coef = clip_coef(total_sumsq, max_norm);
+  float su = 0.f, sp = 0.f;
+  if (patch < npatch) {
+    float g[KK], p[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      g[k] = d.g[patch * KK + k] * coef;
+      p[k] = d.p[patch * KK + k];
+    }
+    float row[KH], col[KW];
+    if (PASS == 1) {
+#pragma unroll
+      for (int a = 0; a < KH; ++a) {
+        float m = 0.f;
+#pragma unroll
+        for (int b = 0; b < KW; ++b) m += g[a * KW + b] * g[a * KW + b] + 1e-30f;
+        row[a] = d.row[patch * KH + a] * d.beta2t + (m / KW) * (1.0f - d.beta2t);
+        d.row[patch * KH + a] = row[a];
+      }
+#pragma unroll
+      for (int b = 0; b < KW; ++b) {
+        float m = 0.f;
+#pragma unroll
+        for (int a = 0; a < KH; ++a) m += g[a * KW + b] * g[a * KW + b] + 1e-30f;
+        col[b] = d.col[patch * KW + b] * d.beta2t + (m / KH) * (1.0f - d.beta2t);
+        d.col[patch * KW + b] = col[b];
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < KH; ++a) row[a] = d.row[patch * KH + a];
+#pragma unroll
+      for (int b = 0; b < KW; ++b) col[b] = d.col[patch * KW + b];
+    }
+    float rmean = 0.f;
+#pragma unroll
+    for (int a = 0; a < KH; ++a) rmean += row[a];
+    rmean /= KH;
+    float rf[KH], cf[KW];
+#pragma unroll
+    for (int a = 0; a < KH; ++a) rf[a] = rsqrtf(row[a] / rmean);
+#pragma unroll
+    for (int b = 0; b < KW; ++b) cf[b] = rsqrtf(col[b]);
+    if (PASS == 1) {
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        const float u = rf[k / KW] * cf[k % KW] * g[k];
+        su += u * u;
+        sp += p[k] * p[k];
+      }
+    } else {
+      const float n = (float)d.n;
+      const float rms_u = __fsqrt_rn(d.acc[0] / n);
+      const float rms_p = __fsqrt_rn(d.acc[1] / n);
+      const float lr = fmaxf(1e-3f, rms_p) * d.rel_step;
+      const float scale = lr / fmaxf(1.0f, rms_u);  // clip_threshold = 1
+#pragma unroll
+      for (int k = 0; k < KK; ++k) d.p[patch * KK + k] = p[k] - scale * (rf[k / KW] * cf[k % KW] * g[k]);
+    }
+  }
+  if (PASS == 1) {
+    su = block_sum(su, red);
+    sp = block_sum(sp, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(&d.acc[0], su);
+      atomicAdd(&d.acc[1], sp);
+    }
+  }
+}
+
+// ---- 3. small 1-D / 2-D tensors: one CTA per tensor ---------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+    adafactor_small_kernel(const sb_tensor_desc* __restrict__ descs, const float* __restrict__ total_sumsq,
+                           float max_norm) {
+  extern __shared__ float sm[];  // rows [R] | cols [C]
+  __shared__ float red[32];
+  const sb_tensor_desc d = descs[blockIdx.x];
+  const float coef = clip_coef(total_sumsq, max_norm);
+  const long long n = d.n;
+  float su = 0.f, sp = 0.f;
+  if (d.cols == 0) {  // 1-D: exp_avg_sq in d.row
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float g = d.g[i] * coef;
+      const float v = d.row[i] * d.beta2t + (g * g + 1e-30f) * (1.0f - d.beta2t);
+      d.row[i] = v;
+      const float u = g * rsqrtf(v);
+      su += u * u;
+      const float p = d.p[i];
+      sp += p * p;
+    }
+    su = block_sum(su, red);
+    sp = block_sum(sp, red);
+    const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * d.rel_step;
+    const float scale = lr / fmaxf(1.0f, __fsqrt_rn(su / (float)n));
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float g = d.g[i] * coef;
+      d.p[i] -= scale * g * rsqrtf(d.row[i]);
+    }
+    if (threadIdx.x == 0) d.acc[1] = sp;
+    return;
+  }
+  const int R = d.rows, C = d.cols;
+  float* srow = sm;
+  float* scol = sm + R;
+  for (int i = threadIdx.x; i < R + C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+    const float g = d.g[i] * coef;
+    const float u = g * g + 1e-30f;
+    atomicAdd(&srow[r], u);
+    atomicAdd(&scol[c], u);
+    const float p = d.p[i];
+    sp += p * p;
+  }
+  __syncthreads();
+  float rpart = 0.f;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float v = d.row[r] * d.beta2t + (srow[r] / C) * (1.0f - d.beta2t);
+    d.row[r] = v;
+    srow[r] = v;
+    rpart += v;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = d.col[c] * d.beta2t + (scol[c] / R) * (1.0f - d.beta2t);
+    d.col[c] = v;
+    scol[c] = rsqrtf(v);
+  }
+  const float rmean = block_sum(rpart, red) / R;
+  sp = block_sum(sp, red);
+  for (int r = threadIdx.x; r < R; r += blockDim.x) srow[r] = rsqrtf(srow[r] / rmean);
+  __syncthreads();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+    const float u = srow[r] * scol[c] * d.g[i] * coef;
+    su += u * u;
+  }
+  su = block_sum(su, red);
+  const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * d.rel_step;
+  const float scale = lr / fmaxf(1.0f, __fsqrt_rn(su / (float)n));
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+    d.p[i] -= scale * srow[r] * scol[c] * d.g[i] * coef;
+  }
+  if (threadIdx.x == 0) d.acc[1] = sp;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
+                             sb_stream_t stream) {
+  if (!descs_dev || !block_map_dev || nblocks < 1 || !total) return SB_ERR_ARG;
+  grad_sumsq_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, (const int2*)block_map_dev, total);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+template <int KH, int KW>
+static int launch_conv(const sb_tensor_desc* descs, const int* bm, int nblocks, const float* total, float max_norm,
+                       int pass, cudaStream_t s) {
+  if (pass == 1)
+    adafactor_conv_kernel<KH, KW, 1><<<nblocks, 128, 0, s>>>(descs, (const int2*)bm, total, max_norm);
+  else
+    adafactor_conv_kernel<KH, KW, 2><<<nblocks, 128, 0, s>>>(descs, (const int2*)bm, total, max_norm);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
+                                 const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
+  if (!descs_dev || !block_map_dev || nblocks < 1 || (pass != 1 && pass != 2)) return SB_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (KH == 1 && KW == 1) return launch_conv<1, 1>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 3 && KW == 3) return launch_conv<3, 3>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 4 && KW == 4) return launch_conv<4, 4>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 8 && KW == 8) return launch_conv<8, 8>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  return SB_ERR_ARG;
+}
+
+extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
+                                  const float* total_sumsq, float max_norm, sb_stream_t stream) {
+  if (!descs_dev || ntensors < 1 || max_rows_plus_cols * sizeof(float) > 96 * 1024) return SB_ERR_ARG;
+  const size_t smem = (size_t)(max_rows_plus_cols > 0 ? max_rows_plus_cols : 1) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(adafactor_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
+        cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  adafactor_small_kernel<<<ntensors, 1024, smem, (cudaStream_t)stream>>>(descs_dev, total_sumsq, max_norm);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

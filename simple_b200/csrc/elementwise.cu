@@ -52,6 +52,8 @@ __device__ __forceinline__ long long view_off(const View& v, int H, int W, int C
 
 struct PrepParams {
   int B, H, W, C;
+  int add_f32;              // `add` holds fp32
+  int in_f32;               // main input holds fp32 instead of bf16 (tiny deep layers: InstanceNorm over <= 30 pixels)
   View in;                  // main input
   const __nv_bfloat16* add; // optional plain [B,H,W,C], added to main (skip connection)
   int relu_in;              // forward: apply ReLU to main first;  backward: mask d_main by (main > 0)
@@ -100,14 +102,19 @@ __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, 
 // value of (main [+relu] + add) for 8 channels; also returns raw main
 __device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x, int c, float* z, float* mainv,
                                        bool fwd_relu) {
-  const BF8 m = *reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) +
-                                              view_off(q.in, q.H, q.W, q.C, b, y, x, c));
-  bf8_to_f(m, mainv);
+  const long long off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
+  if (q.in_f32) {
+    ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
+  } else {
+    bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) z[j] = (fwd_relu && q.relu_in) ? fmaxf(mainv[j], 0.f) : mainv[j];
   if (q.add) {
     float a[8];
-    bf8_to_f(*reinterpret_cast<const BF8*>(q.add + (((long long)b * q.H + y) * q.W + x) * q.C + c), a);
+    const long long aoff = (((long long)b * q.H + y) * q.W + x) * q.C + c;
+    if (q.add_f32) ld8f(reinterpret_cast<const float*>(q.add) + aoff, a);
+    else bf8_to_f(*reinterpret_cast<const BF8*>(q.add + aoff), a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] += a[j];
   }
@@ -504,6 +511,8 @@ static View mk_view(const sb_view* v) {
 static int fill(PrepParams& q, const sb_prep_args* a) {
   if (!a || a->C % 8 || a->C < 8 || a->C / 8 > 256) return SB_ERR_ARG;
   q.B = a->B; q.H = a->H; q.W = a->W; q.C = a->C;
+  q.in_f32 = a->in_f32;
+  q.add_f32 = a->add_f32;
   q.in = mk_view(&a->in);
   q.add = (const __nv_bfloat16*)a->add;
   q.relu_in = a->relu_in;

@@ -215,6 +215,11 @@ class InjectedRand:
         self.pos = 0
         self.device = device
         self.seed = 0
+        # Optional test hook: discrete decisions (posterior pre-activations, sampled latent symbols) recorded from the
+        # oracle.  bf16 upstream error can flip a near-tie; forcing the recorded decision keeps the rest of the
+        # comparison meaningful while the natural flip rate is reported in `mismatch`.
+        self.force = {}
+        self.mismatch = {}
 
     def _next(self, kind, shape):
         k, t = self.log[self.pos]
@@ -353,8 +358,10 @@ class NextFramePredictor(nn.Module):
             Co, Ho, Wo = es[i + 1]
             lay = s2d_in(Hi, Wi, Ci, 4, 2, 1)
             P['down_lay'].append(lay)
-            P['down'].append(ConvSpec(f'down{i}', lay.H2, lay.W2, 4 * Ci, Ho, Wo, Co, taps22, relu=True))
-        P['mid'] = [ConvSpec(f'mid{i}', 3, 2, 768, 3, 2, 768, taps33, relu=True, bwd_mask=(i == 0)) for i in range(2)]
+            P['down'].append(ConvSpec(f'down{i}', lay.H2, lay.W2, 4 * Ci, Ho, Wo, Co, taps22, relu=True,
+                                      out_f32=(Ho * Wo <= 30)))
+        P['mid'] = [ConvSpec(f'mid{i}', 3, 2, 768, 3, 2, 768, taps33, relu=True, bwd_mask=(i == 0), out_f32=True)
+                    for i in range(2)]
         P['up'], P['up_lay'] = [], []
         shape = es[5]
         for i in range(5):
@@ -363,7 +370,7 @@ class NextFramePredictor(nn.Module):
             lay = s2d_out(Hi, Wi, Ho, Wo, Co)
             P['up_lay'].append(lay)
             P['up'].append(ConvSpec(f'up{i}', Hi, Wi, Ci, Hi + 1, Wi + 1, 4 * Co, [(-dy, -dx) for dy, dx in taps22],
-                                    relu=True, transposed=True, bias_tile=4))
+                                    relu=True, transposed=True, bias_tile=4, out_f32=(Ho * Wo <= 30)))
             shape = ds[i]
         P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False)
         # posterior encoder of the stochastic model (train only)
@@ -481,6 +488,7 @@ class NextFramePredictor(nn.Module):
             main = self._conv(f'down{i}', P['down'][i], A)
         nrm = self.downscale_layers[9]
         _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias)
+        aux['skips'], aux['x5'], aux['y4'] = skips, x5, main
         # ---- bottleneck heads and latent (tiny tensors; fp32, NCHW semantics of the reference)
         h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
         value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
@@ -496,6 +504,7 @@ class NextFramePredictor(nn.Module):
             h = self._posterior(h, ps, action, epsilon, rand, aux)
         else:
             bits, _ = sm.bits_predictor(h.reshape(B, -1), rand)
+            bits = self._forced(rand, 'sampled_bits', bits)
             aux['bits'] = bits
             h = sm.add_bits(h, bits)
         x_mid = h.mean(dim=(2, 3))
@@ -541,6 +550,7 @@ class NextFramePredictor(nn.Module):
         x2 = sm.mean_attentions[1](c2.float().permute(0, 3, 1, 2).contiguous())
         x = sm.dense1(torch.cat((x1, x2), dim=-1))
         aux['posterior_pre'] = x
+        x = x + (self._forced(rand, 'posterior_pre', x.detach()) - x.detach())
         bits_clean = (2 * (0 < x).float()).detach() - 1
         x = torch.tanh(x + rand.truncnorm(x.shape))
         bits = x + (2 * (0 < x).float() - 1 - x).detach()
@@ -551,12 +561,25 @@ class NextFramePredictor(nn.Module):
         _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean)
         sm.lstm_loss = sm.lstm_loss.to(lstm_loss.device) + lstm_loss
         bits_pred, _ = sm.bits_predictor(flat, rand)
+        bits_pred = self._forced(rand, 'sampled_bits', bits_pred)
         aux['bits_pred'] = bits_pred
         bits_pred = bits_clean + (bits_pred - bits_clean).detach()
         bits = mix(bits_pred, bits, 1 - (1 - epsilon) * c.latent_rnn_max_sampling, rand)
         aux['bits'] = bits
         res = sm.add_bits(layer, bits)
         return mix(res, layer, 1 - (1 - epsilon) * c.latent_use_max_probability, rand)
+
+    @staticmethod
+    def _forced(rand, key, value):
+        force = getattr(rand, 'force', None)
+        if not force or key not in force:
+            return value
+        f = force[key].to(value.device)
+        if key == 'posterior_pre':
+            rand.mismatch[key] = float(((f > 0) != (value > 0)).float().mean())
+        else:
+            rand.mismatch[key] = float((f != value).float().mean())
+        return f
 
     def forward_internal(self, x, action, target=None, epsilon=0):
         """Runs the network and returns the INTERNAL logits (bf16 [B,H,W,768], colour-major) + reward + value."""

@@ -85,6 +85,8 @@ def _prep_args(spec, B, main, add, sums, gamma, beta, sc, sh, out1, out2, seed, 
     a.inp = spec.lay_in.view(main)
     a.add = _ptr(add)
     a.relu_in = int(spec.relu_in)
+    a.in_f32 = int(main is not None and main.dtype == torch.float32)
+    a.add_f32 = int(add is not None and add.dtype == torch.float32)
     a.sums = _ptr(sums)
     a.eps = spec.eps
     a.gamma, a.beta = _ptr(gamma), _ptr(beta)
@@ -155,8 +157,8 @@ class FusedPrep(torch.autograd.Function):
             bsums = torch.zeros(B, spec.C, 4, device=dev, dtype=torch.float32)
             a.bsums = bsums.data_ptr()
             _lib.check(_lib.lib().sb_prep_bwd_reduce(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_reduce')
-        d_main = torch.empty_like(main)
-        d_add = torch.empty_like(add) if has_add else None
+        d_main = torch.empty(main.shape, device=dev, dtype=torch.bfloat16)
+        d_add = torch.empty(add.shape, device=dev, dtype=torch.bfloat16) if has_add else None
         a.d_main = spec.lay_in.view(d_main)
         a.d_add = _ptr(d_add)
         _lib.check(_lib.lib().sb_prep_bwd_apply(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_apply')
@@ -185,8 +187,9 @@ class ConvSpec:
     """
 
     def __init__(self, name, Ha, Wa, Ca, Ho, Wo, N, taps, relu, transposed=False, need_dgrad=True, bias_tile=1,
-                 bwd_mask=False):
+                 bwd_mask=False, out_f32=False):
         self.name = name
+        self.out_f32 = out_f32  # keep the output in fp32 (tiny deep layers feeding an InstanceNorm over few pixels)
         self.Ha, self.Wa, self.Ca, self.Ho, self.Wo, self.N = Ha, Wa, Ca, Ho, Wo, N
         self.taps, self.relu, self.transposed = taps, relu, transposed
         self.need_dgrad, self.bias_tile = need_dgrad, bias_tile
@@ -258,9 +261,10 @@ class TapConv(torch.autograd.Function):
         splits = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
         if splits > 1:
             acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits)
-            y = _bias_act(acc, bias_f, spec.relu)
+            y = _bias_act(acc, bias_f, spec.relu, spec.out_f32)
         else:
-            y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu)
+            y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu,
+                         out_dtype=torch.float32 if spec.out_f32 else torch.bfloat16)
         ctx.spec, ctx.pw = spec, pw
         ctx.has_bias = bias is not None
         ctx.save_for_backward(a, y if spec.bwd_mask else None)
@@ -272,7 +276,7 @@ class TapConv(torch.autograd.Function):
         a, y = ctx.saved_tensors
         if y is not None:
             dy = dy * (y > 0)
-        dy = dy.contiguous()
+        dy = dy.contiguous().to(torch.bfloat16)
         B = a.shape[0]
         da = None
         if spec.need_dgrad and ctx.needs_input_grad[1]:
@@ -293,9 +297,8 @@ class TapConv(torch.autograd.Function):
         dweight = pw.unpack_grad(dwp)
         dbias = None
         if ctx.has_bias:
-            dbias = colsum(dy.reshape(-1, spec.N))
-            if spec.bias_tile > 1:
-                dbias = dbias.reshape(spec.bias_tile, -1).sum(0)
+            # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
+            dbias = colsum(dy.reshape(-1, spec.N // spec.bias_tile))
             if pw.operm is not None:
                 dbias = dbias[pw.operm.long()]
         return None, da, dweight, dbias, None
@@ -322,14 +325,14 @@ def _wgrad_splits(B, Ho, Wo, M, Ccols, T):
     return int(min(want, ptiles))
 
 
-def _bias_act(acc, bias, relu):
-    """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16."""
+def _bias_act(acc, bias, relu, keep_f32=False):
+    """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16 (or fp32)."""
     y = acc
     if bias is not None:
         y = y + bias
     if relu:
         y = torch.relu(y)
-    return y.bfloat16()
+    return y if keep_f32 else y.bfloat16()
 
 
 def tap_conv(spec, a, weight, bias, pw):
