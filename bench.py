@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the SimPLe world-model hot path on B200 (contract: see the task description / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  # the reference's own CPU path (baseline)
+
+One "step" = one world-model optimiser step on one synthetic batch: NextFramePredictor forward (train branch), the
+four/five losses, backward, clip_grad_norm_, Adafactor, and the scheduled-sampling frame feedback -- BASELINE.json
+configs[1] ("World-model training ... bf16 on 1xB200, batch 64, with Adafactor").  `value` = global frames/s with the
+replay resident in HBM; `e2e` = the same step fed from pinned host memory with the loss read back every step.
+Also reported: simulated env-steps/s (configs[2]: 16 agents x 50 steps with a PPO policy), the tensor-core roofline of
+the tcgen05 GEMM kernels, the HBM roofline of the fused softmax-CE kernel, and the reference's CPU number.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ALG_GFLOP_PER_FRAME_TRAIN = 36.80  # conv/deconv fwd+bwd per sample (algorithmic)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic "Atari-like" replay: constant background + moving sprites from a 16-colour palette
+# ----------------------------------------------------------------------------------------------------------------
+def synth_replay(n, n_action, seed, device='cpu'):
+    g = torch.Generator().manual_seed(seed)
+    H, W = 105, 80
+    palette = torch.randint(0, 256, (16, 3), generator=g, dtype=torch.uint8)
+    frames = palette[0].view(1, 3, 1, 1).repeat(n + 4, 1, H, W)
+    pos = torch.randint(0, 60, (10, 2), generator=g)
+    vel = torch.randint(-2, 3, (10, 2), generator=g)
+    col = torch.randint(1, 16, (10,), generator=g)
+    for t in range(n + 4):
+        for s in range(10):
+            y = int((pos[s, 0] + vel[s, 0] * t) % (H - 8))
+            x = int((pos[s, 1] + vel[s, 1] * t) % (W - 8))
+            frames[t, :, y:y + 8, x:x + 8] = palette[col[s]].view(3, 1, 1)
+    obs = torch.stack([frames[t:t + 4].reshape(12, H, W) for t in range(n)])
+    new_obs = frames[4:n + 4].clone()
+    a = torch.randint(0, n_action, (n,), generator=g)
+    action = torch.nn.functional.one_hot(a, n_action).to(torch.uint8)
+    reward = torch.randint(0, 3, (n,), generator=g, dtype=torch.uint8)
+    value = torch.randn(n, generator=g)
+    return dict(obs=obs.to(device), new_obs=new_obs.to(device), action=action.to(device), reward=reward.to(device),
+                value=value.to(device))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', 1400.0), d.get('bf16_tflops', 1590.0), 'measured'
+    return 6650.0, 1400.0, 1590.0, 'fallback'
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the step (baseline/_ref copy, else the oracle port)
+# ----------------------------------------------------------------------------------------------------------------
+def reference_cpu_step_time(batch, steps, warmup, n_action=3):
+    """Times `steps` world-model optimiser steps of the reference on the host CPU (fp32, all cores)."""
+    import numpy as np
+    from oracle import wm_oracle as O
+    from oracle.ref_loader import load_reference
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.default_config(device='cpu', batch_size=batch)
+    ref = load_reference()
+    data = synth_replay(warmup + steps + 2, n_action, seed=0)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    times = []
+    if ref is not None:
+        kind = 'reference'
+        model = ref.nfp.NextFramePredictor(cfg, n_action)
+        opt = ref.adafactor.Adafactor(model.parameters())
+        model.train()
+        model.init_internal_states(batch)
+        frames = data['obs'][:batch].float() / 255
+        for j in range(warmup + steps):
+            idx = torch.arange(batch) + j
+            new_states = data['new_obs'][idx].long()
+            t0 = time.perf_counter()
+            logits, rew, val = model(frames, data['action'][idx].float(), new_states.float() / 255, 0)
+            lstm = model.stochastic_model.get_lstm_loss()
+            loss, *_ = O.wm_losses(cfg, logits, rew, val, lstm, new_states, data['reward'][idx].long(), data['value'][idx])
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), cfg.clip_grad_norm)
+            opt.step()
+            frames = torch.cat((frames[:, 3:], torch.argmax(logits.detach(), dim=1).float() / 255), dim=1)
+            float(loss)
+            if j >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = 'port'
+        torch.manual_seed(0)
+        from simple_b200.next_frame_predictor import NextFramePredictor
+        p = {k: v.clone().requires_grad_(True) for k, v in NextFramePredictor(cfg, n_action).state_dict().items()}
+        st = O.init_state(cfg, batch)
+        opt_state = {k: {} for k in p}
+        frames = data['obs'][:batch].float() / 255
+        for j in range(warmup + steps):
+            idx = torch.arange(batch) + j
+            new_states = data['new_obs'][idx].long()
+            t0 = time.perf_counter()
+            logits, rew, val, lstm = O.forward(p, cfg, st, frames, data['action'][idx].float(), new_states.float() / 255,
+                                               0, O.GlobalRand(), training=True)
+            loss, *_ = O.wm_losses(cfg, logits, rew, val, lstm, new_states, data['reward'][idx].long(), data['value'][idx])
+            names = list(p)
+            gl = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+            present = [(k, g) for k, g in zip(names, gl) if g is not None]
+            clipped, _ = O.clip_grad_norm([g for _, g in present], cfg.clip_grad_norm)
+            with torch.no_grad():
+                for (k, _), g in zip(present, clipped):
+                    p[k].copy_(O.adafactor_step(p[k].detach(), g, opt_state[k]))
+            frames = torch.cat((frames[:, 3:], torch.argmax(logits.detach(), dim=1).float() / 255), dim=1)
+            if j >= warmup:
+                times.append(time.perf_counter() - t0)
+    return kind, sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 16  # bounded sample of the B=64 workload: one reference step on a quarter batch (a CPU step at 64 takes ~15 s)
+    steps, warmup = max(1, min(args.steps, 4)), max(2, min(args.warmup, 3))
+    kind, sec = reference_cpu_step_time(batch, steps, warmup)
+    v = batch / sec
+    line = {
+        'impl': 'reference', 'metric': 'world_model_train_frames_per_s', 'value': v, 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'world-model training step (fwd+loss+bwd+clip+Adafactor), Atari-100k shape 4x105x80x3, '
+                               'batch 64 on the GPU arm; reference CPU arm times a bounded sample: batch 16 per step'},
+        'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': kind,
+                         'sample': f'{steps} optimiser steps at batch {batch} after {warmup} warm-up steps, fp32, '
+                                   f'torch CPU backend, {os.cpu_count()} threads'},
+        'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# own arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch.distributed as dist
+    from simple_b200 import _lib, profiling
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.parallel import FlatGradSync, init_distributed
+    from simple_b200.policy import CnnPolicy
+    from simple_b200.simulated_env import Discrete, make_simulated_env
+    from simple_b200.trainer import Trainer
+    from types import SimpleNamespace
+
+    rank, world, local = init_distributed()
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.lib().sb_init(local), 'sb_init')
+    B, n_action, K, W_ = args.batch, 3, args.steps, max(3, args.warmup)
+    cfg = SimpleNamespace(
+        agents=args.agents, batch_size=B, bottleneck_bits=128, bottleneck_noise=0.1, clip_grad_norm=1.0, compress_steps=5,
+        device=str(dev), done_on_last_rollout_step=True, dropout=0.15, filter_double_steps=3, frame_shape=(3, 105, 80),
+        hidden_layers=2, hidden_size=96, input_noise=0.05, latent_rnn_max_sampling=0.5, latent_state_size=128,
+        latent_use_max_probability=0.8, recurrent_state_size=64, residual_dropout=0.5, rollout_length=50,
+        save_models=False, scheduled_sampling_decay_steps=22250, stacking=4, stack_internal_states=True,
+        target_loss_clipping=0.03, use_stochastic_model=True, use_wandb=False)
+    torch.manual_seed(0)  # identical replicas
+    model = NextFramePredictor(cfg, n_action).to(dev)
+    trainer = Trainer(model, cfg)
+    if world > 1:
+        trainer.grad_sync = FlatGradSync(model)
+    n_rec = B + K + W_ + 60
+    host = synth_replay(n_rec, n_action, seed=1 + rank)
+    data = {k: v.to(dev) for k, v in host.items()}
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    starts = torch.arange(B, device=dev)
+
+    def one_step(frames, j, src, from_host):
+        idx = starts + j
+        if from_host:  # the batch of this step is a contiguous slice of the pinned host replay: 4 async H2D copies
+            new_states = src['new_obs'][j:j + B].to(dev, non_blocking=True)
+            action = src['action'][j:j + B].to(dev, non_blocking=True).float()
+            reward = src['reward'][j:j + B].to(dev, non_blocking=True).long()
+            value = src['value'][j:j + B].to(dev, non_blocking=True)
+        else:
+            new_states, action = src['new_obs'][idx], src['action'][idx].float()
+            reward, value = src['reward'][idx].long(), src['value'][idx]
+        out = trainer.train_step(frames, action, new_states, reward, value, 0)
+        nxt = trainer.preprocess_state(out['argmax'], per_sample=True)
+        return torch.cat((frames[:, 3:], nxt), dim=1), out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, src, from_host, j0):
+        frames = trainer.preprocess_state(data['obs'][starts], per_sample=False)
+        if from_host:
+            frames = trainer.preprocess_state(pinned['obs'][:B].to(dev, non_blocking=True), per_sample=False)
+        model.init_internal_states(B)
+        for j in range(W_):
+            frames, out = one_step(frames, j0 + j, src, from_host)
+            if from_host:
+                float(out['loss'])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.lib().sb_launch_count()
+        e0.record()
+        for j in range(nsteps):
+            frames, out = one_step(frames, j0 + W_ + j, src, from_host)
+            if from_host:
+                float(out['loss'])  # device->host read of the step's result
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, _lib.lib().sb_launch_count() - l0, float(out['loss'])
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, last_loss = timed(K, data, False, 0)
+    clocks = sampler.finish() if sampler else None
+    ms_e2e, _, _ = timed(K, pinned, True, 0)
+    frames_per_s = B * world * K / (ms * 1e-3)
+    e2e_fps = B * world * K / (ms_e2e * 1e-3)
+    h2d = B * (3 * 105 * 80 + n_action + 1 + 4)
+    line = {
+        'metric': 'world_model_train_frames_per_s', 'value': frames_per_s, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': K, 'warmup': W_, 'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': 'world-model training step (NextFramePredictor train fwd + losses + bwd + clip_grad_norm '
+                               '+ Adafactor + frame feedback), Atari-100k shape 4x105x80x3, n_action=3',
+                   'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2': 'inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush'},
+        'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / K},
+        'gpu_launches': int(launches), 'last_loss': last_loss, 'clocks': clocks,
+    }
+
+    if rank == 0:
+        hbm, tf_sus, tf_burst, how = peaks()
+        # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps
+        frames = trainer.preprocess_state(data['obs'][starts], per_sample=False)
+        model.init_internal_states(B)
+        for j in range(2):
+            frames, _ = one_step(frames, j, data, False)
+        torch.cuda.synchronize()
+        profiling.RECORDER = rec = profiling.Recorder()
+        for j in range(2, 5):
+            frames, _ = one_step(frames, j, data, False)
+        summ = rec.summary()
+        profiling.RECORDER = None
+        gem = [summ[k] for k in ('tap_gemm_kernel', 'tap_wgrad_kernel') if k in summ]
+        if gem:
+            fl, tm, nl = sum(g['work'] for g in gem), sum(g['ms'] for g in gem), sum(g['launches'] for g in gem)
+            ach = fl / (tm * 1e-3) / 1e12
+            line['roofline'] = {'bound': 'tensor', 'kernel': 'tap_gemm_kernel+tap_wgrad_kernel (tcgen05)',
+                                'achieved': ach, 'peak': tf_sus, 'unit': 'TFLOP/s', 'frac': ach / tf_sus,
+                                'traffic': None, 'peak_source': f'{how} sustained bf16',
+                                'launches_per_step': nl / 3, 'ms_per_step': tm / 3,
+                                'alg_gflop_per_step': fl / 3 / 1e9}
+            line['roofline_by_layer'] = {
+                t: {'ms': v[0] / 3, 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None}
+                for g in gem for t, v in sorted(g['by_tag'].items())}
+        if 'pixel_ce_kernel' in summ:
+            c = summ['pixel_ce_kernel']
+            ach = c['work'] / (c['ms'] * 1e-3) / 1e9
+            line['roofline_ce'] = {'bound': 'hbm', 'kernel': 'pixel_ce_kernel', 'achieved': ach, 'peak': hbm,
+                                   'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'peak_source': how,
+                                   'ms_per_launch': c['ms'] / c['launches'],
+                                   'alg_bytes_per_launch': c['work'] / c['launches']}
+    # ---- simulated rollout: agents x 50 steps with a PPO-style CNN policy (configs[2]); agents sharded over ranks
+    A = args.agents
+    cfg_env = SimpleNamespace(**{**vars(cfg), 'agents': A})
+    env = make_simulated_env(cfg_env, model, Discrete(n_action))
+    policy = CnnPolicy((12, 105, 80), n_action).to(dev)
+    env.restart_all(data['obs'][:A])
+
+    def rollout():
+        obs = env.reset()
+        for _ in range(cfg.rollout_length):
+            _, action, _ = policy.act(obs)
+            obs, rew, done, _ = env.step(action)
+        return rew
+
+    rollout()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.rollouts):
+        rollout()
+    e1.record()
+    barrier()
+    rms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([rms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rms = float(t)
+    line['rollout'] = {'metric': 'simulated_env_steps_per_s', 'value': A * world * cfg.rollout_length * args.rollouts / (rms * 1e-3),
+                       'unit': 'env-steps/s', 'agents_per_gpu': A, 'steps': cfg.rollout_length,
+                       'ms_per_env_step_batch': rms / (cfg.rollout_length * args.rollouts)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, sec = reference_cpu_step_time(16, 2, 2)
+        line['cpu_baseline'] = {'value': 16 / sec, 'unit': 'frames/s', 'cores': os.cpu_count(), 'kind': kind,
+                                'sample': '2 optimiser steps at batch 16 after 2 warm-up steps (gate conv active), fp32, '
+                                          f'torch CPU backend, {os.cpu_count()} threads'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', type=str, default='own', choices=['own', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--agents', type=int, default=16, help='simulated agents per GPU')
+    ap.add_argument('--rollouts', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()

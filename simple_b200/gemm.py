@@ -4,7 +4,7 @@ import functools
 
 import torch
 
-from . import _lib
+from . import _lib, profiling
 
 
 @functools.lru_cache(maxsize=None)
@@ -40,7 +40,7 @@ def _taps(args, taps):
 
 
 def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bias=None, relu=False, splits=1,
-             accumulate=False, box=None):
+             accumulate=False, box=None, tag=None, flops=0.0):
     """out[b,y,x,n] (+)= sum_t sum_c a[b,y+dy_t,x+dx_t,c] * w[n, t*C+c].  a: bf16 [B,H,W,C]; w: bf16 [N, >=T*C]."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and a.is_contiguous() and a.dim() == 4
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.dim() == 2
@@ -61,11 +61,15 @@ def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bia
     args.out = out.data_ptr(); args.out_f32 = int(out.dtype == torch.float32); args.ldo = out.shape[3]
     args.bias = bias.data_ptr() if bias is not None else None
     args.relu = int(relu); args.splits = splits; args.accumulate = int(accumulate)
+    rec = profiling.RECORDER
+    ev0 = rec.start() if rec is not None else None
     _lib.check(_lib.lib().sb_tap_gemm(ctypes.byref(args), _lib.stream_ptr()), 'sb_tap_gemm')
+    if rec is not None:
+        rec.stop('tap_gemm_kernel', tag, flops, 'flop', ev0)
     return out
 
 
-def tap_wgrad(a, dy, taps, dw, splits=1, box=None):
+def tap_wgrad(a, dy, taps, dw, splits=1, box=None, tag=None, flops=0.0):
     """dw[n, t*C+c] += sum_{b,y,x} dy[b,y,x,n] * a[b,y+dy_t,x+dx_t,c].  dw: fp32 [N, >=T*C] (accumulated)."""
     assert a.dtype == torch.bfloat16 and a.is_contiguous() and dy.dtype == torch.bfloat16 and dy.is_contiguous()
     assert dw.dtype == torch.float32 and dw.is_contiguous()
@@ -79,5 +83,9 @@ def tap_wgrad(a, dy, taps, dw, splits=1, box=None):
     args.bw, args.bh, args.bb = bw, bh, bb
     _taps(args, taps)
     args.dw = dw.data_ptr(); args.ldw = dw.shape[1]; args.splits = splits
+    rec = profiling.RECORDER
+    ev0 = rec.start() if rec is not None else None
     _lib.check(_lib.lib().sb_tap_wgrad(ctypes.byref(args), _lib.stream_ptr()), 'sb_tap_wgrad')
+    if rec is not None:
+        rec.stop('tap_wgrad_kernel', tag, flops, 'flop', ev0)
     return dw

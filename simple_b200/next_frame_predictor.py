@@ -350,8 +350,10 @@ class NextFramePredictor(nn.Module):
         P['timing'] = [timing_signal_nhwc(s[0], s[1], s[2]).to(dev) for s in tshapes]
         P['stoch_timing'] = timing_signal_nhwc(c.hidden_size, H, W).to(dev)
         # gate 3x3 on XS (state 0..63 | x_start 64..75 | zero pad to 128), no dgrad (inputs are detached / data)
-        P['gate'] = ConvSpec('gate', H, W, 128, H, W, 128, taps33, relu=False, need_dgrad=False)
-        P['embed'] = ConvSpec('embed', H, W, 128, H, W, 96, [(0, 0)], relu=False)
+        HW = H * W
+        P['gate'] = ConvSpec('gate', H, W, 128, H, W, 128, taps33, relu=False, need_dgrad=False,
+                             flops=2.0 * HW * 128 * 76 * 9)
+        P['embed'] = ConvSpec('embed', H, W, 128, H, W, 96, [(0, 0)], relu=False, flops=2.0 * HW * 96 * 76)
         P['down'], P['down_lay'] = [], []
         for i in range(5):
             Ci, Hi, Wi = es[i]
@@ -359,9 +361,9 @@ class NextFramePredictor(nn.Module):
             lay = s2d_in(Hi, Wi, Ci, 4, 2, 1)
             P['down_lay'].append(lay)
             P['down'].append(ConvSpec(f'down{i}', lay.H2, lay.W2, 4 * Ci, Ho, Wo, Co, taps22, relu=True,
-                                      out_f32=(Ho * Wo <= 30)))
-        P['mid'] = [ConvSpec(f'mid{i}', 3, 2, 768, 3, 2, 768, taps33, relu=True, bwd_mask=(i == 0), out_f32=True)
-                    for i in range(2)]
+                                      out_f32=(Ho * Wo <= 30), flops=2.0 * Ho * Wo * Co * Ci * 16))
+        P['mid'] = [ConvSpec(f'mid{i}', 3, 2, 768, 3, 2, 768, taps33, relu=True, bwd_mask=(i == 0), out_f32=True,
+                             flops=2.0 * 6 * 768 * 768 * 9) for i in range(2)]
         P['up'], P['up_lay'] = [], []
         shape = es[5]
         for i in range(5):
@@ -370,17 +372,21 @@ class NextFramePredictor(nn.Module):
             lay = s2d_out(Hi, Wi, Ho, Wo, Co)
             P['up_lay'].append(lay)
             P['up'].append(ConvSpec(f'up{i}', Hi, Wi, Ci, Hi + 1, Wi + 1, 4 * Co, [(-dy, -dx) for dy, dx in taps22],
-                                    relu=True, transposed=True, bias_tile=4, out_f32=(Ho * Wo <= 30)))
+                                    relu=True, transposed=True, bias_tile=4, out_f32=(Ho * Wo <= 30),
+                                    flops=2.0 * Hi * Wi * Ci * Co * 16))
             shape = ds[i]
-        P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False)
+        P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False, flops=2.0 * HW * 768 * 96)
         # posterior encoder of the stochastic model (train only)
-        P['s_embed'] = ConvSpec('s_embed', H, W, 64, H, W, 96, [(0, 0)], relu=False, need_dgrad=False)
+        P['s_embed'] = ConvSpec('s_embed', H, W, 64, H, W, 96, [(0, 0)], relu=False, need_dgrad=False,
+                                flops=2.0 * HW * 96 * 15)
         l1 = s2d_in(H, W, 96, 8, 4, 2)
         P['s_lay1'] = l1
-        P['s_conv1'] = ConvSpec('s_conv1', l1.H2, l1.W2, 16 * 96, 26, 20, 128, taps22, relu=False)
+        P['s_conv1'] = ConvSpec('s_conv1', l1.H2, l1.W2, 16 * 96, 26, 20, 128, taps22, relu=False,
+                                flops=2.0 * 520 * 128 * 96 * 64)
         l2 = s2d_in(26, 20, 128, 8, 4, 2)
         P['s_lay2'] = l2
-        P['s_conv2'] = ConvSpec('s_conv2', l2.H2, l2.W2, 16 * 128, 6, 5, 512, taps22, relu=False)
+        P['s_conv2'] = ConvSpec('s_conv2', l2.H2, l2.W2, 16 * 128, 6, 5, 512, taps22, relu=False,
+                                flops=2.0 * 30 * 512 * 128 * 64)
         # fused elementwise stages
         T = P['timing']
         drop = c.dropout

@@ -7,7 +7,7 @@ import ctypes
 
 import torch
 
-from . import _lib
+from . import _lib, profiling
 from .gemm import tap_gemm, tap_wgrad
 
 
@@ -187,8 +187,9 @@ class ConvSpec:
     """
 
     def __init__(self, name, Ha, Wa, Ca, Ho, Wo, N, taps, relu, transposed=False, need_dgrad=True, bias_tile=1,
-                 bwd_mask=False, out_f32=False):
+                 bwd_mask=False, out_f32=False, flops=0.0):
         self.name = name
+        self.flops = flops  # ALGORITHMIC flops per sample of the forward contraction, for rooflines
         self.out_f32 = out_f32  # keep the output in fp32 (tiny deep layers feeding an InstanceNorm over few pixels)
         self.Ha, self.Wa, self.Ca, self.Ho, self.Wo, self.N = Ha, Wa, Ca, Ho, Wo, N
         self.taps, self.relu, self.transposed = taps, relu, transposed
@@ -260,11 +261,13 @@ class TapConv(torch.autograd.Function):
         B = a.shape[0]
         splits = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
         if splits > 1:
-            acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits)
+            acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits, tag=spec.name + '.fwd',
+                           flops=spec.flops * B)
             y = _bias_act(acc, bias_f, spec.relu, spec.out_f32)
         else:
             y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu,
-                         out_dtype=torch.float32 if spec.out_f32 else torch.bfloat16)
+                         out_dtype=torch.float32 if spec.out_f32 else torch.bfloat16, tag=spec.name + '.fwd',
+                         flops=spec.flops * B)
         ctx.spec, ctx.pw = spec, pw
         ctx.has_bias = bias is not None
         ctx.save_for_backward(a, y if spec.bwd_mask else None)
@@ -283,17 +286,21 @@ class TapConv(torch.autograd.Function):
             w_op = pw.fwd if spec.transposed else pw.tr
             splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
             if splits > 1:
-                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits).bfloat16()
+                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits, tag=spec.name + '.dgrad',
+                              flops=spec.flops * B).bfloat16()
             else:
-                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca)
+                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
+                              flops=spec.flops * B)
         T = len(spec.taps)
         if spec.transposed:
             # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
             dwp = torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
-            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=_wgrad_splits(B, spec.Ha, spec.Wa, spec.Ca, spec.N, T))
+            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=_wgrad_splits(B, spec.Ha, spec.Wa, spec.Ca, spec.N, T),
+                      tag=spec.name + '.wgrad', flops=spec.flops * B)
         else:
             dwp = torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
-            tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T))
+            tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T),
+                      tag=spec.name + '.wgrad', flops=spec.flops * B)
         dweight = pw.unpack_grad(dwp)
         dbias = None
         if ctx.has_bias:
@@ -388,9 +395,13 @@ class PixelCE(torch.autograd.Function):
         amax = torch.empty(B, 3, H, W, device=logits.device, dtype=torch.uint8) if want_argmax else None
         n = float(B * 3 * HW)
         dl = logits.detach()
+        rec = profiling.RECORDER
+        ev0 = rec.start() if rec is not None else None
         _lib.check(_lib.lib().sb_pixel_ce(dl.data_ptr(), target_u8.data_ptr(), B, HW, clip, 1.0 / n, dl.data_ptr(),
                                           _ptr(amax), loss_sum.data_ptr(), dbias.data_ptr(), _lib.stream_ptr()),
                    'sb_pixel_ce')
+        if rec is not None:  # algorithmic bytes: read logits + write dlogits (bf16) + targets + argmax
+            rec.stop('pixel_ce_kernel', 'train', B * HW * (768 * 2 * 2 + 3 + 3), 'byte', ev0)
         ctx.save_for_backward(dl)
         ctx.unit_grad = unit_grad
         loss = (loss_sum / n - clip).float().reshape(())

@@ -1,0 +1,159 @@
+"""Device-resident simulated environment (drop-in for simple/subproc_vec_env.py:398-457 + simple/simulated_env.py).
+
+`make_simulated_env(config, model, action_space)` returns a vectorised env with the reference's surface
+(`reset`, `step`, `env_method('restart', frames, indices=j)`, `num_envs`, `observation_space`, `action_space`,
+`close`).  The reference ships every frame stack through 16 echo subprocesses over pipes (D2H -> pickle -> H2D per
+step); here the frame stack, the recurrent state and the rewards never leave the GPU: one step is
+one-hot(actions) -> NextFramePredictor eval forward -> fused argmax decode -> u8 frame-stack shift.
+
+Reference quirks kept on purpose: dropout stays active in eval; `done` is never True
+(subproc_vec_env.py:433-440 computes it after the counter was reset); the value head is added to the reward of the
+last step of a rollout; observations are the u8 round trip of the frame stack, returned as float 0..255.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+class Box:
+    def __init__(self, low, high, shape, dtype=np.uint8):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.low = np.full(self.shape, low, dtype=self.dtype)
+        self.high = np.full(self.shape, high, dtype=self.dtype)
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
+
+
+class SimulatedEnv:
+    """Per-agent view kept for surface compatibility (simple/simulated_env.py:9-64): holds the initial frames."""
+
+    def __init__(self, vec, index):
+        self._vec, self._index = vec, index
+        self.main = index == 0
+
+    @property
+    def initial_frames(self):
+        return self._vec._initial[self._index] if self._vec._has_initial[self._index] else None
+
+    def restart(self, initial_frames):
+        self._vec._set_initial(self._index, initial_frames)
+
+    def get_initial_frames(self):
+        return self._vec._initial[self._index]
+
+    def reset(self):
+        if not self._vec._has_initial[self._index]:
+            raise ValueError('This environment has not been initialized. Call the restart function.')
+        return self._vec._initial[self._index]
+
+    def close(self):
+        return None
+
+
+class SimulatedVecEnv:
+
+    def __init__(self, config, model, action_space, reference_types=False):
+        self.config = config
+        self.model = model
+        self.action_space = action_space
+        self.n_action = action_space.n
+        self.num_envs = config.agents
+        c, h, w = config.frame_shape
+        self.stack_channels = c * int(config.stacking)
+        self.observation_space = Box(0, 255, (self.stack_channels, h, w), np.uint8)
+        self.device = torch.device(config.device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('simple_b200 simulated env runs on CUDA only; there is no CPU fallback')
+        self.reference_types = reference_types
+        self._initial = torch.zeros(self.num_envs, self.stack_channels, h, w, dtype=torch.uint8, device=self.device)
+        self._has_initial = [False] * self.num_envs
+        self.envs = [SimulatedEnv(self, i) for i in range(self.num_envs)]
+        self.step_count = 0
+        self.frames = None  # u8 [A,12,H,W] on device
+        self.closed = False
+
+    # ---- reference surface --------------------------------------------------------------------------------------
+    def _set_initial(self, index, frames):
+        self._initial[index].copy_(torch.as_tensor(frames).to(torch.uint8), non_blocking=True)
+        self._has_initial[index] = True
+
+    def restart_all(self, frames_u8):
+        """Batched form of `env_method('restart', f, indices=j)` for all agents: u8 [A,12,H,W] (one device copy)."""
+        self._initial.copy_(frames_u8.to(torch.uint8), non_blocking=True)
+        self._has_initial = [True] * self.num_envs
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+        return [getattr(self.envs[i], method_name)(*method_args, **method_kwargs) for i in idx]
+
+    def reset(self):
+        if not all(self._has_initial):
+            raise ValueError('This environment has not been initialized. Call the restart function.')
+        return self._initial.float()
+
+    def step_async(self, actions):
+        self._pending = self._step(actions)
+
+    def step_wait(self):
+        out, self._pending = self._pending, None
+        return out
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.closed = True
+
+    # ---- one simulated step (subproc_vec_env.py:409-445) ----------------------------------------------------------
+    @torch.no_grad()
+    def _step(self, actions):
+        cfg = self.config
+        model = self.model
+        A = self.num_envs
+        if self.step_count == 0:
+            self.frames = self._initial.clone()
+            if cfg.stack_internal_states:
+                model.init_internal_states(A)
+            model.repack()  # weights are static during a rollout: pack once, not every step
+        self.step_count += 1
+        a = torch.as_tensor(actions, device=self.device).long().reshape(A, -1)[:, :1]
+        onehot = torch.zeros(A, 1, self.n_action, device=self.device).scatter_(2, a.unsqueeze(-1), 1.0)
+        model.eval()
+        auto = model._auto_repack
+        model._auto_repack = False
+        try:
+            logits, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot)
+        finally:
+            model._auto_repack = auto
+        new = ops.pixel_argmax(logits)  # u8 [A,3,H,W]
+        c = cfg.frame_shape[0]
+        self.frames = torch.cat((self.frames[:, c:], new), dim=1)
+        rewards = (torch.argmax(reward_pred, dim=1) - 1).to(torch.float32)
+        if self.step_count == cfg.rollout_length:
+            self.step_count = 0
+            rewards = rewards + value_pred.float()
+        if cfg.done_on_last_rollout_step:
+            done = self.step_count == cfg.rollout_length  # evaluated after the reset above: always False (ref quirk)
+        else:
+            done = False
+        obs = self.frames.float()
+        if self.reference_types:  # exactly the host-side types VecPytorchWrapper hands out (envs.py:109-118)
+            return obs, rewards.double().cpu().unsqueeze(1), np.full(A, done, dtype=bool), tuple({} for _ in range(A))
+        return obs, rewards.unsqueeze(1), np.full(A, done, dtype=bool), tuple({} for _ in range(A))
+
+
+def make_simulated_env(config, model, action_space, reference_types=False):
+    return SimulatedVecEnv(config, model, action_space, reference_types=reference_types)
+
+
+def shard_agents(n_agents, rank, world_size):
+    """Agent-sharded rollouts (no collective): the slice of global agent indices simulated by `rank`."""
+    per = -(-n_agents // world_size)
+    return range(min(n_agents, rank * per), min(n_agents, (rank + 1) * per))
