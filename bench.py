@@ -213,48 +213,47 @@ def run_own(args):
     trainer = Trainer(model, cfg)
     if world > 1:
         trainer.grad_sync = FlatGradSync(model)
-    n_rec = B + K + W_ + 60
+    n_rec = B + K + W_ + 80
     host = synth_replay(n_rec, n_action, seed=1 + rank)
     data = {k: v.to(dev) for k, v in host.items()}
     pinned = {k: v.pin_memory() for k, v in host.items()}
+    from simple_b200.trainer import StepRunner
     starts = torch.arange(B, device=dev)
-
-    def one_step(frames, j, src, from_host):
-        idx = starts + j
-        if from_host:  # the batch of this step is a contiguous slice of the pinned host replay: 4 async H2D copies
-            new_states = src['new_obs'][j:j + B].to(dev, non_blocking=True)
-            action = src['action'][j:j + B].to(dev, non_blocking=True).float()
-            reward = src['reward'][j:j + B].to(dev, non_blocking=True).long()
-            value = src['value'][j:j + B].to(dev, non_blocking=True)
-        else:
-            new_states, action = src['new_obs'][idx], src['action'][idx].float()
-            reward, value = src['reward'][idx].long(), src['value'][idx]
-        out = trainer.train_step(frames, action, new_states, reward, value, 0)
-        nxt = trainer.preprocess_state(out['argmax'], per_sample=True)
-        return torch.cat((frames[:, 3:], nxt), dim=1), out
+    replay = dict(obs=data['obs'], new_obs=data['new_obs'], action=data['action'].float(), reward=data['reward'].long(),
+                  value=data['value'])
+    use_graph = not args.no_graph and world == 1
+    runner = StepRunner(trainer, replay, B, use_graph=use_graph, resident=True)
+    runner_host = StepRunner(trainer, replay, B, use_graph=use_graph, resident=False)
+    pinned['action_f'] = host['action'].float().pin_memory()
+    pinned['reward_l'] = host['reward'].long().pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(nsteps, src, from_host, j0):
-        frames = trainer.preprocess_state(data['obs'][starts], per_sample=False)
-        if from_host:
-            frames = trainer.preprocess_state(pinned['obs'][:B].to(dev, non_blocking=True), per_sample=False)
-        model.init_internal_states(B)
-        for j in range(W_):
-            frames, out = one_step(frames, j0 + j, src, from_host)
+    def run_steps(r, n, j0, from_host):
+        for j in range(n):
+            if from_host:  # this step's batch: a contiguous slice of the pinned host replay, 4 async H2D copies
+                k = j0 + j
+                r.load_batch(pinned['new_obs'][k:k + B], pinned['action_f'][k:k + B], pinned['reward_l'][k:k + B],
+                             pinned['value'][k:k + B])
+            r.step()
             if from_host:
-                float(out['loss'])
+                float(r.last['loss'])  # device->host read of the step's result
+
+    def timed(nsteps, from_host):
+        r = runner_host if from_host else runner
+        r.begin(starts, 0)
+        if from_host:
+            r.frames.copy_(trainer.preprocess_state(pinned['obs'][:B].to(dev, non_blocking=True), per_sample=False))
+        run_steps(r, W_ + 3, 0, from_host)  # warm-up (first step of the window, graph warm-up + capture)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _lib.lib().sb_launch_count()
+        # launches = eager launches (host-side counter) + graph replays x kernels recorded in the captured step
+        l0 = _lib.lib().sb_launch_count() + r.replays * r.graph_kernels
         e0.record()
-        for j in range(nsteps):
-            frames, out = one_step(frames, j0 + W_ + j, src, from_host)
-            if from_host:
-                float(out['loss'])  # device->host read of the step's result
+        run_steps(r, nsteps, W_ + 3, from_host)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -262,14 +261,14 @@ def run_own(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t)
-        return ms, _lib.lib().sb_launch_count() - l0, float(out['loss'])
+        return ms, _lib.lib().sb_launch_count() + r.replays * r.graph_kernels - l0, float(r.last['loss'])
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, last_loss = timed(K, data, False, 0)
+    ms, launches, last_loss = timed(K, False)
     clocks = sampler.finish() if sampler else None
-    ms_e2e, _, _ = timed(K, pinned, True, 0)
+    ms_e2e, _, _ = timed(K, True)
     frames_per_s = B * world * K / (ms * 1e-3)
     e2e_fps = B * world * K / (ms_e2e * 1e-3)
     h2d = B * (3 * 105 * 80 + n_action + 1 + 4)
@@ -283,20 +282,20 @@ def run_own(args):
                    'l2': 'inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush'},
         'e2e': {'value': e2e_fps, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / K},
-        'gpu_launches': int(launches), 'last_loss': last_loss, 'clocks': clocks,
+        'gpu_launches': int(launches), 'last_loss': last_loss, 'clocks': clocks, 'cuda_graph': bool(use_graph),
     }
 
     if rank == 0:
         hbm, tf_sus, tf_burst, how = peaks()
         # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps
-        frames = trainer.preprocess_state(data['obs'][starts], per_sample=False)
-        model.init_internal_states(B)
+        eager = StepRunner(trainer, replay, B, use_graph=False, resident=True)
+        eager.begin(starts, 0)
         for j in range(2):
-            frames, _ = one_step(frames, j, data, False)
+            eager.step()
         torch.cuda.synchronize()
         profiling.RECORDER = rec = profiling.Recorder()
-        for j in range(2, 5):
-            frames, _ = one_step(frames, j, data, False)
+        for j in range(3):
+            eager.step()
         summ = rec.summary()
         profiling.RECORDER = None
         gem = [summ[k] for k in ('tap_gemm_kernel', 'tap_wgrad_kernel') if k in summ]
@@ -369,6 +368,7 @@ def main():
     ap.add_argument('--agents', type=int, default=16, help='simulated agents per GPU')
     ap.add_argument('--rollouts', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='run every step eagerly (no CUDA graph replay)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -116,10 +116,11 @@ typedef struct {
   float eps;
   const float* gamma;
   const float* beta;
-  const float* Ta;         /* fp32 [H,W,C] or NULL */
+  const float* Ta;         /* separable timing table fp32 [(H+W), C/2] (rows y=0..H-1, then x=0..W-1) or NULL */
   void* out1;              /* optional plain bf16 */
   float p;                 /* dropout probability */
   unsigned long long seed; /* Philox key */
+  const unsigned long long* seed_ptr; /* optional DEVICE seed added to `seed` (changes between CUDA-graph replays) */
   unsigned int stream_id;  /* Philox stream (one per dropout site) */
   const uint8_t* keep;     /* optional explicit keep mask u8 [B,H,W,C] ("randomness as input" parity mode) */
   const float* Tb;
@@ -153,6 +154,9 @@ int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs
 /* fp32 (O,I,KH,KW) master weight -> bf16 GEMM operands (see DESIGN.md "weight packing"). */
 int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
                  const int* operm, void* fwd, void* tr, sb_stream_t stream);
+/* inverse map for gradients: fp32 packed [Opad, T*s*s*Ipad] (layout of `fwd`) -> reference layout (O,I,KH,KW). */
+int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s, int Ipad, int Opad,
+                        const int* iperm, const int* operm, float* out, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Multi-tensor fused clip_grad_norm_ + Adafactor (fairseq defaults: eps=(1e-30,1e-3), clip_threshold=1,
@@ -173,9 +177,10 @@ typedef struct {
   float* acc;      /* 2 floats: sum u^2, sum p^2 (RMS state) */
   long long n;     /* elements */
   int rows, cols;  /* 2-D: shape; 1-D: cols = 0; 4-D: unused */
-  float beta2t;    /* 1 - step^-0.8 */
-  float rel_step;  /* min(1e-2, 1/sqrt(step)) */
+  float* stepf;    /* DEVICE step counter of this tensor (float); beta2 = 1 - step^-0.8, rel_step = min(1e-2, step^-1/2) */
 } sb_tensor_desc;
+/* step counters += 1 for every descriptor (first call of a step; keeps CUDA-graph replays self-contained) */
+int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, sb_stream_t stream);
 int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
                   sb_stream_t stream);
 int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,

@@ -63,7 +63,7 @@ class PrepArgs(ctypes.Structure):
         ('inp', SbView), ('add', ctypes.c_void_p), ('relu_in', ctypes.c_int), ('in_f32', ctypes.c_int), ('add_f32', ctypes.c_int),
         ('sums', ctypes.c_void_p), ('eps', ctypes.c_float), ('gamma', ctypes.c_void_p), ('beta', ctypes.c_void_p),
         ('Ta', ctypes.c_void_p), ('out1', ctypes.c_void_p),
-        ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('stream_id', ctypes.c_uint),
+        ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('seed_ptr', ctypes.c_void_p), ('stream_id', ctypes.c_uint),
         ('keep', ctypes.c_void_p), ('Tb', ctypes.c_void_p), ('sc', ctypes.c_void_p), ('sh', ctypes.c_void_p),
         ('out2', SbView), ('g2', SbView), ('g1', ctypes.c_void_p), ('bsums', ctypes.c_void_p),
         ('d_main', SbView), ('d_add', ctypes.c_void_p),
@@ -108,7 +108,9 @@ class _Sigs:
     sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
     sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
+    sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_grad_sumsq = [_p, _p, _i, _p, _p]
+    sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]
     sb_adafactor_small = [_p, _i, _i, _p, _f, _p]
 

@@ -15,8 +15,7 @@ import torch
 from . import _lib
 
 _DESC = np.dtype([('p', np.uint64), ('g', np.uint64), ('row', np.uint64), ('col', np.uint64), ('acc', np.uint64),
-                  ('n', np.int64), ('rows', np.int32), ('cols', np.int32), ('beta2t', np.float32),
-                  ('rel_step', np.float32)])
+                  ('n', np.int64), ('rows', np.int32), ('cols', np.int32), ('stepf', np.uint64)])
 assert _DESC.itemsize == 64
 
 
@@ -48,6 +47,7 @@ class Adafactor(torch.optim.Optimizer):
             else:
                 st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32)
             st['RMS'] = 0
+            st['step_dev'] = torch.zeros(1, device=p.device, dtype=torch.float32)  # device mirror of `step`
         return st
 
     @torch.no_grad()
@@ -76,13 +76,22 @@ class Adafactor(torch.optim.Optimizer):
             return loss
         dev = active[0][0].device
         n = len(active)
-        descs = np.zeros(n, dtype=_DESC)
-        acc = torch.zeros(n, 2, device=dev, dtype=torch.float32)
-        total = torch.zeros(1, device=dev, dtype=torch.float32)
+        key = tuple(id(p) for p, _ in active)
+        rec = self._cache.get(key)
+        if rec is None:
+            # per parameter-set record: pinned host descriptors (CUDA-graph replays re-read them), device copies,
+            # accumulators and block maps.  Two sets exist in practice: with and without gate.* (first step of a window).
+            host = torch.zeros(n * 64, dtype=torch.uint8)
+            rec = dict(host=host, np=host.numpy().view(_DESC), dev=torch.zeros(n * 64, dtype=torch.uint8, device=dev),
+                       acc=torch.zeros(n, 2, device=dev, dtype=torch.float32),
+                       total=torch.zeros(1, device=dev, dtype=torch.float32), maps=self._build_maps(active, dev),
+                       params=[p for p, _ in active], pin=torch.zeros(n * 64, dtype=torch.uint8).pin_memory())
+            self._cache[key] = rec
+        descs = rec['np']
+        acc, total = rec['acc'], rec['total']
         for i, (p, g) in enumerate(active):
             st = self._init_state(p)
             st['step'] += 1
-            t = st['step']
             d = descs[i]
             d['p'], d['g'] = p.data_ptr(), g.data_ptr()
             if p.dim() >= 2:
@@ -92,17 +101,34 @@ class Adafactor(torch.optim.Optimizer):
             d['acc'] = acc.data_ptr() + 8 * i
             d['n'] = p.numel()
             d['rows'], d['cols'] = (p.shape[0], p.shape[1]) if p.dim() == 2 else (0, 0)
-            d['beta2t'] = 1.0 - math.pow(t, -0.8)
-            d['rel_step'] = min(1e-2, 1.0 / math.sqrt(t))
+            d['stepf'] = st['step_dev'].data_ptr()
             st['RMS'] = _LazyRMS(acc, i, p.numel())
-        key = tuple(id(p) for p, _ in active)
-        maps = self._cache.get(key)
-        if maps is None:
-            maps = self._build_maps(active, dev)
-            self._cache = {key: maps}
-        descs_dev = torch.from_numpy(descs.view(np.uint8)).to(dev, non_blocking=True)
+        self._launch(rec, n, max_grad_norm)
+        self.last_key = key
+        return loss
+
+    def advance_for_replay(self, key):
+        """Host-side bookkeeping for one replay of a CUDA graph that captured `step()` on parameter set `key`: the
+        device step counters advance inside the graph; this keeps the reference-visible `state[p]['step']` in sync."""
+        for p in self._cache[key]['params']:
+            self.state[p]['step'] += 1
+
+    def _launch(self, rec, n, max_grad_norm):
+        maps, acc, total, descs_dev = rec['maps'], rec['acc'], rec['total'], rec['dev']
+        # Descriptors hold pointers only.  Pageable source => the copy is synchronous w.r.t. the host buffer, so the next
+        # step may rewrite it; under CUDA-graph capture the pointers are static and the device copy is already valid.
+        if torch.cuda.is_current_stream_capturing():
+            # gradients allocated during capture live at graph-private addresses: upload them through a pinned staging
+            # buffer whose content never changes afterwards (every replay re-issues the same small copy)
+            rec['pin'].copy_(rec['host'])
+            descs_dev.copy_(rec['pin'], non_blocking=True)
+        else:
+            descs_dev.copy_(rec['host'])
+        acc.zero_()
+        total.zero_()
         L = _lib.lib()
         s = _lib.stream_ptr()
+        _lib.check(L.sb_adafactor_tick(descs_dev.data_ptr(), n, s), 'sb_adafactor_tick')
         mn = float(max_grad_norm) if max_grad_norm is not None else 0.0
         _lib.check(L.sb_grad_sumsq(descs_dev.data_ptr(), maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
                                    total.data_ptr(), s), 'sb_grad_sumsq')
@@ -117,8 +143,6 @@ class Adafactor(torch.optim.Optimizer):
             _lib.check(L.sb_adafactor_small(sub.data_ptr(), idx.numel(), rc, total.data_ptr(), mn, s),
                        'sb_adafactor_small')
         self.grad_norm_sq = total
-        self._keep = (descs_dev, acc)
-        return loss
 
     @staticmethod
     def _build_maps(active, dev):

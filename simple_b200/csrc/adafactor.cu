@@ -58,6 +58,9 @@ __global__ void __launch_bounds__(128)
   __shared__ float red[8];
   const int2 bm = block_map[blockIdx.x];  // (tensor, first patch)
   const sb_tensor_desc d = descs[bm.x];
+  const float tstep = *d.stepf;
+  const float beta2t = 1.0f - powf(tstep, -0.8f);            // adafactor.py:170
+  const float rel_step = fminf(1e-2f, rsqrtf(tstep));        // adafactor.py:84-94 (relative_step, no warm-up)
   const long long patch = (long long)bm.y + threadIdx.x;
   const long long npatch = d.n / KK;
   const float coef = clip_coef(total_sumsq, max_norm);
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(128)
         float m = 0.f;
 #pragma unroll
         for (int b = 0; b < KW; ++b) m += g[a * KW + b] * g[a * KW + b] + 1e-30f;
-        row[a] = d.row[patch * KH + a] * d.beta2t + (m / KW) * (1.0f - d.beta2t);
+        row[a] = d.row[patch * KH + a] * beta2t + (m / KW) * (1.0f - beta2t);
         d.row[patch * KH + a] = row[a];
       }
 #pragma unroll
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(128)
         float m = 0.f;
 #pragma unroll
         for (int a = 0; a < KH; ++a) m += g[a * KW + b] * g[a * KW + b] + 1e-30f;
-        col[b] = d.col[patch * KW + b] * d.beta2t + (m / KH) * (1.0f - d.beta2t);
+        col[b] = d.col[patch * KW + b] * beta2t + (m / KH) * (1.0f - beta2t);
         d.col[patch * KW + b] = col[b];
       }
     } else {
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(128)
       const float n = (float)d.n;
       const float rms_u = __fsqrt_rn(d.acc[0] / n);
       const float rms_p = __fsqrt_rn(d.acc[1] / n);
-      const float lr = fmaxf(1e-3f, rms_p) * d.rel_step;
+      const float lr = fmaxf(1e-3f, rms_p) * rel_step;
       const float scale = lr / fmaxf(1.0f, rms_u);  // clip_threshold = 1
 #pragma unroll
       for (int k = 0; k < KK; ++k) d.p[patch * KK + k] = p[k] - scale * (rf[k / KW] * cf[k % KW] * g[k]);
@@ -138,11 +141,14 @@ __global__ void __launch_bounds__(1024)
   const sb_tensor_desc d = descs[blockIdx.x];
   const float coef = clip_coef(total_sumsq, max_norm);
   const long long n = d.n;
+  const float tstep = *d.stepf;
+  const float beta2t = 1.0f - powf(tstep, -0.8f);
+  const float rel_step = fminf(1e-2f, rsqrtf(tstep));
   float su = 0.f, sp = 0.f;
   if (d.cols == 0) {  // 1-D: exp_avg_sq in d.row
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
       const float g = d.g[i] * coef;
-      const float v = d.row[i] * d.beta2t + (g * g + 1e-30f) * (1.0f - d.beta2t);
+      const float v = d.row[i] * beta2t + (g * g + 1e-30f) * (1.0f - beta2t);
       d.row[i] = v;
       const float u = g * rsqrtf(v);
       su += u * u;
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(1024)
     }
     su = block_sum(su, red);
     sp = block_sum(sp, red);
-    const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * d.rel_step;
+    const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * rel_step;
     const float scale = lr / fmaxf(1.0f, __fsqrt_rn(su / (float)n));
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
       const float g = d.g[i] * coef;
@@ -163,27 +169,40 @@ __global__ void __launch_bounds__(1024)
   const int R = d.rows, C = d.cols;
   float* srow = sm;
   float* scol = sm + R;
-  for (int i = threadIdx.x; i < R + C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
-    const float g = d.g[i] * coef;
-    const float u = g * g + 1e-30f;
-    atomicAdd(&srow[r], u);
-    atomicAdd(&scol[c], u);
-    const float p = d.p[i];
-    sp += p * p;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // sweep 1 (warp per row, lanes stride the columns: coalesced, no atomics): row sums of g^2+eps and sum p^2
+  for (int r = warp; r < R; r += nw) {
+    float rs = 0.f;
+    const float* gr = d.g + (long long)r * C;
+    const float* pr = d.p + (long long)r * C;
+    for (int c = lane; c < C; c += 32) {
+      const float g = gr[c] * coef;
+      rs += g * g + 1e-30f;
+      const float p = pr[c];
+      sp += p * p;
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) srow[r] = rs;
+  }
+  // sweep 2 (thread per column, rows looped: coalesced across threads): column sums
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float cs = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float g = d.g[(long long)r * C + c] * coef;
+      cs += g * g + 1e-30f;
+    }
+    scol[c] = cs;
   }
   __syncthreads();
   float rpart = 0.f;
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    const float v = d.row[r] * d.beta2t + (srow[r] / C) * (1.0f - d.beta2t);
+    const float v = d.row[r] * beta2t + (srow[r] / C) * (1.0f - beta2t);
     d.row[r] = v;
     srow[r] = v;
     rpart += v;
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float v = d.col[c] * d.beta2t + (scol[c] / R) * (1.0f - d.beta2t);
+    const float v = d.col[c] * beta2t + (scol[c] / R) * (1.0f - beta2t);
     d.col[c] = v;
     scol[c] = rsqrtf(v);
   }
@@ -191,24 +210,43 @@ __global__ void __launch_bounds__(1024)
   sp = block_sum(sp, red);
   for (int r = threadIdx.x; r < R; r += blockDim.x) srow[r] = rsqrtf(srow[r] / rmean);
   __syncthreads();
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
-    const float u = srow[r] * scol[c] * d.g[i] * coef;
-    su += u * u;
+  for (int r = warp; r < R; r += nw) {
+    const float rf = srow[r];
+    const float* gr = d.g + (long long)r * C;
+    for (int c = lane; c < C; c += 32) {
+      const float u = rf * scol[c] * gr[c] * coef;
+      su += u * u;
+    }
   }
   su = block_sum(su, red);
-  const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * d.rel_step;
+  const float lr = fmaxf(1e-3f, __fsqrt_rn(sp / (float)n)) * rel_step;
   const float scale = lr / fmaxf(1.0f, __fsqrt_rn(su / (float)n));
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = (int)(i / C), c = (int)(i - (long long)r * C);
-    d.p[i] -= scale * srow[r] * scol[c] * d.g[i] * coef;
+  for (int r = warp; r < R; r += nw) {
+    const float rf = srow[r] * scale * coef;
+    const float* gr = d.g + (long long)r * C;
+    float* pr = d.p + (long long)r * C;
+    for (int c = lane; c < C; c += 32) pr[c] -= rf * scol[c] * gr[c];
   }
   if (threadIdx.x == 0) d.acc[1] = sp;
+}
+
+// step counters live on the device (one float per tensor) so that a captured CUDA graph advances them by itself
+__global__ void adafactor_tick_kernel(const sb_tensor_desc* __restrict__ descs, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) *descs[i].stepf += 1.0f;
 }
 
 }  // namespace sb
 
 using namespace sb;
+
+extern "C" int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, sb_stream_t stream) {
+  if (!descs_dev || ntensors < 1) return SB_ERR_ARG;
+  adafactor_tick_kernel<<<(ntensors + 127) / 128, 128, 0, (cudaStream_t)stream>>>(descs_dev, ntensors);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
 
 extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
                              sb_stream_t stream) {

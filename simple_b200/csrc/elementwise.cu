@@ -61,13 +61,14 @@ struct PrepParams {
   float eps;
   const float* gamma;
   const float* beta;
-  const float* Ta;          // [H,W,C] or NULL
+  const float* Ta;          // separable timing table [(H+W), C/2] or NULL
   __nv_bfloat16* out1;      // optional plain [B,H,W,C]: value after Ta (skip / h)
   float p;                  // dropout probability (0 = none)
   unsigned long long seed;
+  const unsigned long long* seed_ptr;  // optional device-resident seed (added to `seed`): CUDA-graph replays
   unsigned int stream_id;
   const uint8_t* keep;      // parity mode: explicit keep mask, uint8 [B,H,W,C]
-  const float* Tb;          // [H,W,C] or NULL
+  const float* Tb;          // separable timing table [(H+W), C/2] or NULL
   const float* sc;          // [B,C] or NULL: x = x*sc + sh  (ActionInjector with sc = sigmoid(dense1(a)), sh = dense2(a))
   const float* sh;
   View out2;
@@ -90,8 +91,9 @@ __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, 
     }
     return;
   }
+  const unsigned long long seed = q.seed_ptr ? q.seed + *q.seed_ptr : q.seed;
   const uint4 r = philox4x32(make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), q.stream_id, 0u),
-                             make_uint2((uint32_t)q.seed, (uint32_t)(q.seed >> 32)));
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   const uint32_t thr = (uint32_t)(q.p * 65536.0f);
   k[0] = (r.x & 0xffff) >= thr; k[1] = (r.x >> 16) >= thr;
   k[2] = (r.y & 0xffff) >= thr; k[3] = (r.y >> 16) >= thr;
@@ -100,8 +102,7 @@ __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, 
 }
 
 // value of (main [+relu] + add) for 8 channels; also returns raw main
-__device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x, int c, float* z, float* mainv,
-                                       bool fwd_relu) {
+__device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x, int c, float* z, float* mainv) {
   const long long off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
   if (q.in_f32) {
     ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
@@ -109,7 +110,7 @@ __device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x,
     bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) z[j] = (fwd_relu && q.relu_in) ? fmaxf(mainv[j], 0.f) : mainv[j];
+  for (int j = 0; j < 8; ++j) z[j] = q.relu_in ? fmaxf(mainv[j], 0.f) : mainv[j];
   if (q.add) {
     float a[8];
     const long long aoff = (((long long)b * q.H + y) * q.W + x) * q.C + c;
@@ -120,55 +121,68 @@ __device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x,
   }
 }
 
-// forward chain up to the value before the injector (xd); xhat / xn optionally returned
-__device__ __forceinline__ void fwd_chain(const PrepParams& q, int b, int y, int x, int c, const float* z, float* xhat,
-                                          float* xn, float* xd, bool* k) {
+// Timing signals are separable (simple/utils.py:129-154): the first C/2 channels depend on the row only, the others
+// on the column only.  Table layout: [(H + W), C/2] = rows for y = 0..H-1, then rows for x = 0..W-1.
+__device__ __forceinline__ void add_timing(const float* T, int H, int C, int y, int x, int c, float* v) {
+  const int half = C >> 1;
+  const float* t = (c < half) ? T + (long long)y * half + c : T + (long long)(H + x) * half + (c - half);
+  float tv[8];
+  ld8f(t, tv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] += tv[j];
+}
+
+// Per-thread constants: every thread owns one 8-channel vector of one sample for its whole pixel loop.
+struct ChanCtx {
+  float mean[8], rstd[8], gamma[8], beta[8], sc[8], sh[8];
+};
+__device__ __forceinline__ void load_ctx(const PrepParams& q, int b, int c, ChanCtx& k) {
   const float invP = 1.0f / (float)(q.H * q.W);
-  const long long pix = ((long long)b * q.H + y) * q.W + x;
-  float g[8], bt[8];
   if (q.sums) {
-    ld8f(q.gamma + c, g);
-    ld8f(q.beta + c, bt);
+    ld8f(q.gamma + c, k.gamma);
+    ld8f(q.beta + c, k.beta);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s1 = q.sums[((long long)b * q.C + c + j) * 2], s2 = q.sums[((long long)b * q.C + c + j) * 2 + 1];
+      k.mean[j] = s1 * invP;
+      const float var = fmaxf(s2 * invP - k.mean[j] * k.mean[j], 0.f);
+      k.rstd[j] = rsqrtf(var + q.eps);
+    }
   }
+  if (q.sc) {
+    ld8f(q.sc + (long long)b * q.C + c, k.sc);
+    ld8f(q.sh + (long long)b * q.C + c, k.sh);
+  }
+}
+
+// forward chain up to the value before the injector (xd)
+__device__ __forceinline__ void fwd_chain(const PrepParams& q, const ChanCtx& k, int b, int y, int x, int c,
+                                          const float* z, float* xhat, float* xn, float* xd, bool* keep) {
+  const long long pix = ((long long)b * q.H + y) * q.W + x;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float v = z[j];
     if (q.sums) {
-      const float s1 = q.sums[((long long)b * q.C + c + j) * 2], s2 = q.sums[((long long)b * q.C + c + j) * 2 + 1];
-      const float mean = s1 * invP;
-      const float var = fmaxf(s2 * invP - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + q.eps);
-      xhat[j] = (v - mean) * rstd;
-      v = xhat[j] * g[j] + bt[j];
+      xhat[j] = (z[j] - k.mean[j]) * k.rstd[j];
+      xn[j] = xhat[j] * k.gamma[j] + k.beta[j];
     } else {
-      xhat[j] = v;
+      xhat[j] = z[j];
+      xn[j] = z[j];
     }
-    xn[j] = v;
   }
-  if (q.Ta) {
-    float t[8];
-    ld8f(q.Ta + ((long long)y * q.W + x) * q.C + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xn[j] += t[j];
-  }
+  if (q.Ta) add_timing(q.Ta, q.H, q.C, y, x, c, xn);
   if (q.p > 0.f) {
-    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, k);
+    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, keep);
     const float inv_keep = 1.0f / (1.0f - q.p);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xd[j] = k[j] ? xn[j] * inv_keep : 0.f;
+    for (int j = 0; j < 8; ++j) xd[j] = keep[j] ? xn[j] * inv_keep : 0.f;
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       xd[j] = xn[j];
-      k[j] = true;
+      keep[j] = true;
     }
   }
-  if (q.Tb) {
-    float t[8];
-    ld8f(q.Tb + ((long long)y * q.W + x) * q.C + c, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xd[j] += t[j];
-  }
+  if (q.Tb) add_timing(q.Tb, q.H, q.C, y, x, c, xd);
 }
 
 // iteration space: logical pixels, extended to the padded extent of `ext` when it is an s2d view
@@ -180,53 +194,49 @@ __device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y
   }
 }
 
-__global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ PrepParams q) {
+// grid = (pixel slabs, B); block = CV * PL threads: thread = (8-channel vector cv, pixel lane pl)
+__global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
   int y0, ny, x0, nx;
   iter_space(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
-  const long long total = (long long)q.B * ny * nx * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long r = i / CV;
-    const int xx = (int)(r % nx) + x0;
-    r /= nx;
-    const int yy = (int)(r % ny) + y0;
-    const int b = (int)(r / ny);
-    const int c = cv * 8;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int b = blockIdx.y, c = cv * 8;
+  const int NP = ny * nx;
+  const int p_begin = blockIdx.x * pix_per_slab;
+  const int p_end = min(NP, p_begin + pix_per_slab);
+  ChanCtx k;
+  load_ctx(q, b, c, k);
+  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
+    const int yy = pix / nx + y0, xx = pix % nx + x0;
     __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy, xx, c);
     if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
       *reinterpret_cast<uint4*>(o2) = make_uint4(0, 0, 0, 0);
       continue;
     }
     float z[8], mainv[8], xhat[8], xn[8], xd[8];
-    bool k[8];
-    load_z(q, b, yy, xx, c, z, mainv, true);
-    fwd_chain(q, b, yy, xx, c, z, xhat, xn, xd, k);
+    bool keep[8];
+    load_z(q, b, yy, xx, c, z, mainv);
+    fwd_chain(q, k, b, yy, xx, c, z, xhat, xn, xd, keep);
     if (q.out1) *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(xn);
     if (q.sc) {
-      float s[8], h[8];
-      ld8f(q.sc + (long long)b * q.C + c, s);
-      ld8f(q.sh + (long long)b * q.C + c, h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * s[j] + h[j];
+      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * k.sc[j] + k.sh[j];
     }
     *reinterpret_cast<BF8*>(o2) = f_to_bf8(xd);
   }
 }
 
 // gradient wrt the normalised value (gx) for 8 channels, plus g2
-__device__ __forceinline__ void bwd_gx(const PrepParams& q, int b, int y, int x, int c, const bool* k, float* g2,
-                                       float* gx) {
+__device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCtx& k, int b, int y, int x, int c,
+                                       const bool* keep, float* g2, float* gx) {
   bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) +
                                          view_off(q.g2, q.H, q.W, q.C, b, y, x, c)),
            g2);
-  float s[8];
-  if (q.sc) ld8f(q.sc + (long long)b * q.C + c, s);
   const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float v = q.sc ? g2[j] * s[j] : g2[j];
-    gx[j] = k[j] ? v * inv_keep : 0.f;
+    const float v = q.sc ? g2[j] * k.sc[j] : g2[j];
+    gx[j] = keep[j] ? v * inv_keep : 0.f;
   }
   if (q.g1) {
     float t[8];
@@ -257,29 +267,29 @@ __global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ 
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
-  if (pl < PL) {
-    for (int pix = p_begin + pl; pix < p_end; pix += PL) {
-      const int y = pix / q.W, x = pix - y * q.W;
-      float z[8], mainv[8];
-      load_z(q, b, y, x, c, z, mainv, true);
-      if (MODE == 0) {
+  ChanCtx k;
+  if (MODE == 1) load_ctx(q, b, c, k);
+  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
+    const int y = pix / q.W, x = pix - y * q.W;
+    float z[8], mainv[8];
+    load_z(q, b, y, x, c, z, mainv);
+    if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][j] += z[j];
-          acc[1][j] += z[j] * z[j];
-        }
-      } else {
-        float xhat[8], xn[8], xd[8], g2[8], gx[8];
-        bool k[8];
-        fwd_chain(q, b, y, x, c, z, xhat, xn, xd, k);
-        bwd_gx(q, b, y, x, c, k, g2, gx);
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += z[j];
+        acc[1][j] += z[j] * z[j];
+      }
+    } else {
+      float xhat[8], xn[8], xd[8], g2[8], gx[8];
+      bool keep[8];
+      fwd_chain(q, k, b, y, x, c, z, xhat, xn, xd, keep);
+      bwd_gx(q, k, b, y, x, c, keep, g2, gx);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][j] += gx[j];
-          acc[1][j] += gx[j] * xhat[j];
-          acc[2][j] += g2[j] * xd[j];
-          acc[3][j] += g2[j];
-        }
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += gx[j];
+        acc[1][j] += gx[j] * xhat[j];
+        acc[2][j] += g2[j] * xd[j];
+        acc[3][j] += g2[j];
       }
     }
   }
@@ -299,43 +309,43 @@ __global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ 
   }
 }
 
-__global__ void __launch_bounds__(256) prep_bwd_apply_kernel(const __grid_constant__ PrepParams q) {
+__global__ void __launch_bounds__(256)
+    prep_bwd_apply_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
   int y0, ny, x0, nx;
   iter_space(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int b = blockIdx.y, c = cv * 8;
+  const int NP = ny * nx;
+  const int p_begin = blockIdx.x * pix_per_slab;
+  const int p_end = min(NP, p_begin + pix_per_slab);
   const float invP = 1.0f / (float)(q.H * q.W);
-  const long long total = (long long)q.B * ny * nx * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long r = i / CV;
-    const int xx = (int)(r % nx) + x0;
-    r /= nx;
-    const int yy = (int)(r % ny) + y0;
-    const int b = (int)(r / ny);
-    const int c = cv * 8;
+  ChanCtx k;
+  load_ctx(q, b, c, k);
+  float m1[8], m2[8];
+  if (q.sums) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long sb_ = ((long long)b * q.C + c + j);
+      m1[j] = q.bsums[sb_ * 4] * invP;
+      m2[j] = q.bsums[sb_ * 4 + 1] * invP;
+    }
+  }
+  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
+    const int yy = pix / nx + y0, xx = pix % nx + x0;
     __nv_bfloat16* dm = reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy, xx, c);
     if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
       *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
       continue;
     }
     float z[8], mainv[8], xhat[8], xn[8], xd[8], g2[8], gx[8], dz[8];
-    bool k[8];
-    load_z(q, b, yy, xx, c, z, mainv, true);
-    fwd_chain(q, b, yy, xx, c, z, xhat, xn, xd, k);
-    bwd_gx(q, b, yy, xx, c, k, g2, gx);
+    bool keep[8];
+    load_z(q, b, yy, xx, c, z, mainv);
+    fwd_chain(q, k, b, yy, xx, c, z, xhat, xn, xd, keep);
+    bwd_gx(q, k, b, yy, xx, c, keep, g2, gx);
     if (q.sums) {
-      float g[8];
-      ld8f(q.gamma + c, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const long long sb_ = ((long long)b * q.C + c + j);
-        const float s1 = q.sums[sb_ * 2], s2 = q.sums[sb_ * 2 + 1];
-        const float mean = s1 * invP;
-        const float var = fmaxf(s2 * invP - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + q.eps);
-        const float m1 = q.bsums[sb_ * 4] * invP, m2 = q.bsums[sb_ * 4 + 1] * invP;
-        dz[j] = rstd * g[j] * (gx[j] - m1 - xhat[j] * m2);
-      }
+      for (int j = 0; j < 8; ++j) dz[j] = k.rstd[j] * k.gamma[j] * (gx[j] - m1[j] - xhat[j] * m2[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) dz[j] = gx[j];
@@ -469,26 +479,68 @@ struct PackParams {
   __nv_bfloat16* fwd;
   __nv_bfloat16* tr;
 };
+// one thread per (o,i) patch: reads KH*KW contiguous fp32, writes bf16 at stride Ipad (coalesced across threads in i)
 __global__ void __launch_bounds__(256) pack_conv_kernel(const __grid_constant__ PackParams q) {
   const int KK = q.KH * q.KW;
-  const long long total = (long long)q.O * q.I * KK;
+  const long long npatch = (long long)q.O * q.I;
   const int TW = q.KW / q.s, PH = q.s * q.s, T = (q.KH / q.s) * TW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    // idx enumerates (o, k, i) with i fastest so that the fwd writes are coalesced
-    const int i = (int)(idx % q.I);
-    long long r = idx / q.I;
-    const int kk = (int)(r % KK);
-    const int o = (int)(r / KK);
-    const int ky = kk / q.KW, kx = kk - ky * q.KW;
-    const int dy = ky / q.s, py = ky - dy * q.s, dx = kx / q.s, px = kx - dx * q.s;
-    const int t = dy * TW + dx, ph = py * q.s + px;
-    const float v = q.w[((long long)o * q.I + i) * KK + kk];
+  const long long ldf = (long long)T * PH * q.Ipad;
+  for (long long patch = (long long)blockIdx.x * blockDim.x + threadIdx.x; patch < npatch;
+       patch += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(patch / q.I), i = (int)(patch - (long long)o * q.I);
     const int oo = q.operm ? q.operm[o] : o;
     const int ii = q.iperm ? q.iperm[i] : i;
-    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-    if (q.fwd) q.fwd[(long long)oo * ((long long)T * PH * q.Ipad) + ((long long)t * PH + ph) * q.Ipad + ii] = bv;
-    if (q.tr) q.tr[((long long)ph * q.Ipad + ii) * ((long long)T * q.Opad) + (long long)t * q.Opad + oo] = bv;
+    const float* src = q.w + patch * KK;
+    __nv_bfloat16* dst = q.fwd + (long long)oo * ldf + ii;
+    for (int kk = 0; kk < KK; ++kk) {
+      const int ky = kk / q.KW, kx = kk - ky * q.KW;
+      const int dy = ky / q.s, py = ky - dy * q.s, dx = kx / q.s, px = kx - dx * q.s;
+      dst[(long long)((dy * TW + dx) * PH + py * q.s + px) * q.Ipad] = __float2bfloat16_rn(src[kk]);
+    }
+  }
+}
+
+// inverse of the above for gradients: packed fp32 [Opad, T*PH*Ipad] -> reference layout [O, I, KH, KW]
+__global__ void __launch_bounds__(256) unpack_conv_kernel(const __grid_constant__ PackParams q, const float* packed,
+                                                          float* out) {
+  const int KK = q.KH * q.KW;
+  const long long npatch = (long long)q.O * q.I;
+  const int TW = q.KW / q.s, PH = q.s * q.s, T = (q.KH / q.s) * TW;
+  const long long ldf = (long long)T * PH * q.Ipad;
+  for (long long patch = (long long)blockIdx.x * blockDim.x + threadIdx.x; patch < npatch;
+       patch += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(patch / q.I), i = (int)(patch - (long long)o * q.I);
+    const int oo = q.operm ? q.operm[o] : o;
+    const int ii = q.iperm ? q.iperm[i] : i;
+    const float* src = packed + (long long)oo * ldf + ii;
+    float* dst = out + patch * KK;
+    for (int kk = 0; kk < KK; ++kk) {
+      const int ky = kk / q.KW, kx = kk - ky * q.KW;
+      const int dy = ky / q.s, py = ky - dy * q.s, dx = kx / q.s, px = kx - dx * q.s;
+      dst[kk] = src[(long long)((dy * TW + dx) * PH + py * q.s + px) * q.Ipad];
+    }
+  }
+}
+
+// tr[:, t*Opad:(t+1)*Opad] = fwd[:, t*PHI:(t+1)*PHI]^T for every tap t (32x32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+    transpose_taps_kernel(const __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ tr, int Opad, int PHI,
+                          int T) {
+  __shared__ unsigned short tile[32][33];
+  const int t = blockIdx.z;
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(fwd) + (long long)t * PHI;
+  unsigned short* dst = reinterpret_cast<unsigned short*>(tr) + (long long)t * Opad;
+  const long long lds = (long long)T * PHI, ldd = (long long)T * Opad;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < Opad && c < PHI) ? src[(long long)r * lds + c] : (unsigned short)0;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;  // dst row = source column
+    if (c < PHI && r < Opad) dst[(long long)c * ldd + r] = tile[tx][j];
   }
 }
 
@@ -518,7 +570,7 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   q.relu_in = a->relu_in;
   q.sums = a->sums; q.eps = a->eps; q.gamma = a->gamma; q.beta = a->beta;
   q.Ta = a->Ta; q.out1 = (__nv_bfloat16*)a->out1;
-  q.p = a->p; q.seed = a->seed; q.stream_id = a->stream_id; q.keep = a->keep;
+  q.p = a->p; q.seed = a->seed; q.seed_ptr = a->seed_ptr; q.stream_id = a->stream_id; q.keep = a->keep;
   q.Tb = a->Tb; q.sc = a->sc; q.sh = a->sh;
   q.out2 = mk_view(&a->out2);
   q.g2 = mk_view(&a->g2);
@@ -530,11 +582,11 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   if ((q.sc == nullptr) != (q.sh == nullptr)) return SB_ERR_ARG;
   return SB_OK;
 }
-static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* threads) {
+static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* threads, int P = -1) {
   const int CV = q.C / 8;
   *PL = 256 / CV < 1 ? 1 : 256 / CV;
   *threads = CV * (*PL);
-  const int P = q.H * q.W;
+  if (P < 0) P = q.H * q.W;
   int want = (148 * 4 + q.B - 1) / q.B;  // ~4 CTAs per SM over the whole grid
   if (want < 1) want = 1;
   int per = (P + want - 1) / want;
@@ -561,10 +613,11 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   PrepParams q;
   int rc = fill(q, a);
   if (rc || !q.in.p || !q.out2.p) return SB_ERR_ARG;
-  int y0, ny, x0, nx;
+  int ny, nx;
   if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
-  (void)y0; (void)x0;
-  prep_fwd_kernel<<<grid_for((long long)q.B * ny * nx * (q.C / 8)), 256, 0, (cudaStream_t)stream>>>(q);
+  int PL, slabs, pps, threads;
+  reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
+  prep_fwd_kernel<<<dim3(slabs, q.B), threads, 0, (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -589,7 +642,9 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   if (rc || !q.in.p || !q.g2.p || !q.d_main.p || (q.sums && !q.bsums)) return SB_ERR_ARG;
   int ny, nx;
   if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
-  prep_bwd_apply_kernel<<<grid_for((long long)q.B * ny * nx * (q.C / 8)), 256, 0, (cudaStream_t)stream>>>(q);
+  int PL, slabs, pps, threads;
+  reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
+  prep_bwd_apply_kernel<<<dim3(slabs, q.B), threads, 0, (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -631,13 +686,38 @@ extern "C" int sb_gru_blend_bwd(const void* G, const float* s_old, const void* d
   return SB_OK;
 }
 
+static int fill_pack(PackParams& q, const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad,
+                     const int* iperm, const int* operm) {
+  if (s < 1 || KH % s || KW % s || Ipad < I || Opad < O) return SB_ERR_ARG;
+  q.w = w; q.O = O; q.I = I; q.KH = KH; q.KW = KW; q.s = s; q.Ipad = Ipad; q.Opad = Opad;
+  q.iperm = iperm; q.operm = operm; q.fwd = nullptr; q.tr = nullptr;
+  return SB_OK;
+}
+
 extern "C" int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
                             const int* operm, void* fwd, void* tr, sb_stream_t stream) {
-  if (!w || s < 1 || KH % s || KW % s || Ipad < I || Opad < O || (!fwd && !tr)) return SB_ERR_ARG;
   PackParams q;
-  q.w = w; q.O = O; q.I = I; q.KH = KH; q.KW = KW; q.s = s; q.Ipad = Ipad; q.Opad = Opad;
-  q.iperm = iperm; q.operm = operm; q.fwd = (__nv_bfloat16*)fwd; q.tr = (__nv_bfloat16*)tr;
-  pack_conv_kernel<<<grid_for((long long)O * I * KH * KW), 256, 0, (cudaStream_t)stream>>>(q);
+  if (!w || !fwd || fill_pack(q, w, O, I, KH, KW, s, Ipad, Opad, iperm, operm)) return SB_ERR_ARG;
+  q.fwd = (__nv_bfloat16*)fwd;
+  pack_conv_kernel<<<grid_for((long long)O * I), 256, 0, (cudaStream_t)stream>>>(q);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  if (tr) {
+    const int T = (KH / s) * (KW / s), PHI = s * s * Ipad;
+    dim3 grid((PHI + 31) / 32, (Opad + 31) / 32, T);
+    transpose_taps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)fwd, (__nv_bfloat16*)tr, Opad,
+                                                                  PHI, T);
+    ++g_launches;
+    SB_CHECK_LAUNCH();
+  }
+  return SB_OK;
+}
+
+extern "C" int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s, int Ipad, int Opad,
+                                   const int* iperm, const int* operm, float* out, sb_stream_t stream) {
+  PackParams q;
+  if (!packed || !out || fill_pack(q, nullptr, O, I, KH, KW, s, Ipad, Opad, iperm, operm)) return SB_ERR_ARG;
+  unpack_conv_kernel<<<grid_for((long long)O * I), 256, 0, (cudaStream_t)stream>>>(q, packed, out);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -430,9 +430,14 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   rc = make_map_2d(&tmB, a->w, a->N, a->ntaps * a->C, a->ldw, BN);
   if (rc) return rc;
   dim3 grid(p.tiles_x * p.tiles_y * tiles_b, (a->N + BN - 1) / BN, p.splits);
+  // short K loops (1x1 convolutions: logits, embeddings) are epilogue-bound: 2 stages fit 2 CTAs per SM so that one
+  // CTA's epilogue overlaps the other's main loop
+  const bool shortk = (KT + p.splits - 1) / p.splits <= 2;
   switch (BN) {
-    case 256: return launch_tap_gemm<256, 4>(tmA, tmB, p, grid, stream);
-    case 192: return launch_tap_gemm<192, 5>(tmA, tmB, p, grid, stream);
+    case 256: return shortk ? launch_tap_gemm<256, 2>(tmA, tmB, p, grid, stream)
+                            : launch_tap_gemm<256, 4>(tmA, tmB, p, grid, stream);
+    case 192: return shortk ? launch_tap_gemm<192, 2>(tmA, tmB, p, grid, stream)
+                            : launch_tap_gemm<192, 5>(tmA, tmB, p, grid, stream);
     case 128: return launch_tap_gemm<128, 3>(tmA, tmB, p, grid, stream);
     default: return launch_tap_gemm<96, 3>(tmA, tmB, p, grid, stream);
   }

@@ -160,8 +160,15 @@ class StochasticModel(nn.Module):  # :124-206
         res = self.lstm_loss
         if reset:
             dev = res.device if isinstance(res, torch.Tensor) else None
-            self.lstm_loss = torch.tensor(0., device=dev)
+            self.lstm_loss = torch.zeros((), device=dev)  # (no host->device copy: CUDA-graph capturable)
         return res
+
+
+def timing_signal_sep(C, H, W):
+    """Separable form of the timing signal consumed by the fused kernels: [(H+W), C/2] fp32.  Rows 0..H-1 hold the
+    first C/2 channels (functions of the row index only), rows H..H+W-1 the last C/2 (functions of the column)."""
+    t = timing_signal_nhwc(C, H, W)
+    return torch.cat((t[:, 0, :C // 2], t[0, :, C // 2:]), dim=0).contiguous()
 
 
 def timing_signal_nhwc(C, H, W, min_timescale=1.0, max_timescale=1.0e4):
@@ -183,9 +190,9 @@ class DeviceRand:
     """Fast-path randomness for the small latent tensors (torch's CUDA generator); the big dropout masks are Philox
     streams generated inside the fused kernels from (seed, stream_id, element index)."""
 
-    def __init__(self, device):
+    def __init__(self, device, seed):
         self.device = device
-        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.seed = seed  # int64 device tensor: read by the kernels at run time (CUDA-graph safe)
 
     def keep_mask(self, shape, p):
         return (torch.rand(shape, device=self.device) >= p).float()
@@ -303,8 +310,15 @@ class NextFramePredictor(nn.Module):
         self.value_estimator = ValueEstimator(middle_shape[0] * middle_shape[1] * middle_shape[2])
         self.stochastic_model = StochasticModel(c, middle_shape, n_action)
 
+        # Recurrent state lives in PERSISTENT buffers (stable addresses => CUDA-graph replayable); a forward leaves its
+        # new state in `_pending` and `commit_state()` copies it in (after the backward pass, which still needs the old
+        # gate operand).  A forward auto-commits a pending state first, so plain `model(x, a)` loops behave like the
+        # reference.
         self._state = None        # fp32 [B,H,W,64] recurrent state (detached)
         self._xs_prev = None      # bf16 [B,H,W,128]: previous step's (state | x_start | 0) operand of the gate conv
+        self._has_prev = False
+        self._pending = None
+        self._seed_dev = None
         self._plan = None
         self._packed = None
         self._auto_repack = True
@@ -315,16 +329,34 @@ class NextFramePredictor(nn.Module):
     def init_internal_states(self, batch_size):
         dev = self.logits.weight.device
         H, W = self.config.frame_shape[1:]
-        self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
-        self._xs_prev = None
+        if self._state is not None and self._state.shape[0] == batch_size and self._state.device == dev:
+            self._state.zero_()  # keep the buffers (and their addresses)
+        else:
+            self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
+            self._xs_prev = torch.zeros(batch_size, H, W, 128, device=dev, dtype=torch.bfloat16)
+        self._has_prev = False
+        self._pending = None
+
+    def commit_state(self):
+        """Make the state computed by the last forward current (next_frame_predictor.py:303,312 of the reference)."""
+        if self._pending is None:
+            return
+        xs, s_new = self._pending
+        self._xs_prev.copy_(xs)
+        if s_new is not None:
+            self._state.copy_(s_new)
+        self._has_prev = True
+        self._pending = None
 
     @property
     def internal_states(self):
+        self.commit_state()
         return None if self._state is None else self._state.permute(0, 3, 1, 2)
 
     @property
     def last_x_start(self):
-        return None if self._xs_prev is None else self._xs_prev[..., 64:76].float().permute(0, 3, 1, 2)
+        self.commit_state()
+        return self._xs_prev[..., 64:76].float().permute(0, 3, 1, 2) if self._has_prev else None
 
     def load_state_dict(self, *a, **kw):
         r = super().load_state_dict(*a, **kw)
@@ -347,8 +379,8 @@ class NextFramePredictor(nn.Module):
         # timing tables (next_frame_predictor.py:234,241,270): index 0, encoder 1..5, decoder 6..10
         es, ds = self._enc_shapes, self._dec_shapes
         tshapes = [es[0]] + [es[i] for i in range(5)] + [ds[i] for i in range(5)]
-        P['timing'] = [timing_signal_nhwc(s[0], s[1], s[2]).to(dev) for s in tshapes]
-        P['stoch_timing'] = timing_signal_nhwc(c.hidden_size, H, W).to(dev)
+        P['timing'] = [timing_signal_sep(s[0], s[1], s[2]).to(dev) for s in tshapes]
+        P['stoch_timing'] = timing_signal_sep(c.hidden_size, H, W).to(dev)
         # gate 3x3 on XS (state 0..63 | x_start 64..75 | zero pad to 128), no dgrad (inputs are detached / data)
         HW = H * W
         P['gate'] = ConvSpec('gate', H, W, 128, H, W, 128, taps33, relu=False, need_dgrad=False,
@@ -409,7 +441,7 @@ class NextFramePredictor(nn.Module):
         P['prep_final'] = PrepSpec(H, W, 96, P['up_lay'][4], plain(H, W, 96), relu_in=True, norm=True, Ta=T[10])
         P['prep_s0'] = PrepSpec(H, W, 96, plain(H, W, 96), l1, Ta=P['stoch_timing'], inject=True)
         P['prep_s1'] = PrepSpec(26, 20, 128, plain(26, 20, 128), l2, relu_in=True)
-        P['tmean10'] = T[10].mean(dim=(0, 1))
+        P['tmean10'] = timing_signal_nhwc(96, H, W).mean(dim=(0, 1)).to(dev)
         return P
 
     def _build_packed(self):
@@ -475,11 +507,11 @@ class NextFramePredictor(nn.Module):
         ops.standardize(x.contiguous().float(), dst=xs, coff=64)
         if self._state is None or self._state.shape[0] != B:
             self.init_internal_states(B)
-        if self._xs_prev is not None:
+        s_new = None
+        if self._has_prev:
             G = self._conv('gate', P['gate'], self._xs_prev)
             xs, s_new = ops.GruBlend.apply(G, self._state, xs)
-            self._state = s_new
-        self._xs_prev = xs.detach()
+        self._pending = (xs.detach(), s_new)
         e = self._conv('embed', P['embed'], xs)
         # ---- encoder (K1, K3, K4, K8)
         skips = []
@@ -494,7 +526,6 @@ class NextFramePredictor(nn.Module):
             main = self._conv(f'down{i}', P['down'][i], A)
         nrm = self.downscale_layers[9]
         _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias)
-        aux['skips'], aux['x5'], aux['y4'] = skips, x5, main
         # ---- bottleneck heads and latent (tiny tensors; fp32, NCHW semantics of the reference)
         h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
         value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
@@ -511,7 +542,7 @@ class NextFramePredictor(nn.Module):
         else:
             bits, _ = sm.bits_predictor(h.reshape(B, -1), rand)
             bits = self._forced(rand, 'sampled_bits', bits)
-            aux['bits'] = bits
+            aux['bits'] = bits.detach()
             h = sm.add_bits(h, bits)
         x_mid = h.mean(dim=(2, 3))
         hm = h.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
@@ -555,7 +586,7 @@ class NextFramePredictor(nn.Module):
         c2 = self._conv('s_conv2', P['s_conv2'], A)  # [B,6,5,512]
         x2 = sm.mean_attentions[1](c2.float().permute(0, 3, 1, 2).contiguous())
         x = sm.dense1(torch.cat((x1, x2), dim=-1))
-        aux['posterior_pre'] = x
+        aux['posterior_pre'] = x.detach()
         x = x + (self._forced(rand, 'posterior_pre', x.detach()) - x.detach())
         bits_clean = (2 * (0 < x).float()).detach() - 1
         x = torch.tanh(x + rand.truncnorm(x.shape))
@@ -568,10 +599,10 @@ class NextFramePredictor(nn.Module):
         sm.lstm_loss = sm.lstm_loss.to(lstm_loss.device) + lstm_loss
         bits_pred, _ = sm.bits_predictor(flat, rand)
         bits_pred = self._forced(rand, 'sampled_bits', bits_pred)
-        aux['bits_pred'] = bits_pred
+        aux['bits_pred'] = bits_pred.detach()
         bits_pred = bits_clean + (bits_pred - bits_clean).detach()
         bits = mix(bits_pred, bits, 1 - (1 - epsilon) * c.latent_rnn_max_sampling, rand)
-        aux['bits'] = bits
+        aux['bits'] = bits.detach()  # (detached: nothing may keep last step's autograd graph alive)
         res = sm.add_bits(layer, bits)
         return mix(res, layer, 1 - (1 - epsilon) * c.latent_use_max_probability, rand)
 
@@ -599,7 +630,15 @@ class NextFramePredictor(nn.Module):
         elif self._auto_repack:
             self.repack()
         self._weights_cache = self._weights()
-        rand = self.parity_rand if self.parity_rand is not None else DeviceRand(dev)
+        self.commit_state()
+        if self._seed_dev is None or self._seed_dev.device != dev:
+            # derived from torch.manual_seed() without consuming the global generator
+            self._seed_dev = torch.full((1,), torch.initial_seed() & ((1 << 40) - 1), dtype=torch.int64, device=dev)
+        if self.parity_rand is not None:
+            rand = self.parity_rand
+        else:
+            self._seed_dev.add_(1)  # new Philox streams every forward; the backward of this step re-reads the value
+            rand = DeviceRand(dev, self._seed_dev)
         return self._trunk(x, action, target, epsilon, rand)
 
     def forward(self, x, action, target=None, epsilon=0):

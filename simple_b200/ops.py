@@ -93,7 +93,11 @@ def _prep_args(spec, B, main, add, sums, gamma, beta, sc, sh, out1, out2, seed, 
     a.Ta = _ptr(spec.Ta)
     a.out1 = _ptr(out1)
     a.p = float(spec.p)
-    a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    if isinstance(seed, torch.Tensor):  # device-resident seed (int64 tensor): survives CUDA-graph replay
+        a.seed = 0
+        a.seed_ptr = seed.data_ptr()
+    else:
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     a.stream_id = spec.stream_id
     a.keep = _ptr(keep)
     a.Tb = _ptr(spec.Tb)
@@ -213,16 +217,6 @@ class PackedWeight:
         self.operm = torch.tensor(operm, dtype=torch.int32, device=dev) if operm is not None else None
         self.fwd = torch.zeros(self.Opad, self.T * self.PH * self.Ipad, device=dev, dtype=torch.bfloat16)
         self.tr = torch.zeros(self.PH * self.Ipad, self.T * self.Opad, device=dev, dtype=torch.bfloat16)
-        # gather index: reference (o,i,ky,kx) -> column-major position in the packed "fwd" layout
-        o = torch.arange(O, device=dev).view(O, 1, 1, 1)
-        i = torch.arange(I, device=dev).view(1, I, 1, 1)
-        ky = torch.arange(KH, device=dev).view(1, 1, KH, 1)
-        kx = torch.arange(KW, device=dev).view(1, 1, 1, KW)
-        t = (ky // s) * (KW // s) + (kx // s)
-        ph = (ky % s) * s + (kx % s)
-        oo = self.operm.long()[o] if self.operm is not None else o
-        ii = self.iperm.long()[i] if self.iperm is not None else i
-        self.gather = (oo * (self.T * self.PH * self.Ipad) + (t * self.PH + ph) * self.Ipad + ii).reshape(-1)
         self.pack(weight)
 
     def pack(self, weight):
@@ -234,7 +228,11 @@ class PackedWeight:
 
     def unpack_grad(self, g_packed):
         """fp32 gradient in packed 'fwd' layout -> reference layout [O,I,KH,KW]."""
-        return g_packed.reshape(-1)[self.gather].reshape(self.O, self.I, self.KH, self.KW)
+        out = torch.empty(self.O, self.I, self.KH, self.KW, device=g_packed.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sb_unpack_conv_grad(g_packed.data_ptr(), self.O, self.I, self.KH, self.KW, self.s,
+                                                  self.Ipad, self.Opad, _ptr(self.iperm), _ptr(self.operm),
+                                                  out.data_ptr(), _lib.stream_ptr()), 'sb_unpack_conv_grad')
+        return out
 
 
 def colsum(t2d):

@@ -119,13 +119,13 @@ class Trainer:
         out['loss'].backward()
         grads = self.grad_sync(self.model) if self.grad_sync is not None else None
         self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads)
+        self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous state
         return out
 
     def train(self, epoch, env, steps=15000):
         if epoch == 0:
             steps *= 3
         cfg = self.config
-        c, h, w = cfg.frame_shape
         rollout_len = cfg.rollout_length
         B = cfg.batch_size
         dev = torch.device(cfg.device)
@@ -141,35 +141,25 @@ class Trainer:
         if self._replay_key != key:
             self._replay = DeviceReplay(env.buffer, dev, rollout_len)
             self._replay_key = key
+            self._runner = None
         rp = self._replay
+        if getattr(self, '_runner', None) is None:
+            self._runner = StepRunner(self, dict(obs=rp.obs, new_obs=rp.new_obs, action=rp.action, reward=rp.reward,
+                                                 value=rp.value), B, use_graph=getattr(cfg, 'cuda_graph', True))
+        runner = self._runner
         try:
             from tqdm import trange
             iterator = trange(0, steps, rollout_len, desc='Training world model', unit_scale=rollout_len)
         except ImportError:
             iterator = range(0, steps, rollout_len)
-        n_losses = 5 if cfg.use_stochastic_model else 4
-        names = ['loss', 'loss_reconstruct', 'loss_value', 'loss_reward', 'loss_lstm'][:n_losses]
         metrics = {}
         for i in iterator:
             epsilon = self.epsilon_schedule(epoch, i)
-            starts = rp.sample_starts(B)
-            frames = self.preprocess_state(rp.obs[starts], per_sample=False)
-            if cfg.stack_internal_states:
-                self.model.init_internal_states(B)
-            losses = torch.zeros(n_losses, device=dev)
+            runner.begin(rp.sample_starts(B), epsilon)
             for j in range(rollout_len):
-                idx = starts + j
-                new_states_u8 = rp.new_obs[idx]
-                out = self.train_step(frames, rp.action[idx], new_states_u8, rp.reward[idx], rp.value[idx], epsilon)
-                if j < rollout_len - 1:
-                    # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode
-                    use_gt = (torch.rand(B, device=dev) < epsilon).reshape(B, 1, 1, 1)
-                    nxt = torch.where(use_gt, new_states_u8, out['argmax'])
-                    nxt = self.preprocess_state(nxt, per_sample=True)
-                    frames = torch.cat((frames[:, c:], nxt), dim=1)
-                losses += torch.stack([out[k].detach().float() for k in names])
-            host = (losses / rollout_len).tolist()  # the only host sync of the window
-            metrics = dict(zip(names, host))
+                runner.step()
+            host = (runner.losses / rollout_len).tolist()  # the only host sync of the window
+            metrics = dict(zip(runner.names, host))
             if self.logger is not None:
                 d = {'model_step': self.model_step, 'epsilon': epsilon}
                 d.update(metrics)
@@ -181,3 +171,98 @@ class Trainer:
         if cfg.save_models:
             torch.save(self.model.state_dict(), os.path.join('models', 'model.pt'))
         return metrics
+
+
+class StepRunner:
+    """Runs the optimiser steps of one window (simple/trainer.py:104-154) on static device buffers.
+
+    The first step of a window differs (no gate convolution, gate.* without gradient) and runs eagerly; every other
+    step is identical work on identical addresses, so it is captured ONCE into a CUDA graph (forward, fused loss,
+    backward, clip + Adafactor, frame feedback, state commit, index advance) and replayed: one launch per step instead
+    of ~1500, which removes the host from the critical path (Blackwell guide, guideline 9).
+    """
+
+    def __init__(self, trainer, replay, B, use_graph=True, resident=True):
+        self.trainer, self.replay, self.B = trainer, replay, B
+        cfg = trainer.config
+        dev = torch.device(cfg.device)
+        c, h, w = cfg.frame_shape
+        self.c = c
+        self.use_graph = use_graph
+        self.resident = resident
+        self.idx = torch.zeros(B, dtype=torch.long, device=dev)
+        self.frames = torch.zeros(B, c * int(cfg.stacking), h, w, device=dev)
+        self.eps = torch.zeros((), device=dev)
+        n_losses = 5 if cfg.use_stochastic_model else 4
+        self.names = ['loss', 'loss_reconstruct', 'loss_value', 'loss_reward', 'loss_lstm'][:n_losses]
+        self.losses = torch.zeros(n_losses, device=dev)
+        self.inp = dict(new_obs=torch.zeros(B, c, h, w, dtype=torch.uint8, device=dev),
+                        action=torch.zeros(B, replay['action'].shape[1], device=dev),
+                        reward=torch.zeros(B, dtype=torch.long, device=dev), value=torch.zeros(B, device=dev))
+        self.graph = None
+        self.graph_key = None
+        self.graph_kernels = 0  # kernels of this library recorded in the captured step
+        self.replays = 0
+        self.warm = 0
+        self.j = 0
+        self.last = None
+
+    def begin(self, starts, epsilon):
+        rp = self.replay
+        self.idx.copy_(starts)
+        self.frames.copy_(self.trainer.preprocess_state(rp['obs'][self.idx], per_sample=False))
+        self.eps.fill_(float(epsilon))
+        self.losses.zero_()
+        if self.trainer.config.stack_internal_states:
+            self.trainer.model.init_internal_states(self.B)
+        self.j = 0
+
+    def load_batch(self, new_obs, action, reward, value):
+        """Non-resident mode (host-fed): copy this step's batch into the static input buffers."""
+        self.inp['new_obs'].copy_(new_obs, non_blocking=True)
+        self.inp['action'].copy_(action, non_blocking=True)
+        self.inp['reward'].copy_(reward, non_blocking=True)
+        self.inp['value'].copy_(value, non_blocking=True)
+
+    def _body(self):
+        tr, rp, B = self.trainer, self.replay, self.B
+        if self.resident:
+            idx = self.idx
+            new_states, action, reward, value = rp['new_obs'][idx], rp['action'][idx], rp['reward'][idx], rp['value'][idx]
+        else:
+            new_states, action, reward, value = (self.inp['new_obs'], self.inp['action'], self.inp['reward'],
+                                                 self.inp['value'])
+        out = tr.train_step(self.frames, action, new_states, reward, value, self.eps)
+        # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode
+        use_gt = (torch.rand(B, device=self.frames.device) < self.eps).reshape(B, 1, 1, 1)
+        nxt = torch.where(use_gt, new_states, out['argmax'])
+        nxt = tr.preprocess_state(nxt, per_sample=True)
+        self.frames.copy_(torch.cat((self.frames[:, self.c:], nxt), dim=1))
+        self.losses += torch.stack([out[k].detach().float() for k in self.names])
+        self.idx += 1
+        self.last = {k: v.detach() for k, v in out.items()}  # no reference to this step's autograd graph survives
+
+    def step(self):
+        opt = self.trainer.optimizer
+        if self.j == 0 or not self.use_graph:
+            self._body()
+        elif self.graph is None and self.warm < 2:
+            self._body()  # eager warm-up of the steady-state step before capture
+            self.warm += 1
+        elif self.graph is None:
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+            from . import _lib
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.lib().sb_launch_count()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph_kernels = int(_lib.lib().sb_launch_count() - l0)
+            self.graph, self.graph_key = g, opt.last_key
+            g.replay()  # capture only records: run the step that was just captured
+            self.replays += 1
+        else:
+            opt.advance_for_replay(self.graph_key)
+            self.graph.replay()
+            self.replays += 1
+        self.j += 1

@@ -72,15 +72,22 @@ def _prep_reference(spec, main_nchw, add_nchw, gamma, beta, sc, sh, keep_nchw, r
     if gamma is not None:
         x = F.instance_norm(z, weight=gamma, bias=beta, eps=1e-6)
     if spec.Ta is not None:
-        x = x + spec.Ta.permute(2, 0, 1)
+        x = x + spec.Ta_full.permute(2, 0, 1)
     out1 = x
     if spec.p > 0:
         x = x * (keep_nchw / (1 - spec.p))
     if spec.Tb is not None:
-        x = x + spec.Tb.permute(2, 0, 1)
+        x = x + spec.Tb_full.permute(2, 0, 1)
     if sc is not None:
         x = x * sc[:, :, None, None] + sh[:, :, None, None]
     return out1, x
+
+
+def _sep_table(H, W, C):
+    """random separable timing table: ([(H+W), C/2] for the kernel, [H,W,C] for the reference)"""
+    th, tw = torch.randn(H, C // 2, device=DEV), torch.randn(W, C // 2, device=DEV)
+    full = torch.cat((th[:, None, :].expand(H, W, C // 2), tw[None, :, :].expand(H, W, C // 2)), dim=2).contiguous()
+    return torch.cat((th, tw), dim=0).contiguous(), full
 
 
 @pytest.mark.parametrize('case', ['enc0', 'enc', 'dec', 'final', 's2d4'])
@@ -89,32 +96,34 @@ def test_fused_prep_fwd_bwd(case):
     from simple_b200.ops import PrepSpec, plain, s2d_in, s2d_out
     torch.manual_seed(2)
     B = 3
+    Ta_full = Tb_full = None
     if case == 'enc0':
         H, W, C = 21, 16, 96
-        Ta, Tb = torch.randn(H, W, C, device=DEV), torch.randn(H, W, C, device=DEV)
+        (Ta, Ta_full), (Tb, Tb_full) = _sep_table(H, W, C), _sep_table(H, W, C)
         spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 4, 2, 1), Ta=Ta, want_out1=True, p=0.15, Tb=Tb)
         norm = inj = add = False
     elif case == 'enc':
         H, W, C = 13, 10, 192
-        Tb = torch.randn(H, W, C, device=DEV)
+        Tb, Tb_full = _sep_table(H, W, C)
         spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 4, 2, 1), relu_in=True, norm=True, want_out1=True,
                         p=0.15, Tb=Tb)
         norm, inj, add = True, False, False
     elif case == 'dec':
         H, W, C = 13, 10, 96  # output of a convT from 6x5 with output_padding (1,0)
-        Ta = torch.randn(H, W, C, device=DEV)
+        Ta, Ta_full = _sep_table(H, W, C)
         spec = PrepSpec(H, W, C, s2d_out(6, 5, H, W, C), plain(H, W, C), relu_in=True, norm=True, Ta=Ta, p=0.15,
                         inject=True)
         norm, inj, add = True, True, True
     elif case == 'final':
         H, W, C = 7, 6, 96
-        Ta = torch.randn(H, W, C, device=DEV)
+        Ta, Ta_full = _sep_table(H, W, C)
         spec = PrepSpec(H, W, C, s2d_out(3, 3, H, W, C), plain(H, W, C), relu_in=True, norm=True, Ta=Ta)
         norm, inj, add = True, False, True
     else:
         H, W, C = 26, 20, 128
         spec = PrepSpec(H, W, C, plain(H, W, C), s2d_in(H, W, C, 8, 4, 2), relu_in=True)
         norm = inj = add = False
+    spec.Ta_full, spec.Tb_full = Ta_full, Tb_full
     main_l = (torch.randn(B, C, H, W, device=DEV)).bfloat16().float()
     # physical main tensor in the input layout (random garbage in the padding positions of s2d-phase inputs)
     lay = spec.lay_in
