@@ -324,11 +324,13 @@ def run_own(args):
     policy = CnnPolicy((12, 105, 80), n_action).to(dev)
     env.restart_all(data['obs'][:A])
 
+    env.use_graph = not args.no_graph
+    env.attach_policy(policy)  # policy.act is part of the captured step (sampled on the device from the last obs)
+
     def rollout():
-        obs = env.reset()
+        env.reset()
         for _ in range(cfg.rollout_length):
-            _, action, _ = policy.act(obs)
-            obs, rew, done, _ = env.step(action)
+            obs, rew, done, _ = env.step(None)
         return rew
 
     rollout()

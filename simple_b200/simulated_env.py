@@ -75,7 +75,8 @@ class SimulatedVecEnv:
         self._has_initial = [False] * self.num_envs
         self.envs = [SimulatedEnv(self, i) for i in range(self.num_envs)]
         self.step_count = 0
-        self.frames = None  # u8 [A,12,H,W] on device
+        self.frames = None  # u8 [A,12,H,W] on device (static buffer)
+        self.use_graph = bool(getattr(config, 'cuda_graph', True))
         self.closed = False
 
     # ---- reference surface --------------------------------------------------------------------------------------
@@ -112,41 +113,99 @@ class SimulatedVecEnv:
         self.closed = True
 
     # ---- one simulated step (subproc_vec_env.py:409-445) ----------------------------------------------------------
+    def _alloc_static(self):
+        A, dev = self.num_envs, self.device
+        c, h, w = self.config.frame_shape
+        self.frames = torch.zeros(A, self.stack_channels, h, w, dtype=torch.uint8, device=dev)
+        self._act = torch.zeros(A, 1, dtype=torch.long, device=dev)
+        self._obs = torch.zeros(A, self.stack_channels, h, w, device=dev)
+        self._rew = torch.zeros(A, device=dev)
+        self._val = torch.zeros(A, device=dev)
+        self._graph = None
+        self._warm = 0
+        self._policy = None
+
+    def _core(self):
+        """Device-only arithmetic of one step on static buffers (CUDA-graph capturable): optional policy act,
+        one-hot, world-model eval forward, fused argmax decode, u8 frame-stack shift, reward decode."""
+        cfg, model, A = self.config, self.model, self.num_envs
+        if self._policy is not None:
+            _, action, _ = self._policy.act(self._obs)
+            self._act.copy_(action.reshape(A, 1))
+        onehot = torch.zeros(A, 1, self.n_action, device=self.device).scatter_(2, self._act.unsqueeze(-1), 1.0)
+        logits, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot)
+        new = ops.pixel_argmax(logits)  # u8 [A,3,H,W]
+        c = cfg.frame_shape[0]
+        self.frames.copy_(torch.cat((self.frames[:, c:], new), dim=1))
+        self._obs.copy_(self.frames)
+        self._rew.copy_((torch.argmax(reward_pred, dim=1) - 1).to(torch.float32))
+        self._val.copy_(value_pred.float())
+        model.commit_state()
+
     @torch.no_grad()
-    def _step(self, actions):
-        cfg = self.config
+    def _advance(self):
+        """Runs `_core` eagerly for the first step of a rollout (no recurrent gate yet) and during warm-up, then as a
+        replayed CUDA graph."""
         model = self.model
-        A = self.num_envs
-        if self.step_count == 0:
-            self.frames = self._initial.clone()
-            if cfg.stack_internal_states:
-                model.init_internal_states(A)
-            model.repack()  # weights are static during a rollout: pack once, not every step
-        self.step_count += 1
-        a = torch.as_tensor(actions, device=self.device).long().reshape(A, -1)[:, :1]
-        onehot = torch.zeros(A, 1, self.n_action, device=self.device).scatter_(2, a.unsqueeze(-1), 1.0)
         model.eval()
         auto = model._auto_repack
         model._auto_repack = False
         try:
-            logits, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot)
+            first = not model._has_prev
+            if first or not self.use_graph:
+                self._core()
+            elif self._graph is None and self._warm < 2:
+                self._core()
+                self._warm += 1
+            elif self._graph is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._core()
+                self._graph = g
+                g.replay()
+            else:
+                self._graph.replay()
         finally:
             model._auto_repack = auto
-        new = ops.pixel_argmax(logits)  # u8 [A,3,H,W]
-        c = cfg.frame_shape[0]
-        self.frames = torch.cat((self.frames[:, c:], new), dim=1)
-        rewards = (torch.argmax(reward_pred, dim=1) - 1).to(torch.float32)
+
+    @torch.no_grad()
+    def _step(self, actions):
+        cfg = self.config
+        A = self.num_envs
+        if self.frames is None:
+            self._alloc_static()
+        if self.step_count == 0:
+            self.frames.copy_(self._initial)
+            self._obs.copy_(self._initial)
+            if cfg.stack_internal_states:
+                self.model.init_internal_states(A)
+            self.model.repack()  # weights are static during a rollout: pack once, not every step
+        self.step_count += 1
+        if actions is not None:
+            self._act.copy_(torch.as_tensor(actions, device=self.device).long().reshape(A, -1)[:, :1])
+        self._advance()
+        rewards = self._rew.clone()
         if self.step_count == cfg.rollout_length:
             self.step_count = 0
-            rewards = rewards + value_pred.float()
+            rewards = rewards + self._val
         if cfg.done_on_last_rollout_step:
             done = self.step_count == cfg.rollout_length  # evaluated after the reset above: always False (ref quirk)
         else:
             done = False
-        obs = self.frames.float()
+        obs = self._obs.clone()
         if self.reference_types:  # exactly the host-side types VecPytorchWrapper hands out (envs.py:109-118)
             return obs, rewards.double().cpu().unsqueeze(1), np.full(A, done, dtype=bool), tuple({} for _ in range(A))
         return obs, rewards.unsqueeze(1), np.full(A, done, dtype=bool), tuple({} for _ in range(A))
+
+    def attach_policy(self, policy):
+        """Fuse `policy.act` into the captured step: `step(None)` then samples the actions on the device from the
+        current observation (used by bench.py; PPO drivers that call `act` themselves keep using `step(actions)`)."""
+        if self.frames is None:
+            self._alloc_static()
+        self._policy = policy
+        self._graph = None
+        self._warm = 0
 
 
 def make_simulated_env(config, model, action_space, reference_types=False):
