@@ -1,0 +1,61 @@
+"""Data-parallel plumbing on CPU: world_size 2 over gloo (the N>1 path of bench.py uses the same code over NCCL)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from simple_b200.parallel import FlatGradSync, broadcast_parameters, init_distributed
+    r, w, _ = init_distributed('gloo')
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)  # different initial weights per rank ...
+    model = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+    broadcast_parameters(model, src=0)  # ... made identical
+    sync = FlatGradSync(model)
+    params = list(model.parameters())
+    for step in range(2):
+        for i, p in enumerate(params):
+            p.grad = torch.full_like(p, float(rank + 1 + i + 10 * step))
+        if step == 1:
+            params[0].grad = None  # like gate.* on the first step of a window: absent on every rank
+        views = sync(model)
+        res = {i: views[p].clone() for i, p in enumerate(params) if p in views}
+        out.put((rank, step, {i: v for i, v in res.items()}, [p.detach().clone() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_grad_sync_averages_over_ranks():
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world * 2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    by = {(r, s): (g, w) for r, s, g, w in got}
+    for step in range(2):
+        g0, w0 = by[(0, step)]
+        g1, w1 = by[(1, step)]
+        assert all(torch.equal(a, b) for a, b in zip(w0, w1))  # identical replicas
+        assert set(g0) == set(g1) == ({0, 1, 2, 3} if step == 0 else {1, 2, 3})
+        for i in g0:
+            want = (1 + i + 10 * step + 2 + i + 10 * step) / 2.0  # mean over the two ranks
+            assert torch.equal(g0[i], g1[i]) and float(g0[i].flatten()[0]) == want
