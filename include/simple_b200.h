@@ -188,6 +188,22 @@ int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev,
 int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
                        const float* total_sumsq, float max_norm, sb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Latent-bit predictor (simple/next_frame_predictor.py:66-121; K11/K12).
+ * sb_lstm_sample: the 16-step LSTM sampling pass in one launch (one CTA per sample, fp32):
+ *   x0,h0,c0 [B,128]; LSTMCell weights w_ih,w_hh [512,128], b_ih,b_hh [512]; dense5 w5 [256,128], b5 [256];
+ *   dense4 w4 [128,256], b4 [128]; noise [B,16,256] Exp(1) draws or NULL (then Philox with *seed_ptr);
+ *   out: bits [B,128] in {-1,+1} (LSB first per byte), ints [B,16].
+ * sb_lstm_cell_fwd/bwd: fused pointwise part of one teacher-forced LSTMCell step.
+ * --------------------------------------------------------------------------------------------------------- */
+int sb_lstm_sample(const float* x0, const float* h0, const float* c0, const float* w_ih, const float* w_hh,
+                   const float* b_ih, const float* b_hh, const float* w5, const float* b5, const float* w4,
+                   const float* b4, const float* noise, const unsigned long long* seed_ptr, int B, float* bits,
+                   int* ints, sb_stream_t stream);
+int sb_lstm_cell_fwd(const float* pre, const float* c_prev, float* act, float* c, float* h, int B, sb_stream_t stream);
+int sb_lstm_cell_bwd(const float* act, const float* c_prev, const float* c, const float* dh, const float* dc,
+                     float* dpre, float* dc_prev, int B, sb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,9 @@ class _Sigs:
     sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
+    sb_lstm_sample = [_p] * 13 + [_i, _p, _p, _p]
+    sb_lstm_cell_fwd = [_p, _p, _p, _p, _p, _i, _p]
+    sb_lstm_cell_bwd = [_p, _p, _p, _p, _p, _p, _p, _i, _p]
     sb_grad_sumsq = [_p, _p, _i, _p, _p]
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]

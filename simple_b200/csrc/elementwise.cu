@@ -132,56 +132,72 @@ __device__ __forceinline__ void add_timing(const float* T, int H, int C, int y, 
   for (int j = 0; j < 8; ++j) v[j] += tv[j];
 }
 
-// Per-thread constants: every thread owns one 8-channel vector of one sample for its whole pixel loop.
-struct ChanCtx {
-  float mean[8], rstd[8], gamma[8], beta[8], sc[8], sh[8];
+// Per-(b,c) constants of one sample live in SHARED memory (8 arrays of C floats), not registers: the fused chain
+// needs up to 64 of them per thread, which capped occupancy at 2 CTAs/SM and left the kernels latency-bound.
+struct ChanCst {
+  const float *mean, *rstd, *gamma, *beta, *sc, *sh, *m1, *m2;
 };
-__device__ __forceinline__ void load_ctx(const PrepParams& q, int b, int c, ChanCtx& k) {
+__device__ __forceinline__ ChanCst load_cst(const PrepParams& q, int b, float* sm, bool bwd) {
+  const int C = q.C;
   const float invP = 1.0f / (float)(q.H * q.W);
-  if (q.sums) {
-    ld8f(q.gamma + c, k.gamma);
-    ld8f(q.beta + c, k.beta);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s1 = q.sums[((long long)b * q.C + c + j) * 2], s2 = q.sums[((long long)b * q.C + c + j) * 2 + 1];
-      k.mean[j] = s1 * invP;
-      const float var = fmaxf(s2 * invP - k.mean[j] * k.mean[j], 0.f);
-      k.rstd[j] = rsqrtf(var + q.eps);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f, g = 1.f, bt = 0.f, m1 = 0.f, m2 = 0.f;
+    if (q.sums) {
+      const float s1 = q.sums[((long long)b * C + c) * 2], s2 = q.sums[((long long)b * C + c) * 2 + 1];
+      mean = s1 * invP;
+      const float var = fmaxf(s2 * invP - mean * mean, 0.f);
+      rstd = rsqrtf(var + q.eps);
+      g = q.gamma[c];
+      bt = q.beta[c];
+      if (bwd && q.bsums) {
+        m1 = q.bsums[((long long)b * C + c) * 4] * invP;
+        m2 = q.bsums[((long long)b * C + c) * 4 + 1] * invP;
+      }
     }
+    sm[c] = mean; sm[C + c] = rstd; sm[2 * C + c] = g; sm[3 * C + c] = bt;
+    sm[4 * C + c] = q.sc ? q.sc[(long long)b * C + c] : 1.f;
+    sm[5 * C + c] = q.sh ? q.sh[(long long)b * C + c] : 0.f;
+    sm[6 * C + c] = m1; sm[7 * C + c] = m2;
   }
-  if (q.sc) {
-    ld8f(q.sc + (long long)b * q.C + c, k.sc);
-    ld8f(q.sh + (long long)b * q.C + c, k.sh);
+  __syncthreads();
+  ChanCst k;
+  k.mean = sm; k.rstd = sm + C; k.gamma = sm + 2 * C; k.beta = sm + 3 * C;
+  k.sc = sm + 4 * C; k.sh = sm + 5 * C; k.m1 = sm + 6 * C; k.m2 = sm + 7 * C;
+  return k;
+}
+
+__device__ __forceinline__ void keep_for(const PrepParams& q, int b, int y, int x, int c, bool* keep) {
+  if (q.p > 0.f) {
+    const long long pix = ((long long)b * q.H + y) * q.W + x;
+    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, keep);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = true;
   }
 }
 
-// forward chain up to the value before the injector (xd)
-__device__ __forceinline__ void fwd_chain(const PrepParams& q, const ChanCtx& k, int b, int y, int x, int c,
-                                          const float* z, float* xhat, float* xn, float* xd, bool* keep) {
-  const long long pix = ((long long)b * q.H + y) * q.W + x;
+// forward chain: xhat (normalised), xn (after affine + Ta), xd (after dropout + Tb, before the injector)
+__device__ __forceinline__ void fwd_chain(const PrepParams& q, const ChanCst& k, int y, int x, int c, const float* z,
+                                          const bool* keep, float* xhat, float* xn, float* xd) {
+  if (q.sums) {
+    float mean[8], rstd[8], g[8], bt[8];
+    ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.beta + c, bt);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (q.sums) {
-      xhat[j] = (z[j] - k.mean[j]) * k.rstd[j];
-      xn[j] = xhat[j] * k.gamma[j] + k.beta[j];
-    } else {
+    for (int j = 0; j < 8; ++j) {
+      xhat[j] = (z[j] - mean[j]) * rstd[j];
+      xn[j] = xhat[j] * g[j] + bt[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       xhat[j] = z[j];
       xn[j] = z[j];
     }
   }
   if (q.Ta) add_timing(q.Ta, q.H, q.C, y, x, c, xn);
-  if (q.p > 0.f) {
-    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, keep);
-    const float inv_keep = 1.0f / (1.0f - q.p);
+  const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xd[j] = keep[j] ? xn[j] * inv_keep : 0.f;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      xd[j] = xn[j];
-      keep[j] = true;
-    }
-  }
+  for (int j = 0; j < 8; ++j) xd[j] = keep[j] ? xn[j] * inv_keep : 0.f;
   if (q.Tb) add_timing(q.Tb, q.H, q.C, y, x, c, xd);
 }
 
@@ -195,7 +211,8 @@ __device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y
 }
 
 // grid = (pixel slabs, B); block = CV * PL threads: thread = (8-channel vector cv, pixel lane pl)
-__global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+__global__ void __launch_bounds__(256, 3) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+  extern __shared__ float sm[];
   int y0, ny, x0, nx;
   iter_space(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
@@ -204,8 +221,7 @@ __global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ P
   const int NP = ny * nx;
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
-  ChanCtx k;
-  load_ctx(q, b, c, k);
+  const ChanCst k = load_cst(q, b, sm, false);
   for (int pix = p_begin + pl; pix < p_end; pix += PL) {
     const int yy = pix / nx + y0, xx = pix % nx + x0;
     __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy, xx, c);
@@ -216,28 +232,30 @@ __global__ void __launch_bounds__(256) prep_fwd_kernel(const __grid_constant__ P
     float z[8], mainv[8], xhat[8], xn[8], xd[8];
     bool keep[8];
     load_z(q, b, yy, xx, c, z, mainv);
-    fwd_chain(q, k, b, yy, xx, c, z, xhat, xn, xd, keep);
+    keep_for(q, b, yy, xx, c, keep);
+    fwd_chain(q, k, yy, xx, c, z, keep, xhat, xn, xd);
     if (q.out1) *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(xn);
     if (q.sc) {
+      float sc[8], sh[8];
+      ld8f(k.sc + c, sc); ld8f(k.sh + c, sh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * k.sc[j] + k.sh[j];
+      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * sc[j] + sh[j];
     }
     *reinterpret_cast<BF8*>(o2) = f_to_bf8(xd);
   }
 }
 
 // gradient wrt the normalised value (gx) for 8 channels, plus g2
-__device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCtx& k, int b, int y, int x, int c,
+__device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCst& k, int b, int y, int x, int c,
                                        const bool* keep, float* g2, float* gx) {
   bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) +
                                          view_off(q.g2, q.H, q.W, q.C, b, y, x, c)),
            g2);
   const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
+  float sc[8];
+  ld8f(k.sc + c, sc);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float v = q.sc ? g2[j] * k.sc[j] : g2[j];
-    gx[j] = keep[j] ? v * inv_keep : 0.f;
-  }
+  for (int j = 0; j < 8; ++j) gx[j] = keep[j] ? g2[j] * sc[j] * inv_keep : 0.f;
   if (q.g1) {
     float t[8];
     bf8_to_f(*reinterpret_cast<const BF8*>(q.g1 + (((long long)b * q.H + y) * q.W + x) * q.C + c), t);
@@ -249,10 +267,11 @@ __device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCtx& k, in
 // ---------------------------------------------------------------------------------------------------------------
 // per-(b,c) reductions over pixels.  MODE 0: sum z, sum z^2 (2 values).  MODE 1: backward sums (4 values).
 // grid = (slabs, B); block = CV * PL threads (thread = one 8-channel vector x one pixel lane)
+// shared memory: [8*C constants (MODE 1)] then the [PL][CV][NV*8] reduction scratch
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL,
-                                                        int pix_per_slab) {
+__global__ void __launch_bounds__(256, (MODE == 0 ? 4 : 2)) reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL,
+                                                           int pix_per_slab) {
   constexpr int NV = MODE == 0 ? 2 : 4;
   extern __shared__ float sm[];
   const int CV = q.C / 8;
@@ -267,22 +286,45 @@ __global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ 
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
-  ChanCtx k;
-  if (MODE == 1) load_ctx(q, b, c, k);
-  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
+  ChanCst k;
+  float* scratch = sm;
+  if (MODE == 1) {
+    k = load_cst(q, b, sm, false);
+    scratch = sm + 8 * q.C;
+  }
+  if (MODE == 0) {
+    // statistics: 4 independent pixel loads in flight per thread (memory-level parallelism)
+    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += 4 * PL) {
+      float z[4][8], mainv[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pix = pix0 + u * PL;
+        if (pix < p_end) {
+          const int y = pix / q.W, x = pix - y * q.W;
+          load_z(q, b, y, x, c, z[u], mainv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += z[u][j];
+          acc[1][j] += z[u][j] * z[u][j];
+        }
+    }
+  }
+  for (int pix = p_begin + pl; MODE == 1 && pix < p_end; pix += PL) {
     const int y = pix / q.W, x = pix - y * q.W;
     float z[8], mainv[8];
     load_z(q, b, y, x, c, z, mainv);
-    if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += z[j];
-        acc[1][j] += z[j] * z[j];
-      }
-    } else {
+    {
       float xhat[8], xn[8], xd[8], g2[8], gx[8];
       bool keep[8];
-      fwd_chain(q, k, b, y, x, c, z, xhat, xn, xd, keep);
+      keep_for(q, b, y, x, c, keep);
+      fwd_chain(q, k, y, x, c, z, keep, xhat, xn, xd);
       bwd_gx(q, k, b, y, x, c, keep, g2, gx);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -293,8 +335,8 @@ __global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ 
       }
     }
   }
-  // reduce over pixel lanes through shared memory: sm[pl][cv][v][j]
-  float* mine = sm + ((size_t)pl * CV + cv) * (NV * 8);
+  // reduce over pixel lanes through shared memory: scratch[pl][cv][v][j]
+  float* mine = scratch + ((size_t)pl * CV + cv) * (NV * 8);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -304,13 +346,14 @@ __global__ void __launch_bounds__(256) reduce_bc_kernel(const __grid_constant__ 
     const int cvv = i / (NV * 8), rem = i % (NV * 8);
     const int v = rem / 8, j = rem % 8;
     float s = 0.f;
-    for (int l = 0; l < PL; ++l) s += sm[((size_t)l * CV + cvv) * (NV * 8) + rem];
+    for (int l = 0; l < PL; ++l) s += scratch[((size_t)l * CV + cvv) * (NV * 8) + rem];
     atomicAdd(out + ((long long)b * q.C + cvv * 8 + j) * NV + v, s);
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     prep_bwd_apply_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+  extern __shared__ float sm[];
   int y0, ny, x0, nx;
   iter_space(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
@@ -319,18 +362,7 @@ __global__ void __launch_bounds__(256)
   const int NP = ny * nx;
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
-  const float invP = 1.0f / (float)(q.H * q.W);
-  ChanCtx k;
-  load_ctx(q, b, c, k);
-  float m1[8], m2[8];
-  if (q.sums) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long sb_ = ((long long)b * q.C + c + j);
-      m1[j] = q.bsums[sb_ * 4] * invP;
-      m2[j] = q.bsums[sb_ * 4 + 1] * invP;
-    }
-  }
+  const ChanCst k = load_cst(q, b, sm, true);
   for (int pix = p_begin + pl; pix < p_end; pix += PL) {
     const int yy = pix / nx + y0, xx = pix % nx + x0;
     __nv_bfloat16* dm = reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy, xx, c);
@@ -338,14 +370,19 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
       continue;
     }
-    float z[8], mainv[8], xhat[8], xn[8], xd[8], g2[8], gx[8], dz[8];
+    float z[8], mainv[8], g2[8], gx[8], dz[8];
     bool keep[8];
     load_z(q, b, yy, xx, c, z, mainv);
-    fwd_chain(q, k, b, yy, xx, c, z, xhat, xn, xd, keep);
+    keep_for(q, b, yy, xx, c, keep);
     bwd_gx(q, k, b, yy, xx, c, keep, g2, gx);
-    if (q.sums) {
+    if (q.sums) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
+      float mean[8], rstd[8], g[8], m1[8], m2[8];
+      ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.m1 + c, m1); ld8f(k.m2 + c, m2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = k.rstd[j] * k.gamma[j] * (gx[j] - m1[j] - xhat[j] * m2[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (z[j] - mean[j]) * rstd[j];
+        dz[j] = rstd[j] * g[j] * (gx[j] - m1[j] - xhat * m2[j]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) dz[j] = gx[j];
@@ -587,7 +624,7 @@ static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* 
   *PL = 256 / CV < 1 ? 1 : 256 / CV;
   *threads = CV * (*PL);
   if (P < 0) P = q.H * q.W;
-  int want = (148 * 4 + q.B - 1) / q.B;  // ~4 CTAs per SM over the whole grid
+  int want = (148 * 6 + q.B - 1) / q.B;  // ~6 CTAs per SM over the whole grid
   if (want < 1) want = 1;
   int per = (P + want - 1) / want;
   if (per < *PL) per = *PL;
@@ -617,7 +654,7 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
-  prep_fwd_kernel<<<dim3(slabs, q.B), threads, 0, (cudaStream_t)stream>>>(q, PL, pps);
+  prep_fwd_kernel<<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -629,7 +666,7 @@ extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
   if (rc || !q.in.p || !q.g2.p || !q.bsums) return SB_ERR_ARG;
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads);
-  const size_t smem = (size_t)threads * 4 * 8 * sizeof(float);
+  const size_t smem = ((size_t)threads * 4 * 8 + 8 * (size_t)q.C) * sizeof(float);
   reduce_bc_kernel<1><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
@@ -644,7 +681,7 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
-  prep_bwd_apply_kernel<<<dim3(slabs, q.B), threads, 0, (cudaStream_t)stream>>>(q, PL, pps);
+  prep_bwd_apply_kernel<<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

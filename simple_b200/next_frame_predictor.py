@@ -88,48 +88,40 @@ class BitsPredictor(nn.Module):  # :66-121
         self.dense5 = nn.Linear(state_size, 2 ** bits_at_once)
         self.lstm = nn.LSTMCell(state_size, state_size)
 
-    def _cell(self, x, h, c):
-        gates = F.linear(x, self.lstm.weight_ih, self.lstm.bias_ih) + F.linear(h, self.lstm.weight_hh, self.lstm.bias_hh)
-        i, f, g, o = gates.chunk(4, dim=1)
-        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-        return torch.sigmoid(o) * torch.tanh(c), c
-
     def forward(self, x, rand, target_bits=None):
         """x: [B,4608] (C,H,W order).  Teacher-forced loss when target_bits is given, else sampled bits in {-1,+1}."""
         n = self.total_number_bits // self.bits_at_once
-        first = self.dense1(x)
-        h = self.dense2(x)
-        c = self.dense3(x)
+        B = x.shape[0]
+        # dense1..3 share their input: one [B,4608] x [4608,384] GEMM instead of three
+        w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
+        b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
+        first, h, c = F.linear(x, w123, b123).chunk(3, dim=1)
         if target_bits is not None:
             tb = target_bits.reshape(-1, n, self.bits_at_once).clamp(min=0.)
             w = (2 ** torch.arange(self.bits_at_once, device=x.device)).float()
             tints = (tb * w).sum(-1).long()  # LSB first, on device (the reference round-trips through the host)
-            emb = self.dense4(F.one_hot(tints, 2 ** self.bits_at_once).float())
+            # dense4(one_hot(t)) == W4[:, t] + b4: an embedding lookup instead of a 256-wide matmul
+            emb = F.embedding(tints, self.dense4.weight.t()) + self.dense4.bias
             emb = emb * (rand.keep_mask(emb.shape, 0.1) / 0.9)
-            tin = torch.cat((first.unsqueeze(1), emb), dim=1)
+            tin = torch.cat((first.unsqueeze(1), emb), dim=1)[:, :n]
+            # teacher forcing: every LSTM input is known up front, so the input half of the gates is ONE GEMM over
+            # all 16 steps; only the recurrent half stays sequential, with the pointwise cell fused (sb_lstm_cell_*)
+            xw = F.linear(tin, self.lstm.weight_ih, self.lstm.bias_ih + self.lstm.bias_hh)  # [B,16,512]
+            whh_t = self.lstm.weight_hh.t()
             outs = []
             for i in range(n):
-                h, c = self._cell(tin[:, i, :], h, c)
+                h, c = ops.LstmCell.apply(torch.addmm(xw[:, i], h, whh_t), c)
                 outs.append(h)
             outs = torch.stack(outs, dim=1)
             outs = outs * (rand.keep_mask(outs.shape, 0.1) / 0.9)
             pred = self.dense5(outs)
             loss = F.cross_entropy(pred.permute(0, 2, 1), tints)
             return pred, loss / self.config.rollout_length
-        samples = []
-        inp = first
-        with torch.no_grad():  # integer outputs: nothing to differentiate (SURVEY 9.8)
-            for i in range(n):
-                h, c = self._cell(inp, h, c)
-                logits = self.dense5(h)
-                # multinomial(exp(logits), 1) == argmax(exp(logits) / Exp(1) noise)
-                s = torch.argmax(torch.exp(logits) / rand.exponential(logits.shape), dim=-1)
-                samples.append(s)
-                inp = self.dense4.weight.t()[s] + self.dense4.bias  # dense4(one_hot(s))
-            ints = torch.stack(samples, dim=1)
-            shifts = torch.arange(self.bits_at_once, device=x.device)
-            bits = ((ints.unsqueeze(-1) >> shifts) & 1).float().reshape(-1, self.total_number_bits)
-        return 2 * bits - 1, 0.0
+        # sampling: integer outputs, nothing to differentiate (SURVEY 9.8) -> one persistent kernel for all 16 steps
+        noise = rand.sample_noise(B, n) if hasattr(rand, 'sample_noise') else None
+        bits, _ = ops.lstm_sample(first, h, c, self.lstm, self.dense5, self.dense4, noise=noise,
+                                  seed=getattr(rand, 'seed', None) if noise is None else None)
+        return bits, 0.0
 
 
 class StochasticModel(nn.Module):  # :124-206
@@ -246,6 +238,10 @@ class InjectedRand:
 
     def exponential(self, shape):
         return self._next('exp', shape)
+
+    def sample_noise(self, B, n):
+        """The n consecutive Exp(1) draws [B,256] of one sampling pass (one per torch.multinomial call)."""
+        return torch.stack([self._next('exp', (B, 256)) for _ in range(n)], dim=1).contiguous()
 
     def truncnorm(self, shape):
         return self._next('truncnorm', shape)

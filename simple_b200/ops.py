@@ -424,3 +424,52 @@ def pixel_argmax(logits):
     _lib.check(_lib.lib().sb_pixel_ce(logits.data_ptr(), None, B, H * W, 0.0, 0.0, None, amax.data_ptr(), None, None,
                                       _lib.stream_ptr()), 'sb_pixel_ce')
     return amax
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# latent-bit predictor
+# ---------------------------------------------------------------------------------------------------------------
+def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None):
+    """16-step autoregressive sampling of BitsPredictor (next_frame_predictor.py:109-121) in one kernel launch.
+    Returns bits [B,128] in {-1,+1}.  `noise`: explicit Exp(1) draws [B,16,256] (parity mode), else Philox(seed)."""
+    B = x0.shape[0]
+    f = lambda t: t.detach().float().contiguous()
+    x0, h0, c0 = f(x0), f(h0), f(c0)
+    w = [f(t) for t in (lstm.weight_ih, lstm.weight_hh, lstm.bias_ih, lstm.bias_hh, dense5.weight, dense5.bias,
+                        dense4.weight, dense4.bias)]
+    bits = torch.empty(B, 128, device=x0.device, dtype=torch.float32)
+    ints = torch.empty(B, 16, device=x0.device, dtype=torch.int32)
+    noise = f(noise) if noise is not None else None
+    _lib.check(_lib.lib().sb_lstm_sample(x0.data_ptr(), h0.data_ptr(), c0.data_ptr(), *[t.data_ptr() for t in w],
+                                         _ptr(noise), _ptr(seed), B, bits.data_ptr(), ints.data_ptr(),
+                                         _lib.stream_ptr()), 'sb_lstm_sample')
+    return bits, ints
+
+
+class LstmCell(torch.autograd.Function):
+    """Pointwise part of nn.LSTMCell: (pre-activations [B,512], c_prev [B,128]) -> (h, c)."""
+
+    @staticmethod
+    def forward(ctx, pre, c_prev):
+        B = pre.shape[0]
+        pre, c_prev = pre.contiguous(), c_prev.contiguous()
+        act = torch.empty_like(pre)
+        c = torch.empty_like(c_prev)
+        h = torch.empty_like(c_prev)
+        _lib.check(_lib.lib().sb_lstm_cell_fwd(pre.data_ptr(), c_prev.data_ptr(), act.data_ptr(), c.data_ptr(),
+                                               h.data_ptr(), B, _lib.stream_ptr()), 'sb_lstm_cell_fwd')
+        ctx.save_for_backward(act, c_prev, c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        act, c_prev, c = ctx.saved_tensors
+        B = act.shape[0]
+        dh = dh.contiguous() if dh is not None else None
+        dc = dc.contiguous() if dc is not None else None
+        dpre = torch.empty_like(act)
+        dc_prev = torch.empty_like(c)
+        _lib.check(_lib.lib().sb_lstm_cell_bwd(act.data_ptr(), c_prev.data_ptr(), c.data_ptr(), _ptr(dh), _ptr(dc),
+                                               dpre.data_ptr(), dc_prev.data_ptr(), B, _lib.stream_ptr()),
+                   'sb_lstm_cell_bwd')
+        return dpre, dc_prev

@@ -1,0 +1,36 @@
+"""One eager world-model training step (B=64) bracketed by cudaProfilerStart/Stop, for ncu:
+   ncu --profile-from-start off ... python tools/ncu_step.py [batch]"""
+import os
+import sys
+import torch
+from types import SimpleNamespace
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import synth_replay  # noqa: E402
+from simple_b200.next_frame_predictor import NextFramePredictor  # noqa: E402
+from simple_b200.trainer import StepRunner, Trainer  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+dev = torch.device('cuda:0')
+cfg = SimpleNamespace(
+    agents=16, batch_size=B, bottleneck_bits=128, bottleneck_noise=0.1, clip_grad_norm=1.0, compress_steps=5,
+    device=str(dev), done_on_last_rollout_step=True, dropout=0.15, filter_double_steps=3, frame_shape=(3, 105, 80),
+    hidden_layers=2, hidden_size=96, input_noise=0.05, latent_rnn_max_sampling=0.5, latent_state_size=128,
+    latent_use_max_probability=0.8, recurrent_state_size=64, residual_dropout=0.5, rollout_length=50,
+    save_models=False, scheduled_sampling_decay_steps=22250, stacking=4, stack_internal_states=True,
+    target_loss_clipping=0.03, use_stochastic_model=True, use_wandb=False)
+torch.manual_seed(0)
+model = NextFramePredictor(cfg, 3).to(dev)
+trainer = Trainer(model, cfg)
+d = {k: v.to(dev) for k, v in synth_replay(B + 20, 3, 1).items()}
+replay = dict(obs=d['obs'], new_obs=d['new_obs'], action=d['action'].float(), reward=d['reward'].long(), value=d['value'])
+r = StepRunner(trainer, replay, B, use_graph=False)
+r.begin(torch.arange(B, device=dev), 0)
+for _ in range(3):
+    r.step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+r.step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print('loss', float(r.last['loss']))
