@@ -25,14 +25,11 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return copysignf((1.0f - t) / (1.0f + t), x);
 }
 
-__device__ __forceinline__ float dot128(const float* __restrict__ w, const float* __restrict__ v) {
-  float s = 0.f;
-#pragma unroll 8
-  for (int k = 0; k < kH; k += 4) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(w + k));
-    s += a.x * v[k] + a.y * v[k + 1] + a.z * v[k + 2] + a.w * v[k + 3];
-  }
-  return s;
+// One warp computes one output row: lane l holds elements 4l..4l+3 of the 128-vector, reads the matching float4 of the
+// weight row (a fully coalesced 512-byte row per warp instruction) and the partial sums are reduced with shuffles.
+__device__ __forceinline__ float row_dot(const float* __restrict__ w_row, const float4 v, int lane) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(w_row) + lane);
+  return a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
 }
 
 __global__ void __launch_bounds__(512)
@@ -41,11 +38,13 @@ __global__ void __launch_bounds__(512)
                        const float* __restrict__ b_hh, const float* __restrict__ w5, const float* __restrict__ b5,
                        const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ noise,
                        const unsigned long long* seed_ptr, float* __restrict__ bits, int* __restrict__ ints) {
-  __shared__ float x[kH], h[kH], c[kH], gates[4 * kH], score[kV];
+  __shared__ __align__(16) float x[kH], h[kH];
+  __shared__ float c[kH], gates[4 * kH], score[kV];
   __shared__ int sym[kSteps];
   __shared__ float red_v[8];
   __shared__ int red_i[8];
   const int b = blockIdx.x, t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;  // 16 warps
   if (t < kH) {
     x[t] = x0[b * kH + t];
     h[t] = h0[b * kH + t];
@@ -54,8 +53,18 @@ __global__ void __launch_bounds__(512)
   __syncthreads();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   for (int step = 0; step < kSteps; ++step) {
-    // gates = W_ih x + b_ih + W_hh h + b_hh   (PyTorch LSTMCell order: i, f, g, o)
-    gates[t] = b_ih[t] + b_hh[t] + dot128(w_ih + (size_t)t * kH, x) + dot128(w_hh + (size_t)t * kH, h);
+    // gates = W_ih x + b_ih + W_hh h + b_hh   (PyTorch LSTMCell order: i, f, g, o); warp w owns rows 32w .. 32w+31
+    {
+      const float4 xv = reinterpret_cast<const float4*>(x)[lane];
+      const float4 hv = reinterpret_cast<const float4*>(h)[lane];
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int row = warp * 32 + r;
+        float s = row_dot(w_ih + (size_t)row * kH, xv, lane) + row_dot(w_hh + (size_t)row * kH, hv, lane);
+        s = warp_sum(s);
+        if (lane == 0) gates[row] = s + b_ih[row] + b_hh[row];
+      }
+    }
     __syncthreads();
     if (t < kH) {
       const float ig = sigmoidf_(gates[t]), fg = sigmoidf_(gates[kH + t]);
@@ -65,17 +74,25 @@ __global__ void __launch_bounds__(512)
       h[t] = og * tanh_acc(cn);
     }
     __syncthreads();
-    if (t < kV) {
-      const float logit = b5[t] + dot128(w5 + (size_t)t * kH, h);
-      float q;
-      if (noise) {
-        q = noise[((size_t)b * kSteps + step) * kV + t];
-      } else {
-        const uint4 r = philox4x32(make_uint4((uint32_t)t, (uint32_t)step, (uint32_t)b, 0x4c53544du),
-                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-        q = -logf(((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
+    {
+      const float4 hv = reinterpret_cast<const float4*>(h)[lane];
+#pragma unroll 8
+      for (int r = 0; r < 16; ++r) {  // 256 logits: warp w owns rows 16w .. 16w+15
+        const int row = warp * 16 + r;
+        float s = warp_sum(row_dot(w5 + (size_t)row * kH, hv, lane));
+        if (lane == 0) {
+          const float logit = s + b5[row];
+          float q;
+          if (noise) {
+            q = noise[((size_t)b * kSteps + step) * kV + row];
+          } else {
+            const uint4 rr = philox4x32(make_uint4((uint32_t)row, (uint32_t)step, (uint32_t)b, 0x4c53544du),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            q = -logf(((float)(rr.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
+          }
+          score[row] = expf(logit) / q;  // sample_with_temperature(T=1): multinomial(exp(logits))
+        }
       }
-      score[t] = expf(logit) / q;  // sample_with_temperature(T=1): multinomial(exp(logits))
     }
     __syncthreads();
     // argmax over 256 scores, first index on ties

@@ -59,6 +59,7 @@ struct TapGemmDev {
   int B, Ho, Wo;
   int bw, bh, bb, rows;
   int tiles_x, tiles_y;
+  int m_tiles, n_tiles;
   int C, kchunks, ntaps;
   int tap_dy[SB_MAX_TAPS], tap_dx[SB_MAX_TAPS];
   int N, splits;
@@ -68,45 +69,47 @@ struct TapGemmDev {
   int relu, atomic;
 };
 
-constexpr int kGemmThreads = 192;
-constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16
+constexpr int kGemmThreads = 192;        // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kFwdThreads = 320;         // tap GEMM: TMA warp, MMA warp, 8 epilogue warps
+constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 bf16
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
+// Persistent, warp-specialised tap GEMM.  Each CTA (one per SM) walks the tile list tile = blockIdx.x + i*gridDim.x.
+// The accumulator is double-buffered in TMEM (2 x BN columns): while the 8 epilogue warps drain tile i, the MMA warp
+// already accumulates tile i+1, and the TMA warp runs ahead through the shared-memory ring across tile boundaries.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kFwdThreads, 1)
     tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ TapGemmDev p) {
   constexpr int B_BYTES = BN * 128;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kATileBytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x;
-  const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
-  const int n0 = blockIdx.y * BN;
   const int KT = p.ntaps * p.kchunks;
-  const int k_begin = (int)((long long)KT * blockIdx.z / p.splits);
-  const int k_end = (int)((long long)KT * (blockIdx.z + 1) / p.splits);
-  const int nk = k_end - k_begin;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 8);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -123,97 +126,130 @@ __global__ void __launch_bounds__(kGemmThreads)
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)B_BYTES;
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        const int kk = k_begin + i;
-        const int t = kk / p.kchunks;
-        const int c0 = (kk - t * p.kchunks) * 64;
-        mbar_expect_tx(&full[s], tx_bytes);
-        tma_load_4d(sA + s * kATileBytes, &tmA, &full[s], c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b0);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], t * p.C + c0, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int mt = (tile / p.n_tiles) % p.m_tiles;
+        const int sp = tile / (p.n_tiles * p.m_tiles);
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * BN;
+        const int k_begin = (int)((long long)KT * sp / p.splits);
+        const int k_end = (int)((long long)KT * (sp + 1) / p.splits);
+        for (int kk = k_begin; kk < k_end; ++kk, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const int t = kk / p.kchunks;
+          const int c0 = (kk - t * p.kchunks) * 64;
+          mbar_expect_tx(&full[s], tx_bytes);
+          tma_load_4d(sA + s * kATileBytes, &tmA, &full[s], c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b0);
+          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], t * p.C + c0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      for (int i = 0; i < nk; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(&full[s], ph);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int sp = tile / (p.n_tiles * p.m_tiles);
+        const int nk = (int)((long long)KT * (sp + 1) / p.splits) - (int)((long long)KT * sp / p.splits);
+        const int as = tcount & 1;
+        const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+        mbar_wait(&tempty[as], aph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
-        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
+          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&tfull[as]);
       }
-      umma_commit(tmem_full);
     }
   } else {
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int lg = warp & 3;
+    const int e = warp - 2;          // 0..7
+    const int lg = warp & 3;         // TMEM lane quarter this warp may access
+    const int half = e >> 2;         // interleaved 32-column chunks: half 0 takes chunks 0,2,4.., half 1 takes 1,3,5..
     const int r = lg * 32 + lane;
     const int xl = r % p.bw, yl = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
-    const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
-    const bool valid = (r < p.rows) && (x < p.Wo) && (y < p.Ho) && (b < p.B);
-    const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % p.n_tiles;
+      const int mt = (tile / p.n_tiles) % p.m_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.bw + xl, y = ty * p.bh + yl, b = tb * p.bb + bl, n0 = nt * BN;
+      const bool valid = (r < p.rows) && (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+      const int as = tcount & 1;
+      const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      if (n0 + c >= p.N) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float f[32];
+      for (int c = half * 32; c < BN; c += 64) {
+        if (n0 + c >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      const int nb = n0 + c;
-      if (p.atomic) {
-        float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (nb + j < p.N) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-      } else {
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (p.out_f32) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const int nb = n0 + c;
+        if (p.atomic) {
           float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            if (nb + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            if (nb + j < p.N) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
         } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + nb;
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (nb + j < p.N) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&t0);
-              pk.y = *reinterpret_cast<uint32_t*>(&t1);
-              pk.z = *reinterpret_cast<uint32_t*>(&t2);
-              pk.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(o + j) = pk;
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (nb + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (nb + j < p.N) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(o + j) = pk;
+              }
             }
           }
         }
       }
+      // this warp is done reading the accumulator stage: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
     }
   }
   tc_fence_before();
@@ -222,9 +258,8 @@ __global__ void __launch_bounds__(kGemmThreads)
 }
 
 template <int BN, int STAGES>
-static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmDev& p, dim3 grid,
-                           cudaStream_t stream) {
-  constexpr int smem = STAGES * (kATileBytes + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmDev& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kATileBytes + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tap_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -232,7 +267,9 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
       return SB_ERR_CUDA;
     configured = true;
   }
-  tap_gemm_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < 148 ? total : 148;
+  tap_gemm_kernel<BN, STAGES><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, p);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -429,17 +466,13 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   if (rc) return rc;
   rc = make_map_2d(&tmB, a->w, a->N, a->ntaps * a->C, a->ldw, BN);
   if (rc) return rc;
-  dim3 grid(p.tiles_x * p.tiles_y * tiles_b, (a->N + BN - 1) / BN, p.splits);
-  // short K loops (1x1 convolutions: logits, embeddings) are epilogue-bound: 2 stages fit 2 CTAs per SM so that one
-  // CTA's epilogue overlaps the other's main loop
-  const bool shortk = (KT + p.splits - 1) / p.splits <= 2;
+  p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+  p.n_tiles = (a->N + BN - 1) / BN;
   switch (BN) {
-    case 256: return shortk ? launch_tap_gemm<256, 2>(tmA, tmB, p, grid, stream)
-                            : launch_tap_gemm<256, 4>(tmA, tmB, p, grid, stream);
-    case 192: return shortk ? launch_tap_gemm<192, 2>(tmA, tmB, p, grid, stream)
-                            : launch_tap_gemm<192, 5>(tmA, tmB, p, grid, stream);
-    case 128: return launch_tap_gemm<128, 3>(tmA, tmB, p, grid, stream);
-    default: return launch_tap_gemm<96, 3>(tmA, tmB, p, grid, stream);
+    case 256: return launch_tap_gemm<256, 4>(tmA, tmB, p, stream);
+    case 192: return launch_tap_gemm<192, 5>(tmA, tmB, p, stream);
+    case 128: return launch_tap_gemm<128, 6>(tmA, tmB, p, stream);
+    default: return launch_tap_gemm<96, 6>(tmA, tmB, p, stream);
   }
 }
 
