@@ -107,7 +107,7 @@ def reference_cpu_step_time(batch, steps, warmup, n_action=3):
     torch.set_num_threads(os.cpu_count())
     cfg = O.default_config(device='cpu', batch_size=batch)
     ref = load_reference()
-    data = synth_replay(warmup + steps + 2, n_action, seed=0)
+    data = synth_replay(batch + warmup + steps + 2, n_action, seed=0)
     torch.manual_seed(0)
     np.random.seed(0)
     times = []
