@@ -133,6 +133,8 @@ typedef struct {
   float* bsums;            /* [B,C,4]: sum gx, sum gx*xhat, sum g2*xd (d sc), sum g2 (d sh); caller zeroes */
   sb_view d_main;          /* grad wrt in (layout of in), masked by in>0 when relu_in */
   void* d_add;             /* grad wrt add (plain) or NULL */
+  float* dcol;             /* optional fp32 [C] (caller zeroes): += column sums of d_main over b,y,x = the bias gradient
+                              of the convolution that produced `in` (sb_prep_bwd_apply only) */
 } sb_prep_args;
 int sb_stats(const sb_prep_args* args, float* sums /* [B,C,2], caller zeroes */, sb_stream_t stream);
 int sb_prep(const sb_prep_args* args, sb_stream_t stream);
@@ -168,6 +170,8 @@ int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s
  *                       per block; pass 1 updates row/col states and acc[0]=sum u^2, acc[1]=sum p^2 (caller zeroes
  *                       acc), pass 2 applies the update.  g is scaled by min(1, max_norm/(sqrt(total)+1e-6)).
  *   sb_adafactor_small: 1-D (cols==0, state in `row`) and 2-D tensors, one CTA per descriptor.
+ *   sb_adafactor_big2d: large 2-D tensors, one thread-block cluster of 8 CTAs per descriptor (row bands; column sums
+ *                       and RMS partials combined through distributed shared memory).
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct {
   float* p;        /* parameter, fp32, reference layout */
@@ -186,6 +190,8 @@ int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int
 int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
                       const float* total_sumsq, float max_norm, int pass, sb_stream_t stream);
 int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
+                       const float* total_sumsq, float max_norm, sb_stream_t stream);
+int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, int ntensors, int max_cols, int max_rows,
                        const float* total_sumsq, float max_norm, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------

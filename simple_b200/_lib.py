@@ -66,7 +66,7 @@ class PrepArgs(ctypes.Structure):
         ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('seed_ptr', ctypes.c_void_p), ('stream_id', ctypes.c_uint),
         ('keep', ctypes.c_void_p), ('Tb', ctypes.c_void_p), ('sc', ctypes.c_void_p), ('sh', ctypes.c_void_p),
         ('out2', SbView), ('g2', SbView), ('g1', ctypes.c_void_p), ('bsums', ctypes.c_void_p),
-        ('d_main', SbView), ('d_add', ctypes.c_void_p),
+        ('d_main', SbView), ('d_add', ctypes.c_void_p), ('dcol', ctypes.c_void_p),
     ]
 
 
@@ -116,6 +116,7 @@ class _Sigs:
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]
     sb_adafactor_small = [_p, _i, _i, _p, _f, _p]
+    sb_adafactor_big2d = [_p, _i, _i, _i, _p, _f, _p]
 
 
 EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version'] + [n for n in dir(_Sigs) if n.startswith('sb_')]

@@ -137,6 +137,11 @@ class Adafactor(torch.optim.Optimizer):
             for pas in (1, 2):
                 _lib.check(L.sb_adafactor_conv(sub.data_ptr(), bm.data_ptr(), bm.shape[0], kh, kw, total.data_ptr(), mn,
                                                pas, s), 'sb_adafactor_conv')
+        if maps['big2d'] is not None:
+            idx, mc, mr = maps['big2d']
+            sub = descs_dev.view(n, 64)[idx].contiguous()
+            _lib.check(L.sb_adafactor_big2d(sub.data_ptr(), idx.numel(), mc, mr, total.data_ptr(), mn, s),
+                       'sb_adafactor_big2d')
         if maps['small'] is not None:
             idx, rc = maps['small']
             sub = descs_dev.view(n, 64)[idx].contiguous()
@@ -149,17 +154,23 @@ class Adafactor(torch.optim.Optimizer):
         sumsq = []
         conv = {}
         small = []
+        big = []
         rc = 1
         for i, (p, _) in enumerate(active):
             nchunks = -(-p.numel() // 4096)
             sumsq += [(i, c) for c in range(nchunks)]
             if p.dim() == 4:
                 conv.setdefault((p.shape[2], p.shape[3]), []).append(i)
+            elif p.dim() == 2 and p.numel() >= 49152 and p.shape[0] >= 8:
+                big.append(i)  # one 8-CTA cluster per tensor instead of a single CTA
             else:
                 small.append(i)
                 if p.dim() == 2:
                     rc = max(rc, p.shape[0] + p.shape[1])
-        maps = {'sumsq': torch.tensor(sumsq, dtype=torch.int32, device=dev), 'conv': {}, 'small': None}
+        maps = {'sumsq': torch.tensor(sumsq, dtype=torch.int32, device=dev), 'conv': {}, 'small': None, 'big2d': None}
+        if big:
+            maps['big2d'] = (torch.tensor(big, dtype=torch.long, device=dev), max(active[i][0].shape[1] for i in big),
+                             max(active[i][0].shape[0] for i in big))
         for k, idxs in conv.items():
             bm = []
             for local, i in enumerate(idxs):

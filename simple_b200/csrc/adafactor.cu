@@ -8,6 +8,7 @@
 //                             sum u^2 / sum p^2, pass 2 applies p -= lr * u / max(1, RMS(u)).
 //   3. sb_adafactor_small   : 1-D / 2-D tensors, one CTA per tensor (block-local reductions).
 // HBM-bound: ~12 B/param minimum (read p, g; write p) + state; see DESIGN.md.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "../../include/simple_b200.h"
 
@@ -230,6 +231,119 @@ __global__ void __launch_bounds__(1024)
   if (threadIdx.x == 0) d.acc[1] = sp;
 }
 
+// ---- 3b. large 2-D tensors (e.g. bits_predictor.dense1-3: [128, 4608]): one thread-block CLUSTER of 8 CTAs per
+// tensor.  CTA k owns a band of rows; column sums, the row-state mean and the two RMS sums are combined through
+// distributed shared memory (3 cluster barriers) instead of running 590 k parameters through a single SM.
+constexpr int kClusterCtas = 8;
+namespace cg = cooperative_groups;
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    adafactor_2d_cluster_kernel(const sb_tensor_desc* __restrict__ descs, const float* __restrict__ total_sumsq,
+                                float max_norm) {
+  extern __shared__ float sm[];  // colpart [C] | cf [C] | rowf [rows_per]
+  __shared__ float red[32];
+  __shared__ float part[3][kClusterCtas];  // per-CTA partials of: sum(new row state), sum p^2, sum u^2
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const sb_tensor_desc d = descs[blockIdx.x / kClusterCtas];
+  const int R = d.rows, C = d.cols;
+  const int rows_per = (R + kClusterCtas - 1) / kClusterCtas;
+  const int r0 = min(R, rank * rows_per), r1 = min(R, r0 + rows_per);
+  float* colpart = sm;
+  float* cf = sm + C;
+  float* rowf = sm + 2 * C;
+  const float coef = clip_coef(total_sumsq, max_norm);
+  const float tstep = *d.stepf;
+  const float beta2t = 1.0f - powf(tstep, -0.8f);
+  const float rel_step = fminf(1e-2f, rsqrtf(tstep));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  cluster.sync();  // every CTA of the cluster is running before its shared memory is written remotely
+  // sweep 1: row sums of g^2+eps (warp per row) -> new row state; sum p^2
+  float sp = 0.f, rpart = 0.f;
+  for (int r = r0 + warp; r < r1; r += nw) {
+    float rs = 0.f;
+    const float* gr = d.g + (long long)r * C;
+    const float* pr = d.p + (long long)r * C;
+    for (int c = lane; c < C; c += 32) {
+      const float g = gr[c] * coef;
+      rs += g * g + 1e-30f;
+      const float p = pr[c];
+      sp += p * p;
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) {
+      const float v = d.row[r] * beta2t + (rs / C) * (1.0f - beta2t);
+      d.row[r] = v;
+      rowf[r - r0] = v;
+      rpart += v;
+    }
+  }
+  // sweep 2: partial column sums over this CTA's rows (thread per column, coalesced across threads)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float cs = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const float g = d.g[(long long)r * C + c] * coef;
+      cs += g * g + 1e-30f;
+    }
+    colpart[c] = cs;
+  }
+  rpart = block_sum(rpart, red);
+  sp = block_sum(sp, red);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kClusterCtas; ++k) {
+      float(*rp)[kClusterCtas] = cluster.map_shared_rank(part, k);
+      rp[0][rank] = rpart;
+      rp[1][rank] = sp;
+    }
+  }
+  cluster.sync();
+  // column slice of this CTA: total over the 8 partials -> new col state -> rsqrt factor broadcast to every CTA
+  {
+    const int c0 = (int)((long long)C * rank / kClusterCtas), c1 = (int)((long long)C * (rank + 1) / kClusterCtas);
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+      float cs = 0.f;
+      for (int k = 0; k < kClusterCtas; ++k) cs += cluster.map_shared_rank(colpart, k)[c];
+      const float v = d.col[c] * beta2t + (cs / R) * (1.0f - beta2t);
+      d.col[c] = v;
+      const float f = rsqrtf(v);
+      for (int k = 0; k < kClusterCtas; ++k) cluster.map_shared_rank(cf, k)[c] = f;
+    }
+  }
+  float rsum = 0.f, spt = 0.f;
+  for (int k = 0; k < kClusterCtas; ++k) {
+    rsum += part[0][k];
+    spt += part[1][k];
+  }
+  const float rmean = rsum / R;
+  cluster.sync();
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) rowf[r - r0] = rsqrtf(rowf[r - r0] / rmean);
+  __syncthreads();
+  float su = 0.f;
+  for (int r = r0 + warp; r < r1; r += nw) {
+    const float rf = rowf[r - r0];
+    const float* gr = d.g + (long long)r * C;
+    for (int c = lane; c < C; c += 32) {
+      const float u = rf * cf[c] * gr[c] * coef;
+      su += u * u;
+    }
+  }
+  su = block_sum(su, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < kClusterCtas; ++k) cluster.map_shared_rank(part, k)[2][rank] = su;
+  cluster.sync();
+  float sut = 0.f;
+  for (int k = 0; k < kClusterCtas; ++k) sut += part[2][k];
+  const float n = (float)d.n;
+  const float lr = fmaxf(1e-3f, __fsqrt_rn(spt / n)) * rel_step;
+  const float scale = lr / fmaxf(1.0f, __fsqrt_rn(sut / n));
+  for (int r = r0 + warp; r < r1; r += nw) {
+    const float rf = rowf[r - r0] * scale * coef;
+    const float* gr = d.g + (long long)r * C;
+    float* pr = d.p + (long long)r * C;
+    for (int c = lane; c < C; c += 32) pr[c] -= rf * cf[c] * gr[c];
+  }
+  if (threadIdx.x == 0 && rank == 0) d.acc[1] = spt;
+}
+
 // step counters live on the device (one float per tensor) so that a captured CUDA graph advances them by itself
 __global__ void adafactor_tick_kernel(const sb_tensor_desc* __restrict__ descs, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,6 +406,25 @@ extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors,
     configured = true;
   }
   adafactor_small_kernel<<<ntensors, 1024, smem, (cudaStream_t)stream>>>(descs_dev, total_sumsq, max_norm);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, int ntensors, int max_cols, int max_rows,
+                                  const float* total_sumsq, float max_norm, sb_stream_t stream) {
+  if (!descs_dev || ntensors < 1 || max_cols < 1 || max_rows < 1) return SB_ERR_ARG;
+  const size_t smem = ((size_t)2 * max_cols + (max_rows + kClusterCtas - 1) / kClusterCtas) * sizeof(float);
+  if (smem > 200 * 1024) return SB_ERR_ARG;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(adafactor_2d_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+        cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  adafactor_2d_cluster_kernel<<<ntensors * kClusterCtas, 1024, smem, (cudaStream_t)stream>>>(descs_dev, total_sumsq,
+                                                                                            max_norm);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -36,19 +36,22 @@ __device__ __forceinline__ void ld8f(const float* p, float* f) {
 }
 
 // A bf16 tensor holding a logical [B,H,W,C] activation, either plain NHWC or padded space-to-depth:
-//   s2d element (b, y2, x2, (py*s+px)*C + c) = logical (b, s*y2+py-pad, s*x2+px-pad, c)
+//   s2d element (b, y2, x2, (py*s+px)*C + c) = logical (b, s*y2+py-pad, s*x2+px-pad, c);  s is a power of two
 struct View {
   void* p;
   int kind;  // 0 plain, 1 s2d
   int s, pad, H2, W2;
+  int sh;    // log2(s)
 };
 __device__ __forceinline__ long long view_off(const View& v, int H, int W, int C, int b, int y, int x, int c) {
   if (v.kind == 0) return (((long long)b * H + y) * W + x) * C + c;
   const int yp = y + v.pad, xp = x + v.pad;
-  const int y2 = yp / v.s, x2 = xp / v.s;
-  const int ph = (yp - y2 * v.s) * v.s + (xp - x2 * v.s);
+  const int y2 = yp >> v.sh, x2 = xp >> v.sh;
+  const int ph = ((yp & (v.s - 1)) << v.sh) + (xp & (v.s - 1));
   return ((((long long)b * v.H2 + y2) * v.W2 + x2) * (v.s * v.s) + ph) * C + c;
 }
+// n / d for 0 <= n < 2^17, 2 <= d < 300 with m = ceil(2^32 / d) (exact in that range); m == 0 encodes d == 1
+__device__ __forceinline__ int fast_div(int n, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n; }
 
 struct PrepParams {
   int B, H, W, C;
@@ -78,7 +81,19 @@ struct PrepParams {
   float* bsums;             // [B,C,4]: sum gx, sum gx*xhat, sum g2*xd, sum g2
   View d_main;              // grad wrt main (same layout as in)
   __nv_bfloat16* d_add;     // grad wrt add (plain) or NULL
+  float* dcol;              // optional [C]: += column sums of d_main (the producing conv's bias gradient)
+  // host-precomputed
+  uint32_t w_magic;         // fast_div magic of W
+  uint32_t nx_magic;        // fast_div magic of the iteration-space width (see iter_space)
 };
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void unpack8(const uint4& r, float* f) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+}
 
 // keep decisions for 8 consecutive channels from one Philox call (16 random bits each)
 __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, long long elem_index, bool* k) {
@@ -101,21 +116,38 @@ __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, 
   k[6] = (r.w & 0xffff) >= thr; k[7] = (r.w >> 16) >= thr;
 }
 
+// Raw operands of one (pixel, 8-channel vector): loads are ISSUED for several pixels before any is consumed, so that
+// a thread keeps 4-8 independent 16-byte loads in flight (these kernels are bound by bytes in flight per SM).
+struct RawZ {
+  uint4 m, a;
+};
+template <bool F32>
+__device__ __forceinline__ void issue_z(const PrepParams& q, int b, int y, int x, int c, RawZ& r) {
+  if (F32) return;
+  r.m = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + view_off(q.in, q.H, q.W, q.C, b, y, x, c));
+  if (q.add) r.a = ldg16(q.add + (((long long)b * q.H + y) * q.W + x) * q.C + c);
+}
 // value of (main [+relu] + add) for 8 channels; also returns raw main
-__device__ __forceinline__ void load_z(const PrepParams& q, int b, int y, int x, int c, float* z, float* mainv) {
-  const long long off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
-  if (q.in_f32) {
-    ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
+template <bool F32>
+__device__ __forceinline__ void finish_z(const PrepParams& q, const RawZ& r, int b, int y, int x, int c, float* z,
+                                         float* mainv) {
+  float a[8];
+  if (F32) {
+    const long long off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
+    if (q.in_f32) ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
+    else bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
+    if (q.add) {
+      const long long aoff = (((long long)b * q.H + y) * q.W + x) * q.C + c;
+      if (q.add_f32) ld8f(reinterpret_cast<const float*>(q.add) + aoff, a);
+      else bf8_to_f(*reinterpret_cast<const BF8*>(q.add + aoff), a);
+    }
   } else {
-    bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
+    unpack8(r.m, mainv);
+    if (q.add) unpack8(r.a, a);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) z[j] = q.relu_in ? fmaxf(mainv[j], 0.f) : mainv[j];
   if (q.add) {
-    float a[8];
-    const long long aoff = (((long long)b * q.H + y) * q.W + x) * q.C + c;
-    if (q.add_f32) ld8f(reinterpret_cast<const float*>(q.add) + aoff, a);
-    else bf8_to_f(*reinterpret_cast<const BF8*>(q.add + aoff), a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] += a[j];
   }
@@ -211,7 +243,9 @@ __device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y
 }
 
 // grid = (pixel slabs, B); block = CV * PL threads: thread = (8-channel vector cv, pixel lane pl)
-__global__ void __launch_bounds__(256, 3) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+template <bool F32>
+__global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+  constexpr int U = F32 ? 1 : 4;
   extern __shared__ float sm[];
   int y0, ny, x0, nx;
   iter_space(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
@@ -222,35 +256,57 @@ __global__ void __launch_bounds__(256, 3) prep_fwd_kernel(const __grid_constant_
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, false);
-  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
-    const int yy = pix / nx + y0, xx = pix % nx + x0;
-    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy, xx, c);
-    if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
-      *reinterpret_cast<uint4*>(o2) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    float z[8], mainv[8], xhat[8], xn[8], xd[8];
-    bool keep[8];
-    load_z(q, b, yy, xx, c, z, mainv);
-    keep_for(q, b, yy, xx, c, keep);
-    fwd_chain(q, k, yy, xx, c, z, keep, xhat, xn, xd);
-    if (q.out1) *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(xn);
-    if (q.sc) {
-      float sc[8], sh[8];
-      ld8f(k.sc + c, sc); ld8f(k.sh + c, sh);
+  for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
+    RawZ raw[U];
+    int yy[U], xx[U];
+    bool ins[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) xd[j] = xd[j] * sc[j] + sh[j];
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * PL;
+      const int row = fast_div(pix, q.nx_magic);
+      yy[u] = row + y0;
+      xx[u] = pix - row * nx + x0;
+      ins[u] = pix < p_end && yy[u] >= 0 && yy[u] < q.H && xx[u] >= 0 && xx[u] < q.W;
+      if (ins[u]) issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
     }
-    *reinterpret_cast<BF8*>(o2) = f_to_bf8(xd);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pix0 + u * PL >= p_end) break;
+      __nv_bfloat16* o2 =
+          reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy[u], xx[u], c);
+      if (!ins[u]) {
+        *reinterpret_cast<uint4*>(o2) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      float z[8], mainv[8], xhat[8], xn[8], xd[8];
+      bool keep[8];
+      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      keep_for(q, b, yy[u], xx[u], c, keep);
+      fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
+      if (q.out1)
+        *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy[u]) * q.W + xx[u]) * q.C + c) = f_to_bf8(xn);
+      if (q.sc) {
+        float sc[8], sh[8];
+        ld8f(k.sc + c, sc); ld8f(k.sh + c, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xd[j] = xd[j] * sc[j] + sh[j];
+      }
+      *reinterpret_cast<BF8*>(o2) = f_to_bf8(xd);
+    }
   }
 }
 
 // gradient wrt the normalised value (gx) for 8 channels, plus g2
-__device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCst& k, int b, int y, int x, int c,
-                                       const bool* keep, float* g2, float* gx) {
-  bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) +
-                                         view_off(q.g2, q.H, q.W, q.C, b, y, x, c)),
-           g2);
+struct RawG {
+  uint4 g2, g1;
+};
+__device__ __forceinline__ void issue_g(const PrepParams& q, int b, int y, int x, int c, RawG& r) {
+  r.g2 = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) + view_off(q.g2, q.H, q.W, q.C, b, y, x, c));
+  if (q.g1) r.g1 = ldg16(q.g1 + (((long long)b * q.H + y) * q.W + x) * q.C + c);
+}
+__device__ __forceinline__ void finish_gx(const PrepParams& q, const ChanCst& k, const RawG& r, int c, const bool* keep,
+                                          float* g2, float* gx) {
+  unpack8(r.g2, g2);
   const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
   float sc[8];
   ld8f(k.sc + c, sc);
@@ -258,9 +314,28 @@ __device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCst& k, in
   for (int j = 0; j < 8; ++j) gx[j] = keep[j] ? g2[j] * sc[j] * inv_keep : 0.f;
   if (q.g1) {
     float t[8];
-    bf8_to_f(*reinterpret_cast<const BF8*>(q.g1 + (((long long)b * q.H + y) * q.W + x) * q.C + c), t);
+    unpack8(r.g1, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) gx[j] += t[j];
+  }
+}
+
+// reduce over pixel lanes through shared memory, then one atomic per (channel, value): scratch[pl][cv][NV*8]
+template <int NV>
+__device__ __forceinline__ void lane_reduce_atomic(float (*acc)[8], float* scratch, int CV, int PL, int cv, int pl,
+                                                   float* out, long long out_base, int out_stride_c) {
+  float* mine = scratch + ((size_t)pl * CV + cv) * (NV * 8);
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * NV * 8; i += blockDim.x) {
+    const int cvv = i / (NV * 8), rem = i % (NV * 8);
+    const int v = rem / 8, j = rem % 8;
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += scratch[((size_t)l * CV + cvv) * (NV * 8) + rem];
+    atomicAdd(out + out_base + (long long)(cvv * 8 + j) * out_stride_c + v, s);
   }
 }
 
@@ -269,10 +344,11 @@ __device__ __forceinline__ void bwd_gx(const PrepParams& q, const ChanCst& k, in
 // grid = (slabs, B); block = CV * PL threads (thread = one 8-channel vector x one pixel lane)
 // shared memory: [8*C constants (MODE 1)] then the [PL][CV][NV*8] reduction scratch
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256, (MODE == 0 ? 4 : 2)) reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL,
-                                                           int pix_per_slab) {
+template <int MODE, bool F32>
+__global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
+    reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL, int pix_per_slab) {
   constexpr int NV = MODE == 0 ? 2 : 4;
+  constexpr int U = F32 ? 1 : (MODE == 0 ? 4 : 2);
   extern __shared__ float sm[];
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -292,67 +368,54 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 4 : 2)) reduce_bc_kernel(con
     k = load_cst(q, b, sm, false);
     scratch = sm + 8 * q.C;
   }
-  if (MODE == 0) {
-    // statistics: 4 independent pixel loads in flight per thread (memory-level parallelism)
-    for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += 4 * PL) {
-      float z[4][8], mainv[8];
+  for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
+    RawZ raw[U];
+    RawG rg[U];
+    int yy[U], xx[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int pix = pix0 + u * PL;
-        if (pix < p_end) {
-          const int y = pix / q.W, x = pix - y * q.W;
-          load_z(q, b, y, x, c, z[u], mainv);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) z[u][j] = 0.f;
-        }
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * PL;
+      yy[u] = fast_div(pix, q.w_magic);
+      xx[u] = pix - yy[u] * q.W;
+      if (pix < p_end) {
+        issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
+        if (MODE == 1) issue_g(q, b, yy[u], xx[u], c, rg[u]);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u) {
+      if (pix0 + u * PL >= p_end) break;
+      float z[8], mainv[8];
+      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          acc[0][j] += z[u][j];
-          acc[1][j] += z[u][j] * z[u][j];
+          acc[0][j] += z[j];
+          acc[1][j] += z[j] * z[j];
         }
-    }
-  }
-  for (int pix = p_begin + pl; MODE == 1 && pix < p_end; pix += PL) {
-    const int y = pix / q.W, x = pix - y * q.W;
-    float z[8], mainv[8];
-    load_z(q, b, y, x, c, z, mainv);
-    {
-      float xhat[8], xn[8], xd[8], g2[8], gx[8];
-      bool keep[8];
-      keep_for(q, b, y, x, c, keep);
-      fwd_chain(q, k, y, x, c, z, keep, xhat, xn, xd);
-      bwd_gx(q, k, b, y, x, c, keep, g2, gx);
+      } else {
+        float xhat[8], xn[8], xd[8], g2[8], gx[8];
+        bool keep[8];
+        keep_for(q, b, yy[u], xx[u], c, keep);
+        fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
+        finish_gx(q, k, rg[u], c, keep, g2, gx);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += gx[j];
-        acc[1][j] += gx[j] * xhat[j];
-        acc[2][j] += g2[j] * xd[j];
-        acc[3][j] += g2[j];
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += gx[j];
+          acc[1][j] += gx[j] * xhat[j];
+          acc[2][j] += g2[j] * xd[j];
+          acc[3][j] += g2[j];
+        }
       }
     }
   }
-  // reduce over pixel lanes through shared memory: scratch[pl][cv][v][j]
-  float* mine = scratch + ((size_t)pl * CV + cv) * (NV * 8);
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mine[v * 8 + j] = acc[v][j];
-  __syncthreads();
-  for (int i = threadIdx.x; i < CV * NV * 8; i += blockDim.x) {
-    const int cvv = i / (NV * 8), rem = i % (NV * 8);
-    const int v = rem / 8, j = rem % 8;
-    float s = 0.f;
-    for (int l = 0; l < PL; ++l) s += scratch[((size_t)l * CV + cvv) * (NV * 8) + rem];
-    atomicAdd(out + ((long long)b * q.C + cvv * 8 + j) * NV + v, s);
-  }
+  lane_reduce_atomic<NV>(acc, scratch, CV, PL, cv, pl, out, (long long)b * q.C * NV, NV);
 }
 
-__global__ void __launch_bounds__(256, 3)
+template <bool F32>
+__global__ void __launch_bounds__(256, 2)
     prep_bwd_apply_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
+  constexpr int U = F32 ? 1 : 2;
   extern __shared__ float sm[];
   int y0, ny, x0, nx;
   iter_space(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
@@ -363,36 +426,71 @@ __global__ void __launch_bounds__(256, 3)
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, true);
-  for (int pix = p_begin + pl; pix < p_end; pix += PL) {
-    const int yy = pix / nx + y0, xx = pix % nx + x0;
-    __nv_bfloat16* dm = reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy, xx, c);
-    if (yy < 0 || yy >= q.H || xx < 0 || xx >= q.W) {
-      *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    float z[8], mainv[8], g2[8], gx[8], dz[8];
-    bool keep[8];
-    load_z(q, b, yy, xx, c, z, mainv);
-    keep_for(q, b, yy, xx, c, keep);
-    bwd_gx(q, k, b, yy, xx, c, keep, g2, gx);
-    if (q.sums) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
-      float mean[8], rstd[8], g[8], m1[8], m2[8];
-      ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.m1 + c, m1); ld8f(k.m2 + c, m2);
+  float dsum[1][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xhat = (z[j] - mean[j]) * rstd[j];
-        dz[j] = rstd[j] * g[j] * (gx[j] - m1[j] - xhat * m2[j]);
+  for (int j = 0; j < 8; ++j) dsum[0][j] = 0.f;
+  for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
+    RawZ raw[U];
+    RawG rg[U];
+    int yy[U], xx[U];
+    bool ins[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = pix0 + u * PL;
+      const int row = fast_div(pix, q.nx_magic);
+      yy[u] = row + y0;
+      xx[u] = pix - row * nx + x0;
+      ins[u] = pix < p_end && yy[u] >= 0 && yy[u] < q.H && xx[u] >= 0 && xx[u] < q.W;
+      if (ins[u]) {
+        issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
+        issue_g(q, b, yy[u], xx[u], c, rg[u]);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = gx[j];
     }
-    if (q.d_add) *reinterpret_cast<BF8*>(q.d_add + (((long long)b * q.H + yy) * q.W + xx) * q.C + c) = f_to_bf8(dz);
-    if (q.relu_in) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dz[j] = mainv[j] > 0.f ? dz[j] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      if (pix0 + u * PL >= p_end) break;
+      __nv_bfloat16* dm =
+          reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy[u], xx[u], c);
+      if (!ins[u]) {
+        *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      float z[8], mainv[8], g2[8], gx[8], dz[8];
+      bool keep[8];
+      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      keep_for(q, b, yy[u], xx[u], c, keep);
+      finish_gx(q, k, rg[u], c, keep, g2, gx);
+      if (q.sums) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
+        float mean[8], rstd[8], g[8], m1[8], m2[8];
+        ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.m1 + c, m1); ld8f(k.m2 + c, m2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (z[j] - mean[j]) * rstd[j];
+          dz[j] = rstd[j] * g[j] * (gx[j] - m1[j] - xhat * m2[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = gx[j];
+      }
+      if (q.d_add)
+        *reinterpret_cast<BF8*>(q.d_add + (((long long)b * q.H + yy[u]) * q.W + xx[u]) * q.C + c) = f_to_bf8(dz);
+      if (q.relu_in) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = mainv[j] > 0.f ? dz[j] : 0.f;
+      }
+      const BF8 o = f_to_bf8(dz);
+      *reinterpret_cast<BF8*>(dm) = o;
+      if (q.dcol) {  // bias gradient of the conv that produced `main`: sums of the bf16-rounded values it will see
+        float r8[8];
+        bf8_to_f(o, r8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dsum[0][j] += r8[j];
+      }
     }
-    *reinterpret_cast<BF8*>(dm) = f_to_bf8(dz);
+  }
+  if (q.dcol) {
+    __syncthreads();  // the per-channel constants in shared memory are dead: reuse the space as reduction scratch
+    lane_reduce_atomic<1>(dsum, sm, CV, PL, cv, pl, q.dcol, 0, 1);
   }
 }
 
@@ -595,8 +693,13 @@ using namespace sb;
 static View mk_view(const sb_view* v) {
   View r;
   r.p = v->p; r.kind = v->kind; r.s = v->s; r.pad = v->pad; r.H2 = v->H2; r.W2 = v->W2;
+  r.sh = 0;
+  while ((1 << r.sh) < r.s) ++r.sh;
   return r;
 }
+static bool view_ok(const View& v) { return v.kind == 0 || (v.s >= 1 && (1 << v.sh) == v.s); }
+static uint32_t div_magic(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); }
+static int iter_nx(const View& v, int W) { return v.kind == 0 ? W : v.s * v.W2; }
 static int fill(PrepParams& q, const sb_prep_args* a) {
   if (!a || a->C % 8 || a->C < 8 || a->C / 8 > 256) return SB_ERR_ARG;
   q.B = a->B; q.H = a->H; q.W = a->W; q.C = a->C;
@@ -615,6 +718,11 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   q.bsums = a->bsums;
   q.d_main = mk_view(&a->d_main);
   q.d_add = (__nv_bfloat16*)a->d_add;
+  q.dcol = a->dcol;
+  if (!view_ok(q.in) || !view_ok(q.out2) || !view_ok(q.g2) || !view_ok(q.d_main)) return SB_ERR_ARG;
+  if (q.H > 1 && (q.W >= 300 || (long long)q.H * q.W >= (1 << 17))) return SB_ERR_ARG;  // fast_div range
+  q.w_magic = q.H > 1 ? div_magic(q.W) : 1u;  // single-row tensors (column sums of a matrix): row index is always 0
+  q.nx_magic = 0;
   if (q.sums && (!q.gamma || !q.beta)) return SB_ERR_ARG;
   if ((q.sc == nullptr) != (q.sh == nullptr)) return SB_ERR_ARG;
   return SB_OK;
@@ -640,7 +748,10 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads);
   const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
-  reduce_bc_kernel<0><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
+  if (q.in_f32 || q.add_f32)
+    reduce_bc_kernel<0, true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
+  else
+    reduce_bc_kernel<0, false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -654,7 +765,12 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
-  prep_fwd_kernel<<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
+  if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
+  q.nx_magic = div_magic(nx);
+  if (q.in_f32 || q.add_f32)
+    prep_fwd_kernel<true><<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
+  else
+    prep_fwd_kernel<false><<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -667,7 +783,10 @@ extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads);
   const size_t smem = ((size_t)threads * 4 * 8 + 8 * (size_t)q.C) * sizeof(float);
-  reduce_bc_kernel<1><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
+  if (q.in_f32 || q.add_f32)
+    reduce_bc_kernel<1, true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
+  else
+    reduce_bc_kernel<1, false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -681,7 +800,14 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
-  prep_bwd_apply_kernel<<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
+  if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
+  q.nx_magic = div_magic(nx);
+  // shared memory: 8*C per-channel constants, reused as the [PL][CV][8] scratch of the bias-gradient reduction
+  const size_t smem = (size_t)(8 * q.C > threads * 8 ? 8 * q.C : threads * 8) * sizeof(float);
+  if (q.in_f32 || q.add_f32)
+    prep_bwd_apply_kernel<true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, PL, pps);
+  else
+    prep_bwd_apply_kernel<false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, PL, pps);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

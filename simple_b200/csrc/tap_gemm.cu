@@ -55,6 +55,20 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, int rows, int k, int ld,
   return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
 }
 
+// bf16 output [B,Ho,Wo,ldo] -> 4-D map (N, Wo, Ho, B), box (32 channels, bw, bh, bb), 64B swizzle: the epilogue
+// stages 128 rows x 32 columns (64-byte rows) in shared memory and TMA-stores them (full-line writes, OOB clipped).
+static int make_map_out(CUtensorMap* m, const void* ptr, int B, int H, int W, int N, int ld, int bw, int bh, int bb) {
+  if (((uintptr_t)ptr & 15) || (ld % 8)) return SB_ERR_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
+}
+
 struct TapGemmDev {
   int B, Ho, Wo;
   int bw, bh, bb, rows;
@@ -67,11 +81,14 @@ struct TapGemmDev {
   int out_f32, ldo;
   const float* bias;
   int relu, atomic;
+  int tma_out;  // bf16 output through the shared-memory staged TMA store path
 };
 
 constexpr int kGemmThreads = 192;        // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kFwdThreads = 320;         // tap GEMM: TMA warp, MMA warp, 8 epilogue warps
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 bf16
+constexpr int kStageOutBytes = 128 * 64;  // epilogue staging buffer: 128 rows x 32 bf16
+constexpr int kOutBufs = 4;               // 2 column halves x double buffering
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -84,14 +101,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kFwdThreads, 1)
     tap_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ TapGemmDev p) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmDev p) {
   constexpr int B_BYTES = BN * 128;
   constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kATileBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* sO = sB + STAGES * B_BYTES;  // [kOutBufs][128 rows][64 B], 64B-swizzled
+  uint64_t* full = reinterpret_cast<uint64_t*>(sO + kOutBufs * kStageOutBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
   uint64_t* tempty = tfull + 2;       // [2] accumulator drained
@@ -183,64 +201,122 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const int half = e >> 2;         // interleaved 32-column chunks: half 0 takes chunks 0,2,4.., half 1 takes 1,3,5..
     const int r = lg * 32 + lane;
     const int xl = r % p.bw, yl = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
+    const bool issuer = ((e & 3) == 0) && lane == 0;  // one TMA-store issuing thread per column half
+    const uint32_t bar_id = 1u + (uint32_t)half;       // named barrier of the 4 warps (128 threads) of this half
+    uint32_t ochunk = 0;                                // staged chunks so far (staging-buffer parity)
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % p.n_tiles;
       const int mt = (tile / p.n_tiles) % p.m_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.bw + xl, y = ty * p.bh + yl, b = tb * p.bb + bl, n0 = nt * BN;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+      const int x = x0 + xl, y = y0 + yl, b = b0 + bl, n0 = nt * BN;
       const bool valid = (r < p.rows) && (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
       const int as = tcount & 1;
       const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+      if (p.tma_out) {
+        // bf16 output: TMEM -> registers -> (bias, ReLU, bf16) -> 64B-swizzled staging tile -> TMA store.
+        // Every output line is written in full 64-byte rows by the TMA engine instead of 16-byte scattered stores.
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
-        if (n0 + c >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        float f[32];
+        for (int c = half * 32; c < BN; c += 64) {
+          if (n0 + c >= p.N) break;  // uniform over the 128 threads of this half
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
+          if (issuer) bulk_wait_read<1>();  // the store that used this staging buffer two chunks ago has drained
+          tmem_ld_wait();
+          const int nb = n0 + c;
+          float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int nb = n0 + c;
-        if (p.atomic) {
-          float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (nb + j < p.N) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (p.out_f32) {
+          named_bar_sync(bar_id, 128);  // staging buffer is free (issuer waited above)
+          uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOutBytes;
+          if (r < p.rows) {
+            uint8_t* row = buf + r * 64;
+            const int sw = (r >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0);
+              pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2);
+              pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = pk;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);  // all 128 rows staged
+          if (issuer) {
+            tma_store_4d(&tmO, buf, nb, x0, y0, b0);
+            bulk_commit();
+          }
+          ++ochunk;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = half * 32; c < BN; c += 64) {
+          if (n0 + c >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
+          tmem_ld_wait();
+          if (!valid) continue;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const int nb = n0 + c;
+          if (p.atomic) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              if (nb + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (nb + j < p.N) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + nb;
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (nb + j < p.N) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (nb + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + nb;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (nb + j < p.N) {
+                  uint4 pk;
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                  __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                  __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                  *reinterpret_cast<uint4*>(o + j) = pk;
+                }
               }
             }
           }
@@ -251,6 +327,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
+    if (issuer) bulk_wait_all();  // staged tiles must be read out before the CTA (and its shared memory) retires
   }
   tc_fence_before();
   __syncthreads();
@@ -258,8 +335,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 }
 
 template <int BN, int STAGES>
-static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmDev& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kATileBytes + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
+static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TapGemmDev& p,
+                           cudaStream_t stream) {
+  constexpr int smem = STAGES * (kATileBytes + BN * 128) + kOutBufs * kStageOutBytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "tap_gemm_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tap_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -269,7 +348,7 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < 148 ? total : 148;
-  tap_gemm_kernel<BN, STAGES><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, p);
+  tap_gemm_kernel<BN, STAGES><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -461,18 +540,25 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   else if (a->N % 128 == 0) BN = 128;
   else if (a->N <= 96) BN = 96;
   else BN = 128;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
   rc = make_map_nhwc(&tmA, a->a, a->B, a->H, a->W, a->C, a->bw, a->bh, a->bb);
   if (rc) return rc;
   rc = make_map_2d(&tmB, a->w, a->N, a->ntaps * a->C, a->ldw, BN);
   if (rc) return rc;
+  p.tma_out = (!atomic && !a->out_f32 && a->N % 32 == 0) ? 1 : 0;
+  if (p.tma_out) {
+    rc = make_map_out(&tmO, a->out, a->B, a->Ho, a->Wo, a->N, a->ldo, a->bw, a->bh, a->bb);
+    if (rc) return rc;
+  } else {
+    tmO = tmA;  // unused
+  }
   p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
   p.n_tiles = (a->N + BN - 1) / BN;
   switch (BN) {
-    case 256: return launch_tap_gemm<256, 4>(tmA, tmB, p, stream);
-    case 192: return launch_tap_gemm<192, 5>(tmA, tmB, p, stream);
-    case 128: return launch_tap_gemm<128, 6>(tmA, tmB, p, stream);
-    default: return launch_tap_gemm<96, 6>(tmA, tmB, p, stream);
+    case 256: return launch_tap_gemm<256, 4>(tmA, tmB, tmO, p, stream);
+    case 192: return launch_tap_gemm<192, 4>(tmA, tmB, tmO, p, stream);
+    case 128: return launch_tap_gemm<128, 6>(tmA, tmB, tmO, p, stream);
+    default: return launch_tap_gemm<96, 6>(tmA, tmB, tmO, p, stream);
   }
 }
 

@@ -404,6 +404,10 @@ class NextFramePredictor(nn.Module):
                                     flops=2.0 * Hi * Wi * Ci * Co * 16))
             shape = ds[i]
         P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False, flops=2.0 * HW * 768 * 96)
+        P['logits'].dbias_src = self.logits_dbias = {}
+        # convs whose output has exactly one consumer, a fused prep stage: that stage's backward emits their bias grad
+        for sp in [P['embed'], P['s_embed'], P['mid'][1]] + P['down'] + P['up']:
+            sp.dbias_src = {}
         # posterior encoder of the stochastic model (train only)
         P['s_embed'] = ConvSpec('s_embed', H, W, 64, H, W, 96, [(0, 0)], relu=False, need_dgrad=False,
                                 flops=2.0 * HW * 96 * 15)
@@ -517,11 +521,12 @@ class NextFramePredictor(nn.Module):
             nrm = self.downscale_layers[2 * i - 1] if i > 0 else None
             km = keep((B, sp.C, sp.H, sp.W), sp.p)
             skip, A = fused_prep(sp, main, gamma=nrm.weight if nrm is not None else None,
-                                 beta=nrm.bias if nrm is not None else None, seed=seed, keep=km)
+                                 beta=nrm.bias if nrm is not None else None, seed=seed, keep=km,
+                                 dbias_dst=(P['embed'] if i == 0 else P['down'][i - 1]).dbias_src)
             skips.append(skip)
             main = self._conv(f'down{i}', P['down'][i], A)
         nrm = self.downscale_layers[9]
-        _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias)
+        _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias, dbias_dst=P['down'][4].dbias_src)
         # ---- bottleneck heads and latent (tiny tensors; fp32, NCHW semantics of the reference)
         h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
         value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
@@ -556,11 +561,13 @@ class NextFramePredictor(nn.Module):
             sp = P['prep_dec'][i]
             sc, sh = self.action_injectors[i + 1].scale_shift(action)
             km = keep((B, sp.C, sp.H, sp.W), sp.p)
-            _, A = fused_prep(sp, main, add=add, gamma=nrm.weight, beta=nrm.bias, sc=sc, sh=sh, seed=seed, keep=km)
+            _, A = fused_prep(sp, main, add=add, gamma=nrm.weight, beta=nrm.bias, sc=sc, sh=sh, seed=seed, keep=km,
+                              dbias_dst=(P['mid'][1] if i == 0 else P['up'][i - 1]).dbias_src)
             main = self._conv(f'up{i}', P['up'][i], A)
             add = skips[4 - i]
             nrm = self.upscale_layers[2 * i + 1]
-        _, hf = fused_prep(P['prep_final'], main, add=add, gamma=nrm.weight, beta=nrm.bias)
+        _, hf = fused_prep(P['prep_final'], main, add=add, gamma=nrm.weight, beta=nrm.bias,
+                           dbias_dst=P['up'][4].dbias_src)
         # x_fin = mean_hw(IN(z)*gamma + beta + timing) == beta + mean_hw(timing): the normalised part has zero mean
         x_fin = (nrm.bias + P['tmean10']).unsqueeze(0).expand(B, -1)
         reward_pred = self.reward_estimator(torch.cat((x_mid, x_fin), dim=1))
@@ -575,7 +582,7 @@ class NextFramePredictor(nn.Module):
         B = layer.shape[0]
         e = self._conv('s_embed', P['s_embed'], ps)
         sc, sh = sm.action_injector.scale_shift(action)
-        _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh)
+        _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh, dbias_dst=P['s_embed'].dbias_src)
         c1 = self._conv('s_conv1', P['s_conv1'], A)  # [B,26,20,128], pre-ReLU
         x1 = sm.mean_attentions[0](c1.float().permute(0, 3, 1, 2).contiguous())
         _, A = fused_prep(P['prep_s1'], c1)
@@ -626,6 +633,7 @@ class NextFramePredictor(nn.Module):
         elif self._auto_repack:
             self.repack()
         self._weights_cache = self._weights()
+        self.logits_dbias.clear()
         self.commit_state()
         if self._seed_dev is None or self._seed_dev.device != dev:
             # derived from torch.manual_seed() without consuming the global generator

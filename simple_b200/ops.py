@@ -119,7 +119,7 @@ class FusedPrep(torch.autograd.Function):
     """z = relu?(main)+add; x = IN(z)*gamma+beta + Ta; out1 = x; out2 = (dropout(x)+Tb)*sc + sh, with layout change."""
 
     @staticmethod
-    def forward(ctx, spec, main, add, gamma, beta, sc, sh, seed, keep):
+    def forward(ctx, spec, main, add, gamma, beta, sc, sh, seed, keep, dbias_dst=None):
         B = main.shape[0]
         dev = main.device
         sums = stats_raw(spec, main, add) if spec.norm else None
@@ -131,7 +131,7 @@ class FusedPrep(torch.autograd.Function):
         out2 = torch.empty(spec.lay_out.shape(B), device=dev, dtype=torch.bfloat16)
         a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, out1, out2, seed, keep)
         _lib.check(_lib.lib().sb_prep(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep')
-        ctx.spec, ctx.seed = spec, seed
+        ctx.spec, ctx.seed, ctx.dbias_dst = spec, seed, dbias_dst
         ctx.save_for_backward(main, add, sums, gamma_f, beta_f, sc_f, sh_f, keep)
         ctx.has = (add is not None, gamma is not None, sc is not None)
         if out1 is None:
@@ -165,16 +165,24 @@ class FusedPrep(torch.autograd.Function):
         d_add = torch.empty(add.shape, device=dev, dtype=torch.bfloat16) if has_add else None
         a.d_main = spec.lay_in.view(d_main)
         a.d_add = _ptr(d_add)
+        dcol = None
+        if ctx.dbias_dst is not None:  # bias gradient of the conv that produced `main`, fused into this pass
+            dcol = torch.zeros(spec.C, device=dev, dtype=torch.float32)
+            a.dcol = dcol.data_ptr()
         _lib.check(_lib.lib().sb_prep_bwd_apply(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_apply')
+        if dcol is not None:
+            ctx.dbias_dst['dbias'] = dcol
         dgamma = bsums[:, :, 1].sum(0) if has_norm else None
         dbeta = bsums[:, :, 0].sum(0) if has_norm else None
         dsc = bsums[:, :, 2].contiguous() if has_inj else None
         dsh = bsums[:, :, 3].contiguous() if has_inj else None
-        return None, d_main, d_add, dgamma, dbeta, dsc, dsh, None, None
+        return None, d_main, d_add, dgamma, dbeta, dsc, dsh, None, None, None
 
 
-def fused_prep(spec, main, add=None, gamma=None, beta=None, sc=None, sh=None, seed=0, keep=None):
-    out1, out2 = FusedPrep.apply(spec, main, add, gamma, beta, sc, sh, seed, keep)
+def fused_prep(spec, main, add=None, gamma=None, beta=None, sc=None, sh=None, seed=0, keep=None, dbias_dst=None):
+    """`dbias_dst`: the `dbias_src` dict of the ConvSpec that produced `main` when this stage is the ONLY consumer of
+    that output: its backward then also emits the conv's bias gradient (column sums of d_main)."""
+    out1, out2 = FusedPrep.apply(spec, main, add, gamma, beta, sc, sh, seed, keep, dbias_dst)
     return (out1 if spec.want_out1 else None), out2
 
 
@@ -202,6 +210,9 @@ class ConvSpec:
         # fused elementwise stage that consumed the output; a residual branch bypasses that stage)
         self.bwd_mask = bwd_mask
         self.neg_taps = [(-dy, -dx) for dy, dx in taps]
+        # optional side channel {'dbias': tensor}: a fused consumer of the output (PixelCE) already produced the
+        # column sums of the incoming gradient, so backward skips its own pass over dy
+        self.dbias_src = None
 
 
 class PackedWeight:
@@ -302,8 +313,9 @@ class TapConv(torch.autograd.Function):
         dweight = pw.unpack_grad(dwp)
         dbias = None
         if ctx.has_bias:
+            ext = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
             # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
-            dbias = colsum(dy.reshape(-1, spec.N // spec.bias_tile))
+            dbias = ext if ext is not None else colsum(dy.reshape(-1, spec.N // spec.bias_tile))
             if pw.operm is not None:
                 dbias = dbias[pw.operm.long()]
         return None, da, dweight, dbias, None
@@ -385,7 +397,7 @@ class PixelCE(torch.autograd.Function):
     produced in the same pass and overwrites the logits buffer."""
 
     @staticmethod
-    def forward(ctx, logits, target_u8, clip, want_argmax, unit_grad):
+    def forward(ctx, logits, target_u8, clip, want_argmax, unit_grad, dbias_dst=None):
         B, H, W, _ = logits.shape
         HW = H * W
         loss_sum = torch.zeros(1, device=logits.device, dtype=torch.float64)
@@ -402,6 +414,8 @@ class PixelCE(torch.autograd.Function):
             rec.stop('pixel_ce_kernel', 'train', B * HW * (768 * 2 * 2 + 3 + 3), 'byte', ev0)
         ctx.save_for_backward(dl)
         ctx.unit_grad = unit_grad
+        if dbias_dst is not None and unit_grad:  # column sums of the gradient, for the logits conv's bias
+            dbias_dst['dbias'] = dbias
         loss = (loss_sum / n - clip).float().reshape(())
         if amax is None:
             amax = torch.empty(0, device=logits.device, dtype=torch.uint8)
@@ -413,8 +427,8 @@ class PixelCE(torch.autograd.Function):
         (dl,) = ctx.saved_tensors
         # the training loss enters the total with weight 1 (trainer.py:141); honour other weights generically
         if ctx.unit_grad:  # caller guarantees d(total)/d(loss) == 1: skip a full pass over the gradient
-            return dl, None, None, None, None
-        return dl * gloss.to(dl.dtype), None, None, None, None
+            return dl, None, None, None, None, None
+        return dl * gloss.to(dl.dtype), None, None, None, None, None
 
 
 def pixel_argmax(logits):

@@ -28,7 +28,7 @@ def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsi
         B, H, W, _ = logits.shape
         out['logits_ref'] = logits.detach().reshape(B, H, W, 3, 256).permute(0, 4, 3, 1, 2).float().clone()
     loss_reconstruct, argmax = ops.PixelCE.apply(logits, new_states_u8.contiguous(), float(config.target_loss_clipping),
-                                                 True, True)
+                                                 True, True, getattr(model, 'logits_dbias', None))
     loss_value = F.mse_loss(value_pred, values)
     loss_reward = F.cross_entropy(reward_pred, rewards)
     loss = loss_reconstruct + loss_value + loss_reward
