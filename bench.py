@@ -221,7 +221,8 @@ def run_own(args):
     starts = torch.arange(B, device=dev)
     replay = dict(obs=data['obs'], new_obs=data['new_obs'], action=data['action'].float(), reward=data['reward'].long(),
                   value=data['value'])
-    use_graph = not args.no_graph and world == 1
+    # the NCCL all-reduce of the data-parallel step is captured into the step graph as well (SB_DP_GRAPH=0: eager)
+    use_graph = not args.no_graph and (world == 1 or os.environ.get('SB_DP_GRAPH', '1') != '0')
     runner = StepRunner(trainer, replay, B, use_graph=use_graph, resident=True)
     runner_host = StepRunner(trainer, replay, B, use_graph=use_graph, resident=False)
     pinned['action_f'] = host['action'].float().pin_memory()

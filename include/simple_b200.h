@@ -156,6 +156,9 @@ int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs
 /* fp32 (O,I,KH,KW) master weight -> bf16 GEMM operands (see DESIGN.md "weight packing"). */
 int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,
                  const int* operm, void* fwd, void* tr, sb_stream_t stream);
+/* tr[:, t*Opad:(t+1)*Opad] = fwd[:, t*PHI:(t+1)*PHI]^T per tap (the second half of sb_pack_conv, for operands whose
+ * `fwd` was refreshed in place by sb_adafactor_conv_packed).  PHI = s*s*Ipad. */
+int sb_transpose_taps(const void* fwd, void* tr, int Opad, int PHI, int T, sb_stream_t stream);
 /* inverse map for gradients: fp32 packed [Opad, T*s*s*Ipad] (layout of `fwd`) -> reference layout (O,I,KH,KW). */
 int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s, int Ipad, int Opad,
                         const int* iperm, const int* operm, float* out, sb_stream_t stream);
@@ -166,7 +169,7 @@ int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s
  * Replaces: simple/trainer.py:148 and simple/adafactor.py:113-212 (K16, K17).
  * Descriptors and block maps live in DEVICE memory (built by the host wrapper each step; one small H2D copy).
  *   sb_grad_sumsq:      block_map[i] = (tensor, first 4096-element chunk); *total += sum g^2  (caller zeroes total)
- *   sb_adafactor_conv:  4-D weights (O,I,KH,KW) of one kernel size; block_map[i] = (tensor, first patch), 128 patches
+ *   sb_adafactor_conv:  4-D weights (O,I,KH,KW) of one kernel size; block_map[i] = (descriptor index, first patch), 128 patches
  *                       per block; pass 1 updates row/col states and acc[0]=sum u^2, acc[1]=sum p^2 (caller zeroes
  *                       acc), pass 2 applies the update.  g is scaled by min(1, max_norm/(sqrt(total)+1e-6)).
  *   sb_adafactor_small: 1-D (cols==0, state in `row`) and 2-D tensors, one CTA per descriptor.
@@ -183,15 +186,30 @@ typedef struct {
   int rows, cols;  /* 2-D: shape; 1-D: cols = 0; 4-D: unused */
   float* stepf;    /* DEVICE step counter of this tensor (float); beta2 = 1 - step^-0.8, rel_step = min(1e-2, step^-1/2) */
 } sb_tensor_desc;
+/* Packed-layout companion of a 4-D weight's descriptor (sb_adafactor_conv_packed): the gradient is read from the fp32
+ * buffer sb_tap_wgrad accumulated into (layout of sb_pack_conv's `fwd`) and pass 2 also rewrites the bf16 operand. */
+typedef struct {
+  const float* gpacked; /* fp32 [Opad, T*s*s*Ipad] */
+  void* fwd;            /* bf16, same layout */
+  const int* iperm;     /* or NULL */
+  const int* operm;     /* or NULL */
+  int O, I, s, Ipad, Opad;
+  int pad_[3];
+} sb_pack_desc;         /* 64 bytes */
 /* step counters += 1 for every descriptor (first call of a step; keeps CUDA-graph replays self-contained) */
 int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, sb_stream_t stream);
-int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
-                  sb_stream_t stream);
+/* glen_dev: optional per-descriptor gradient length (a packed gradient buffer is longer than its parameter) */
+int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev, int nblocks,
+                  float* total, sb_stream_t stream);
 int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
                       const float* total_sumsq, float max_norm, int pass, sb_stream_t stream);
-int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
+int sb_adafactor_conv_packed(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev, const int* block_map_dev,
+                             int nblocks, int KH, int KW, const float* total_sumsq, float max_norm, int pass,
+                             sb_stream_t stream);
+/* index_dev: optional list of descriptor indices handled by this launch (NULL = descriptors 0..ntensors-1) */
+int sb_adafactor_small(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors, int max_rows_plus_cols,
                        const float* total_sumsq, float max_norm, sb_stream_t stream);
-int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, int ntensors, int max_cols, int max_rows,
+int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors, int max_cols, int max_rows,
                        const float* total_sumsq, float max_norm, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -206,6 +224,18 @@ int sb_lstm_sample(const float* x0, const float* h0, const float* c0, const floa
                    const float* b_ih, const float* b_hh, const float* w5, const float* b5, const float* w4,
                    const float* b4, const float* noise, const unsigned long long* seed_ptr, int B, float* bits,
                    int* ints, sb_stream_t stream);
+/* Second-generation latent-bit kernels: transposed weights (whhT [128,512] = W_hh^T, w5T [128,256] = W5^T), input-gate
+ * pre-activations by table lookup (E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh; G0 [B,512] for the first step), one
+ * or two samples per CTA.  sb_lstm_teacher_fwd/bwd run all 16 teacher-forced LSTMCell steps and their backward through
+ * time in one launch each: xw [B,16,512] input-gate pre-activations -> hs [B,16,128]; saved act [B,16,512], cs [B,16,128];
+ * backward emits dpre [B,16,512] (= d xw; dW_hh = dpre^T h_prev on the host side), dh0, dc0 [B,128]. */
+int sb_lstm_sample2(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
+                    const float* w5T, const float* b5, const float* noise, const unsigned long long* seed_ptr, int B,
+                    float* bits, int* ints, sb_stream_t stream);
+int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B, float* hs,
+                        float* act, float* cs, sb_stream_t stream);
+int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, const float* c0, const float* whh, int B,
+                        float* dpre, float* dh0, float* dc0, sb_stream_t stream);
 int sb_lstm_cell_fwd(const float* pre, const float* c_prev, float* act, float* c, float* h, int B, sb_stream_t stream);
 int sb_lstm_cell_bwd(const float* act, const float* c_prev, const float* c, const float* dh, const float* dc,
                      float* dpre, float* dc_prev, int B, sb_stream_t stream);

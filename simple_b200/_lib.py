@@ -111,12 +111,17 @@ class _Sigs:
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_lstm_sample = [_p] * 13 + [_i, _p, _p, _p]
     sb_lstm_cell_fwd = [_p, _p, _p, _p, _p, _i, _p]
+    sb_lstm_sample2 = [_p] * 9 + [_i, _p, _p, _p]
+    sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
+    sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
     sb_lstm_cell_bwd = [_p, _p, _p, _p, _p, _p, _p, _i, _p]
-    sb_grad_sumsq = [_p, _p, _i, _p, _p]
+    sb_grad_sumsq = [_p, _p, _p, _i, _p, _p]
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]
-    sb_adafactor_small = [_p, _i, _i, _p, _f, _p]
-    sb_adafactor_big2d = [_p, _i, _i, _i, _p, _f, _p]
+    sb_adafactor_small = [_p, _p, _i, _i, _p, _f, _p]
+    sb_adafactor_conv_packed = [_p, _p, _p, _i, _i, _i, _p, _f, _i, _p]
+    sb_transpose_taps = [_p, _p, _i, _i, _i, _p]
+    sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
 
 
 EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version'] + [n for n in dir(_Sigs) if n.startswith('sb_')]

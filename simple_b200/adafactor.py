@@ -17,6 +17,10 @@ from . import _lib
 _DESC = np.dtype([('p', np.uint64), ('g', np.uint64), ('row', np.uint64), ('col', np.uint64), ('acc', np.uint64),
                   ('n', np.int64), ('rows', np.int32), ('cols', np.int32), ('stepf', np.uint64)])
 assert _DESC.itemsize == 64
+_PACK = np.dtype([('gpacked', np.uint64), ('fwd', np.uint64), ('iperm', np.uint64), ('operm', np.uint64),
+                  ('O', np.int32), ('I', np.int32), ('s', np.int32), ('Ipad', np.int32), ('Opad', np.int32),
+                  ('pad_', np.int32, (3,))])
+assert _PACK.itemsize == 64
 
 
 class Adafactor(torch.optim.Optimizer):
@@ -51,15 +55,22 @@ class Adafactor(torch.optim.Optimizer):
         return st
 
     @torch.no_grad()
-    def step(self, closure=None, max_grad_norm=None, grads=None):
+    def step(self, closure=None, max_grad_norm=None, grads=None, packed=None):
         """One optimisation step.  `max_grad_norm` fuses torch.nn.utils.clip_grad_norm_(params, max_grad_norm) in
         front (simple/trainer.py:148); `grads` optionally maps parameters to externally held gradient tensors
-        (e.g. views of an all-reduced flat buffer) instead of `p.grad`."""
+        (e.g. views of an all-reduced flat buffer) instead of `p.grad`; `packed` optionally maps 4-D parameters to
+        their `ops.PackedWeight`: their gradient is then read in the packed GEMM-operand layout (`pw.gpacked`, or
+        `grads[p]` holding a tensor of that layout) and the bf16 operands are refreshed by the update itself."""
         loss = closure() if closure is not None else None
         active = []
         for group in self.param_groups:
             for p in group['params']:
-                g = grads.get(p) if grads is not None else p.grad
+                pw = packed.get(p) if packed is not None else None
+                g = grads.get(p) if grads is not None else None
+                if g is None:
+                    g = pw.gpacked if pw is not None and pw.gpacked is not None else (p.grad if grads is None else None)
+                if pw is not None and (g is None or g.dim() != 2):
+                    pw = None  # reference-layout gradient: plain path
                 if g is None:
                     continue  # adafactor.py:125-126 -- e.g. gate.* on the first step of a rollout window
                 if not p.is_cuda:
@@ -68,28 +79,33 @@ class Adafactor(torch.optim.Optimizer):
                     raise RuntimeError('unsupported parameter for the fused Adafactor')
                 if not g.is_contiguous():
                     g = g.contiguous()
-                    if grads is None:
+                    if grads is None and pw is None:
                         p.grad = g
                 assert p.is_contiguous()
-                active.append((p, g))
+                active.append((p, g, pw))
         if not active:
             return loss
         dev = active[0][0].device
         n = len(active)
-        key = tuple(id(p) for p, _ in active)
+        key = tuple((id(p), pw is not None) for p, _, pw in active)
         rec = self._cache.get(key)
         if rec is None:
             # per parameter-set record: pinned host descriptors (CUDA-graph replays re-read them), device copies,
             # accumulators and block maps.  Two sets exist in practice: with and without gate.* (first step of a window).
-            host = torch.zeros(n * 64, dtype=torch.uint8)
-            rec = dict(host=host, np=host.numpy().view(_DESC), dev=torch.zeros(n * 64, dtype=torch.uint8, device=dev),
+            # host layout: [n x sb_tensor_desc (64 B)] [n x sb_pack_desc (64 B)] [n x int64 gradient length]
+            nbytes = n * (64 + 64 + 8)
+            host = torch.zeros(nbytes, dtype=torch.uint8)
+            hn = host.numpy()
+            rec = dict(host=host, np=hn[:n * 64].view(_DESC), packs=hn[n * 64:n * 128].view(_PACK),
+                       glen=hn[n * 128:].view(np.int64), dev=torch.zeros(nbytes, dtype=torch.uint8, device=dev),
                        acc=torch.zeros(n, 2, device=dev, dtype=torch.float32),
                        total=torch.zeros(1, device=dev, dtype=torch.float32), maps=self._build_maps(active, dev),
-                       params=[p for p, _ in active], pin=torch.zeros(n * 64, dtype=torch.uint8).pin_memory())
+                       params=[p for p, _, _ in active], pin=torch.zeros(nbytes, dtype=torch.uint8).pin_memory(),
+                       any_packed=any(pw is not None for _, _, pw in active))
             self._cache[key] = rec
-        descs = rec['np']
+        descs, packs, glen = rec['np'], rec['packs'], rec['glen']
         acc, total = rec['acc'], rec['total']
-        for i, (p, g) in enumerate(active):
+        for i, (p, g, pw) in enumerate(active):
             st = self._init_state(p)
             st['step'] += 1
             d = descs[i]
@@ -102,8 +118,19 @@ class Adafactor(torch.optim.Optimizer):
             d['n'] = p.numel()
             d['rows'], d['cols'] = (p.shape[0], p.shape[1]) if p.dim() == 2 else (0, 0)
             d['stepf'] = st['step_dev'].data_ptr()
+            glen[i] = g.numel()
+            if pw is not None:
+                assert tuple(g.shape) == tuple(pw.fwd.shape)
+                k = packs[i]
+                k['gpacked'], k['fwd'] = g.data_ptr(), pw.fwd.data_ptr()
+                k['iperm'] = pw.iperm.data_ptr() if pw.iperm is not None else 0
+                k['operm'] = pw.operm.data_ptr() if pw.operm is not None else 0
+                k['O'], k['I'], k['s'], k['Ipad'], k['Opad'] = pw.O, pw.I, pw.s, pw.Ipad, pw.Opad
             st['RMS'] = _LazyRMS(acc, i, p.numel())
         self._launch(rec, n, max_grad_norm)
+        for _, _, pw in active:
+            if pw is not None:
+                pw.refresh_transposed()  # `fwd` was rewritten by the update: re-derive the per-tap transpose
         self.last_key = key
         return loss
 
@@ -114,53 +141,58 @@ class Adafactor(torch.optim.Optimizer):
             self.state[p]['step'] += 1
 
     def _launch(self, rec, n, max_grad_norm):
-        maps, acc, total, descs_dev = rec['maps'], rec['acc'], rec['total'], rec['dev']
+        maps, acc, total, dev_buf = rec['maps'], rec['acc'], rec['total'], rec['dev']
         # Descriptors hold pointers only.  Pageable source => the copy is synchronous w.r.t. the host buffer, so the next
         # step may rewrite it; under CUDA-graph capture the pointers are static and the device copy is already valid.
         if torch.cuda.is_current_stream_capturing():
             # gradients allocated during capture live at graph-private addresses: upload them through a pinned staging
             # buffer whose content never changes afterwards (every replay re-issues the same small copy)
             rec['pin'].copy_(rec['host'])
-            descs_dev.copy_(rec['pin'], non_blocking=True)
+            dev_buf.copy_(rec['pin'], non_blocking=True)
         else:
-            descs_dev.copy_(rec['host'])
+            dev_buf.copy_(rec['host'])
         acc.zero_()
         total.zero_()
         L = _lib.lib()
         s = _lib.stream_ptr()
-        _lib.check(L.sb_adafactor_tick(descs_dev.data_ptr(), n, s), 'sb_adafactor_tick')
+        descs_ptr = dev_buf.data_ptr()
+        packs_ptr = descs_ptr + n * 64
+        glen_ptr = descs_ptr + n * 128
+        _lib.check(L.sb_adafactor_tick(descs_ptr, n, s), 'sb_adafactor_tick')
         mn = float(max_grad_norm) if max_grad_norm is not None else 0.0
-        _lib.check(L.sb_grad_sumsq(descs_dev.data_ptr(), maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
+        _lib.check(L.sb_grad_sumsq(descs_ptr, glen_ptr, maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
                                    total.data_ptr(), s), 'sb_grad_sumsq')
-        for (kh, kw), (idx, bm) in maps['conv'].items():
-            sub = descs_dev.view(n, 64)[idx].contiguous()
+        for (kh, kw, is_packed), bm in maps['conv'].items():
             for pas in (1, 2):
-                _lib.check(L.sb_adafactor_conv(sub.data_ptr(), bm.data_ptr(), bm.shape[0], kh, kw, total.data_ptr(), mn,
-                                               pas, s), 'sb_adafactor_conv')
+                if is_packed:
+                    _lib.check(L.sb_adafactor_conv_packed(descs_ptr, packs_ptr, bm.data_ptr(), bm.shape[0], kh, kw,
+                                                          total.data_ptr(), mn, pas, s), 'sb_adafactor_conv_packed')
+                else:
+                    _lib.check(L.sb_adafactor_conv(descs_ptr, bm.data_ptr(), bm.shape[0], kh, kw, total.data_ptr(), mn,
+                                                   pas, s), 'sb_adafactor_conv')
         if maps['big2d'] is not None:
             idx, mc, mr = maps['big2d']
-            sub = descs_dev.view(n, 64)[idx].contiguous()
-            _lib.check(L.sb_adafactor_big2d(sub.data_ptr(), idx.numel(), mc, mr, total.data_ptr(), mn, s),
+            _lib.check(L.sb_adafactor_big2d(descs_ptr, idx.data_ptr(), idx.numel(), mc, mr, total.data_ptr(), mn, s),
                        'sb_adafactor_big2d')
         if maps['small'] is not None:
             idx, rc = maps['small']
-            sub = descs_dev.view(n, 64)[idx].contiguous()
-            _lib.check(L.sb_adafactor_small(sub.data_ptr(), idx.numel(), rc, total.data_ptr(), mn, s),
+            _lib.check(L.sb_adafactor_small(descs_ptr, idx.data_ptr(), idx.numel(), rc, total.data_ptr(), mn, s),
                        'sb_adafactor_small')
         self.grad_norm_sq = total
 
     @staticmethod
     def _build_maps(active, dev):
+        """Launch geometry of one parameter set.  Every map refers to descriptors by their index in `active`."""
         sumsq = []
         conv = {}
         small = []
         big = []
         rc = 1
-        for i, (p, _) in enumerate(active):
-            nchunks = -(-p.numel() // 4096)
+        for i, (p, g, pw) in enumerate(active):
+            nchunks = -(-g.numel() // 4096)
             sumsq += [(i, c) for c in range(nchunks)]
             if p.dim() == 4:
-                conv.setdefault((p.shape[2], p.shape[3]), []).append(i)
+                conv.setdefault((p.shape[2], p.shape[3], pw is not None), []).append(i)
             elif p.dim() == 2 and p.numel() >= 49152 and p.shape[0] >= 8:
                 big.append(i)  # one 8-CTA cluster per tensor instead of a single CTA
             else:
@@ -169,17 +201,16 @@ class Adafactor(torch.optim.Optimizer):
                     rc = max(rc, p.shape[0] + p.shape[1])
         maps = {'sumsq': torch.tensor(sumsq, dtype=torch.int32, device=dev), 'conv': {}, 'small': None, 'big2d': None}
         if big:
-            maps['big2d'] = (torch.tensor(big, dtype=torch.long, device=dev), max(active[i][0].shape[1] for i in big),
-                             max(active[i][0].shape[0] for i in big))
+            maps['big2d'] = (torch.tensor(big, dtype=torch.int32, device=dev),
+                             max(active[i][0].shape[1] for i in big), max(active[i][0].shape[0] for i in big))
         for k, idxs in conv.items():
             bm = []
-            for local, i in enumerate(idxs):
+            for i in idxs:
                 npatch = active[i][0].numel() // (k[0] * k[1])
-                bm += [(local, b * 128) for b in range(-(-npatch // 128))]
-            maps['conv'][k] = (torch.tensor(idxs, dtype=torch.long, device=dev),
-                               torch.tensor(bm, dtype=torch.int32, device=dev))
+                bm += [(i, b * 128) for b in range(-(-npatch // 128))]
+            maps['conv'][k] = torch.tensor(bm, dtype=torch.int32, device=dev)
         if small:
-            maps['small'] = (torch.tensor(small, dtype=torch.long, device=dev), rc)
+            maps['small'] = (torch.tensor(small, dtype=torch.int32, device=dev), rc)
         return maps
 
 

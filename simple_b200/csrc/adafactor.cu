@@ -35,12 +35,14 @@ __device__ __forceinline__ float clip_coef(const float* total_sumsq, float max_n
 
 // ---- 1. global gradient norm ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const int2* __restrict__ block_map, float* total) {
+    grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const long long* __restrict__ glen,
+                      const int2* __restrict__ block_map, float* total) {
   __shared__ float red[8];
   const int2 bm = block_map[blockIdx.x];  // (tensor, first element)
   const sb_tensor_desc d = descs[bm.x];
+  const long long n = glen ? glen[bm.x] : d.n;  // a packed gradient buffer is longer than its parameter (zero padding)
   const long long begin = (long long)bm.y * 4096;
-  const long long end = begin + 4096 < d.n ? begin + 4096 : d.n;
+  const long long end = begin + 4096 < n ? begin + 4096 : n;
   float s = 0.f;
   for (long long i = begin + threadIdx.x; i < end; i += 256) {
     const float g = d.g[i];
@@ -51,10 +53,21 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- 2. conv-type weights ---------------------------------------------------------------------------------------
-template <int KH, int KW, int PASS>
+// PACKED: the gradient is read straight from the packed fp32 buffer the wgrad kernel accumulated into (layout of the
+// bf16 GEMM operand `fwd`, see sb_pack_conv) and pass 2 also refreshes that bf16 operand, so that neither an
+// unpack-gradient pass nor a re-pack pass over the 68 M weights exists.  Threads of a warp hold consecutive input
+// channels i of one output channel o: packed reads / bf16 writes are contiguous across the warp for every tap.
+template <int KH, int KW>
+__device__ __forceinline__ int packed_tap_offset(int k, int sh, int s, int Ipad) {
+  const int ky = k / KW, kx = k % KW;
+  const int dy = ky >> sh, py = ky & (s - 1), dx = kx >> sh, px = kx & (s - 1);
+  return ((dy * (KW >> sh) + dx) * (s * s) + py * s + px) * Ipad;
+}
+
+template <int KH, int KW, int PASS, bool PACKED>
 __global__ void __launch_bounds__(128)
-    adafactor_conv_kernel(const sb_tensor_desc* __restrict__ descs, const int2* __restrict__ block_map,
-                          const float* __restrict__ total_sumsq, float max_norm) {
+    adafactor_conv_kernel(const sb_tensor_desc* __restrict__ descs, const sb_pack_desc* __restrict__ packs,
+                          const int2* __restrict__ block_map, const float* __restrict__ total_sumsq, float max_norm) {
   constexpr int KK = KH * KW;
   __shared__ float red[8];
   const int2 bm = block_map[blockIdx.x];  // (tensor, first patch)
@@ -63,15 +76,43 @@ __global__ void __launch_bounds__(128)
   const float beta2t = 1.0f - powf(tstep, -0.8f);            // adafactor.py:170
   const float rel_step = fminf(1e-2f, rsqrtf(tstep));        // adafactor.py:84-94 (relative_step, no warm-up)
   const long long patch = (long long)bm.y + threadIdx.x;
-  const long long npatch = d.n / KK;
+  const long long npatch = PACKED ? (long long)packs[bm.x].O * packs[bm.x].I : d.n / KK;
   const float coef = clip_coef(total_sumsq, max_norm);
   float su = 0.f, sp = 0.f;
   if (patch < npatch) {
     float g[KK], p[KK];
+    long long gbase = 0;  // PACKED: offset of (o, i) in the packed buffer
+    int sh = 0, s = 1, Ipad = 0;
+    if (PACKED) {
+      const sb_pack_desc pk = packs[bm.x];
+      const int o = (int)(patch / pk.I), i = (int)(patch - (long long)o * pk.I);
+      const int oo = pk.operm ? pk.operm[o] : o;
+      const int ii = pk.iperm ? pk.iperm[i] : i;
+      s = pk.s; Ipad = pk.Ipad;
+      while ((1 << sh) < s) ++sh;
+      gbase = (long long)oo * ((KH >> sh) * (KW >> sh) * s * s * Ipad) + ii;
 #pragma unroll
-    for (int k = 0; k < KK; ++k) {
-      g[k] = d.g[patch * KK + k] * coef;
-      p[k] = d.p[patch * KK + k];
+      for (int k = 0; k < KK; ++k) g[k] = pk.gpacked[gbase + packed_tap_offset<KH, KW>(k, sh, s, Ipad)] * coef;
+    } else if (KK % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < KK; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(d.g + patch * KK + k);
+        g[k] = v.x * coef; g[k + 1] = v.y * coef; g[k + 2] = v.z * coef; g[k + 3] = v.w * coef;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KK; ++k) g[k] = d.g[patch * KK + k] * coef;
+    }
+    // the 16 (64) weights of a patch are contiguous: 16-byte accesses (4x fewer L1 wavefronts than scalar ones)
+    if (KK % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < KK; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(d.p + patch * KK + k);
+        p[k] = v.x; p[k + 1] = v.y; p[k + 2] = v.z; p[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KK; ++k) p[k] = d.p[patch * KK + k];
     }
     float row[KH], col[KW];
     if (PASS == 1) {
@@ -120,7 +161,21 @@ __global__ void __launch_bounds__(128)
       const float lr = fmaxf(1e-3f, rms_p) * rel_step;
       const float scale = lr / fmaxf(1.0f, rms_u);  // clip_threshold = 1
 #pragma unroll
-      for (int k = 0; k < KK; ++k) d.p[patch * KK + k] = p[k] - scale * (rf[k / KW] * cf[k % KW] * g[k]);
+      for (int k = 0; k < KK; ++k) p[k] -= scale * (rf[k / KW] * cf[k % KW] * g[k]);
+      if (KK % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < KK; k += 4)
+          *reinterpret_cast<float4*>(d.p + patch * KK + k) = make_float4(p[k], p[k + 1], p[k + 2], p[k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < KK; ++k) d.p[patch * KK + k] = p[k];
+      }
+      if (PACKED) {
+        __nv_bfloat16* fw = reinterpret_cast<__nv_bfloat16*>(packs[bm.x].fwd);
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+          fw[gbase + packed_tap_offset<KH, KW>(k, sh, s, Ipad)] = __float2bfloat16_rn(p[k]);
+      }
     }
   }
   if (PASS == 1) {
@@ -135,11 +190,11 @@ __global__ void __launch_bounds__(128)
 
 // ---- 3. small 1-D / 2-D tensors: one CTA per tensor ---------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-    adafactor_small_kernel(const sb_tensor_desc* __restrict__ descs, const float* __restrict__ total_sumsq,
-                           float max_norm) {
+    adafactor_small_kernel(const sb_tensor_desc* __restrict__ descs, const int* __restrict__ index,
+                           const float* __restrict__ total_sumsq, float max_norm) {
   extern __shared__ float sm[];  // rows [R] | cols [C]
   __shared__ float red[32];
-  const sb_tensor_desc d = descs[blockIdx.x];
+  const sb_tensor_desc d = descs[index ? index[blockIdx.x] : blockIdx.x];
   const float coef = clip_coef(total_sumsq, max_norm);
   const long long n = d.n;
   const float tstep = *d.stepf;
@@ -234,17 +289,18 @@ __global__ void __launch_bounds__(1024)
 // ---- 3b. large 2-D tensors (e.g. bits_predictor.dense1-3: [128, 4608]): one thread-block CLUSTER of 8 CTAs per
 // tensor.  CTA k owns a band of rows; column sums, the row-state mean and the two RMS sums are combined through
 // distributed shared memory (3 cluster barriers) instead of running 590 k parameters through a single SM.
+static_assert(sizeof(sb_tensor_desc) == 64 && sizeof(sb_pack_desc) == 64, "descriptor ABI");
 constexpr int kClusterCtas = 8;
 namespace cg = cooperative_groups;
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
-    adafactor_2d_cluster_kernel(const sb_tensor_desc* __restrict__ descs, const float* __restrict__ total_sumsq,
-                                float max_norm) {
+    adafactor_2d_cluster_kernel(const sb_tensor_desc* __restrict__ descs, const int* __restrict__ index,
+                                const float* __restrict__ total_sumsq, float max_norm) {
   extern __shared__ float sm[];  // colpart [C] | cf [C] | rowf [rows_per]
   __shared__ float red[32];
   __shared__ float part[3][kClusterCtas];  // per-CTA partials of: sum(new row state), sum p^2, sum u^2
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const sb_tensor_desc d = descs[blockIdx.x / kClusterCtas];
+  const sb_tensor_desc d = descs[index ? index[blockIdx.x / kClusterCtas] : blockIdx.x / kClusterCtas];
   const int R = d.rows, C = d.cols;
   const int rows_per = (R + kClusterCtas - 1) / kClusterCtas;
   const int r0 = min(R, rank * rows_per), r1 = min(R, r0 + rows_per);
@@ -362,40 +418,62 @@ extern "C" int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, 
   return SB_OK;
 }
 
-extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, float* total,
-                             sb_stream_t stream) {
+extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev,
+                             int nblocks, float* total, sb_stream_t stream) {
   if (!descs_dev || !block_map_dev || nblocks < 1 || !total) return SB_ERR_ARG;
-  grad_sumsq_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, (const int2*)block_map_dev, total);
+  grad_sumsq_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, glen_dev, (const int2*)block_map_dev, total);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
 
 template <int KH, int KW>
-static int launch_conv(const sb_tensor_desc* descs, const int* bm, int nblocks, const float* total, float max_norm,
-                       int pass, cudaStream_t s) {
-  if (pass == 1)
-    adafactor_conv_kernel<KH, KW, 1><<<nblocks, 128, 0, s>>>(descs, (const int2*)bm, total, max_norm);
-  else
-    adafactor_conv_kernel<KH, KW, 2><<<nblocks, 128, 0, s>>>(descs, (const int2*)bm, total, max_norm);
+static int launch_conv(const sb_tensor_desc* descs, const sb_pack_desc* packs, const int* bm, int nblocks,
+                       const float* total, float max_norm, int pass, cudaStream_t s) {
+  const int2* m = (const int2*)bm;
+  if (packs) {
+    if (pass == 1) adafactor_conv_kernel<KH, KW, 1, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+    else adafactor_conv_kernel<KH, KW, 2, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+  } else {
+    if (pass == 1) adafactor_conv_kernel<KH, KW, 1, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+    else adafactor_conv_kernel<KH, KW, 2, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+  }
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
 
-extern "C" int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
-                                 const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
+static int conv_dispatch(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev, const int* block_map_dev,
+                         int nblocks, int KH, int KW, const float* total_sumsq, float max_norm, int pass,
+                         sb_stream_t stream) {
   if (!descs_dev || !block_map_dev || nblocks < 1 || (pass != 1 && pass != 2)) return SB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  if (KH == 1 && KW == 1) return launch_conv<1, 1>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
-  if (KH == 3 && KW == 3) return launch_conv<3, 3>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
-  if (KH == 4 && KW == 4) return launch_conv<4, 4>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
-  if (KH == 8 && KW == 8) return launch_conv<8, 8>(descs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 1 && KW == 1)
+    return launch_conv<1, 1>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 3 && KW == 3)
+    return launch_conv<3, 3>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 4 && KW == 4)
+    return launch_conv<4, 4>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+  if (KH == 8 && KW == 8)
+    return launch_conv<8, 8>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
   return SB_ERR_ARG;
 }
 
-extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors, int max_rows_plus_cols,
-                                  const float* total_sumsq, float max_norm, sb_stream_t stream) {
+extern "C" int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
+                                 const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
+  return conv_dispatch(descs_dev, nullptr, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, stream);
+}
+
+extern "C" int sb_adafactor_conv_packed(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev,
+                                        const int* block_map_dev, int nblocks, int KH, int KW,
+                                        const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
+  if (!packs_dev) return SB_ERR_ARG;
+  return conv_dispatch(descs_dev, packs_dev, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, stream);
+}
+
+extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors,
+                                  int max_rows_plus_cols, const float* total_sumsq, float max_norm,
+                                  sb_stream_t stream) {
   if (!descs_dev || ntensors < 1 || max_rows_plus_cols * sizeof(float) > 96 * 1024) return SB_ERR_ARG;
   const size_t smem = (size_t)(max_rows_plus_cols > 0 ? max_rows_plus_cols : 1) * sizeof(float);
   static bool configured = false;
@@ -405,14 +483,14 @@ extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, int ntensors,
       return SB_ERR_CUDA;
     configured = true;
   }
-  adafactor_small_kernel<<<ntensors, 1024, smem, (cudaStream_t)stream>>>(descs_dev, total_sumsq, max_norm);
+  adafactor_small_kernel<<<ntensors, 1024, smem, (cudaStream_t)stream>>>(descs_dev, index_dev, total_sumsq, max_norm);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
 
-extern "C" int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, int ntensors, int max_cols, int max_rows,
-                                  const float* total_sumsq, float max_norm, sb_stream_t stream) {
+extern "C" int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors, int max_cols,
+                                  int max_rows, const float* total_sumsq, float max_norm, sb_stream_t stream) {
   if (!descs_dev || ntensors < 1 || max_cols < 1 || max_rows < 1) return SB_ERR_ARG;
   const size_t smem = ((size_t)2 * max_cols + (max_rows + kClusterCtas - 1) / kClusterCtas) * sizeof(float);
   if (smem > 200 * 1024) return SB_ERR_ARG;
@@ -423,8 +501,8 @@ extern "C" int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, int ntensors,
       return SB_ERR_CUDA;
     configured = true;
   }
-  adafactor_2d_cluster_kernel<<<ntensors * kClusterCtas, 1024, smem, (cudaStream_t)stream>>>(descs_dev, total_sumsq,
-                                                                                            max_norm);
+  adafactor_2d_cluster_kernel<<<ntensors * kClusterCtas, 1024, smem, (cudaStream_t)stream>>>(descs_dev, index_dev,
+                                                                                            total_sumsq, max_norm);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -43,12 +43,16 @@ struct View {
   int s, pad, H2, W2;
   int sh;    // log2(s)
 };
-__device__ __forceinline__ long long view_off(const View& v, int H, int W, int C, int b, int y, int x, int c) {
-  if (v.kind == 0) return (((long long)b * H + y) * W + x) * C + c;
+// element offsets fit 32 bits (the launchers reject tensors of 2^31 elements or more)
+__device__ __forceinline__ uint32_t view_off(const View& v, int H, int W, int C, int b, int y, int x, int c) {
+  if (v.kind == 0) return (uint32_t)(((b * H + y) * W + x) * C + c);
   const int yp = y + v.pad, xp = x + v.pad;
   const int y2 = yp >> v.sh, x2 = xp >> v.sh;
   const int ph = ((yp & (v.s - 1)) << v.sh) + (xp & (v.s - 1));
-  return ((((long long)b * v.H2 + y2) * v.W2 + x2) * (v.s * v.s) + ph) * C + c;
+  return (uint32_t)(((((b * v.H2 + y2) * v.W2 + x2) << (2 * v.sh)) + ph) * C + c);
+}
+__device__ __forceinline__ uint32_t plain_off(int H, int W, int C, int b, int y, int x, int c) {
+  return (uint32_t)(((b * H + y) * W + x) * C + c);
 }
 // n / d for 0 <= n < 2^17, 2 <= d < 300 with m = ceil(2^32 / d) (exact in that range); m == 0 encodes d == 1
 __device__ __forceinline__ int fast_div(int n, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n; }
@@ -95,8 +99,9 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
   f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
 }
 
-// keep decisions for 8 consecutive channels from one Philox call (16 random bits each)
-__device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, long long elem_index, bool* k) {
+// keep decisions for 8 consecutive channels: 16 random bits each from one hash4x32 call (counter = vector index)
+__device__ __forceinline__ void keep8(const PrepParams& q, const uint2 key, uint32_t vec_index, uint32_t elem_index,
+                                      bool* k) {
   if (q.keep) {
     const uint2 m = *reinterpret_cast<const uint2*>(q.keep + elem_index);
 #pragma unroll
@@ -106,14 +111,18 @@ __device__ __forceinline__ void keep8(const PrepParams& q, long long vec_index, 
     }
     return;
   }
-  const unsigned long long seed = q.seed_ptr ? q.seed + *q.seed_ptr : q.seed;
-  const uint4 r = philox4x32(make_uint4((uint32_t)vec_index, (uint32_t)(vec_index >> 32), q.stream_id, 0u),
-                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint4 r = hash4x32(vec_index, key);
   const uint32_t thr = (uint32_t)(q.p * 65536.0f);
   k[0] = (r.x & 0xffff) >= thr; k[1] = (r.x >> 16) >= thr;
   k[2] = (r.y & 0xffff) >= thr; k[3] = (r.y >> 16) >= thr;
   k[4] = (r.z & 0xffff) >= thr; k[5] = (r.z >> 16) >= thr;
   k[6] = (r.w & 0xffff) >= thr; k[7] = (r.w >> 16) >= thr;
+}
+// per-launch dropout key (seed may live on the device so that CUDA-graph replays draw fresh masks)
+__device__ __forceinline__ uint2 dropout_key(const PrepParams& q) {
+  if (q.p <= 0.f || q.keep) return make_uint2(0u, 0u);
+  const unsigned long long seed = q.seed_ptr ? q.seed + *q.seed_ptr : q.seed;
+  return hash_key(seed, q.stream_id);
 }
 
 // Raw operands of one (pixel, 8-channel vector): loads are ISSUED for several pixels before any is consumed, so that
@@ -125,7 +134,7 @@ template <bool F32>
 __device__ __forceinline__ void issue_z(const PrepParams& q, int b, int y, int x, int c, RawZ& r) {
   if (F32) return;
   r.m = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + view_off(q.in, q.H, q.W, q.C, b, y, x, c));
-  if (q.add) r.a = ldg16(q.add + (((long long)b * q.H + y) * q.W + x) * q.C + c);
+  if (q.add) r.a = ldg16(q.add + plain_off(q.H, q.W, q.C, b, y, x, c));
 }
 // value of (main [+relu] + add) for 8 channels; also returns raw main
 template <bool F32>
@@ -133,11 +142,11 @@ __device__ __forceinline__ void finish_z(const PrepParams& q, const RawZ& r, int
                                          float* mainv) {
   float a[8];
   if (F32) {
-    const long long off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
+    const uint32_t off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
     if (q.in_f32) ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
     else bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
     if (q.add) {
-      const long long aoff = (((long long)b * q.H + y) * q.W + x) * q.C + c;
+      const uint32_t aoff = plain_off(q.H, q.W, q.C, b, y, x, c);
       if (q.add_f32) ld8f(reinterpret_cast<const float*>(q.add) + aoff, a);
       else bf8_to_f(*reinterpret_cast<const BF8*>(q.add + aoff), a);
     }
@@ -198,10 +207,10 @@ __device__ __forceinline__ ChanCst load_cst(const PrepParams& q, int b, float* s
   return k;
 }
 
-__device__ __forceinline__ void keep_for(const PrepParams& q, int b, int y, int x, int c, bool* keep) {
+__device__ __forceinline__ void keep_for(const PrepParams& q, const uint2 key, int b, int y, int x, int c, bool* keep) {
   if (q.p > 0.f) {
-    const long long pix = ((long long)b * q.H + y) * q.W + x;
-    keep8(q, pix * (q.C / 8) + c / 8, pix * q.C + c, keep);
+    const uint32_t e = plain_off(q.H, q.W, q.C, b, y, x, c);
+    keep8(q, key, e >> 3, e, keep);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) keep[j] = true;
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, false);
+  const uint2 dkey = dropout_key(q);
   for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
     RawZ raw[U];
     int yy[U], xx[U];
@@ -281,10 +291,10 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
       float z[8], mainv[8], xhat[8], xn[8], xd[8];
       bool keep[8];
       finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
-      keep_for(q, b, yy[u], xx[u], c, keep);
+      keep_for(q, dkey, b, yy[u], xx[u], c, keep);
       fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
       if (q.out1)
-        *reinterpret_cast<BF8*>(q.out1 + (((long long)b * q.H + yy[u]) * q.W + xx[u]) * q.C + c) = f_to_bf8(xn);
+        *reinterpret_cast<BF8*>(q.out1 + plain_off(q.H, q.W, q.C, b, yy[u], xx[u], c)) = f_to_bf8(xn);
       if (q.sc) {
         float sc[8], sh[8];
         ld8f(k.sc + c, sc); ld8f(k.sh + c, sh);
@@ -302,7 +312,7 @@ struct RawG {
 };
 __device__ __forceinline__ void issue_g(const PrepParams& q, int b, int y, int x, int c, RawG& r) {
   r.g2 = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) + view_off(q.g2, q.H, q.W, q.C, b, y, x, c));
-  if (q.g1) r.g1 = ldg16(q.g1 + (((long long)b * q.H + y) * q.W + x) * q.C + c);
+  if (q.g1) r.g1 = ldg16(q.g1 + plain_off(q.H, q.W, q.C, b, y, x, c));
 }
 __device__ __forceinline__ void finish_gx(const PrepParams& q, const ChanCst& k, const RawG& r, int c, const bool* keep,
                                           float* g2, float* gx) {
@@ -368,6 +378,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
     k = load_cst(q, b, sm, false);
     scratch = sm + 8 * q.C;
   }
+  const uint2 dkey = MODE == 1 ? dropout_key(q) : make_uint2(0u, 0u);
   for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
     RawZ raw[U];
     RawG rg[U];
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
       } else {
         float xhat[8], xn[8], xd[8], g2[8], gx[8];
         bool keep[8];
-        keep_for(q, b, yy[u], xx[u], c, keep);
+        keep_for(q, dkey, b, yy[u], xx[u], c, keep);
         fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
         finish_gx(q, k, rg[u], c, keep, g2, gx);
 #pragma unroll
@@ -426,6 +437,7 @@ __global__ void __launch_bounds__(256, 2)
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, true);
+  const uint2 dkey = dropout_key(q);
   float dsum[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dsum[0][j] = 0.f;
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(256, 2)
       float z[8], mainv[8], g2[8], gx[8], dz[8];
       bool keep[8];
       finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
-      keep_for(q, b, yy[u], xx[u], c, keep);
+      keep_for(q, dkey, b, yy[u], xx[u], c, keep);
       finish_gx(q, k, rg[u], c, keep, g2, gx);
       if (q.sums) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
         float mean[8], rstd[8], g[8], m1[8], m2[8];
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(256, 2)
         for (int j = 0; j < 8; ++j) dz[j] = gx[j];
       }
       if (q.d_add)
-        *reinterpret_cast<BF8*>(q.d_add + (((long long)b * q.H + yy[u]) * q.W + xx[u]) * q.C + c) = f_to_bf8(dz);
+        *reinterpret_cast<BF8*>(q.d_add + plain_off(q.H, q.W, q.C, b, yy[u], xx[u], c)) = f_to_bf8(dz);
       if (q.relu_in) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dz[j] = mainv[j] > 0.f ? dz[j] : 0.f;
@@ -720,6 +732,16 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   q.d_add = (__nv_bfloat16*)a->d_add;
   q.dcol = a->dcol;
   if (!view_ok(q.in) || !view_ok(q.out2) || !view_ok(q.g2) || !view_ok(q.d_main)) return SB_ERR_ARG;
+  {  // 32-bit element offsets: the largest view (padded space-to-depth extent included) must stay below 2^31 elements
+    long long worst = (long long)q.B * q.H * q.W * q.C;
+    const View* vs[4] = {&q.in, &q.out2, &q.g2, &q.d_main};
+    for (const View* v : vs)
+      if (v->kind == 1) {
+        const long long e = (long long)q.B * v->H2 * v->W2 * v->s * v->s * q.C;
+        if (e > worst) worst = e;
+      }
+    if (worst >= (1LL << 31)) return SB_ERR_ARG;
+  }
   if (q.H > 1 && (q.W >= 300 || (long long)q.H * q.W >= (1 << 17))) return SB_ERR_ARG;  // fast_div range
   q.w_magic = q.H > 1 ? div_magic(q.W) : 1u;  // single-row tensors (column sums of a matrix): row index is always 0
   q.nx_magic = 0;
@@ -873,6 +895,16 @@ extern "C" int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s,
     ++g_launches;
     SB_CHECK_LAUNCH();
   }
+  return SB_OK;
+}
+
+extern "C" int sb_transpose_taps(const void* fwd, void* tr, int Opad, int PHI, int T, sb_stream_t stream) {
+  if (!fwd || !tr || Opad < 1 || PHI < 1 || T < 1) return SB_ERR_ARG;
+  dim3 grid((PHI + 31) / 32, (Opad + 31) / 32, T);
+  transpose_taps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)fwd, (__nv_bfloat16*)tr, Opad,
+                                                                PHI, T);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
   return SB_OK;
 }
 

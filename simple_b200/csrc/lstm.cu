@@ -132,6 +132,245 @@ __global__ void __launch_bounds__(512)
   if (t < kSteps * 8) bits[(size_t)b * (kSteps * 8) + t] = ((sym[t >> 3] >> (t & 7)) & 1) ? 1.0f : -1.0f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second-generation kernels: thread-per-output-row matrix-vector products on TRANSPOSED weights (coalesced loads, no
+// shuffle reductions, 16-32 independent loads in flight per thread) and S samples per CTA sharing every weight load.
+//   whhT [128,512] = W_hh^T, w5T [128,256] = W5^T,
+//   E [256,512]    = input-gate pre-activations of every symbol: W_ih (W4[:,s] + b4) + b_ih + b_hh  (dense4 of a one-hot
+//                    vector is a column lookup, so the input half of the LSTM gates is a table lookup as well),
+//   G0 [B,512]     = W_ih x0 + b_ih + b_hh for the first step.
+// The small GEMMs that build E / G0 and the transposes are plain library calls on the host side.
+// ---------------------------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void gates_matvec(const float* __restrict__ whhT, const float (*h)[kH], int t, float* acc) {
+#pragma unroll 16
+  for (int k = 0; k < kH; ++k) {
+    const float w = __ldg(whhT + k * (4 * kH) + t);
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = fmaf(w, h[s][k], acc[s]);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(512)
+    lstm_sample2_kernel(const float* __restrict__ G0, const float* __restrict__ h0, const float* __restrict__ c0,
+                        const float* __restrict__ E, const float* __restrict__ whhT, const float* __restrict__ w5T,
+                        const float* __restrict__ b5, const float* __restrict__ noise,
+                        const unsigned long long* seed_ptr, int B, float* __restrict__ bits, int* __restrict__ ints) {
+  __shared__ float h[S][kH], c[S][kH], gates[S][4 * kH], part[S][kV], score[S][kV];
+  __shared__ int sym[S][kSteps];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b0 = blockIdx.x * S;
+  for (int i = t; i < S * kH; i += 512) {
+    const int s = i / kH, j = i - s * kH;
+    const int b = min(b0 + s, B - 1);
+    h[s][j] = h0[b * kH + j];
+    c[s][j] = c0[b * kH + j];
+  }
+  __syncthreads();
+  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  for (int step = 0; step < kSteps; ++step) {
+    {  // gates: thread t owns gate row t (PyTorch LSTMCell order i, f, g, o) of all S samples
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int b = min(b0 + s, B - 1);
+        acc[s] = step == 0 ? G0[(size_t)b * 4 * kH + t] : E[(size_t)sym[s][step - 1] * 4 * kH + t];
+      }
+      gates_matvec<S>(whhT, h, t, acc);
+#pragma unroll
+      for (int s = 0; s < S; ++s) gates[s][t] = acc[s];
+    }
+    __syncthreads();
+    if (t < S * kH) {
+      const int s = t / kH, j = t - s * kH;
+      const float ig = sigmoidf_(gates[s][j]), fg = sigmoidf_(gates[s][kH + j]);
+      const float gg = tanh_acc(gates[s][2 * kH + j]), og = sigmoidf_(gates[s][3 * kH + j]);
+      const float cn = fg * c[s][j] + ig * gg;
+      c[s][j] = cn;
+      h[s][j] = og * tanh_acc(cn);
+    }
+    __syncthreads();
+    {  // 256 logits: thread = (k half, logit n); the two halves of the contraction are combined through `part`
+      const int n = t & (kV - 1), half = t >> 8;
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = 0.f;
+#pragma unroll 16
+      for (int k = half * (kH / 2); k < (half + 1) * (kH / 2); ++k) {
+        const float w = __ldg(w5T + k * kV + n);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(w, h[s][k], acc[s]);
+      }
+      if (half == 1) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) part[s][n] = acc[s];
+      }
+      __syncthreads();
+      if (half == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int b = min(b0 + s, B - 1);
+          const float logit = acc[s] + part[s][n] + b5[n];
+          float q;
+          if (noise) {
+            q = noise[((size_t)b * kSteps + step) * kV + n];
+          } else {
+            const uint4 rr = philox4x32(make_uint4((uint32_t)n, (uint32_t)step, (uint32_t)b, 0x4c53544du),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            q = -logf(((float)(rr.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
+          }
+          score[s][n] = expf(logit) / q;  // sample_with_temperature(T=1): multinomial(exp(logits))
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < S) {  // argmax over the 256 scores of sample `warp`, first index on ties (torch.multinomial / argmax)
+      float v = -1.0f;
+      int i = 0;
+#pragma unroll
+      for (int j = 0; j < kV / 32; ++j) {  // ascending index: strict > keeps the first maximum
+        const float sv = score[warp][lane + 32 * j];
+        if (sv > v) {
+          v = sv;
+          i = lane + 32 * j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) {
+          v = ov;
+          i = oi;
+        }
+      }
+      if (lane == 0) sym[warp][step] = i;
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < S * kSteps; i += 512) {
+    const int s = i / kSteps, k = i - s * kSteps;
+    if (b0 + s < B) ints[(b0 + s) * kSteps + k] = sym[s][k];
+  }
+  for (int i = t; i < S * kSteps * 8; i += 512) {
+    const int s = i / (kSteps * 8), k = i - s * (kSteps * 8);
+    if (b0 + s < B) bits[(size_t)(b0 + s) * (kSteps * 8) + k] = ((sym[s][k >> 3] >> (k & 7)) & 1) ? 1.0f : -1.0f;
+  }
+}
+
+// Teacher-forced pass (next_frame_predictor.py:97-100): all 16 LSTMCell steps of S samples in one CTA.
+//   xw [B,16,512] = input-gate pre-activations (W_ih x_t + b_ih + b_hh, one GEMM over all steps on the host side)
+//   -> hs [B,16,128] (outputs), act [B,16,512] (post-activation gates) and cs [B,16,128] (cell states) for backward
+template <int S>
+__global__ void __launch_bounds__(512)
+    lstm_teacher_fwd_kernel(const float* __restrict__ xw, const float* __restrict__ h0, const float* __restrict__ c0,
+                            const float* __restrict__ whhT, int B, float* __restrict__ hs, float* __restrict__ act,
+                            float* __restrict__ cs) {
+  __shared__ float h[S][kH], c[S][kH], gates[S][4 * kH];
+  const int t = threadIdx.x;
+  const int b0 = blockIdx.x * S;
+  for (int i = t; i < S * kH; i += 512) {
+    const int s = i / kH, j = i - s * kH;
+    const int b = min(b0 + s, B - 1);
+    h[s][j] = h0[b * kH + j];
+    c[s][j] = c0[b * kH + j];
+  }
+  __syncthreads();
+  for (int step = 0; step < kSteps; ++step) {
+    float acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = xw[((size_t)min(b0 + s, B - 1) * kSteps + step) * 4 * kH + t];
+    gates_matvec<S>(whhT, h, t, acc);
+#pragma unroll
+    for (int s = 0; s < S; ++s) gates[s][t] = acc[s];
+    __syncthreads();
+    if (t < S * kH) {
+      const int s = t / kH, j = t - s * kH;
+      const float ig = sigmoidf_(gates[s][j]), fg = sigmoidf_(gates[s][kH + j]);
+      const float gg = tanh_acc(gates[s][2 * kH + j]), og = sigmoidf_(gates[s][3 * kH + j]);
+      const float cn = fg * c[s][j] + ig * gg;
+      const float hn = og * tanh_acc(cn);
+      c[s][j] = cn;
+      h[s][j] = hn;
+      if (b0 + s < B) {
+        const size_t row = (size_t)(b0 + s) * kSteps + step;
+        float* a = act + row * 4 * kH;
+        a[j] = ig; a[kH + j] = fg; a[2 * kH + j] = gg; a[3 * kH + j] = og;
+        cs[row * kH + j] = cn;
+        hs[row * kH + j] = hn;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Backward through time of the pass above.  dhs [B,16,128] = gradient wrt every output; emits the pre-activation
+// gradients dpre [B,16,512] (= gradient wrt xw; dW_hh = dpre^T h_prev is one GEMM on the host side) and dh0, dc0.
+template <int S>
+__global__ void __launch_bounds__(512)
+    lstm_teacher_bwd_kernel(const float* __restrict__ dhs, const float* __restrict__ act, const float* __restrict__ cs,
+                            const float* __restrict__ c0, const float* __restrict__ whh, int B,
+                            float* __restrict__ dpre_all, float* __restrict__ dh0, float* __restrict__ dc0) {
+  __shared__ float dh[S][kH], dc[S][kH], dpre[S][4 * kH], part[S][4][kH];
+  const int t = threadIdx.x;
+  const int b0 = blockIdx.x * S;
+  for (int i = t; i < S * kH; i += 512) {
+    dh[i / kH][i % kH] = 0.f;
+    dc[i / kH][i % kH] = 0.f;
+  }
+  __syncthreads();
+  for (int step = kSteps - 1; step >= 0; --step) {
+    if (t < S * kH) {
+      const int s = t / kH, j = t - s * kH;
+      const int b = min(b0 + s, B - 1);
+      const size_t row = (size_t)b * kSteps + step;
+      const float* a = act + row * 4 * kH;
+      const float ig = a[j], fg = a[kH + j], gg = a[2 * kH + j], og = a[3 * kH + j];
+      const float cprev = step > 0 ? cs[(row - 1) * kH + j] : c0[b * kH + j];
+      const float tc = tanh_acc(cs[row * kH + j]);
+      const float dhi = dhs[row * kH + j] + dh[s][j];
+      const float dct = dc[s][j] + dhi * og * (1.0f - tc * tc);
+      const float d0 = dct * gg * ig * (1.0f - ig), d1 = dct * cprev * fg * (1.0f - fg);
+      const float d2 = dct * ig * (1.0f - gg * gg), d3 = dhi * tc * og * (1.0f - og);
+      dpre[s][j] = d0; dpre[s][kH + j] = d1; dpre[s][2 * kH + j] = d2; dpre[s][3 * kH + j] = d3;
+      dc[s][j] = dct * fg;
+      if (b0 + s < B) {
+        float* d = dpre_all + row * 4 * kH;
+        d[j] = d0; d[kH + j] = d1; d[2 * kH + j] = d2; d[3 * kH + j] = d3;
+      }
+    }
+    __syncthreads();
+    {  // dh_prev[j] = sum_r dpre[r] * W_hh[r][j]: thread = (quarter of the rows, j), combined through `part`
+      const int j = t & (kH - 1), qr = t >> 7;
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = 0.f;
+#pragma unroll 16
+      for (int r = qr * kH; r < (qr + 1) * kH; ++r) {
+        const float w = __ldg(whh + (size_t)r * kH + j);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(w, dpre[s][r], acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) part[s][qr][j] = acc[s];
+    }
+    __syncthreads();
+    if (t < S * kH) {
+      const int s = t / kH, j = t - s * kH;
+      dh[s][j] = part[s][0][j] + part[s][1][j] + part[s][2][j] + part[s][3][j];
+    }
+    __syncthreads();
+  }
+  for (int i = t; i < S * kH; i += 512) {
+    const int s = i / kH, j = i - s * kH;
+    if (b0 + s < B) {
+      dh0[(b0 + s) * kH + j] = dh[s][j];
+      dc0[(b0 + s) * kH + j] = dc[s][j];
+    }
+  }
+}
+
 // pre [B,4H] (i|f|g|o pre-activations), c_prev [B,H] -> act [B,4H] (post-activation gates, saved), c, h [B,H]
 __global__ void __launch_bounds__(256)
     lstm_cell_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, float* __restrict__ act,
@@ -198,6 +437,44 @@ extern "C" int sb_lstm_cell_bwd(const float* act, const float* c_prev, const flo
                                 float* dpre, float* dc_prev, int B, sb_stream_t stream) {
   if (!act || !c_prev || !c || !dpre || !dc_prev || B < 1) return SB_ERR_ARG;
   lstm_cell_bwd_kernel<<<(B * kH + 255) / 256, 256, 0, (cudaStream_t)stream>>>(act, c_prev, c, dh, dc, dpre, dc_prev, B);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_lstm_sample2(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
+                               const float* w5T, const float* b5, const float* noise,
+                               const unsigned long long* seed_ptr, int B, float* bits, int* ints, sb_stream_t stream) {
+  if (!G0 || !h0 || !c0 || !E || !whhT || !w5T || !b5 || !bits || !ints || B < 1) return SB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B >= 32 && B % 2 == 0)
+    lstm_sample2_kernel<2><<<B / 2, 512, 0, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
+  else
+    lstm_sample2_kernel<1><<<B, 512, 0, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B,
+                                   float* hs, float* act, float* cs, sb_stream_t stream) {
+  if (!xw || !h0 || !c0 || !whhT || !hs || !act || !cs || B < 1) return SB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B >= 32 && B % 2 == 0) lstm_teacher_fwd_kernel<2><<<B / 2, 512, 0, st>>>(xw, h0, c0, whhT, B, hs, act, cs);
+  else lstm_teacher_fwd_kernel<1><<<B, 512, 0, st>>>(xw, h0, c0, whhT, B, hs, act, cs);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, const float* c0,
+                                   const float* whh, int B, float* dpre, float* dh0, float* dc0, sb_stream_t stream) {
+  if (!dhs || !act || !cs || !c0 || !whh || !dpre || !dh0 || !dc0 || B < 1) return SB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B >= 32 && B % 2 == 0)
+    lstm_teacher_bwd_kernel<2><<<B / 2, 512, 0, st>>>(dhs, act, cs, c0, whh, B, dpre, dh0, dc0);
+  else
+    lstm_teacher_bwd_kernel<1><<<B, 512, 0, st>>>(dhs, act, cs, c0, whh, B, dpre, dh0, dc0);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

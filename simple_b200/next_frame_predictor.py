@@ -87,6 +87,8 @@ class BitsPredictor(nn.Module):  # :66-121
         self.dense4 = nn.Linear(2 ** bits_at_once, state_size)
         self.dense5 = nn.Linear(state_size, 2 ** bits_at_once)
         self.lstm = nn.LSTMCell(state_size, state_size)
+        self._sampler_tables = None
+        self.cache_sampler_tables = False  # set while the weights are known to be static (NextFramePredictor.repack)
 
     def forward(self, x, rand, target_bits=None):
         """x: [B,4608] (C,H,W order).  Teacher-forced loss when target_bits is given, else sampled bits in {-1,+1}."""
@@ -107,20 +109,20 @@ class BitsPredictor(nn.Module):  # :66-121
             # teacher forcing: every LSTM input is known up front, so the input half of the gates is ONE GEMM over
             # all 16 steps; only the recurrent half stays sequential, with the pointwise cell fused (sb_lstm_cell_*)
             xw = F.linear(tin, self.lstm.weight_ih, self.lstm.bias_ih + self.lstm.bias_hh)  # [B,16,512]
-            whh_t = self.lstm.weight_hh.t()
-            outs = []
-            for i in range(n):
-                h, c = ops.LstmCell.apply(torch.addmm(xw[:, i], h, whh_t), c)
-                outs.append(h)
-            outs = torch.stack(outs, dim=1)
+            outs = ops.LstmTeacher.apply(xw, h, c, self.lstm.weight_hh)  # one launch for the 16 recurrent steps
             outs = outs * (rand.keep_mask(outs.shape, 0.1) / 0.9)
             pred = self.dense5(outs)
             loss = F.cross_entropy(pred.permute(0, 2, 1), tints)
             return pred, loss / self.config.rollout_length
         # sampling: integer outputs, nothing to differentiate -> one persistent kernel for all 16 steps
         noise = rand.sample_noise(B, n) if hasattr(rand, 'sample_noise') else None
+        tables = self._sampler_tables  # weight-only operands, cached while the weights are static (rollouts)
+        if tables is None:
+            tables = ops.lstm_sampler_tables(self.lstm, self.dense5, self.dense4)
+            if self.cache_sampler_tables:
+                self._sampler_tables = tables
         bits, _ = ops.lstm_sample(first, h, c, self.lstm, self.dense5, self.dense4, noise=noise,
-                                  seed=getattr(rand, 'seed', None) if noise is None else None)
+                                  seed=getattr(rand, 'seed', None) if noise is None else None, tables=tables)
         return bits, 0.0
 
 
@@ -405,9 +407,6 @@ class NextFramePredictor(nn.Module):
             shape = ds[i]
         P['logits'] = ConvSpec('logits', H, W, 96, H, W, 768, [(0, 0)], relu=False, flops=2.0 * HW * 768 * 96)
         P['logits'].dbias_src = self.logits_dbias = {}
-        # convs whose output has exactly one consumer, a fused prep stage: that stage's backward emits their bias grad
-        for sp in [P['embed'], P['s_embed'], P['mid'][1]] + P['down'] + P['up']:
-            sp.dbias_src = {}
         # posterior encoder of the stochastic model (train only)
         P['s_embed'] = ConvSpec('s_embed', H, W, 64, H, W, 96, [(0, 0)], relu=False, need_dgrad=False,
                                 flops=2.0 * HW * 96 * 15)
@@ -442,6 +441,9 @@ class NextFramePredictor(nn.Module):
         P['prep_s0'] = PrepSpec(H, W, 96, plain(H, W, 96), l1, Ta=P['stoch_timing'], inject=True)
         P['prep_s1'] = PrepSpec(26, 20, 128, plain(26, 20, 128), l2, relu_in=True)
         P['tmean10'] = timing_signal_nhwc(96, H, W).mean(dim=(0, 1)).to(dev)
+        # convs whose output has exactly one consumer, a fused prep stage: that stage's backward emits their bias grad
+        for sp in [P['embed'], P['s_embed'], P['mid'][1]] + P['down'] + P['up']:
+            sp.dbias_src = {}
         return P
 
     def _build_packed(self):
@@ -475,14 +477,29 @@ class NextFramePredictor(nn.Module):
                 **{f'up{i}': self.upscale_layers[2 * i] for i in range(5)},
                 **{f'mid{i}': self.middle_network.middle_network[2 * i] for i in range(2)}}
 
-    def repack(self, names=None):
+    def repack(self, names=None, static=False):
         """Refresh the bf16 GEMM operands from the fp32 master weights (after an optimiser step / load)."""
+        bp = self.stochastic_model.bits_predictor
+        bp._sampler_tables = None
+        bp.cache_sampler_tables = bool(static)  # static=True: the caller promises frozen weights until the next repack
         if self._packed is None:
             self._packed = self._build_packed()
             return
         mods = self._weights()
         for k in (names or self._packed.keys()):
             self._packed[k].pack(mods[k].weight)
+
+    def packed_weight_map(self, defer_unpack=None):
+        """{conv weight parameter: its PackedWeight}; `defer_unpack` switches packed-gradient mode (see ops.PackedWeight)
+        on or off for all of them.  Valid after the first forward (the operands are built lazily)."""
+        if self._packed is None:
+            return {}
+        mods = self._weights()
+        if defer_unpack is not None:
+            for pw in self._packed.values():
+                pw.defer_unpack = bool(defer_unpack)
+                pw.gpacked = None
+        return {mods[k].weight: pw for k, pw in self._packed.items()}
 
     def _conv(self, name, spec, a, need_weight_grad=True):
         m = self._weights_cache[name]

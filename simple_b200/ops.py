@@ -228,9 +228,23 @@ class PackedWeight:
         self.operm = torch.tensor(operm, dtype=torch.int32, device=dev) if operm is not None else None
         self.fwd = torch.zeros(self.Opad, self.T * self.PH * self.Ipad, device=dev, dtype=torch.bfloat16)
         self.tr = torch.zeros(self.PH * self.Ipad, self.T * self.Opad, device=dev, dtype=torch.bfloat16)
+        # packed-gradient mode (set by the Trainer fast path): backward leaves the fp32 gradient in the packed layout in
+        # `gpacked` instead of unpacking it into `weight.grad`; the fused Adafactor consumes it and rewrites `fwd`
+        self.defer_unpack = False
+        self.gpacked = None
+        self.fresh = False  # operands already match the master weights (written by the optimiser): skip one re-pack
         self.pack(weight)
 
+    def refresh_transposed(self):
+        """`fwd` was updated in place (sb_adafactor_conv_packed): re-derive `tr` and mark the operands current."""
+        _lib.check(_lib.lib().sb_transpose_taps(self.fwd.data_ptr(), self.tr.data_ptr(), self.Opad, self.PH * self.Ipad,
+                                                self.T, _lib.stream_ptr()), 'sb_transpose_taps')
+        self.fresh = True
+
     def pack(self, weight):
+        if self.fresh:
+            self.fresh = False
+            return
         w = weight.detach()
         assert w.dtype == torch.float32 and w.is_contiguous()
         _lib.check(_lib.lib().sb_pack_conv(w.data_ptr(), self.O, self.I, self.KH, self.KW, self.s, self.Ipad,
@@ -310,7 +324,10 @@ class TapConv(torch.autograd.Function):
             dwp = torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
             tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T),
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
-        dweight = pw.unpack_grad(dwp)
+        if pw.defer_unpack:
+            pw.gpacked, dweight = dwp, None
+        else:
+            dweight = pw.unpack_grad(dwp)
         dbias = None
         if ctx.has_bias:
             ext = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
@@ -443,21 +460,69 @@ def pixel_argmax(logits):
 # ---------------------------------------------------------------------------------------------------------------
 # latent-bit predictor
 # ---------------------------------------------------------------------------------------------------------------
-def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None):
+def lstm_sampler_tables(lstm, dense5, dense4):
+    """Weight-only operands of the sampling kernel (refresh whenever the weights change):
+    whhT [128,512], w5T [128,256], E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh, bias = b_ih + b_hh."""
+    with torch.no_grad():
+        bias = (lstm.bias_ih + lstm.bias_hh).float()
+        emb = dense4.weight.t().float() + dense4.bias.float()  # [256,128]: dense4(one_hot(s)) for every symbol s
+        return dict(whhT=lstm.weight_hh.t().contiguous().float(), w5T=dense5.weight.t().contiguous().float(),
+                    E=torch.addmm(bias, emb, lstm.weight_ih.t().float()).contiguous(), bias=bias,
+                    b5=dense5.bias.detach().float().contiguous())
+
+
+def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None, tables=None):
     """16-step autoregressive sampling of BitsPredictor (next_frame_predictor.py:109-121) in one kernel launch.
     Returns bits [B,128] in {-1,+1}.  `noise`: explicit Exp(1) draws [B,16,256] (parity mode), else Philox(seed)."""
     B = x0.shape[0]
     f = lambda t: t.detach().float().contiguous()
-    x0, h0, c0 = f(x0), f(h0), f(c0)
-    w = [f(t) for t in (lstm.weight_ih, lstm.weight_hh, lstm.bias_ih, lstm.bias_hh, dense5.weight, dense5.bias,
-                        dense4.weight, dense4.bias)]
+    tb = tables if tables is not None else lstm_sampler_tables(lstm, dense5, dense4)
+    with torch.no_grad():
+        G0 = torch.addmm(tb['bias'], f(x0), lstm.weight_ih.t().float())  # [B,512]
+    h0, c0 = f(h0), f(c0)
     bits = torch.empty(B, 128, device=x0.device, dtype=torch.float32)
     ints = torch.empty(B, 16, device=x0.device, dtype=torch.int32)
     noise = f(noise) if noise is not None else None
-    _lib.check(_lib.lib().sb_lstm_sample(x0.data_ptr(), h0.data_ptr(), c0.data_ptr(), *[t.data_ptr() for t in w],
-                                         _ptr(noise), _ptr(seed), B, bits.data_ptr(), ints.data_ptr(),
-                                         _lib.stream_ptr()), 'sb_lstm_sample')
+    _lib.check(_lib.lib().sb_lstm_sample2(G0.data_ptr(), h0.data_ptr(), c0.data_ptr(), tb['E'].data_ptr(),
+                                          tb['whhT'].data_ptr(), tb['w5T'].data_ptr(), tb['b5'].data_ptr(), _ptr(noise),
+                                          _ptr(seed), B, bits.data_ptr(), ints.data_ptr(), _lib.stream_ptr()),
+               'sb_lstm_sample2')
     return bits, ints
+
+
+class LstmTeacher(torch.autograd.Function):
+    """All 16 teacher-forced LSTMCell steps (next_frame_predictor.py:97-100) in one launch, and their backward through
+    time in another.  xw [B,16,512]: input-gate pre-activations (both biases included); returns the outputs [B,16,128]."""
+
+    @staticmethod
+    def forward(ctx, xw, h0, c0, w_hh):
+        B = xw.shape[0]
+        xw, h0, c0 = xw.contiguous(), h0.contiguous(), c0.contiguous()
+        whhT = w_hh.detach().t().contiguous()
+        hs = torch.empty(B, 16, 128, device=xw.device, dtype=torch.float32)
+        act = torch.empty(B, 16, 512, device=xw.device, dtype=torch.float32)
+        cs = torch.empty(B, 16, 128, device=xw.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sb_lstm_teacher_fwd(xw.data_ptr(), h0.data_ptr(), c0.data_ptr(), whhT.data_ptr(), B,
+                                                  hs.data_ptr(), act.data_ptr(), cs.data_ptr(), _lib.stream_ptr()),
+                   'sb_lstm_teacher_fwd')
+        ctx.save_for_backward(act, cs, hs, h0, c0, w_hh)
+        return hs
+
+    @staticmethod
+    def backward(ctx, dhs):
+        act, cs, hs, h0, c0, w_hh = ctx.saved_tensors
+        B = act.shape[0]
+        dhs = dhs.contiguous()
+        whh = w_hh.detach().contiguous()
+        dpre = torch.empty_like(act)
+        dh0 = torch.empty_like(h0)
+        dc0 = torch.empty_like(c0)
+        _lib.check(_lib.lib().sb_lstm_teacher_bwd(dhs.data_ptr(), act.data_ptr(), cs.data_ptr(), c0.data_ptr(),
+                                                  whh.data_ptr(), B, dpre.data_ptr(), dh0.data_ptr(), dc0.data_ptr(),
+                                                  _lib.stream_ptr()), 'sb_lstm_teacher_bwd')
+        h_prev = torch.cat((h0.unsqueeze(1), hs[:, :-1]), dim=1).reshape(-1, 128)
+        dw_hh = dpre.reshape(-1, 512).t() @ h_prev  # [512,128]
+        return dpre, dh0, dc0, dw_hh
 
 
 class LstmCell(torch.autograd.Function):

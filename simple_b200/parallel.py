@@ -41,18 +41,24 @@ class FlatGradSync:
         self.flat = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    def __call__(self, model):
-        active = [p for p in self.params if p.grad is not None]
-        n = sum(p.numel() for p in active)
+    def __call__(self, model, packed=None):
+        """`packed`: optional {param: ops.PackedWeight}; those parameters contribute their packed-layout gradient
+        (`pw.gpacked`, zero-padded, identical layout on every rank) instead of `p.grad`."""
+        active = []
+        for p in self.params:
+            pw = packed.get(p) if packed else None
+            g = pw.gpacked if pw is not None and pw.gpacked is not None else p.grad
+            if g is not None:
+                active.append((p, g))
+        n = sum(g.numel() for _, g in active)
         if self.flat is None or self.flat.numel() < n:
-            self.flat = torch.empty(sum(p.numel() for p in self.params), device=active[0].device, dtype=torch.float32)
+            self.flat = torch.empty(n + (1 << 20), device=active[0][1].device, dtype=torch.float32)
         views = {}
         off = 0
-        for p in active:
-            v = self.flat[off:off + p.numel()].view_as(p)
-            views[p] = v
-            off += p.numel()
-        torch._foreach_copy_(list(views.values()), [p.grad for p in active])
+        for p, g in active:
+            views[p] = self.flat[off:off + g.numel()].view(g.shape)
+            off += g.numel()
+        torch._foreach_copy_(list(views.values()), [g for _, g in active])
         if self.world > 1:
             buf = self.flat[:n]
             dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)

@@ -180,7 +180,7 @@ class SimulatedVecEnv:
             self._obs.copy_(self._initial)
             if cfg.stack_internal_states:
                 self.model.init_internal_states(A)
-            self.model.repack()  # weights are static during a rollout: pack once, not every step
+            self.model.repack(static=True)  # weights are static during a rollout: pack once, not every step
         self.step_count += 1
         if actions is not None:
             self._act.copy_(torch.as_tensor(actions, device=self.device).long().reshape(A, -1)[:, :1])

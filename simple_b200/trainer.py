@@ -85,6 +85,9 @@ class Trainer:
         self._replay = None
         self._replay_key = None
         self.grad_sync = None  # set by simple_b200.parallel for data-parallel training
+        # conv-weight gradients stay in the packed GEMM-operand layout between wgrad and Adafactor (no unpack / re-pack
+        # passes); `p.grad` of those weights is then None after a step.  Set False to get reference-shaped p.grad.
+        self.packed_grads = True
 
     # ---- simple/trainer.py:58-65
     def preprocess_state(self, state_u8, per_sample):
@@ -116,9 +119,13 @@ class Trainer:
         self.model.train()
         out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
         self.optimizer.zero_grad(set_to_none=True)
+        packed = self.model.packed_weight_map(defer_unpack=self.packed_grads) if self.packed_grads else None
         out['loss'].backward()
-        grads = self.grad_sync(self.model) if self.grad_sync is not None else None
-        self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads)
+        grads = self.grad_sync(self.model, packed) if self.grad_sync is not None else None
+        self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads, packed=packed)
+        if packed:
+            for pw in packed.values():
+                pw.gpacked = None
         self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous state
         return out
 

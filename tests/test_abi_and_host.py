@@ -71,6 +71,21 @@ def test_module_matches_reference_parameter_inventory():
     assert m.upscale_layers[8].output_padding == (1, 0)
 
 
+def test_static_plan_builds_on_cpu_and_wires_bias_gradient_side_channels():
+    """The layer plan (layouts, conv specs, timing tables) is pure host logic: it must build without a GPU."""
+    from oracle.wm_oracle import default_config
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    m = NextFramePredictor(default_config(device='cpu'), 3)
+    P = m._build_plan(torch.device('cpu'))
+    assert len(P['down']) == 5 and len(P['up']) == 5 and len(P['prep_dec']) == 5
+    assert P['logits'].dbias_src is m.logits_dbias
+    fused = [P['embed'], P['s_embed'], P['mid'][1]] + P['down'] + P['up']
+    assert all(sp.dbias_src == {} for sp in fused)
+    assert len({id(sp.dbias_src) for sp in fused}) == len(fused)  # one private channel per conv
+    # convs with several consumers of their output (or none that is a fused stage) keep the generic column-sum path
+    assert all(sp.dbias_src is None for sp in (P['gate'], P['mid'][0], P['s_conv1'], P['s_conv2']))
+
+
 def test_layouts_and_tiling_helpers():
     from simple_b200.gemm import choose_box
     from simple_b200.ops import s2d_in, s2d_out

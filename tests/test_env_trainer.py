@@ -100,3 +100,71 @@ def test_state_dict_round_trip_with_reference_keys():
     assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))
     with pytest.raises(ValueError):
         NextFramePredictor(_cfg(hidden_size=64), 3)
+
+
+def test_packed_gradient_mode_matches_reference_layout_mode():
+    """Trainer fast path: conv-weight gradients stay in the packed GEMM-operand layout from wgrad to Adafactor, which
+    also rewrites the bf16 operands.  Fed the SAME gradients (the packed buffers, unpacked for the reference-layout
+    optimiser), both paths must produce the same weights, optimiser state and operands -- over two steps, the second
+    one with the gate conv active.  (Two independent training runs are not comparable: fp32 atomics make the
+    sign-like first Adafactor steps diverge run to run.)"""
+    from bench import synth_replay
+    from simple_b200.adafactor import Adafactor
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.ops import PackedWeight
+    from simple_b200.trainer import wm_loss
+    B = 2
+    cfg = _cfg(batch_size=B)
+    d = {k: v.to(DEV) for k, v in synth_replay(B + 4, 3, 3).items()}
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    torch.manual_seed(0)
+    twin = NextFramePredictor(cfg, 3).to(DEV)  # same initial weights; only ever sees gradients copied from `model`
+    opt, opt_ref = Adafactor(model.parameters()), Adafactor(twin.parameters())
+    model.train()
+    model.init_internal_states(B)
+    frames = d['obs'][:B].float() / 255
+    for j in range(2):
+        idx = torch.arange(B, device=DEV) + j
+        out = wm_loss(model, cfg, frames, d['action'][idx].float(), d['new_obs'][idx], d['reward'][idx].long(),
+                      d['value'][idx], 0)
+        opt.zero_grad(set_to_none=True)
+        packed = model.packed_weight_map(defer_unpack=True)
+        out['loss'].backward()
+        by_name = {k: pw for k, pw in model._packed.items()}
+        mods, tmods = model._weights(), twin._weights()
+        conv_w = {id(mods[k].weight): k for k in mods}
+        for (k, p), q in zip(model.named_parameters(), twin.parameters()):
+            if id(p) in conv_w:
+                pw = by_name[conv_w[id(p)]]
+                assert p.grad is None  # never materialised in the reference layout
+                q.grad = pw.unpack_grad(pw.gpacked) if pw.gpacked is not None else None
+            else:
+                q.grad = p.grad.clone() if p.grad is not None else None
+        if j == 0:
+            assert by_name['gate'].gpacked is None and twin.gate.weight.grad is None
+        else:
+            assert by_name['gate'].gpacked is not None
+        opt.step(max_grad_norm=1.0, packed=packed)
+        opt_ref.step(max_grad_norm=1.0)
+        model.commit_state()
+        torch.cuda.synchronize()
+        assert abs(float(opt.grad_norm_sq) - float(opt_ref.grad_norm_sq)) < 1e-5 * float(opt_ref.grad_norm_sq)
+        for (k, a), b in zip(model.named_parameters(), twin.parameters()):
+            err = float((a - b).abs().max() / (a.abs().max() + 1e-12))
+            assert err < 2e-6, (j, k, err)
+            sa, sb_ = opt.state[a], opt_ref.state[b]
+            assert sa.get('step', 0) == sb_.get('step', 0)
+            for key in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
+                if key in sa:
+                    assert torch.allclose(sa[key], sb_[key], rtol=1e-4, atol=1e-30), (j, k, key)
+        # operands written by the optimiser == operands packed from the (bitwise own) master weights
+        for k, pw in model._packed.items():
+            if pw.gpacked is None:
+                continue
+            assert pw.fresh
+            ref = PackedWeight(mods[k].weight, pw.s, Ipad=pw.Ipad, Opad=pw.Opad,
+                               iperm=pw.iperm.tolist() if pw.iperm is not None else None,
+                               operm=pw.operm.tolist() if pw.operm is not None else None)
+            assert torch.equal(ref.fwd, pw.fwd) and torch.equal(ref.tr, pw.tr), (j, k)
+        frames = torch.cat((frames[:, 3:], out['argmax'].float() / 255), dim=1)
