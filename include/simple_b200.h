@@ -27,6 +27,9 @@ int sb_init(int device);
 /* Number of kernels launched by this library since load (bench.py's gpu_launches claim). */
 long long sb_launch_count(void);
 const char* sb_version(void);
+/* Debug / A-B switch: 1 (default) lets sb_tap_gemm use the CTA-pair (tcgen05 cta_group::2) kernel for large bf16-output
+ * layers, 0 forces the single-CTA kernel.  Returns the previous setting. */
+int sb_set_pair_mode(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores ("tap GEMM").

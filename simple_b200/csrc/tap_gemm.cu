@@ -14,6 +14,7 @@
 namespace sb {
 
 long long g_launches = 0;
+int g_pair_mode = 1;  // 1: use the CTA-pair (cta_group::2) tap GEMM where eligible; 0: single-CTA kernel only
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -355,6 +356,218 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the large bf16-output layers.  One thread-block cluster of two CTAs (one SM
+// pair) owns a 256-row x BN tile: CTA r of the pair TMA-loads the A box of M tile 2*pair+r (128 rows) and HALF of the
+// weight tile (rows n0 + r*BN/2 ..), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads A from each
+// CTA's own shared memory and the two B halves from both, and accumulates 128 lanes x BN columns in each CTA's TMEM.
+// Why: the single-CTA kernel is bound by L2 -> SM operand traffic, not by the tensor pipe (85 FLOP per L2 byte at
+// 128 x 256 tiles against the ~6300 B/clk L2 cap, i.e. ~1.05 PFLOP/s at 1.96 GHz -- exactly where it measures).  The
+// pair halves the B traffic per FLOP (128 FLOP/B at 256 x 256).  Everything else (persistent tile loop, TMEM double
+// buffering, 8 epilogue warps with the 64B-swizzled TMA-store staging) is the single-CTA design.
+// Barrier protocol: full[s] lives in the LEADER (2 arrivals: both producers' arrive.expect_tx, the peer's remotely;
+// the peer's TMA completes its bytes on the leader's barrier through the .cta_group::2 load form); empty[s] / tfull[a]
+// are signalled in BOTH CTAs by one multicast tcgen05.commit; tempty[a] lives in the leader (16 arrivals: the 8
+// epilogue warps of each CTA, the peer's remotely).
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+    tap_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmDev p) {
+  constexpr int BH = BN / 2;           // weight-tile rows held by each CTA of the pair
+  constexpr int B_BYTES = BH * 128;
+  constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kATileBytes;
+  uint8_t* sO = sB + STAGES * B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sO + kOutBufs * kStageOutBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int KT = p.ntaps * p.kchunks;
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated, before any remote arrival / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)B_BYTES;
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int nt = tile % p.n_tiles;
+        const int mt = 2 * (tile / p.n_tiles) + (int)rank;  // may be one past the last M tile: TMA zero-fills / clips
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * BN + (int)rank * BH;
+        for (int kk = 0; kk < KT; ++kk, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const int t = kk / p.kchunks;
+          const int c0 = (kk - t * p.kchunks) * 64;
+          const uint32_t lead_full = mapa_u32(&full[s], 0);
+          mbar_expect_tx_cluster(lead_full, tx_bytes);
+          tma_load_4d_2cta(sA + s * kATileBytes, &tmA, lead_full, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b0);
+          tma_load_2d_2cta(sB + s * B_BYTES, &tmB, lead_full, t * p.C + c0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      int it = 0, tcount = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+        const int as = tcount & 1;
+        const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+        mbar_wait(&tempty[as], aph ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < KT; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full[s], ph);  // both CTAs' operand tiles of this stage have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
+          const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_2cta(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+          }
+          umma_commit_2cta(&empty[s], 3);
+        }
+        umma_commit_2cta(&tfull[as], 3);
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int lg = warp & 3;
+    const int half = e >> 2;
+    const int r = lg * 32 + lane;
+    const bool issuer = ((e & 3) == 0) && lane == 0;
+    const uint32_t bar_id = 1u + (uint32_t)half;
+    uint32_t ochunk = 0;
+    int tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+      const int nt = tile % p.n_tiles;
+      const int mt = 2 * (tile / p.n_tiles) + (int)rank;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * BN;
+      const int as = tcount & 1;
+      const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half * 32; c < BN; c += 64) {
+        if (n0 + c >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
+        if (issuer) bulk_wait_read<1>();
+        tmem_ld_wait();
+        const int nb = n0 + c;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        named_bar_sync(bar_id, 128);
+        uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOutBytes;
+        if (r < p.rows) {
+          uint8_t* row = buf + r * 64;
+          const int sw = (r >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          tma_store_4d(&tmO, buf, nb, x0, y0, b0);  // rows outside the tensor (the odd last M tile) are clipped
+          bulk_commit();
+        }
+        ++ochunk;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[as]);
+        else mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+      }
+    }
+    if (issuer) bulk_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA retires (or frees TMEM) while its peer may still signal it or read its operands
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES>
+static int launch_tap_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TapGemmDev& p,
+                            cudaStream_t stream) {
+  constexpr int smem = STAGES * (kATileBytes + (BN / 2) * 128) + kOutBufs * kStageOutBytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "tap_gemm2_kernel: shared memory budget exceeded");
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tap_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  const int total = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pairs = total < 74 ? total : 74;
+  tap_gemm2_kernel<BN, STAGES><<<2 * pairs, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // wgrad: D[m = dY channel (128/tile), n = A channel (BN/tile)] += sum over a 64-pixel box; both operands MN-major.
 // ------------------------------------------------------------------------------------------------------------------
 struct TapWgradDev {
@@ -554,6 +767,19 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   }
   p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
   p.n_tiles = (a->N + BN - 1) / BN;
+  // CTA-pair kernel: bf16 TMA-store outputs, no split-K, enough 256-row tiles to fill the 74 SM pairs, full N tiles
+  const bool pair_ok = p.tma_out && p.splits == 1 && a->N % BN == 0 && BN != 96 && rows >= 64 &&
+                       ((p.m_tiles + 1) / 2) * p.n_tiles >= 74 && g_pair_mode != 0;
+  if (pair_ok) {
+    CUtensorMap tmBh;
+    rc = make_map_2d(&tmBh, a->w, a->N, a->ntaps * a->C, a->ldw, BN / 2);
+    if (rc) return rc;
+    switch (BN) {
+      case 256: return launch_tap_gemm2<256, 6>(tmA, tmBh, tmO, p, stream);
+      case 192: return launch_tap_gemm2<192, 6>(tmA, tmBh, tmO, p, stream);
+      default: return launch_tap_gemm2<128, 6>(tmA, tmBh, tmO, p, stream);
+    }
+  }
   switch (BN) {
     case 256: return launch_tap_gemm<256, 4>(tmA, tmB, tmO, p, stream);
     case 192: return launch_tap_gemm<192, 4>(tmA, tmB, tmO, p, stream);
@@ -609,4 +835,9 @@ extern "C" int sb_init(int device) {
   return load_driver_entry();
 }
 extern "C" long long sb_launch_count(void) { return sb::g_launches; }
+extern "C" int sb_set_pair_mode(int enabled) {
+  const int prev = sb::g_pair_mode;
+  sb::g_pair_mode = enabled ? 1 : 0;
+  return prev;
+}
 extern "C" const char* sb_version(void) { return "simple_b200 0.1 (sm_100a)"; }

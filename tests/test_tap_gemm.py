@@ -80,3 +80,51 @@ def test_wgrad(C, N, splits):
     torch.cuda.synchronize()
     err = float((dw - ref).abs().max())
     assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), err
+
+
+@pytest.mark.parametrize('B,Ho,Wo,C,N,kind', [(9, 52, 40, 96, 192, 's2d'), (5, 105, 80, 96, 768, '1x1'),
+                                               (7, 105, 80, 128, 128, '3x3'), (33, 26, 20, 192, 384, 's2d')])
+def test_cta_pair_kernel_matches_single_cta_and_reference(B, Ho, Wo, C, N, kind):
+    """Large bf16-output layers run on the CTA-pair (tcgen05 cta_group::2, M = 256) kernel.  It must agree with the
+    single-CTA kernel bit for bit (same products, same fp32 accumulation order per output) and with torch; odd M-tile
+    counts exercise the clipped last half-tile, bias + ReLU the epilogue."""
+    from simple_b200 import _lib
+    from simple_b200.gemm import tap_gemm
+    torch.manual_seed(5)
+    if kind == 's2d':
+        a = torch.randn(B, Ho + 1, Wo + 1, 4 * C, device=_dev()).bfloat16()
+        taps = [(dy, dx) for dy in range(2) for dx in range(2)]
+        Ca = 4 * C
+    elif kind == '3x3':
+        a = torch.randn(B, Ho, Wo, C, device=_dev()).bfloat16()
+        taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+        Ca = C
+    else:
+        a = torch.randn(B, Ho, Wo, C, device=_dev()).bfloat16()
+        taps = [(0, 0)]
+        Ca = C
+    w = (torch.randn(N, len(taps) * Ca, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(N, device=_dev())
+    L = _lib.lib()
+    prev = L.sb_set_pair_mode(1)
+    try:
+        n0 = L.sb_launch_count()
+        out_pair = tap_gemm(a, w, taps, Ho, Wo, N=N, bias=bias, relu=True)
+        L.sb_set_pair_mode(0)
+        out_single = tap_gemm(a, w, taps, Ho, Wo, N=N, bias=bias, relu=True)
+    finally:
+        L.sb_set_pair_mode(prev)
+    torch.cuda.synchronize()
+    assert torch.equal(out_pair, out_single), float((out_pair.float() - out_single.float()).abs().max())
+    # torch reference of the same tap contraction, one sample at a time (fp32)
+    for b in (0, B - 1):
+        acc = torch.zeros(Ho, Wo, N, device=_dev())
+        for t, (dy, dx) in enumerate(taps):
+            src = torch.zeros(Ho, Wo, Ca, device=_dev())
+            ys, ye = max(0, -dy), min(Ho, a.shape[1] - dy)
+            xs, xe = max(0, -dx), min(Wo, a.shape[2] - dx)
+            src[ys:ye, xs:xe] = a[b, ys + dy:ye + dy, xs + dx:xe + dx].float()
+            acc += src @ w[:, t * Ca:(t + 1) * Ca].float().t()
+        ref = F.relu(acc + bias)
+        got = out_pair[b].float()
+        assert torch.allclose(got, ref, rtol=2e-2, atol=5e-2), float((got - ref).abs().max())
