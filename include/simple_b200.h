@@ -139,6 +139,9 @@ typedef struct {
   float* dcol;             /* optional fp32 [C] (caller zeroes): += column sums of d_main over b,y,x = the bias gradient
                               of the convolution that produced `in` (sb_prep_bwd_apply only) */
 } sb_prep_args;
+/* Debug / A-B switch: 1 (default) dispatches to kernel instances specialised at compile time for the feature
+ * combinations of the world model; 0 always runs the fully-runtime instances.  Returns the previous setting. */
+int sb_set_prep_specialize(int enabled);
 int sb_stats(const sb_prep_args* args, float* sums /* [B,C,2], caller zeroes */, sb_stream_t stream);
 int sb_prep(const sb_prep_args* args, sb_stream_t stream);
 int sb_prep_bwd_reduce(const sb_prep_args* args, sb_stream_t stream);

@@ -35,6 +35,19 @@ __device__ __forceinline__ void ld8f(const float* p, float* f) {
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+// Compile-time feature masks.  The fused stages are issue-bound on integer / predicate / branch instructions when every
+// optional piece is a runtime test, so each kernel is instantiated for the handful of feature combinations the network
+// uses (dead pieces vanish) next to one fully-runtime instance (kRT) that serves everything else (tests, parity masks).
+constexpr uint32_t kRT = 0x80000000u;
+enum : uint32_t {
+  F_RELU = 1u, F_NORM = 2u, F_TA = 4u, F_OUT1 = 8u, F_DROP = 16u, F_TB = 32u, F_INJ = 64u, F_ADD = 128u,
+  F_INS2D = 256u, F_OUTS2D = 512u, F_G1 = 1024u, F_DADD = 2048u, F_DCOL = 4096u
+};
+template <uint32_t F, uint32_t BIT>
+__device__ __forceinline__ bool has(bool runtime) {
+  return F == kRT ? runtime : (F & BIT) != 0;
+}
+
 // A bf16 tensor holding a logical [B,H,W,C] activation, either plain NHWC or padded space-to-depth:
 //   s2d element (b, y2, x2, (py*s+px)*C + c) = logical (b, s*y2+py-pad, s*x2+px-pad, c);  s is a power of two
 struct View {
@@ -44,8 +57,9 @@ struct View {
   int sh;    // log2(s)
 };
 // element offsets fit 32 bits (the launchers reject tensors of 2^31 elements or more)
+template <uint32_t F, uint32_t BIT>
 __device__ __forceinline__ uint32_t view_off(const View& v, int H, int W, int C, int b, int y, int x, int c) {
-  if (v.kind == 0) return (uint32_t)(((b * H + y) * W + x) * C + c);
+  if (!has<F, BIT>(v.kind != 0)) return (uint32_t)(((b * H + y) * W + x) * C + c);
   const int yp = y + v.pad, xp = x + v.pad;
   const int y2 = yp >> v.sh, x2 = xp >> v.sh;
   const int ph = ((yp & (v.s - 1)) << v.sh) + (xp & (v.s - 1));
@@ -100,9 +114,10 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
 }
 
 // keep decisions for 8 consecutive channels: 16 random bits each from one hash4x32 call (counter = vector index)
+template <uint32_t F>
 __device__ __forceinline__ void keep8(const PrepParams& q, const uint2 key, uint32_t vec_index, uint32_t elem_index,
                                       bool* k) {
-  if (q.keep) {
+  if (F == kRT && q.keep) {
     const uint2 m = *reinterpret_cast<const uint2*>(q.keep + elem_index);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -119,8 +134,9 @@ __device__ __forceinline__ void keep8(const PrepParams& q, const uint2 key, uint
   k[6] = (r.w & 0xffff) >= thr; k[7] = (r.w >> 16) >= thr;
 }
 // per-launch dropout key (seed may live on the device so that CUDA-graph replays draw fresh masks)
+template <uint32_t F>
 __device__ __forceinline__ uint2 dropout_key(const PrepParams& q) {
-  if (q.p <= 0.f || q.keep) return make_uint2(0u, 0u);
+  if (!has<F, F_DROP>(q.p > 0.f) || (F == kRT && q.keep)) return make_uint2(0u, 0u);
   const unsigned long long seed = q.seed_ptr ? q.seed + *q.seed_ptr : q.seed;
   return hash_key(seed, q.stream_id);
 }
@@ -130,33 +146,35 @@ __device__ __forceinline__ uint2 dropout_key(const PrepParams& q) {
 struct RawZ {
   uint4 m, a;
 };
-template <bool F32>
+template <bool F32, uint32_t F>
 __device__ __forceinline__ void issue_z(const PrepParams& q, int b, int y, int x, int c, RawZ& r) {
   if (F32) return;
-  r.m = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + view_off(q.in, q.H, q.W, q.C, b, y, x, c));
-  if (q.add) r.a = ldg16(q.add + plain_off(q.H, q.W, q.C, b, y, x, c));
+  r.m = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + view_off<F, F_INS2D>(q.in, q.H, q.W, q.C, b, y, x, c));
+  if (has<F, F_ADD>(q.add != nullptr)) r.a = ldg16(q.add + plain_off(q.H, q.W, q.C, b, y, x, c));
 }
 // value of (main [+relu] + add) for 8 channels; also returns raw main
-template <bool F32>
+template <bool F32, uint32_t F>
 __device__ __forceinline__ void finish_z(const PrepParams& q, const RawZ& r, int b, int y, int x, int c, float* z,
                                          float* mainv) {
   float a[8];
+  const bool has_add = has<F, F_ADD>(q.add != nullptr);
   if (F32) {
-    const uint32_t off = view_off(q.in, q.H, q.W, q.C, b, y, x, c);
+    const uint32_t off = view_off<F, F_INS2D>(q.in, q.H, q.W, q.C, b, y, x, c);
     if (q.in_f32) ld8f(reinterpret_cast<const float*>(q.in.p) + off, mainv);
     else bf8_to_f(*reinterpret_cast<const BF8*>(reinterpret_cast<const __nv_bfloat16*>(q.in.p) + off), mainv);
-    if (q.add) {
+    if (has_add) {
       const uint32_t aoff = plain_off(q.H, q.W, q.C, b, y, x, c);
       if (q.add_f32) ld8f(reinterpret_cast<const float*>(q.add) + aoff, a);
       else bf8_to_f(*reinterpret_cast<const BF8*>(q.add + aoff), a);
     }
   } else {
     unpack8(r.m, mainv);
-    if (q.add) unpack8(r.a, a);
+    if (has_add) unpack8(r.a, a);
   }
+  const bool relu = has<F, F_RELU>(q.relu_in != 0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) z[j] = q.relu_in ? fmaxf(mainv[j], 0.f) : mainv[j];
-  if (q.add) {
+  for (int j = 0; j < 8; ++j) z[j] = relu ? fmaxf(mainv[j], 0.f) : mainv[j];
+  if (has_add) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] += a[j];
   }
@@ -207,10 +225,11 @@ __device__ __forceinline__ ChanCst load_cst(const PrepParams& q, int b, float* s
   return k;
 }
 
+template <uint32_t F>
 __device__ __forceinline__ void keep_for(const PrepParams& q, const uint2 key, int b, int y, int x, int c, bool* keep) {
-  if (q.p > 0.f) {
+  if (has<F, F_DROP>(q.p > 0.f)) {
     const uint32_t e = plain_off(q.H, q.W, q.C, b, y, x, c);
-    keep8(q, key, e >> 3, e, keep);
+    keep8<F>(q, key, e >> 3, e, keep);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) keep[j] = true;
@@ -218,9 +237,10 @@ __device__ __forceinline__ void keep_for(const PrepParams& q, const uint2 key, i
 }
 
 // forward chain: xhat (normalised), xn (after affine + Ta), xd (after dropout + Tb, before the injector)
+template <uint32_t F>
 __device__ __forceinline__ void fwd_chain(const PrepParams& q, const ChanCst& k, int y, int x, int c, const float* z,
                                           const bool* keep, float* xhat, float* xn, float* xd) {
-  if (q.sums) {
+  if (has<F, F_NORM>(q.sums != nullptr)) {
     float mean[8], rstd[8], g[8], bt[8];
     ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.beta + c, bt);
 #pragma unroll
@@ -235,16 +255,22 @@ __device__ __forceinline__ void fwd_chain(const PrepParams& q, const ChanCst& k,
       xn[j] = z[j];
     }
   }
-  if (q.Ta) add_timing(q.Ta, q.H, q.C, y, x, c, xn);
-  const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
+  if (has<F, F_TA>(q.Ta != nullptr)) add_timing(q.Ta, q.H, q.C, y, x, c, xn);
+  if (has<F, F_DROP>(q.p > 0.f)) {
+    const float inv_keep = 1.0f / (1.0f - q.p);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) xd[j] = keep[j] ? xn[j] * inv_keep : 0.f;
-  if (q.Tb) add_timing(q.Tb, q.H, q.C, y, x, c, xd);
+    for (int j = 0; j < 8; ++j) xd[j] = keep[j] ? xn[j] * inv_keep : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xd[j] = xn[j];
+  }
+  if (has<F, F_TB>(q.Tb != nullptr)) add_timing(q.Tb, q.H, q.C, y, x, c, xd);
 }
 
 // iteration space: logical pixels, extended to the padded extent of `ext` when it is an s2d view
+template <uint32_t F, uint32_t BIT>
 __device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y0, int* ny, int* x0, int* nx) {
-  if (ext.kind == 0) {
+  if (!has<F, BIT>(ext.kind != 0)) {
     *y0 = 0; *ny = H; *x0 = 0; *nx = W;
   } else {
     *y0 = -ext.pad; *ny = ext.s * ext.H2; *x0 = -ext.pad; *nx = ext.s * ext.W2;
@@ -252,12 +278,12 @@ __device__ __forceinline__ void iter_space(const View& ext, int H, int W, int* y
 }
 
 // grid = (pixel slabs, B); block = CV * PL threads: thread = (8-channel vector cv, pixel lane pl)
-template <bool F32>
+template <bool F32, uint32_t F>
 __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
   constexpr int U = F32 ? 1 : 4;
   extern __shared__ float sm[];
   int y0, ny, x0, nx;
-  iter_space(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
+  iter_space<F, F_OUTS2D>(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int b = blockIdx.y, c = cv * 8;
@@ -265,7 +291,7 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, false);
-  const uint2 dkey = dropout_key(q);
+  const uint2 dkey = dropout_key<F>(q);
   for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
     RawZ raw[U];
     int yy[U], xx[U];
@@ -277,25 +303,25 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
       yy[u] = row + y0;
       xx[u] = pix - row * nx + x0;
       ins[u] = pix < p_end && yy[u] >= 0 && yy[u] < q.H && xx[u] >= 0 && xx[u] < q.W;
-      if (ins[u]) issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
+      if (ins[u]) issue_z<F32, F>(q, b, yy[u], xx[u], c, raw[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (pix0 + u * PL >= p_end) break;
-      __nv_bfloat16* o2 =
-          reinterpret_cast<__nv_bfloat16*>(q.out2.p) + view_off(q.out2, q.H, q.W, q.C, b, yy[u], xx[u], c);
+      __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(q.out2.p) +
+                          view_off<F, F_OUTS2D>(q.out2, q.H, q.W, q.C, b, yy[u], xx[u], c);
       if (!ins[u]) {
         *reinterpret_cast<uint4*>(o2) = make_uint4(0, 0, 0, 0);
         continue;
       }
       float z[8], mainv[8], xhat[8], xn[8], xd[8];
       bool keep[8];
-      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
-      keep_for(q, dkey, b, yy[u], xx[u], c, keep);
-      fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
-      if (q.out1)
+      finish_z<F32, F>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      keep_for<F>(q, dkey, b, yy[u], xx[u], c, keep);
+      fwd_chain<F>(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
+      if (has<F, F_OUT1>(q.out1 != nullptr))
         *reinterpret_cast<BF8*>(q.out1 + plain_off(q.H, q.W, q.C, b, yy[u], xx[u], c)) = f_to_bf8(xn);
-      if (q.sc) {
+      if (has<F, F_INJ>(q.sc != nullptr)) {
         float sc[8], sh[8];
         ld8f(k.sc + c, sc); ld8f(k.sh + c, sh);
 #pragma unroll
@@ -310,19 +336,26 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
 struct RawG {
   uint4 g2, g1;
 };
+template <uint32_t F>
 __device__ __forceinline__ void issue_g(const PrepParams& q, int b, int y, int x, int c, RawG& r) {
-  r.g2 = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) + view_off(q.g2, q.H, q.W, q.C, b, y, x, c));
-  if (q.g1) r.g1 = ldg16(q.g1 + plain_off(q.H, q.W, q.C, b, y, x, c));
+  r.g2 = ldg16(reinterpret_cast<const __nv_bfloat16*>(q.g2.p) + view_off<F, F_OUTS2D>(q.g2, q.H, q.W, q.C, b, y, x, c));
+  if (has<F, F_G1>(q.g1 != nullptr)) r.g1 = ldg16(q.g1 + plain_off(q.H, q.W, q.C, b, y, x, c));
 }
+template <uint32_t F>
 __device__ __forceinline__ void finish_gx(const PrepParams& q, const ChanCst& k, const RawG& r, int c, const bool* keep,
                                           float* g2, float* gx) {
   unpack8(r.g2, g2);
-  const float inv_keep = q.p > 0.f ? 1.0f / (1.0f - q.p) : 1.0f;
-  float sc[8];
-  ld8f(k.sc + c, sc);
+  const float inv_keep = has<F, F_DROP>(q.p > 0.f) ? 1.0f / (1.0f - q.p) : 1.0f;
+  if (has<F, F_INJ>(q.sc != nullptr)) {
+    float sc[8];
+    ld8f(k.sc + c, sc);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) gx[j] = keep[j] ? g2[j] * sc[j] * inv_keep : 0.f;
-  if (q.g1) {
+    for (int j = 0; j < 8; ++j) gx[j] = keep[j] ? g2[j] * sc[j] * inv_keep : 0.f;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gx[j] = keep[j] ? g2[j] * inv_keep : 0.f;
+  }
+  if (has<F, F_G1>(q.g1 != nullptr)) {
     float t[8];
     unpack8(r.g1, t);
 #pragma unroll
@@ -354,7 +387,7 @@ __device__ __forceinline__ void lane_reduce_atomic(float (*acc)[8], float* scrat
 // grid = (slabs, B); block = CV * PL threads (thread = one 8-channel vector x one pixel lane)
 // shared memory: [8*C constants (MODE 1)] then the [PL][CV][NV*8] reduction scratch
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, bool F32>
+template <int MODE, bool F32, uint32_t F>
 __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
     reduce_bc_kernel(const __grid_constant__ PrepParams q, float* out, int PL, int pix_per_slab) {
   constexpr int NV = MODE == 0 ? 2 : 4;
@@ -378,7 +411,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
     k = load_cst(q, b, sm, false);
     scratch = sm + 8 * q.C;
   }
-  const uint2 dkey = MODE == 1 ? dropout_key(q) : make_uint2(0u, 0u);
+  const uint2 dkey = MODE == 1 ? dropout_key<F>(q) : make_uint2(0u, 0u);
   for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * PL) {
     RawZ raw[U];
     RawG rg[U];
@@ -389,15 +422,15 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
       yy[u] = fast_div(pix, q.w_magic);
       xx[u] = pix - yy[u] * q.W;
       if (pix < p_end) {
-        issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
-        if (MODE == 1) issue_g(q, b, yy[u], xx[u], c, rg[u]);
+        issue_z<F32, F>(q, b, yy[u], xx[u], c, raw[u]);
+        if (MODE == 1) issue_g<F>(q, b, yy[u], xx[u], c, rg[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (pix0 + u * PL >= p_end) break;
       float z[8], mainv[8];
-      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      finish_z<F32, F>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -407,9 +440,9 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
       } else {
         float xhat[8], xn[8], xd[8], g2[8], gx[8];
         bool keep[8];
-        keep_for(q, dkey, b, yy[u], xx[u], c, keep);
-        fwd_chain(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
-        finish_gx(q, k, rg[u], c, keep, g2, gx);
+        keep_for<F>(q, dkey, b, yy[u], xx[u], c, keep);
+        fwd_chain<F>(q, k, yy[u], xx[u], c, z, keep, xhat, xn, xd);
+        finish_gx<F>(q, k, rg[u], c, keep, g2, gx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[0][j] += gx[j];
@@ -423,13 +456,13 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
   lane_reduce_atomic<NV>(acc, scratch, CV, PL, cv, pl, out, (long long)b * q.C * NV, NV);
 }
 
-template <bool F32>
+template <bool F32, uint32_t F>
 __global__ void __launch_bounds__(256, 2)
     prep_bwd_apply_kernel(const __grid_constant__ PrepParams q, int PL, int pix_per_slab) {
   constexpr int U = F32 ? 1 : 2;
   extern __shared__ float sm[];
   int y0, ny, x0, nx;
-  iter_space(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
+  iter_space<F, F_INS2D>(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int b = blockIdx.y, c = cv * 8;
@@ -437,7 +470,8 @@ __global__ void __launch_bounds__(256, 2)
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
   const ChanCst k = load_cst(q, b, sm, true);
-  const uint2 dkey = dropout_key(q);
+  const uint2 dkey = dropout_key<F>(q);
+  const bool has_dcol = has<F, F_DCOL>(q.dcol != nullptr);
   float dsum[1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dsum[0][j] = 0.f;
@@ -454,25 +488,25 @@ __global__ void __launch_bounds__(256, 2)
       xx[u] = pix - row * nx + x0;
       ins[u] = pix < p_end && yy[u] >= 0 && yy[u] < q.H && xx[u] >= 0 && xx[u] < q.W;
       if (ins[u]) {
-        issue_z<F32>(q, b, yy[u], xx[u], c, raw[u]);
-        issue_g(q, b, yy[u], xx[u], c, rg[u]);
+        issue_z<F32, F>(q, b, yy[u], xx[u], c, raw[u]);
+        issue_g<F>(q, b, yy[u], xx[u], c, rg[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (pix0 + u * PL >= p_end) break;
-      __nv_bfloat16* dm =
-          reinterpret_cast<__nv_bfloat16*>(q.d_main.p) + view_off(q.d_main, q.H, q.W, q.C, b, yy[u], xx[u], c);
+      __nv_bfloat16* dm = reinterpret_cast<__nv_bfloat16*>(q.d_main.p) +
+                          view_off<F, F_INS2D>(q.d_main, q.H, q.W, q.C, b, yy[u], xx[u], c);
       if (!ins[u]) {
         *reinterpret_cast<uint4*>(dm) = make_uint4(0, 0, 0, 0);
         continue;
       }
       float z[8], mainv[8], g2[8], gx[8], dz[8];
       bool keep[8];
-      finish_z<F32>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
-      keep_for(q, dkey, b, yy[u], xx[u], c, keep);
-      finish_gx(q, k, rg[u], c, keep, g2, gx);
-      if (q.sums) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
+      finish_z<F32, F>(q, raw[u], b, yy[u], xx[u], c, z, mainv);
+      keep_for<F>(q, dkey, b, yy[u], xx[u], c, keep);
+      finish_gx<F>(q, k, rg[u], c, keep, g2, gx);
+      if (has<F, F_NORM>(q.sums != nullptr)) {  // InstanceNorm backward; the affine / timing / dropout values themselves are not needed here
         float mean[8], rstd[8], g[8], m1[8], m2[8];
         ld8f(k.mean + c, mean); ld8f(k.rstd + c, rstd); ld8f(k.gamma + c, g); ld8f(k.m1 + c, m1); ld8f(k.m2 + c, m2);
 #pragma unroll
@@ -484,15 +518,15 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
         for (int j = 0; j < 8; ++j) dz[j] = gx[j];
       }
-      if (q.d_add)
+      if (has<F, F_DADD>(q.d_add != nullptr))
         *reinterpret_cast<BF8*>(q.d_add + plain_off(q.H, q.W, q.C, b, yy[u], xx[u], c)) = f_to_bf8(dz);
-      if (q.relu_in) {
+      if (has<F, F_RELU>(q.relu_in != 0)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) dz[j] = mainv[j] > 0.f ? dz[j] : 0.f;
       }
       const BF8 o = f_to_bf8(dz);
       *reinterpret_cast<BF8*>(dm) = o;
-      if (q.dcol) {  // bias gradient of the conv that produced `main`: sums of the bf16-rounded values it will see
+      if (has_dcol) {  // bias gradient of the conv that produced `main`: sums of the bf16-rounded values it will see
         float r8[8];
         bf8_to_f(o, r8);
 #pragma unroll
@@ -500,7 +534,7 @@ __global__ void __launch_bounds__(256, 2)
       }
     }
   }
-  if (q.dcol) {
+  if (has_dcol) {
     __syncthreads();  // the per-channel constants in shared memory are dead: reuse the space as reduction scratch
     lane_reduce_atomic<1>(dsum, sm, CV, PL, cv, pl, q.dcol, 0, 1);
   }
@@ -710,8 +744,53 @@ static View mk_view(const sb_view* v) {
   return r;
 }
 static bool view_ok(const View& v) { return v.kind == 0 || (v.s >= 1 && (1 << v.sh) == v.s); }
+static int g_prep_specialize = 1;  // 0: always run the fully-runtime kernel instances (A/B testing)
+// feature mask of a parameter block, restricted to the bits a kernel looks at
+static uint32_t feat_mask(const PrepParams& q, uint32_t relevant) {
+  if (!g_prep_specialize) return 0xffffffffu;  // matches no specialised instance
+  uint32_t f = 0;
+  if (q.relu_in) f |= F_RELU;
+  if (q.sums) f |= F_NORM;
+  if (q.Ta) f |= F_TA;
+  if (q.out1) f |= F_OUT1;
+  if (q.p > 0.f) f |= F_DROP;
+  if (q.Tb) f |= F_TB;
+  if (q.sc) f |= F_INJ;
+  if (q.add) f |= F_ADD;
+  if (q.in.kind != 0) f |= F_INS2D;
+  if (q.out2.kind != 0 || q.g2.kind != 0) f |= F_OUTS2D;
+  if (q.g1) f |= F_G1;
+  if (q.d_add) f |= F_DADD;
+  if (q.dcol) f |= F_DCOL;
+  return f & relevant;
+}
+// the feature combinations of the world model's bf16 stages (anything else runs the fully-runtime instance)
+#define SB_FWD_MASKS(X)                                              \
+  X(F_TA | F_OUT1 | F_DROP | F_TB | F_OUTS2D)                        \
+  X(F_RELU | F_NORM | F_OUT1 | F_DROP | F_TB | F_OUTS2D)             \
+  X(F_RELU | F_NORM | F_TA | F_DROP | F_INJ | F_ADD | F_INS2D)       \
+  X(F_RELU | F_NORM | F_TA | F_ADD | F_INS2D)                        \
+  X(F_TA | F_INJ | F_OUTS2D)                                         \
+  X(F_RELU | F_OUTS2D)
+#define SB_STATS_MASKS(X) X(0u) X(F_RELU) X(F_RELU | F_ADD | F_INS2D)
+#define SB_RED1_MASKS(X)                                             \
+  X(F_RELU | F_NORM | F_DROP | F_TB | F_OUTS2D | F_G1)               \
+  X(F_RELU | F_NORM | F_TA | F_DROP | F_INJ | F_ADD | F_INS2D)       \
+  X(F_RELU | F_NORM | F_TA | F_ADD | F_INS2D)                        \
+  X(F_TA | F_INJ | F_OUTS2D)
+#define SB_APPLY_MASKS(X)                                                    \
+  X(F_DROP | F_OUTS2D | F_G1 | F_DCOL)                                       \
+  X(F_RELU | F_NORM | F_DROP | F_OUTS2D | F_G1 | F_DCOL)                     \
+  X(F_RELU | F_NORM | F_DROP | F_INJ | F_ADD | F_INS2D | F_DADD | F_DCOL)    \
+  X(F_RELU | F_NORM | F_ADD | F_INS2D | F_DADD | F_DCOL)                     \
+  X(F_INJ | F_OUTS2D | F_DCOL)                                               \
+  X(F_RELU | F_OUTS2D)
+constexpr uint32_t kFwdBits = F_RELU | F_NORM | F_TA | F_OUT1 | F_DROP | F_TB | F_INJ | F_ADD | F_INS2D | F_OUTS2D;
+constexpr uint32_t kStatsBits = F_RELU | F_ADD | F_INS2D;
+constexpr uint32_t kRed1Bits = F_RELU | F_NORM | F_TA | F_DROP | F_TB | F_INJ | F_ADD | F_INS2D | F_OUTS2D | F_G1;
+constexpr uint32_t kApplyBits = F_RELU | F_NORM | F_DROP | F_INJ | F_ADD | F_INS2D | F_OUTS2D | F_G1 | F_DADD | F_DCOL;
+
 static uint32_t div_magic(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); }
-static int iter_nx(const View& v, int W) { return v.kind == 0 ? W : v.s * v.W2; }
 static int fill(PrepParams& q, const sb_prep_args* a) {
   if (!a || a->C % 8 || a->C < 8 || a->C / 8 > 256) return SB_ERR_ARG;
   q.B = a->B; q.H = a->H; q.W = a->W; q.C = a->C;
@@ -762,6 +841,12 @@ static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* 
   *slabs = (P + per - 1) / per;
 }
 
+extern "C" int sb_set_prep_specialize(int enabled) {
+  const int prev = g_prep_specialize;
+  g_prep_specialize = enabled ? 1 : 0;
+  return prev;
+}
+
 extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) {
   PrepParams q;
   int rc = fill(q, a);
@@ -770,10 +855,18 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads);
   const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
-  if (q.in_f32 || q.add_f32)
-    reduce_bc_kernel<0, true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
-  else
-    reduce_bc_kernel<0, false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, sums, PL, pps);
+  const dim3 grid(slabs, q.B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q.in_f32 || q.add_f32) {
+    reduce_bc_kernel<0, true, kRT><<<grid, threads, smem, st>>>(q, sums, PL, pps);
+  } else {
+    switch (feat_mask(q, kStatsBits)) {
+#define SB_CASE(M) case (M): reduce_bc_kernel<0, false, (M)><<<grid, threads, smem, st>>>(q, sums, PL, pps); break;
+      SB_STATS_MASKS(SB_CASE)
+#undef SB_CASE
+      default: reduce_bc_kernel<0, false, kRT><<<grid, threads, smem, st>>>(q, sums, PL, pps);
+    }
+  }
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -789,10 +882,21 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
   if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
   q.nx_magic = div_magic(nx);
-  if (q.in_f32 || q.add_f32)
-    prep_fwd_kernel<true><<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
-  else
-    prep_fwd_kernel<false><<<dim3(slabs, q.B), threads, 8 * q.C * sizeof(float), (cudaStream_t)stream>>>(q, PL, pps);
+  const dim3 grid(slabs, q.B);
+  const size_t smem = 8 * q.C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q.in_f32 || q.add_f32) {
+    prep_fwd_kernel<true, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+  } else if (q.keep) {
+    prep_fwd_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+  } else {
+    switch (feat_mask(q, kFwdBits)) {
+#define SB_CASE(M) case (M): prep_fwd_kernel<false, (M)><<<grid, threads, smem, st>>>(q, PL, pps); break;
+      SB_FWD_MASKS(SB_CASE)
+#undef SB_CASE
+      default: prep_fwd_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    }
+  }
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -805,10 +909,20 @@ extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
   int PL, slabs, pps, threads;
   reduce_cfg(q, &PL, &slabs, &pps, &threads);
   const size_t smem = ((size_t)threads * 4 * 8 + 8 * (size_t)q.C) * sizeof(float);
-  if (q.in_f32 || q.add_f32)
-    reduce_bc_kernel<1, true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
-  else
-    reduce_bc_kernel<1, false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, q.bsums, PL, pps);
+  const dim3 grid(slabs, q.B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q.in_f32 || q.add_f32) {
+    reduce_bc_kernel<1, true, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+  } else if (q.keep) {
+    reduce_bc_kernel<1, false, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+  } else {
+    switch (feat_mask(q, kRed1Bits)) {
+#define SB_CASE(M) case (M): reduce_bc_kernel<1, false, (M)><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps); break;
+      SB_RED1_MASKS(SB_CASE)
+#undef SB_CASE
+      default: reduce_bc_kernel<1, false, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+    }
+  }
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -826,10 +940,20 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   q.nx_magic = div_magic(nx);
   // shared memory: 8*C per-channel constants, reused as the [PL][CV][8] scratch of the bias-gradient reduction
   const size_t smem = (size_t)(8 * q.C > threads * 8 ? 8 * q.C : threads * 8) * sizeof(float);
-  if (q.in_f32 || q.add_f32)
-    prep_bwd_apply_kernel<true><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, PL, pps);
-  else
-    prep_bwd_apply_kernel<false><<<dim3(slabs, q.B), threads, smem, (cudaStream_t)stream>>>(q, PL, pps);
+  const dim3 grid(slabs, q.B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q.in_f32 || q.add_f32) {
+    prep_bwd_apply_kernel<true, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+  } else if (q.keep) {
+    prep_bwd_apply_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+  } else {
+    switch (feat_mask(q, kApplyBits)) {
+#define SB_CASE(M) case (M): prep_bwd_apply_kernel<false, (M)><<<grid, threads, smem, st>>>(q, PL, pps); break;
+      SB_APPLY_MASKS(SB_CASE)
+#undef SB_CASE
+      default: prep_bwd_apply_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    }
+  }
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -259,6 +259,179 @@ __global__ void __launch_bounds__(512)
   }
 }
 
+// Third generation of the sampler: a thread-block CLUSTER of two CTAs per S samples keeps the recurrent weights
+// RESIDENT in shared memory for all 16 steps (fp32: W_hh^T is 256 KB, W5^T 128 KB -- one SM's 227 KB cannot hold them,
+// a pair can).  CTA r owns hidden units [64r, 64r+64): the 4 x 64 gate rows of those units (128 KB of W_hh^T) and the
+// logits [128r, 128r+128) (64 KB of W5^T).  Per step the halves of h and the two local arg-max candidates cross the
+// pair through distributed shared memory (two cluster barriers); no weight byte is re-read from L2 after the prologue,
+// which was the whole cost of the previous kernels (a dependent chain of L2 round trips per step).
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+template <int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
+    lstm_sample3_kernel(const float* __restrict__ G0, const float* __restrict__ h0, const float* __restrict__ c0,
+                        const float* __restrict__ E, const float* __restrict__ whhT, const float* __restrict__ w5T,
+                        const float* __restrict__ b5, const float* __restrict__ noise,
+                        const unsigned long long* seed_ptr, int B, float* __restrict__ bits, int* __restrict__ ints) {
+  extern __shared__ float wsm[];
+  float* wh = wsm;                    // [128 k][256 local gate rows]: local row g*64+jl <-> global row g*128 + 64r + jl
+  float* w5 = wsm + kH * 256;         // [128 k][128 local logits]:    local ln <-> global logit 128r + ln
+  __shared__ float hbuf[2][S][kH], c[S][kH / 2], gates[S][256], part_g[S][256], part_l[3][S][kH], score[S][kH];
+  __shared__ float slot_v[2][S];
+  __shared__ int slot_i[2][S];
+  __shared__ int sym[S][kSteps];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
+  const int b0 = (blockIdx.x >> 1) * S;
+  for (int i = t; i < kH * 256; i += 512) {
+    const int k = i >> 8, lr = i & 255;
+    wh[i] = __ldg(whhT + k * (4 * kH) + (lr >> 6) * kH + 64 * (int)rank + (lr & 63));
+  }
+  for (int i = t; i < kH * 128; i += 512) {
+    const int k = i >> 7, ln = i & 127;
+    w5[i] = __ldg(w5T + k * kV + 128 * (int)rank + ln);
+  }
+  for (int i = t; i < S * kH; i += 512) {
+    const int s = i / kH, j = i - s * kH;
+    hbuf[0][s][j] = h0[min(b0 + s, B - 1) * kH + j];
+  }
+  for (int i = t; i < S * 64; i += 512) {
+    const int s = i >> 6, jl = i & 63;
+    c[s][jl] = c0[min(b0 + s, B - 1) * kH + 64 * (int)rank + jl];
+  }
+  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  cluster_sync_all();  // both CTAs are running (remote shared-memory writes below) and the local weights are staged
+  for (int step = 0; step < kSteps; ++step) {
+    // h is double-buffered: this step reads h_old, the cells write h_new in BOTH CTAs -- the peer may still be reading
+    // h_old in its gate phase when this CTA's cells are done
+    const float (*h_old)[kH] = hbuf[step & 1];
+    float (*h_new)[kH] = hbuf[(step & 1) ^ 1];
+    {  // gate pre-activations of the local rows: thread = (k half, local row)
+      const int lr = t & 255, kh = t >> 8;
+      const int grow = (lr >> 6) * kH + 64 * (int)rank + (lr & 63);
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        acc[s] = 0.f;
+        if (kh == 0) {
+          const int b = min(b0 + s, B - 1);
+          acc[s] = step == 0 ? G0[(size_t)b * 4 * kH + grow] : E[(size_t)sym[s][step - 1] * 4 * kH + grow];
+        }
+      }
+#pragma unroll 8
+      for (int k = kh * 64; k < kh * 64 + 64; ++k) {
+        const float w = wh[k * 256 + lr];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(w, h_old[s][k], acc[s]);
+      }
+      if (kh == 1) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) part_g[s][lr] = acc[s];
+      }
+      __syncthreads();
+      if (kh == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) gates[s][lr] = acc[s] + part_g[s][lr];
+      }
+    }
+    __syncthreads();
+    if (t < S * 64) {  // LSTM cell of the local hidden units; the new h goes to both CTAs
+      const int s = t >> 6, jl = t & 63;
+      const float ig = sigmoidf_(gates[s][jl]), fg = sigmoidf_(gates[s][64 + jl]);
+      const float gg = tanh_acc(gates[s][128 + jl]), og = sigmoidf_(gates[s][192 + jl]);
+      const float cn = fg * c[s][jl] + ig * gg;
+      const float hn = og * tanh_acc(cn);
+      c[s][jl] = cn;
+      float* dst = &h_new[s][64 * (int)rank + jl];
+      *dst = hn;
+      st_cluster_f32(mapa_u32(dst, peer), hn);
+    }
+    cluster_sync_all();
+    {  // local logits: thread = (k quarter, local logit)
+      const int ln = t & 127, kq = t >> 7;
+      float acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = 0.f;
+#pragma unroll 8
+      for (int k = kq * 32; k < kq * 32 + 32; ++k) {
+        const float w = w5[k * 128 + ln];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fmaf(w, h_new[s][k], acc[s]);
+      }
+      if (kq > 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) part_l[kq - 1][s][ln] = acc[s];
+      }
+      __syncthreads();
+      if (kq == 0) {
+        const int n = 128 * (int)rank + ln;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int b = min(b0 + s, B - 1);
+          const float logit = acc[s] + part_l[0][s][ln] + part_l[1][s][ln] + part_l[2][s][ln] + b5[n];
+          float q;
+          if (noise) {
+            q = noise[((size_t)b * kSteps + step) * kV + n];
+          } else {
+            const uint4 rr = philox4x32(make_uint4((uint32_t)n, (uint32_t)step, (uint32_t)b, 0x4c53544du),
+                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            q = -logf(((float)(rr.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
+          }
+          score[s][ln] = expf(logit) / q;  // sample_with_temperature(T=1): multinomial(exp(logits))
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < S) {  // arg-max of the 128 local scores of sample `warp` (first index on ties)
+      float v = -1.0f;
+      int i = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sv = score[warp][lane + 32 * j];
+        if (sv > v) {
+          v = sv;
+          i = lane + 32 * j;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) {
+          v = ov;
+          i = oi;
+        }
+      }
+      if (lane == 0) {
+        i += 128 * (int)rank;
+        slot_v[rank][warp] = v;
+        slot_i[rank][warp] = i;
+        st_cluster_f32(mapa_u32(&slot_v[rank][warp], peer), v);
+        st_cluster_u32(mapa_u32(&slot_i[rank][warp], peer), (uint32_t)i);
+      }
+    }
+    cluster_sync_all();
+    if (t < S)  // CTA 0 holds the lower symbol indices: it wins ties, like a single arg-max over all 256 scores
+      sym[t][step] = (slot_v[1][t] > slot_v[0][t]) ? slot_i[1][t] : slot_i[0][t];
+    __syncthreads();
+  }
+  if (rank == 0) {
+    for (int i = t; i < S * kSteps; i += 512) {
+      const int s = i / kSteps, k = i - s * kSteps;
+      if (b0 + s < B) ints[(b0 + s) * kSteps + k] = sym[s][k];
+    }
+    for (int i = t; i < S * kSteps * 8; i += 512) {
+      const int s = i / (kSteps * 8), k = i - s * (kSteps * 8);
+      if (b0 + s < B) bits[(size_t)(b0 + s) * (kSteps * 8) + k] = ((sym[s][k >> 3] >> (k & 7)) & 1) ? 1.0f : -1.0f;
+    }
+  }
+}
+
 // Teacher-forced pass (next_frame_predictor.py:97-100): all 16 LSTMCell steps of S samples in one CTA.
 //   xw [B,16,512] = input-gate pre-activations (W_ih x_t + b_ih + b_hh, one GEMM over all steps on the host side)
 //   -> hs [B,16,128] (outputs), act [B,16,512] (post-activation gates) and cs [B,16,128] (cell states) for backward
@@ -442,18 +615,32 @@ extern "C" int sb_lstm_cell_bwd(const float* act, const float* c_prev, const flo
   return SB_OK;
 }
 
+template <int S>
+static int launch_sample3(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
+                          const float* w5T, const float* b5, const float* noise, const unsigned long long* seed_ptr, int B,
+                          float* bits, int* ints, cudaStream_t st) {
+  constexpr int smem = (kH * 256 + kH * 128) * sizeof(float);  // resident weight slices: 192 KB
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(lstm_sample3_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return SB_ERR_CUDA;
+    configured = true;
+  }
+  const int groups = (B + S - 1) / S;
+  lstm_sample3_kernel<S><<<2 * groups, 512, smem, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
 extern "C" int sb_lstm_sample2(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
                                const float* w5T, const float* b5, const float* noise,
                                const unsigned long long* seed_ptr, int B, float* bits, int* ints, sb_stream_t stream) {
   if (!G0 || !h0 || !c0 || !E || !whhT || !w5T || !b5 || !bits || !ints || B < 1) return SB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B >= 32 && B % 2 == 0)
-    lstm_sample2_kernel<2><<<B / 2, 512, 0, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
-  else
-    lstm_sample2_kernel<1><<<B, 512, 0, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
-  ++g_launches;
-  SB_CHECK_LAUNCH();
-  return SB_OK;
+  // one CTA pair (cluster) per one or two samples, recurrent weights resident in the pair's shared memory
+  if (B >= 64 && B % 2 == 0) return launch_sample3<2>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints, st);
+  return launch_sample3<1>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints, st);
 }
 
 extern "C" int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B,

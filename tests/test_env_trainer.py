@@ -152,7 +152,7 @@ def test_packed_gradient_mode_matches_reference_layout_mode():
         assert abs(float(opt.grad_norm_sq) - float(opt_ref.grad_norm_sq)) < 1e-5 * float(opt_ref.grad_norm_sq)
         for (k, a), b in zip(model.named_parameters(), twin.parameters()):
             err = float((a - b).abs().max() / (a.abs().max() + 1e-12))
-            assert err < 2e-6, (j, k, err)
+            assert err < 1e-5, (j, k, err)
             sa, sb_ = opt.state[a], opt_ref.state[b]
             assert sa.get('step', 0) == sb_.get('step', 0)
             for key in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
