@@ -187,6 +187,8 @@ def run_reference(args):
 # own arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_own(args):
+    # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
+    os.environ['NCCL_DEBUG'] = os.environ.get('SB_NCCL_DEBUG', 'WARN')
     import torch.distributed as dist
     from simple_b200 import _lib, profiling
     from simple_b200.next_frame_predictor import NextFramePredictor
@@ -198,6 +200,10 @@ def run_own(args):
 
     rank, world, local = init_distributed()
     dev = torch.device('cuda', local)
+
+    def dbg(msg):
+        if os.environ.get('SB_BENCH_DEBUG'):
+            print(f'[bench rank {rank}] {msg}', file=sys.stderr, flush=True)
     torch.cuda.set_device(dev)
     _lib.check(_lib.lib().sb_init(local), 'sb_init')
     B, n_action, K, W_ = args.batch, 3, args.steps, max(3, args.warmup)
@@ -264,11 +270,13 @@ def run_own(args):
             ms = float(t)
         return ms, _lib.lib().sb_launch_count() + r.replays * r.graph_kernels - l0, float(r.last['loss'])
 
+    dbg('setup done')
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ms, launches, last_loss = timed(K, False)
     clocks = sampler.finish() if sampler else None
+    dbg('resident timed region done')
     ms_e2e, _, _ = timed(K, True)
     frames_per_s = B * world * K / (ms * 1e-3)
     e2e_fps = B * world * K / (ms_e2e * 1e-3)
@@ -286,9 +294,12 @@ def run_own(args):
         'gpu_launches': int(launches), 'last_loss': last_loss, 'clocks': clocks, 'cuda_graph': bool(use_graph),
     }
 
+    dbg('timed regions done')
     if rank == 0:
         hbm, tf_sus, tf_burst, how = peaks()
-        # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps
+        # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps.  Rank 0 only, so the
+        # gradient all-reduce is switched off for it (a collective entered by one rank alone would never return).
+        sync_saved, trainer.grad_sync = trainer.grad_sync, None
         eager = StepRunner(trainer, replay, B, use_graph=False, resident=True)
         eager.begin(starts, 0)
         for j in range(2):
@@ -299,6 +310,7 @@ def run_own(args):
             eager.step()
         summ = rec.summary()
         profiling.RECORDER = None
+        trainer.grad_sync = sync_saved
         gem = [summ[k] for k in ('tap_gemm_kernel', 'tap_wgrad_kernel') if k in summ]
         if gem:
             fl, tm, nl = sum(g['work'] for g in gem), sum(g['ms'] for g in gem), sum(g['launches'] for g in gem)
@@ -334,8 +346,10 @@ def run_own(args):
             obs, rew, done, _ = env.step(None)
         return rew
 
+    dbg('roofline pass done')
     rollout()
     barrier()
+    dbg('rollout warm-up done')
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.rollouts):
@@ -358,7 +372,14 @@ def run_own(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured CUDA graphs hold NCCL work: tearing the process group down underneath them can block forever, so the
+        # ranks meet at a barrier, drain the device and leave without running the communicator's destructor.
+        dbg('leaving')
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -257,6 +257,9 @@ class StepRunner:
             self._body()  # eager warm-up of the steady-state step before capture
             self.warm += 1
         elif self.graph is None:
+            if os.environ.get('SB_BENCH_DEBUG'):
+                import sys
+                print('[StepRunner] capturing the steady-state step', file=sys.stderr, flush=True)
             torch.cuda.synchronize()
             opt.zero_grad(set_to_none=True)
             from . import _lib
@@ -268,6 +271,9 @@ class StepRunner:
             self.graph, self.graph_key = g, opt.last_key
             g.replay()  # capture only records: run the step that was just captured
             self.replays += 1
+            if os.environ.get('SB_BENCH_DEBUG'):
+                torch.cuda.synchronize()
+                print('[StepRunner] captured and replayed once', file=sys.stderr, flush=True)
         else:
             opt.advance_for_replay(self.graph_key)
             self.graph.replay()
