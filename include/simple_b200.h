@@ -152,6 +152,14 @@ int sb_prep_bwd_apply(const sb_prep_args* args, sb_stream_t stream);
 int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
                    sb_stream_t stream);
 
+/* Scheduled-sampling frame feedback (simple/trainer.py:58-65,125-132), in place on the fp32 frame stack [B,C_stack,HW]:
+ * next = gt w.p. *eps_ptr else pred (u8 [B,C_new,HW]); next/255 with each value replaced w.p. p_noise by the frame's lower
+ * median (exact 256-bin histogram); stack = cat(stack[:, C_new:], next).  Randomness: counter-based hash of
+ * (seed + *seed_ptr). */
+int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t* pred, const float* eps_ptr, float p_noise,
+                      const unsigned long long* seed_ptr, unsigned long long seed, int B, int C_stack, int C_new, int HW,
+                      sb_stream_t stream);
+
 /* conv-GRU blend of the recurrent state (simple/next_frame_predictor.py:298-303) and its backward.
  * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld. */
 int sb_gru_blend(const void* G, const float* s_old, float* s_new, void* xs, int xs_ld, long long npix,
@@ -230,6 +238,18 @@ int sb_lstm_sample(const float* x0, const float* h0, const float* c0, const floa
                    const float* b_ih, const float* b_hh, const float* w5, const float* b5, const float* w4,
                    const float* b4, const float* noise, const unsigned long long* seed_ptr, int B, float* bits,
                    int* ints, sb_stream_t stream);
+/* ---------------------------------------------------------------------------------------------------------
+ * MeanAttention of the posterior encoder (simple/utils.py:72-88), one CTA per sample, activations staged in shared memory.
+ * x: bf16 NHWC conv output [B, HW, C]; We [4,C], be [4]: the 1x1 conv; Wd [O, 5C], bd [O]: the dense layer on
+ * cat(am, m) laid out c*5+k.  The softmax follows the reference's memory reinterpretation (groups = flat index mod 4).
+ * fwd saves s [B, 4*HW] (softmax, flat k*HW+hw) and l [B, 5C]; bwd returns dx (bf16, layout of x) and the PER-SAMPLE
+ * parts dWe_part [B,4,C], dbe_part [B,4] (summed over B by the caller; dWd = dy^T l and dbd = sum dy are plain GEMMs).
+ * --------------------------------------------------------------------------------------------------------- */
+int sb_mean_attention_fwd(const void* x, const float* We, const float* be, const float* Wd, const float* bd, int B,
+                          int HW, int C, int O, float* y, float* s_save, float* l_save, sb_stream_t stream);
+int sb_mean_attention_bwd(const void* x, const float* We, const float* Wd, const float* s_save, const float* dy, int B,
+                          int HW, int C, int O, void* dx, float* dWe_part, float* dbe_part, sb_stream_t stream);
+
 /* Second-generation latent-bit kernels: transposed weights (whhT [128,512] = W_hh^T, w5T [128,256] = W5^T), input-gate
  * pre-activations by table lookup (E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh; G0 [B,512] for the first step), one
  * or two samples per CTA.  sb_lstm_teacher_fwd/bwd run all 16 teacher-forced LSTMCell steps and their backward through

@@ -1,0 +1,76 @@
+// Scheduled-sampling frame feedback of the world-model trainer (simple/trainer.py:58-65,125-132), one CTA per sample:
+//   next  = ground-truth frame w.p. epsilon, else the model's own arg-max decode            (u8 [3,HW])
+//   next  = next / 255, each value replaced w.p. input_noise by the frame's (lower) median  (torch.median semantics)
+//   stack = cat(stack[3:], next)                                                            (fp32 [12,HW], in place)
+// The reference does this per sample in Python (median through a sort, CPU multinomial, torch.cat); the previous
+// revision here used ~17 ATen launches including a 118 us gatherMedian.  The pixel values are bytes, so the median is
+// an exact 256-bin histogram walk in shared memory.
+#include "common.cuh"
+#include "../../include/simple_b200.h"
+
+namespace sb {
+extern long long g_launches;
+
+__global__ void __launch_bounds__(512)
+    frame_feedback_kernel(float* __restrict__ stack, const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred,
+                          const float* __restrict__ eps_ptr, float p_noise, const unsigned long long* seed_ptr,
+                          unsigned long long seed, int C_stack, int C_new, int HW) {
+  __shared__ unsigned int hist[256];
+  __shared__ int s_median;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const unsigned long long sd = seed_ptr ? seed + *seed_ptr : seed;
+  const uint2 key = hash_key(sd, 0x46454544u);
+  // scheduled sampling: one uniform per sample
+  const float eps = eps_ptr ? *eps_ptr : 0.f;
+  const bool use_gt = u01(hash4x32(0x7fffff00u + (uint32_t)b, key).x) < eps;
+  const uint8_t* src = (use_gt ? gt : pred) + (size_t)b * C_new * HW;
+  const int n = C_new * HW;
+  if (t < 256) hist[t] = 0u;
+  __syncthreads();
+  if (p_noise > 0.f) {
+    for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[src[i]], 1u);
+    __syncthreads();
+    if (t == 0) {  // lower median: the value at sorted position (n - 1) / 2
+      const unsigned int target = (unsigned int)((n - 1) / 2);
+      unsigned int cum = 0;
+      int v = 0;
+      for (; v < 256; ++v) {
+        cum += hist[v];
+        if (cum > target) break;
+      }
+      s_median = v;
+    }
+    __syncthreads();
+  }
+  const float med = (float)s_median / 255.0f;
+  float* st = stack + (size_t)b * C_stack * HW;
+  const uint32_t thr = (uint32_t)(p_noise * 65536.0f);
+  for (int hw = t; hw < HW; hw += blockDim.x) {
+    // shift: channel c <- channel c + C_new, ascending c (each element is read before this thread overwrites it)
+    for (int c = 0; c < C_stack - C_new; ++c) st[(size_t)c * HW + hw] = st[(size_t)(c + C_new) * HW + hw];
+    uint4 r = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p_noise > 0.f) r = hash4x32((uint32_t)(b * HW + hw), key);
+    const uint32_t bits[4] = {r.x, r.y, r.z, r.w};
+    for (int c = 0; c < C_new; ++c) {
+      const uint32_t rb = (bits[(c >> 1) & 3] >> (16 * (c & 1))) & 0xffffu;  // 16 random bits per value (C_new <= 8)
+      const bool keep = p_noise <= 0.f || rb >= thr;
+      const float v = (float)src[(size_t)c * HW + hw] / 255.0f;
+      st[(size_t)(C_stack - C_new + c) * HW + hw] = keep ? v : med;
+    }
+  }
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t* pred, const float* eps_ptr,
+                                 float p_noise, const unsigned long long* seed_ptr, unsigned long long seed, int B,
+                                 int C_stack, int C_new, int HW, sb_stream_t stream) {
+  if (!stack || !gt || !pred || B < 1 || C_new < 1 || C_new > 8 || C_stack <= C_new || HW < 1) return SB_ERR_ARG;
+  frame_feedback_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr, seed, C_stack,
+                                                            C_new, HW);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}

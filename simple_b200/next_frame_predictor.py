@@ -601,10 +601,10 @@ class NextFramePredictor(nn.Module):
         sc, sh = sm.action_injector.scale_shift(action)
         _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh, dbias_dst=P['s_embed'].dbias_src)
         c1 = self._conv('s_conv1', P['s_conv1'], A)  # [B,26,20,128], pre-ReLU
-        x1 = sm.mean_attentions[0](c1.float().permute(0, 3, 1, 2).contiguous())
+        x1 = ops.mean_attention(c1, sm.mean_attentions[0])
         _, A = fused_prep(P['prep_s1'], c1)
         c2 = self._conv('s_conv2', P['s_conv2'], A)  # [B,6,5,512]
-        x2 = sm.mean_attentions[1](c2.float().permute(0, 3, 1, 2).contiguous())
+        x2 = ops.mean_attention(c2, sm.mean_attentions[1])
         x = sm.dense1(torch.cat((x1, x2), dim=-1))
         aux['posterior_pre'] = x.detach()
         x = x + (self._forced(rand, 'posterior_pre', x.detach()) - x.detach())

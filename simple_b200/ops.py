@@ -409,6 +409,22 @@ def standardize(x, dst=None, coff=0, out_f32=None):
                                          coff, _ptr(out_f32), _lib.stream_ptr()), 'sb_standardize')
 
 
+def frame_feedback(stack, gt_u8, pred_u8, eps, p_noise, seed):
+    """In place: stack [B,12,H,W] fp32 <- cat(stack[:, 3:], noisy(gt or pred)/255); see sb_frame_feedback.
+    eps: 0-d float device tensor (probability of feeding the ground truth); seed: int64 device tensor or int."""
+    B, Cs, H, W = stack.shape
+    Cn = gt_u8.shape[1]
+    assert stack.dtype == torch.float32 and stack.is_contiguous()
+    assert gt_u8.dtype == torch.uint8 and pred_u8.dtype == torch.uint8 and gt_u8.shape == pred_u8.shape
+    gt_u8, pred_u8 = gt_u8.contiguous(), pred_u8.contiguous()
+    seed_ptr, seed_val = (seed.data_ptr(), 0) if isinstance(seed, torch.Tensor) else (None, int(seed))
+    _lib.check(_lib.lib().sb_frame_feedback(stack.data_ptr(), gt_u8.data_ptr(), pred_u8.data_ptr(),
+                                            eps.data_ptr() if isinstance(eps, torch.Tensor) else None, float(p_noise),
+                                            seed_ptr, seed_val & 0xFFFFFFFFFFFFFFFF, B, Cs, Cn, H * W, _lib.stream_ptr()),
+               'sb_frame_feedback')
+    return stack
+
+
 class PixelCE(torch.autograd.Function):
     """Clipped per-pixel CE (simple/trainer.py:134-137) on colour-major bf16 logits [B,H,W,768]; the gradient is
     produced in the same pass and overwrites the logits buffer."""
@@ -460,6 +476,47 @@ def pixel_argmax(logits):
 # ---------------------------------------------------------------------------------------------------------------
 # latent-bit predictor
 # ---------------------------------------------------------------------------------------------------------------
+class MeanAttentionFn(torch.autograd.Function):
+    """simple/utils.py:72-88 on the NHWC bf16 conv output [B,H,W,C] (one CTA per sample; see csrc/mean_attention.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, we, be, wd, bd):
+        B, H, W, C = x.shape
+        HW, O = H * W, wd.shape[0]
+        x = x.contiguous()
+        f = lambda t: t.detach().float().contiguous()
+        we2, be_, wd_, bd_ = f(we).reshape(4, C), f(be), f(wd), f(bd)
+        y = torch.empty(B, O, device=x.device, dtype=torch.float32)
+        s_save = torch.empty(B, 4 * HW, device=x.device, dtype=torch.float32)
+        l_save = torch.empty(B, 5 * C, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sb_mean_attention_fwd(x.data_ptr(), we2.data_ptr(), be_.data_ptr(), wd_.data_ptr(),
+                                                    bd_.data_ptr(), B, HW, C, O, y.data_ptr(), s_save.data_ptr(),
+                                                    l_save.data_ptr(), _lib.stream_ptr()), 'sb_mean_attention_fwd')
+        ctx.save_for_backward(x, we2, wd_, s_save, l_save)
+        ctx.we_shape = we.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, we2, wd_, s_save, l_save = ctx.saved_tensors
+        B, H, W, C = x.shape
+        HW, O = H * W, wd_.shape[0]
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        dwe_part = torch.empty(B, 4, C, device=x.device, dtype=torch.float32)
+        dbe_part = torch.empty(B, 4, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sb_mean_attention_bwd(x.data_ptr(), we2.data_ptr(), wd_.data_ptr(), s_save.data_ptr(),
+                                                    dy.data_ptr(), B, HW, C, O, dx.data_ptr(), dwe_part.data_ptr(),
+                                                    dbe_part.data_ptr(), _lib.stream_ptr()), 'sb_mean_attention_bwd')
+        return dx, dwe_part.sum(0).reshape(ctx.we_shape), dbe_part.sum(0), dy.t() @ l_save, dy.sum(0)
+
+
+def mean_attention(x_nhwc_bf16, module):
+    """module: MeanAttention (input_embedding 1x1 conv to 4 maps + dense on cat(am, m))."""
+    return MeanAttentionFn.apply(x_nhwc_bf16, module.input_embedding.weight, module.input_embedding.bias,
+                                 module.dense.weight, module.dense.bias)
+
+
 def lstm_sampler_tables(lstm, dense5, dense4):
     """Weight-only operands of the sampling kernel (refresh whenever the weights change):
     whhT [128,512], w5T [128,256], E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh, bias = b_ih + b_hh."""

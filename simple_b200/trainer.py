@@ -240,11 +240,10 @@ class StepRunner:
             new_states, action, reward, value = (self.inp['new_obs'], self.inp['action'], self.inp['reward'],
                                                  self.inp['value'])
         out = tr.train_step(self.frames, action, new_states, reward, value, self.eps)
-        # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode
-        use_gt = (torch.rand(B, device=self.frames.device) < self.eps).reshape(B, 1, 1, 1)
-        nxt = torch.where(use_gt, new_states, out['argmax'])
-        nxt = tr.preprocess_state(nxt, per_sample=True)
-        self.frames.copy_(torch.cat((self.frames[:, self.c:], nxt), dim=1))
+        # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode; input noise with
+        # the per-frame median; frame-stack shift -- one kernel, in place on the static frame buffer
+        ops.frame_feedback(self.frames, new_states, out['argmax'], self.eps, float(tr.config.input_noise),
+                           tr.model._seed_dev)
         self.losses += torch.stack([out[k].detach().float() for k in self.names])
         self.idx += 1
         self.last = {k: v.detach() for k, v in out.items()}  # no reference to this step's autograd graph survives

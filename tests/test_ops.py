@@ -418,3 +418,63 @@ def test_gru_blend():
     xs2.backward(gout)
     ref.backward(gout[..., :64].float())
     assert rel(G.grad, Gr.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize('B,H,W,C', [(3, 26, 20, 128), (4, 6, 5, 512), (2, 7, 3, 64)])
+def test_fused_mean_attention_matches_reference_module(B, H, W, C):
+    """csrc/mean_attention.cu vs the plain restatement of simple/utils.py:72-88 (including the memory-reinterpreting
+    softmax grouping), forward and every gradient."""
+    from simple_b200 import ops
+    from simple_b200.next_frame_predictor import MeanAttention
+    torch.manual_seed(11)
+    ma = MeanAttention(C, 30).to(DEV)
+    x = torch.randn(B, H, W, C, device=DEV).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yr = ma(xr)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    ref_grads = [p.grad.clone() for p in ma.parameters()]
+    for p in ma.parameters():
+        p.grad = None
+    xf = x.clone().requires_grad_(True)
+    y = ops.mean_attention(xf, ma)
+    y.backward(dy)
+    torch.cuda.synchronize()
+    # (the torch restatement runs its 1x1 conv on TF32 tensor cores: ~1e-3 relative noise on its side)
+    assert rel(y, yr) < 2e-3, rel(y, yr)
+    assert rel(xf.grad.float().permute(0, 3, 1, 2), xr.grad) < 1e-2  # bf16 output gradient
+    for p, g in zip(ma.parameters(), ref_grads):
+        assert rel(p.grad, g) < 2e-3, rel(p.grad, g)
+
+
+def test_frame_feedback_shift_median_noise_and_scheduled_sampling():
+    from simple_b200 import ops
+    torch.manual_seed(13)
+    B, H, W = 5, 105, 80
+    stack0 = torch.rand(B, 12, H, W, device=DEV)
+    gt = torch.randint(0, 256, (B, 3, H, W), device=DEV, dtype=torch.uint8)
+    pred = torch.randint(0, 40, (B, 3, H, W), device=DEV, dtype=torch.uint8)  # distinguishable from gt
+    one, zero = torch.ones((), device=DEV), torch.zeros((), device=DEV)
+    # no noise: exact shift + exact u8/255 of the selected source
+    for eps, src in ((one, gt), (zero, pred)):
+        st = ops.frame_feedback(stack0.clone(), gt, pred, eps, 0.0, 7)
+        assert torch.equal(st[:, :9], stack0[:, 3:])
+        assert torch.equal(st[:, 9:], src.float() / 255)
+    # noise: replaced values are exactly the per-frame lower median (torch.median semantics), at rate ~p
+    st = ops.frame_feedback(stack0.clone(), gt, pred, one, 0.05, 7)
+    want = gt.float() / 255
+    med = want.reshape(B, -1).median(dim=1).values.reshape(B, 1, 1, 1)
+    changed = st[:, 9:] != want
+    assert torch.equal(st[:, 9:][changed], med.expand_as(want)[changed])
+    rate = float(changed.float().mean())
+    assert 0.04 < rate < 0.06, rate  # (a few replaced values coincide with the median and do not count as changed)
+    st2 = ops.frame_feedback(stack0.clone(), gt, pred, one, 0.05, 8)
+    assert not torch.equal(st2, st)  # another seed, another mask
+    # epsilon = 0.5: roughly half of the samples take the ground truth
+    Bb = 64
+    s_big = torch.zeros(Bb, 12, 8, 8, device=DEV)
+    g_big = torch.full((Bb, 3, 8, 8), 200, device=DEV, dtype=torch.uint8)
+    p_big = torch.full((Bb, 3, 8, 8), 10, device=DEV, dtype=torch.uint8)
+    out = ops.frame_feedback(s_big, g_big, p_big, torch.full((), 0.5, device=DEV), 0.0, 3)
+    took_gt = int((out[:, 9, 0, 0] > 0.5).sum())
+    assert 16 <= took_gt <= 48, took_gt
