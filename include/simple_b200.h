@@ -92,6 +92,9 @@ int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
  * dlogits == NULL selects the decode-only (rollout) variant.
  * Replaces: simple/trainer.py:130,134-137 and simple/subproc_vec_env.py:428 (K14).
  * --------------------------------------------------------------------------------------------------------- */
+/* Debug / A-B switch: 0 (default) = register-staged kernel, 1 = TMA-staged kernel (per-warp shared-memory ring filled by
+ * 512-byte cp.async.bulk copies; measured slower: the copies are too small for the TMA unit).  Returns the previous setting. */
+int sb_set_ce_tma(int enabled);
 int sb_pixel_ce(const void* logits, const uint8_t* target, int B, int HW, float clip, float gscale, void* dlogits,
                 uint8_t* argmax_out, double* loss_sum, float* dbias, sb_stream_t stream);
 
@@ -138,6 +141,8 @@ typedef struct {
   void* d_add;             /* grad wrt add (plain) or NULL */
   float* dcol;             /* optional fp32 [C] (caller zeroes): += column sums of d_main over b,y,x = the bias gradient
                               of the convolution that produced `in` (sb_prep_bwd_apply only) */
+  float* dgb;              /* optional fp32 [C,2] (caller zeroes; sb_prep_bwd_reduce only): += sum over b of bsums[b,c,0..1],
+                              i.e. (d beta, d gamma) of the InstanceNorm affine */
 } sb_prep_args;
 /* Debug / A-B switch: 1 (default) dispatches to kernel instances specialised at compile time for the feature
  * combinations of the world model; 0 always runs the fully-runtime instances.  Returns the previous setting. */

@@ -66,7 +66,7 @@ class PrepArgs(ctypes.Structure):
         ('p', ctypes.c_float), ('seed', ctypes.c_ulonglong), ('seed_ptr', ctypes.c_void_p), ('stream_id', ctypes.c_uint),
         ('keep', ctypes.c_void_p), ('Tb', ctypes.c_void_p), ('sc', ctypes.c_void_p), ('sh', ctypes.c_void_p),
         ('out2', SbView), ('g2', SbView), ('g1', ctypes.c_void_p), ('bsums', ctypes.c_void_p),
-        ('d_main', SbView), ('d_add', ctypes.c_void_p), ('dcol', ctypes.c_void_p),
+        ('d_main', SbView), ('d_add', ctypes.c_void_p), ('dcol', ctypes.c_void_p), ('dgb', ctypes.c_void_p),
     ]
 
 
@@ -86,6 +86,8 @@ def lib():
     L.sb_version.restype = ctypes.c_char_p
     L.sb_set_pair_mode.argtypes = [ctypes.c_int]
     L.sb_set_pair_mode.restype = ctypes.c_int
+    L.sb_set_ce_tma.argtypes = [ctypes.c_int]
+    L.sb_set_ce_tma.restype = ctypes.c_int
     L.sb_set_prep_specialize.argtypes = [ctypes.c_int]
     L.sb_set_prep_specialize.restype = ctypes.c_int
     for name in dir(_Sigs):
@@ -131,7 +133,7 @@ class _Sigs:
     sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
 
 
-EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_prep_specialize'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
 
 
 def check(rc, what):

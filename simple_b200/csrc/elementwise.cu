@@ -100,6 +100,7 @@ struct PrepParams {
   View d_main;              // grad wrt main (same layout as in)
   __nv_bfloat16* d_add;     // grad wrt add (plain) or NULL
   float* dcol;              // optional [C]: += column sums of d_main (the producing conv's bias gradient)
+  float* dgb;               // optional [C,2] (backward reduce): += sum over b of bsums[b,c,0..1] = (d beta, d gamma)
   // host-precomputed
   uint32_t w_magic;         // fast_div magic of W
   uint32_t nx_magic;        // fast_div magic of the iteration-space width (see iter_space)
@@ -366,7 +367,8 @@ __device__ __forceinline__ void finish_gx(const PrepParams& q, const ChanCst& k,
 // reduce over pixel lanes through shared memory, then one atomic per (channel, value): scratch[pl][cv][NV*8]
 template <int NV>
 __device__ __forceinline__ void lane_reduce_atomic(float (*acc)[8], float* scratch, int CV, int PL, int cv, int pl,
-                                                   float* out, long long out_base, int out_stride_c) {
+                                                   float* out, long long out_base, int out_stride_c,
+                                                   float* out2 = nullptr) {
   float* mine = scratch + ((size_t)pl * CV + cv) * (NV * 8);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
@@ -379,6 +381,7 @@ __device__ __forceinline__ void lane_reduce_atomic(float (*acc)[8], float* scrat
     float s = 0.f;
     for (int l = 0; l < PL; ++l) s += scratch[((size_t)l * CV + cvv) * (NV * 8) + rem];
     atomicAdd(out + out_base + (long long)(cvv * 8 + j) * out_stride_c + v, s);
+    if (out2 && v < 2) atomicAdd(out2 + (cvv * 8 + j) * 2 + v, s);  // batch-summed affine gradients
   }
 }
 
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
       }
     }
   }
-  lane_reduce_atomic<NV>(acc, scratch, CV, PL, cv, pl, out, (long long)b * q.C * NV, NV);
+  lane_reduce_atomic<NV>(acc, scratch, CV, PL, cv, pl, out, (long long)b * q.C * NV, NV, MODE == 1 ? q.dgb : nullptr);
 }
 
 template <bool F32, uint32_t F>
@@ -810,6 +813,7 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   q.d_main = mk_view(&a->d_main);
   q.d_add = (__nv_bfloat16*)a->d_add;
   q.dcol = a->dcol;
+  q.dgb = a->dgb;
   if (!view_ok(q.in) || !view_ok(q.out2) || !view_ok(q.g2) || !view_ok(q.d_main)) return SB_ERR_ARG;
   {  // 32-bit element offsets: the largest view (padded space-to-depth extent included) must stay below 2^31 elements
     long long worst = (long long)q.B * q.H * q.W * q.C;

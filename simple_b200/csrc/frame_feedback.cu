@@ -11,7 +11,7 @@
 namespace sb {
 extern long long g_launches;
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
     frame_feedback_kernel(float* __restrict__ stack, const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred,
                           const float* __restrict__ eps_ptr, float p_noise, const unsigned long long* seed_ptr,
                           unsigned long long seed, int C_stack, int C_new, int HW) {
@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(512)
   const float med = (float)s_median / 255.0f;
   float* st = stack + (size_t)b * C_stack * HW;
   const uint32_t thr = (uint32_t)(p_noise * 65536.0f);
-  for (int hw = t; hw < HW; hw += blockDim.x) {
+  // the pixels of a sample are split over gridDim.y CTAs (each recomputes the 25 KB histogram: cheaper than a second pass)
+  const int per = (HW + gridDim.y - 1) / gridDim.y;
+  const int hw_begin = blockIdx.y * per, hw_end = min(HW, hw_begin + per);
+  for (int hw = hw_begin + t; hw < hw_end; hw += blockDim.x) {
     // shift: channel c <- channel c + C_new, ascending c (each element is read before this thread overwrites it)
     for (int c = 0; c < C_stack - C_new; ++c) st[(size_t)c * HW + hw] = st[(size_t)(c + C_new) * HW + hw];
     uint4 r = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -68,7 +71,10 @@ extern "C" int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t*
                                  float p_noise, const unsigned long long* seed_ptr, unsigned long long seed, int B,
                                  int C_stack, int C_new, int HW, sb_stream_t stream) {
   if (!stack || !gt || !pred || B < 1 || C_new < 1 || C_new > 8 || C_stack <= C_new || HW < 1) return SB_ERR_ARG;
-  frame_feedback_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr, seed, C_stack,
+  int split = (2 * 148 + B - 1) / B;  // ~2 CTAs per SM over the whole grid
+  if (split < 1) split = 1;
+  if (split > 16) split = 16;
+  frame_feedback_kernel<<<dim3(B, split), 256, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr, seed, C_stack,
                                                             C_new, HW);
   ++g_launches;
   SB_CHECK_LAUNCH();

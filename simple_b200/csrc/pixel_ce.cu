@@ -63,7 +63,7 @@ __device__ __forceinline__ int half_min(int v) {
 template <bool TRAIN>
 __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, int t, float xt, float clip, float gscale,
                                          uint8_t* amax_dst, __nv_bfloat16* dl_group, float* s_db_group, float2* db,
-                                         float& loss_acc) {
+                                         float& loss_acc, bool valid = true) {
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
   // ---- max in packed bf16 (exact: the inputs are bf16)
@@ -85,7 +85,7 @@ __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, 
     const int i = __ffs(bits) - 1;  // -1 when this lane does not hold the maximum
     const int col = (i < 0) ? 256 : ((q + ((i >> 3) << 4)) << 3) + (i & 7);
     const int first = half_min(col);
-    if (q == 0) *amax_dst = (uint8_t)first;
+    if (q == 0 && valid) *amax_dst = (uint8_t)first;
   }
   if (TRAIN) {
     const float moff = -gm * LOG2E;
@@ -101,8 +101,8 @@ __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, 
     }
     const float s = half_sum(s2.x + s2.y);
     const float ce = gm + log2f(s) * LN2 - xt;
-    loss_acc += fmaxf(ce, clip);  // identical in the 16 lanes; lane 0's copy is used
-    const float scale = (ce > clip) ? gscale : 0.f;
+    if (valid) loss_acc += fmaxf(ce, clip);  // identical in the 16 lanes; lane 0's copy is used
+    const float scale = (valid && ce > clip) ? gscale : 0.f;
     const float inv = scale / s;
     const float2 inv2 = make_float2(inv, inv);
     uint32_t o[8];
@@ -113,10 +113,12 @@ __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, 
       const __nv_bfloat162 h = __floats2bfloat162_rn(d.x, d.y);
       o[k] = *reinterpret_cast<const uint32_t*>(&h);
     }
-    *reinterpret_cast<uint4*>(dl_group + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(dl_group + 128 + q * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    if (valid) {
+      *reinterpret_cast<uint4*>(dl_group + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(dl_group + 128 + q * 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
     // one-hot term: the lane that owns column t overwrites that element (same thread => ordered after its vector store)
-    if (((t >> 3) & 15) == q) {
+    if (valid && ((t >> 3) & 15) == q) {
       const float et = exp2f(fmaf(xt, LOG2E, moff));
       dl_group[t] = __float2bfloat16_rn(et * inv - scale);
       if (s_db_group) atomicAdd(s_db_group + t, -scale);
@@ -124,20 +126,37 @@ __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, 
   }
 }
 
-template <bool TRAIN>
-__global__ void __launch_bounds__(256, 3)
+// target logit out of the registers of the owning lane (no dependent global load): element t of the group lives in lane
+// (t >> 3) & 15 of the half-warp, packed word ((t & 7) >> 1) + 4 * (t >> 7), low or high half by t & 1
+__device__ __forceinline__ float target_logit(const uint4 ra, const uint4 rb, int t, int lane) {
+  const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+  const int widx = ((t & 7) >> 1) + ((t >> 7) << 2);
+  uint32_t sel = w[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) sel = (widx == k) ? w[k] : sel;
+  const uint32_t bits = (t & 1) ? (sel & 0xffff0000u) : (sel << 16);
+  const int src = (lane & 16) | ((t >> 3) & 15);
+  return __uint_as_float(__shfl_sync(0xffffffffu, bits, src));
+}
+
+// Register-staged kernel.  A warp keeps ONE colour (fixed bias-gradient columns per lane) and walks the pixels
+// wslot, wslot + nws, ...; each iteration gives two pixels to each half-warp (four independent 16-byte loads per thread
+// in flight), with the target bytes of the NEXT iteration prefetched so that no dependent load sits on the critical path.
+// All loop bounds are warp-uniform (the reductions are full-mask shuffles).
+template <bool TRAIN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     pixel_ce_kernel(const __nv_bfloat16* __restrict__ logits, const uint8_t* __restrict__ target, int B, int HW,
                     float clip, float gscale, __nv_bfloat16* dlogits, uint8_t* __restrict__ argmax_out,
                     double* __restrict__ loss_sum, float* __restrict__ dbias) {
-  const int lane = threadIdx.x & 31;
-  const int q = lane & 15;
-  const long long npix = (long long)B * HW;
-  // half-warps: 16 per CTA; the total count is a multiple of 3 (host guarantees it) and a half-warp keeps ONE colour,
-  // so its bias-gradient accumulators are 16 registers holding fixed columns
-  const long long hw_global = (long long)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
-  const long long nhw = (long long)gridDim.x * (blockDim.x >> 4);
-  const int g = (int)(hw_global % 3);
-  const long long slot = hw_global / 3, nslots = nhw / 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hh = lane >> 4, q = lane & 15;
+  const int npix = B * HW;  // (the launcher rejects B*HW*3 >= 2^31)
+  const int w_global = blockIdx.x * 8 + warp;
+  const int nwarps = gridDim.x * 8;  // multiple of 3 (host guarantees it)
+  const int g = w_global % 3;
+  const int wslot = w_global / 3, nws = nwarps / 3;
+  const int n_mine = wslot < npix ? (npix - wslot + nws - 1) / nws : 0;  // pixels of this warp
+  const int J = (n_mine + 3) / 4;                                        // 4 pixels per iteration
   __shared__ float s_db[768];
   __shared__ float s_loss[16];
   if (TRAIN) {
@@ -148,43 +167,53 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
   for (int i = 0; i < 8; ++i) db[i] = make_float2(0.f, 0.f);
   float loss_acc = 0.f;
-  const unsigned short* lraw = reinterpret_cast<const unsigned short*>(logits);
-  for (long long pix0 = slot; pix0 < npix; pix0 += 2 * nslots) {
-    const long long pix1 = pix0 + nslots;
-    const bool has1 = pix1 < npix;
-    const __nv_bfloat16* g0 = logits + pix0 * 768 + g * 256;
-    const __nv_bfloat16* g1 = logits + pix1 * 768 + g * 256;
-    // four independent 16-byte loads in flight per thread
-    const uint4 a0 = ld_stream(g0 + q * 8);
-    const uint4 b0 = ld_stream(g0 + 128 + q * 8);
-    uint4 a1 = make_uint4(0, 0, 0, 0), b1 = a1;
-    if (has1) {
+  // pixel k of the warp's list -> (valid, flat pixel, target/argmax offset)
+  auto locate = [&](int k, bool& valid, int& pix, int& o) {
+    valid = k < n_mine;
+    pix = wslot + (valid ? k : 0) * nws;
+    const int bi = pix / HW, hw = pix - bi * HW;
+    o = (bi * 3 + g) * HW + hw;
+  };
+  bool v0, v1;
+  int p0, p1, o0, o1;
+  int t0 = 0, t1 = 0;
+  locate(hh, v0, p0, o0);
+  locate(2 + hh, v1, p1, o1);
+  if (TRAIN) {
+    if (v0) t0 = target[o0];
+    if (v1) t1 = target[o1];
+  }
+  for (int j = 0; j < J; ++j) {
+    const __nv_bfloat16* g0 = logits + (size_t)p0 * 768 + g * 256;
+    const __nv_bfloat16* g1 = logits + (size_t)p1 * 768 + g * 256;
+    uint4 a0 = make_uint4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+    if (v0) {
+      a0 = ld_stream(g0 + q * 8);
+      b0 = ld_stream(g0 + 128 + q * 8);
+    }
+    if (v1) {
       a1 = ld_stream(g1 + q * 8);
       b1 = ld_stream(g1 + 128 + q * 8);
     }
-    const int bi0 = (int)(pix0 / HW), hw0 = (int)(pix0 - (long long)bi0 * HW);
-    const long long o0 = ((long long)bi0 * 3 + g) * HW + hw0;
-    long long o1 = 0;
-    int t0 = 0, t1 = 0;
-    float xt0 = 0.f, xt1 = 0.f;
+    // next iteration's pixels and target bytes (addresses do not depend on data)
+    bool nv0, nv1;
+    int np0, np1, no0, no1;
+    int nt0 = 0, nt1 = 0;
+    locate(4 * (j + 1) + hh, nv0, np0, no0);
+    locate(4 * (j + 1) + 2 + hh, nv1, np1, no1);
     if (TRAIN) {
-      t0 = target[o0];
-      xt0 = __uint_as_float((uint32_t)__ldg(lraw + (pix0 * 768 + g * 256 + t0)) << 16);
+      if (nv0) nt0 = target[no0];
+      if (nv1) nt1 = target[no1];
     }
-    if (has1) {
-      const int bi1 = (int)(pix1 / HW), hw1 = (int)(pix1 - (long long)bi1 * HW);
-      o1 = ((long long)bi1 * 3 + g) * HW + hw1;
-      if (TRAIN) {
-        t1 = target[o1];
-        xt1 = __uint_as_float((uint32_t)__ldg(lraw + (pix1 * 768 + g * 256 + t1)) << 16);
-      }
-    }
+    const float xt0 = TRAIN ? target_logit(a0, b0, t0, lane) : 0.f;
     ce_group<TRAIN>(a0, b0, q, t0, xt0, clip, gscale, argmax_out ? argmax_out + o0 : nullptr,
-                    TRAIN ? dlogits + pix0 * 768 + g * 256 : nullptr, dbias ? s_db + g * 256 : nullptr, db, loss_acc);
-    if (has1)
-      ce_group<TRAIN>(a1, b1, q, t1, xt1, clip, gscale, argmax_out ? argmax_out + o1 : nullptr,
-                      TRAIN ? dlogits + pix1 * 768 + g * 256 : nullptr, dbias ? s_db + g * 256 : nullptr, db,
-                      loss_acc);
+                    TRAIN ? dlogits + (size_t)p0 * 768 + g * 256 : nullptr, (TRAIN && dbias) ? s_db + g * 256 : nullptr, db,
+                    loss_acc, v0);
+    const float xt1 = TRAIN ? target_logit(a1, b1, t1, lane) : 0.f;
+    ce_group<TRAIN>(a1, b1, q, t1, xt1, clip, gscale, argmax_out ? argmax_out + o1 : nullptr,
+                    TRAIN ? dlogits + (size_t)p1 * 768 + g * 256 : nullptr, (TRAIN && dbias) ? s_db + g * 256 : nullptr, db,
+                    loss_acc, v1);
+    v0 = nv0; v1 = nv1; p0 = np0; p1 = np1; o0 = no0; o1 = no1; t0 = nt0; t1 = nt1;
   }
   if (TRAIN) {
     if (dbias) {
@@ -207,14 +236,119 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant: every warp owns a ring of kCeStages shared-memory stages (2 groups = 1 KB each) filled by 1-D bulk
+// copies (cp.async.bulk, completion on an mbarrier) that its lane 0 keeps kCeStages - 1 iterations ahead.  The bytes in
+// flight per SM (~96 KB at 4 CTAs) no longer depend on registers or occupancy -- the register-staged kernel above sits
+// at ~50 KB and 52 % issue utilisation with long-scoreboard stalls -- and the target logit comes out of shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCeStages = 4;
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(256, 4)
+    pixel_ce_tma_kernel(const __nv_bfloat16* __restrict__ logits, const uint8_t* __restrict__ target, int B, int HW,
+                        float clip, float gscale, __nv_bfloat16* dlogits, uint8_t* __restrict__ argmax_out,
+                        double* __restrict__ loss_sum, float* __restrict__ dbias) {
+  __shared__ __align__(128) uint8_t ring[8][kCeStages][1024];
+  __shared__ uint64_t full[8][kCeStages];
+  __shared__ float s_db[768];
+  __shared__ float s_loss[16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hh = lane >> 4, q = lane & 15;
+  const long long npix = (long long)B * HW;
+  // a warp keeps ONE colour (fixed bias-gradient columns per lane) and walks the pixels wslot, wslot + nws, ...;
+  // iteration j gives pixel 2j to its lower half-warp and pixel 2j+1 to the upper one
+  const long long w_global = (long long)blockIdx.x * 8 + warp;
+  const long long nwarps = (long long)gridDim.x * 8;  // multiple of 3 (host guarantees it)
+  const int g = (int)(w_global % 3);
+  const long long wslot = w_global / 3, nws = nwarps / 3;
+  const long long n_mine = wslot < npix ? (npix - wslot + nws - 1) / nws : 0;
+  const long long J = (n_mine + 1) / 2;
+  if (lane == 0) {
+    for (int s = 0; s < kCeStages; ++s) mbar_init(&full[warp][s], 1);
+    fence_mbar_init();
+  }
+  if (TRAIN)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_db[i] = 0.f;
+  __syncthreads();
+  auto issue = [&](long long j) {  // lane 0 only
+    const int s = (int)(j % kCeStages);
+    const long long k0 = 2 * j, k1 = 2 * j + 1;
+    const bool v1 = k1 < n_mine;
+    mbar_expect_tx(&full[warp][s], v1 ? 1024u : 512u);
+    bulk_load_1d(&ring[warp][s][0], logits + (wslot + k0 * nws) * 768 + g * 256, 512u, &full[warp][s]);
+    if (v1) bulk_load_1d(&ring[warp][s][512], logits + (wslot + k1 * nws) * 768 + g * 256, 512u, &full[warp][s]);
+  };
+  if (lane == 0)
+    for (long long j = 0; j < kCeStages && j < J; ++j) issue(j);
+  float2 db[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) db[i] = make_float2(0.f, 0.f);
+  float loss_acc = 0.f;
+  for (long long j = 0; j < J; ++j) {
+    const int s = (int)(j % kCeStages);
+    const uint32_t ph = (uint32_t)(j / kCeStages) & 1u;
+    const long long k = 2 * j + hh;
+    const bool valid = k < n_mine;
+    const long long pix = wslot + (valid ? k : 0) * nws;
+    const int bi = (int)(pix / HW), hw = (int)(pix - (long long)bi * HW);
+    const long long o = ((long long)bi * 3 + g) * HW + hw;
+    int t = 0;
+    if (TRAIN && valid) t = target[o];  // issued before the wait: overlaps the stage's arrival
+    mbar_wait(&full[warp][s], ph);
+    const uint8_t* grp = &ring[warp][s][hh * 512];
+    const uint4 ra = *reinterpret_cast<const uint4*>(grp + q * 16);
+    const uint4 rb = *reinterpret_cast<const uint4*>(grp + 256 + q * 16);
+    float xt = 0.f;
+    if (TRAIN) xt = __uint_as_float((uint32_t)reinterpret_cast<const unsigned short*>(grp)[t] << 16);
+    ce_group<TRAIN>(ra, rb, q, t, xt, clip, gscale, argmax_out ? argmax_out + o : nullptr,
+                    TRAIN ? dlogits + pix * 768 + g * 256 : nullptr, (TRAIN && dbias) ? s_db + g * 256 : nullptr, db,
+                    loss_acc, valid);
+    __syncwarp();  // every lane has read the stage (and its values are in registers) before lane 0 refills it
+    if (lane == 0 && j + kCeStages < J) issue(j + kCeStages);
+  }
+  if (TRAIN) {
+    if (dbias) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int col = g * 256 + ((kk >> 2) << 7) + q * 8 + (kk & 3) * 2;
+        atomicAdd(&s_db[col], db[kk].x);
+        atomicAdd(&s_db[col + 1], db[kk].y);
+      }
+    }
+    if (q == 0) s_loss[threadIdx.x >> 4] = loss_acc;
+    __syncthreads();
+    if (dbias)
+      for (int i = threadIdx.x; i < 768; i += blockDim.x) atomicAdd(&dbias[i], s_db[i]);
+    if (threadIdx.x == 0) {
+      float tt = 0.f;
+      for (int i = 0; i < 16; ++i) tt += s_loss[i];
+      atomicAdd(loss_sum, (double)tt);
+    }
+  }
+}
+
 }  // namespace sb
 
 using namespace sb;
 
+static int g_ce_tma = 0;  // 0: register-staged kernel (default, faster as measured); 1: TMA-staged kernel
+extern "C" int sb_set_ce_tma(int enabled) {
+  const int prev = g_ce_tma;
+  g_ce_tma = enabled ? 1 : 0;
+  return prev;
+}
+
 extern "C" int sb_pixel_ce(const void* logits, const uint8_t* target, int B, int HW, float clip, float gscale,
                            void* dlogits, uint8_t* argmax_out, double* loss_sum, float* dbias, sb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!logits || B < 1 || HW < 1) return SB_ERR_ARG;
+  if (!logits || B < 1 || HW < 1 || (long long)B * HW * 3 >= (1LL << 31)) return SB_ERR_ARG;
   const bool train = dlogits != nullptr;
   if (train && (!target || !loss_sum)) return SB_ERR_ARG;
   if (!train && !argmax_out) return SB_ERR_ARG;
@@ -224,12 +358,24 @@ extern "C" int sb_pixel_ce(const void* logits, const uint8_t* target, int B, int
   const long long cap = 148LL * 3;  // 444 = 3 * 148 CTAs of 256 threads: one resident wave at 3 CTAs per SM
   if (blocks > cap) blocks = cap;
   blocks = ((blocks + 2) / 3) * 3;
-  if (train)
-    pixel_ce_kernel<true><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
-                                                            (__nv_bfloat16*)dlogits, argmax_out, loss_sum, dbias);
+  if (g_ce_tma) {
+    // 8 warps per CTA, one colour per warp: CTA count multiple of 3; 4 CTAs per SM resident
+    long long tb = (npix * 3 + 15) / 16;
+    const long long tcap = 148LL * 4 - (148LL * 4) % 3;
+    if (tb > tcap) tb = tcap;
+    tb = ((tb + 2) / 3) * 3;
+    if (train)
+      pixel_ce_tma_kernel<true><<<(int)tb, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
+                                                             (__nv_bfloat16*)dlogits, argmax_out, loss_sum, dbias);
+    else
+      pixel_ce_tma_kernel<false><<<(int)tb, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
+                                                              nullptr, argmax_out, nullptr, nullptr);
+  } else if (train)
+    pixel_ce_kernel<true, 3><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
+                                                             (__nv_bfloat16*)dlogits, argmax_out, loss_sum, dbias);
   else
-    pixel_ce_kernel<false><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
-                                                             nullptr, argmax_out, nullptr, nullptr);
+    pixel_ce_kernel<false, 3><<<(int)blocks, 256, 0, stream>>>((const __nv_bfloat16*)logits, target, B, HW, clip, gscale,
+                                                              nullptr, argmax_out, nullptr, nullptr);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

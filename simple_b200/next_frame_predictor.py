@@ -314,6 +314,8 @@ class NextFramePredictor(nn.Module):
         # reference.
         self._state = None        # fp32 [B,H,W,64] recurrent state (detached)
         self._xs_prev = None      # bf16 [B,H,W,128]: previous step's (state | x_start | 0) operand of the gate conv
+        self._xs_buf = None       # bf16 [B,H,W,128]: this step's operand (persistent: the zero padding is written once)
+        self._ps_buf = None       # bf16 [B,H,W,64]: posterior input (x_start 12 | target 3 | zero pad)
         self._has_prev = False
         self._pending = None
         self._seed_dev = None
@@ -332,6 +334,7 @@ class NextFramePredictor(nn.Module):
         else:
             self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
             self._xs_prev = torch.zeros(batch_size, H, W, 128, device=dev, dtype=torch.bfloat16)
+            self._xs_buf = torch.zeros(batch_size, H, W, 128, device=dev, dtype=torch.bfloat16)
         self._has_prev = False
         self._pending = None
 
@@ -520,10 +523,14 @@ class NextFramePredictor(nn.Module):
             return rand.big_keep_mask(spec_shape_nchw, p)
 
         # ---- standardise + recurrent state (K5, K6)
-        xs = torch.zeros(B, H, W, 128, device=dev, dtype=torch.bfloat16)
-        ops.standardize(x.contiguous().float(), dst=xs, coff=64)
         if self._state is None or self._state.shape[0] != B:
             self.init_internal_states(B)
+        # XS = [state 64 | x_start 12 | zero pad to 128] lives in a persistent buffer whose padding is zeroed once (a fresh
+        # torch.zeros of 137 MB per step was pure fill traffic); a detached alias keeps this step's autograd graph off it
+        xs = self._xs_buf.detach()
+        if not self._has_prev:
+            xs[..., :64].zero_()  # first step of a window: the recurrent state is zero and the gate conv is skipped
+        ops.standardize(x.contiguous().float(), dst=xs, coff=64)
         s_new = None
         if self._has_prev:
             G = self._conv('gate', P['gate'], self._xs_prev)
@@ -551,7 +558,9 @@ class NextFramePredictor(nn.Module):
         sc0, sh0 = self.action_injectors[0].scale_shift(action)
         h = h * sc0[:, :, None, None] + sh0[:, :, None, None]
         if target is not None:
-            ps = torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16)
+            if self._ps_buf is None or self._ps_buf.shape[0] != B or self._ps_buf.device != dev:
+                self._ps_buf = torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16)  # channels 15..63 stay zero
+            ps = self._ps_buf.detach()
             ops.standardize(target, dst=ps, coff=12, out_f32=target)  # in place, like the reference (:332-334)
         sm = self.stochastic_model
         if training:

@@ -156,10 +156,15 @@ class FusedPrep(torch.autograd.Function):
         a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, None, None, ctx.seed, keep)
         a.g2 = spec.lay_out.view(g2)
         a.g1 = _ptr(g1)
-        bsums = None
+        bsums = dgb = None
         if has_norm or has_inj:
-            bsums = torch.zeros(B, spec.C, 4, device=dev, dtype=torch.float32)
+            # one zero-filled buffer: per-(b,c) sums [B,C,4] + their batch sums for the affine gradients [C,2]
+            buf = torch.zeros(B * spec.C * 4 + spec.C * 2, device=dev, dtype=torch.float32)
+            bsums = buf[:B * spec.C * 4].view(B, spec.C, 4)
             a.bsums = bsums.data_ptr()
+            if has_norm:
+                dgb = buf[B * spec.C * 4:].view(spec.C, 2)
+                a.dgb = dgb.data_ptr()
             _lib.check(_lib.lib().sb_prep_bwd_reduce(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_reduce')
         d_main = torch.empty(main.shape, device=dev, dtype=torch.bfloat16)
         d_add = torch.empty(add.shape, device=dev, dtype=torch.bfloat16) if has_add else None
@@ -172,10 +177,10 @@ class FusedPrep(torch.autograd.Function):
         _lib.check(_lib.lib().sb_prep_bwd_apply(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_apply')
         if dcol is not None:
             ctx.dbias_dst['dbias'] = dcol
-        dgamma = bsums[:, :, 1].sum(0) if has_norm else None
-        dbeta = bsums[:, :, 0].sum(0) if has_norm else None
-        dsc = bsums[:, :, 2].contiguous() if has_inj else None
-        dsh = bsums[:, :, 3].contiguous() if has_inj else None
+        dgamma = dgb[:, 1] if has_norm else None
+        dbeta = dgb[:, 0] if has_norm else None
+        dsc = bsums[:, :, 2] if has_inj else None
+        dsh = bsums[:, :, 3] if has_inj else None
         return None, d_main, d_add, dgamma, dbeta, dsc, dsh, None, None, None
 
 

@@ -14,8 +14,19 @@ def rel(a, b):
 
 
 # ------------------------------------------------------------------------------------------------ pixel CE (K14)
-@pytest.mark.parametrize('B,HW', [(1, 64), (2, 8400), (3, 1000)])
-def test_pixel_ce_vs_oracle(B, HW):
+@pytest.mark.parametrize('tma', [1, 0])
+@pytest.mark.parametrize('B,HW', [(1, 64), (2, 8400), (3, 1000), (1, 7)])
+def test_pixel_ce_vs_oracle(B, HW, tma):
+    """Both kernel variants (TMA-staged shared-memory ring / register-staged) against the numpy oracle."""
+    from simple_b200 import _lib
+    prev = _lib.lib().sb_set_ce_tma(tma)
+    try:
+        _pixel_ce_vs_oracle(B, HW)
+    finally:
+        _lib.lib().sb_set_ce_tma(prev)
+
+
+def _pixel_ce_vs_oracle(B, HW):
     from oracle.wm_oracle import pixel_ce_np
     from simple_b200 import ops
     torch.manual_seed(0)
