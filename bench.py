@@ -295,6 +295,12 @@ def run_own(args):
     }
 
     dbg('timed regions done')
+    if world > 1 and os.environ.get('SB_BENCH_DEBUG'):
+        # replicas must stay identical: same reduced gradient, same deterministic update on every rank
+        cs = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        both = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(both, cs)
+        dbg('parameter checksums per rank: ' + ', '.join(f'{float(c):.10e}' for c in both))
     if rank == 0:
         hbm, tf_sus, tf_burst, how = peaks()
         # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps.  Rank 0 only, so the

@@ -502,6 +502,8 @@ class NextFramePredictor(nn.Module):
             for pw in self._packed.values():
                 pw.defer_unpack = bool(defer_unpack)
                 pw.gpacked = None
+                pw.grad_slot = None  # (a data-parallel gradient arena re-attaches its slots right after, every step)
+                pw.on_ready = None
         return {mods[k].weight: pw for k, pw in self._packed.items()}
 
     def _conv(self, name, spec, a, need_weight_grad=True):

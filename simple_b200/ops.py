@@ -237,6 +237,8 @@ class PackedWeight:
         # `gpacked` instead of unpacking it into `weight.grad`; the fused Adafactor consumes it and rewrites `fwd`
         self.defer_unpack = False
         self.gpacked = None
+        self.grad_slot = None   # optional preallocated (zeroed) fp32 accumulator in the packed layout (DP gradient arena)
+        self.on_ready = None    # optional callback fired when this layer's weight gradient has been launched
         self.fresh = False  # operands already match the master weights (written by the optimiser): skip one re-pack
         self.pack(weight)
 
@@ -320,17 +322,20 @@ class TapConv(torch.autograd.Function):
                 da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
                               flops=spec.flops * B)
         T = len(spec.taps)
+        slot = pw.grad_slot if pw.defer_unpack else None
         if spec.transposed:
             # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
-            dwp = torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
+            dwp = slot if slot is not None else torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
             tap_wgrad(dy, a, spec.neg_taps, dwp, splits=_wgrad_splits(B, spec.Ha, spec.Wa, spec.Ca, spec.N, T),
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         else:
-            dwp = torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
+            dwp = slot if slot is not None else torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
             tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T),
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         if pw.defer_unpack:
             pw.gpacked, dweight = dwp, None
+            if pw.on_ready is not None:
+                pw.on_ready()
         else:
             dweight = pw.unpack_grad(dwp)
         dbias = None

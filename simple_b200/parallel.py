@@ -28,22 +28,120 @@ def init_distributed(backend=None):
 
 
 class FlatGradSync:
-    """Callable for `Trainer.grad_sync`: packs the gradients into one flat fp32 buffer, all-reduces it (mean), and
-    returns {param: view into the buffer} for `Adafactor.step(grads=...)`.
+    """Callable for `Trainer.grad_sync`: gradients live in one flat fp32 arena that is all-reduced (mean) and handed to
+    `Adafactor.step(grads=...)` as {param: view into the arena} -- no copy back.
+
+    Overlap (packed-gradient mode, see ops.PackedWeight): `prepare()` points every conv layer's wgrad accumulator
+    (`pw.grad_slot`) INTO the arena, laid out in the order the backward pass finishes them (decoder first), split into
+    buckets.  When the last layer of a bucket reports its gradient (`pw.on_ready`), the bucket's all-reduce is launched
+    on a side stream and runs over NVLink while the rest of the backward pass keeps the SMs busy; only the last bucket
+    (shallow encoder layers + the 3 M non-conv parameters) is exposed.  Works under CUDA-graph capture (the side stream
+    is forked from / joined to the capturing stream with events).
 
     Parameters whose gradient is None on this step (gate.* on the first step of a window) are None
-    on every rank alike (the condition depends on the step index only), so all ranks pack the same layout.
+    on every rank alike (the condition depends on the step index only), so all ranks see the same layout.
     """
 
-    def __init__(self, model, group=None):
+    # backward completion order of the conv layers (autograd runs the decoder first, the gate conv last)
+    ORDER = ['logits', 'up4', 'up3', 'up2', 'up1', 'up0', 'mid1', 'mid0', 's_conv2', 's_conv1', 's_embed',
+             'down4', 'down3', 'down2', 'down1', 'down0', 'embed', 'gate']
+
+    def __init__(self, model, group=None, n_buckets=4):
         self.params = [p for p in model.parameters()]
         self.group = group
         self.flat = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_buckets = n_buckets
+        self._layout = None      # overlap mode: dict(name -> (offset, numel)), bucket boundaries, tail offset
+        self._comm_stream = None
+        self._avg = dist.ReduceOp.AVG if hasattr(dist.ReduceOp, 'AVG') else None
 
+    # ---- overlap mode ------------------------------------------------------------------------------------------
+    def prepare(self, model, packed):
+        """Call after the forward pass and before backward (packed-gradient mode only)."""
+        if not packed or self.world < 2 or not torch.cuda.is_available():
+            return
+        pws = model._packed
+        dev = next(iter(pws.values())).fwd.device
+        if self._layout is None:
+            names = [n for n in self.ORDER if n in pws] + [n for n in pws if n not in self.ORDER]
+            off, slots = 0, {}
+            for n in names:
+                slots[n] = (off, pws[n].fwd.numel())
+                off += pws[n].fwd.numel()
+            conv_total = off
+            conv_params = {id(p) for p in packed}
+            tail = sum(p.numel() for p in self.params if id(p) not in conv_params)
+            self.flat = torch.zeros(conv_total + tail, device=dev, dtype=torch.float32)
+            # bucket i ends after the first layer that brings the running size past (i+1)/n of the conv total; the last
+            # bucket (whatever follows the final boundary, plus the non-conv tail) is reduced at the end of backward
+            bounds, members, cur = [], [], set()
+            target = [conv_total * (i + 1) / self.n_buckets for i in range(self.n_buckets)]
+            for n in names:
+                cur.add(n)
+                end = slots[n][0] + slots[n][1]
+                if len(bounds) < self.n_buckets - 1 and end >= target[len(bounds)]:
+                    bounds.append(end)
+                    members.append(cur)
+                    cur = set()
+            self._layout = dict(names=names, slots=slots, conv_total=conv_total, bounds=bounds, members=members)
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        L = self._layout
+        self.flat[:L['conv_total']].zero_()  # wgrad accumulates with red.add
+        self._launched = 0
+        self._ready = set()
+        for n in L['names']:
+            o, k = L['slots'][n]
+            pw = pws[n]
+            pw.grad_slot = self.flat[o:o + k].view(pw.fwd.shape)
+            pw.on_ready = (lambda name=n: self._on_ready(name))
+
+    def _all_reduce(self, buf):
+        if self._avg is not None:
+            dist.all_reduce(buf, op=self._avg, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world)
+
+    def _on_ready(self, name):
+        L = self._layout
+        self._ready.add(name)
+        # a bucket goes out once ALL of its layers have reported (robust to the exact autograd execution order, which is
+        # the same on every rank: same graph)
+        while self._launched < len(L['bounds']) and L['members'][self._launched] <= self._ready:
+            lo = L['bounds'][self._launched - 1] if self._launched else 0
+            hi = L['bounds'][self._launched]
+            cur = torch.cuda.current_stream()
+            self._comm_stream.wait_stream(cur)  # this bucket's gradients are complete on the compute stream
+            with torch.cuda.stream(self._comm_stream):
+                self._all_reduce(self.flat[lo:hi])
+            self._launched += 1
+
+    def _finish_overlapped(self, packed):
+        L = self._layout
+        conv = {id(p): pw for p, pw in packed.items()}
+        rest = [p for p in self.params if id(p) not in conv and p.grad is not None]
+        views, off = {}, L['conv_total']
+        for p in rest:
+            views[p] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        if rest:
+            torch._foreach_copy_(list(views.values()), [p.grad for p in rest])
+        lo = L['bounds'][self._launched - 1] if self._launched else 0
+        self._all_reduce(self.flat[lo:off])  # the not-yet-launched buckets + the non-conv tail, on the compute stream
+        torch.cuda.current_stream().wait_stream(self._comm_stream)
+        for p, pw in packed.items():
+            if pw.grad_slot is not None and pw.gpacked is not None:
+                views[p] = pw.grad_slot
+            pw.on_ready = None
+        return views
+
+    # ---- entry point -------------------------------------------------------------------------------------------
     def __call__(self, model, packed=None):
         """`packed`: optional {param: ops.PackedWeight}; those parameters contribute their packed-layout gradient
         (`pw.gpacked`, zero-padded, identical layout on every rank) instead of `p.grad`."""
+        if packed and self._layout is not None and all(pw.grad_slot is not None for pw in packed.values()):
+            return self._finish_overlapped(packed)
         active = []
         for p in self.params:
             pw = packed.get(p) if packed else None
@@ -67,7 +165,13 @@ class FlatGradSync:
 
 
 def broadcast_parameters(model, src=0):
-    """Make every rank start from rank `src`'s weights (same effect as seeding identically)."""
+    """Make every rank hold rank `src`'s weights: at start-up (same effect as seeding identically) and, called once per
+    rollout window by the Trainer, to cancel the ~1e-9/step drift between replicas that the fp32-atomic reductions inside
+    the fused optimiser introduce (the reduced gradient itself is bit-identical on every rank)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
         for p in model.parameters():
             dist.broadcast(p.data, src)
+        packed = getattr(model, '_packed', None)
+        if packed:
+            for pw in packed.values():
+                pw.fresh = False  # the bf16 GEMM operands are re-derived from the synchronised masters

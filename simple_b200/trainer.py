@@ -120,6 +120,8 @@ class Trainer:
         out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
         self.optimizer.zero_grad(set_to_none=True)
         packed = self.model.packed_weight_map(defer_unpack=self.packed_grads) if self.packed_grads else None
+        if self.grad_sync is not None and hasattr(self.grad_sync, 'prepare'):
+            self.grad_sync.prepare(self.model, packed)  # gradient arena + bucketed all-reduce overlapped with backward
         out['loss'].backward()
         grads = self.grad_sync(self.model, packed) if self.grad_sync is not None else None
         self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads, packed=packed)
@@ -162,6 +164,9 @@ class Trainer:
         metrics = {}
         for i in iterator:
             epsilon = self.epsilon_schedule(epoch, i)
+            if self.grad_sync is not None:
+                from .parallel import broadcast_parameters
+                broadcast_parameters(self.model)  # once per window: keeps the data-parallel replicas bit-identical
             runner.begin(rp.sample_starts(B), epsilon)
             for j in range(rollout_len):
                 runner.step()
