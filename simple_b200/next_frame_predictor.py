@@ -90,14 +90,18 @@ class BitsPredictor(nn.Module):  # :66-121
         self._sampler_tables = None
         self.cache_sampler_tables = False  # set while the weights are known to be static (NextFramePredictor.repack)
 
-    def forward(self, x, rand, target_bits=None):
+    def project(self, x):
+        """dense1..3 share their input: one [B,4608] x [4608,384] GEMM instead of three -> (first_input, h0, c0).
+        The training forward calls the predictor twice on the same input (teacher pass, sampling pass): project once."""
+        w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
+        b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
+        return F.linear(x, w123, b123).chunk(3, dim=1)
+
+    def forward(self, x, rand, target_bits=None, proj=None):
         """x: [B,4608] (C,H,W order).  Teacher-forced loss when target_bits is given, else sampled bits in {-1,+1}."""
         n = self.total_number_bits // self.bits_at_once
         B = x.shape[0]
-        # dense1..3 share their input: one [B,4608] x [4608,384] GEMM instead of three
-        w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
-        b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
-        first, h, c = F.linear(x, w123, b123).chunk(3, dim=1)
+        first, h, c = proj if proj is not None else self.project(x)
         if target_bits is not None:
             tb = target_bits.reshape(-1, n, self.bits_at_once).clamp(min=0.)
             w = (2 ** torch.arange(self.bits_at_once, device=x.device)).float()
@@ -506,6 +510,20 @@ class NextFramePredictor(nn.Module):
                 pw.on_ready = None
         return {mods[k].weight: pw for k, pw in self._packed.items()}
 
+    def _injector_bank(self, action, with_posterior):
+        """sigmoid(dense1(a)) and dense2(a) of ALL ActionInjectors (6 trunk + the posterior's) as two GEMMs on the
+        concatenated weights instead of 14 tiny ones (simple/utils.py:98-105; K = n_action)."""
+        mods = list(self.action_injectors) + ([self.stochastic_model.action_injector] if with_posterior else [])
+        a = action.reshape(action.shape[0], -1)
+        w1 = torch.cat([m.dense1.weight for m in mods], dim=0)
+        b1 = torch.cat([m.dense1.bias for m in mods], dim=0)
+        w2 = torch.cat([m.dense2.weight for m in mods], dim=0)
+        b2 = torch.cat([m.dense2.bias for m in mods], dim=0)
+        sc = torch.sigmoid(F.linear(a, w1, b1))
+        sh = F.linear(a, w2, b2)
+        sizes = [m.dense1.weight.shape[0] for m in mods]
+        return list(zip(sc.split(sizes, dim=1), sh.split(sizes, dim=1)))
+
     def _conv(self, name, spec, a, need_weight_grad=True):
         m = self._weights_cache[name]
         return tap_conv(spec, a, m.weight, m.bias, self._packed[name])
@@ -557,7 +575,8 @@ class NextFramePredictor(nn.Module):
         h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
         value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
                               self.value_estimator.dense.bias).squeeze(-1)
-        sc0, sh0 = self.action_injectors[0].scale_shift(action)
+        inj = self._injector_bank(action, training)
+        sc0, sh0 = inj[0]
         h = h * sc0[:, :, None, None] + sh0[:, :, None, None]
         if target is not None:
             if self._ps_buf is None or self._ps_buf.shape[0] != B or self._ps_buf.device != dev:
@@ -567,7 +586,7 @@ class NextFramePredictor(nn.Module):
         sm = self.stochastic_model
         if training:
             ps[..., :12] = xs.detach()[..., 64:76]
-            h = self._posterior(h, ps, action, epsilon, rand, aux)
+            h = self._posterior(h, ps, inj[-1], epsilon, rand, aux)
         else:
             bits, _ = sm.bits_predictor(h.reshape(B, -1), rand)
             bits = self._forced(rand, 'sampled_bits', bits)
@@ -587,7 +606,7 @@ class NextFramePredictor(nn.Module):
         main, add, nrm = y2, y1, mn[3]
         for i in range(5):
             sp = P['prep_dec'][i]
-            sc, sh = self.action_injectors[i + 1].scale_shift(action)
+            sc, sh = inj[i + 1]
             km = keep((B, sp.C, sp.H, sp.W), sp.p)
             _, A = fused_prep(sp, main, add=add, gamma=nrm.weight, beta=nrm.bias, sc=sc, sh=sh, seed=seed, keep=km,
                               dbias_dst=(P['mid'][1] if i == 0 else P['up'][i - 1]).dbias_src)
@@ -602,14 +621,14 @@ class NextFramePredictor(nn.Module):
         logits = self._conv('logits', P['logits'], hf)  # bf16 [B,H,W,768], channel = colour*256 + value
         return logits, reward_pred, value_pred
 
-    def _posterior(self, layer, ps, action, epsilon, rand, aux):
+    def _posterior(self, layer, ps, inj_s, epsilon, rand, aux):
         """StochasticModel.forward, training branch (next_frame_predictor.py:162-197)."""
         c = self.config
         P = self._plan
         sm = self.stochastic_model
         B = layer.shape[0]
         e = self._conv('s_embed', P['s_embed'], ps)
-        sc, sh = sm.action_injector.scale_shift(action)
+        sc, sh = inj_s
         _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh, dbias_dst=P['s_embed'].dbias_src)
         c1 = self._conv('s_conv1', P['s_conv1'], A)  # [B,26,20,128], pre-ReLU
         x1 = ops.mean_attention(c1, sm.mean_attentions[0])
@@ -626,9 +645,10 @@ class NextFramePredictor(nn.Module):
         bits = bits * noise
         bits = mix(bits, x, 1 - epsilon, rand)
         flat = layer.reshape(B, -1)
-        _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean)
+        proj = sm.bits_predictor.project(flat)
+        _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean, proj=proj)
         sm.lstm_loss = sm.lstm_loss.to(lstm_loss.device) + lstm_loss
-        bits_pred, _ = sm.bits_predictor(flat, rand)
+        bits_pred, _ = sm.bits_predictor(flat, rand, proj=[t.detach() for t in proj])
         bits_pred = self._forced(rand, 'sampled_bits', bits_pred)
         aux['bits_pred'] = bits_pred.detach()
         bits_pred = bits_clean + (bits_pred - bits_clean).detach()
