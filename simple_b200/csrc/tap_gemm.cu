@@ -169,15 +169,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const int last_steps = (p.C - (p.kchunks - 1) * 64 + 15) >> 4;  // K=16 steps of the last channel chunk (1..4)
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int sp = tile / (p.n_tiles * p.m_tiles);
-        const int nk = (int)((long long)KT * (sp + 1) / p.splits) - (int)((long long)KT * sp / p.splits);
+        const int k_begin = (int)((long long)KT * sp / p.splits);
+        const int nk = (int)((long long)KT * (sp + 1) / p.splits) - k_begin;
         const int as = tcount & 1;
         const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
         mbar_wait(&tempty[as], aph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        int chunk = k_begin % p.kchunks;  // channel chunk of the next stage (no division in the issue loop)
         for (int i = 0; i < nk; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -185,11 +188,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
           const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+          // channels past C in the last 64-wide chunk are TMA zero fill: skip their K=16 steps (gate/embed: C = 80)
+          const int ksteps = (chunk == p.kchunks - 1) ? last_steps : 4;
+          chunk = (chunk + 1 == p.kchunks) ? 0 : chunk + 1;
+          if (ksteps == 4) {  // (the common case keeps its straight-line issue sequence: this thread is the critical path)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -441,6 +455,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      const int last_steps = (p.C - (p.kchunks - 1) * 64 + 15) >> 4;
       int it = 0, tcount = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
         const int as = tcount & 1;
@@ -448,6 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
         mbar_wait(&tempty[as], aph ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        int chunk = 0;
         for (int i = 0; i < KT; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -455,11 +471,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + s * kATileBytes);
           const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+          const int ksteps = (chunk == p.kchunks - 1) ? last_steps : 4;  // see the single-CTA kernel
+          chunk = (chunk + 1 == p.kchunks) ? 0 : chunk + 1;
+          if (ksteps == 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_2cta(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16_2cta(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+              umma_bf16_2cta(d_tmem, ad, bd, idesc, (uint32_t)((i | k) != 0));
+            }
           }
           umma_commit_2cta(&empty[s], 3);
         }
@@ -650,7 +676,9 @@ __global__ void __launch_bounds__(kGemmThreads)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      // A-channel (N) extent of this tile rounded to the MMA granularity: C = 80 runs N = 80, not the full 128
+      const int n_eff = min(BN, ((p.C - c0 + 15) >> 4) << 4);
+      const uint32_t idesc = make_idesc_bf16(128, n_eff, 1, 1);
       for (int i = 0; i < nk; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -758,7 +786,9 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   if (rc) return rc;
   rc = make_map_2d(&tmB, a->w, a->N, a->ntaps * a->C, a->ldw, BN);
   if (rc) return rc;
-  p.tma_out = (!atomic && !a->out_f32 && a->N % 32 == 0) ? 1 : 0;
+  // TMA-store epilogue: bf16 outputs; a ragged last 32-column chunk is clipped by the TMA unit (the vectorised bias loads
+  // of the epilogue would read past the end, so ragged N is only taken without a bias: dgrad)
+  p.tma_out = (!atomic && !a->out_f32 && (a->N % 32 == 0 || a->bias == nullptr)) ? 1 : 0;
   if (p.tma_out) {
     rc = make_map_out(&tmO, a->out, a->B, a->Ho, a->Wo, a->N, a->ldo, a->bw, a->bh, a->bb);
     if (rc) return rc;

@@ -16,6 +16,10 @@ import torch.nn.functional as F
 from . import ops
 from .ops import ConvSpec, PackedWeight, PrepSpec, fused_prep, plain, s2d_in, s2d_out, tap_conv
 
+# channels of the gate / embedding operand XS = [recurrent state 64 | x_start 12 | zero pad]: 76 rounded up to the tcgen05
+# K step (16).  The second 64-channel TMA box of a pixel is zero-filled past channel 80 and only its first K=16 step runs.
+XS_C = 80
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # parameter containers (same attribute names and creation order as the reference => identical init + state_dict)
@@ -337,8 +341,8 @@ class NextFramePredictor(nn.Module):
             self._state.zero_()  # keep the buffers (and their addresses)
         else:
             self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
-            self._xs_prev = torch.zeros(batch_size, H, W, 128, device=dev, dtype=torch.bfloat16)
-            self._xs_buf = torch.zeros(batch_size, H, W, 128, device=dev, dtype=torch.bfloat16)
+            self._xs_prev = torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16)
+            self._xs_buf = torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16)
         self._has_prev = False
         self._pending = None
 
@@ -386,11 +390,11 @@ class NextFramePredictor(nn.Module):
         tshapes = [es[0]] + [es[i] for i in range(5)] + [ds[i] for i in range(5)]
         P['timing'] = [timing_signal_sep(s[0], s[1], s[2]).to(dev) for s in tshapes]
         P['stoch_timing'] = timing_signal_sep(c.hidden_size, H, W).to(dev)
-        # gate 3x3 on XS (state 0..63 | x_start 64..75 | zero pad to 128), no dgrad (inputs are detached / data)
+        # gate 3x3 on XS (state 0..63 | x_start 64..75 | zero pad to XS_C = 80), no dgrad (inputs are detached / data)
         HW = H * W
-        P['gate'] = ConvSpec('gate', H, W, 128, H, W, 128, taps33, relu=False, need_dgrad=False,
+        P['gate'] = ConvSpec('gate', H, W, XS_C, H, W, 128, taps33, relu=False, need_dgrad=False,
                              flops=2.0 * HW * 128 * 76 * 9)
-        P['embed'] = ConvSpec('embed', H, W, 128, H, W, 96, [(0, 0)], relu=False, flops=2.0 * HW * 96 * 76)
+        P['embed'] = ConvSpec('embed', H, W, XS_C, H, W, 96, [(0, 0)], relu=False, flops=2.0 * HW * 96 * 76)
         P['down'], P['down_lay'] = [], []
         for i in range(5):
             Ci, Hi, Wi = es[i]
@@ -457,11 +461,11 @@ class NextFramePredictor(nn.Module):
         c = self.config
         sm = self.stochastic_model
         pk = {}
-        # gate input order is (state 64, x_start 12) == XS order; pad K 76 -> 128
-        pk['gate'] = PackedWeight(self.gate.weight, 1, Ipad=128)
+        # gate input order is (state 64, x_start 12) == XS order; pad K 76 -> XS_C (a multiple of the MMA K step)
+        pk['gate'] = PackedWeight(self.gate.weight, 1, Ipad=XS_C)
         # input_embedding input order is (x_start 12, state 64): permute to XS order
         perm = [64 + i for i in range(12)] + list(range(64))
-        pk['embed'] = PackedWeight(self.input_embedding.weight, 1, Ipad=128, iperm=perm)
+        pk['embed'] = PackedWeight(self.input_embedding.weight, 1, Ipad=XS_C, iperm=perm)
         for i in range(5):
             pk[f'down{i}'] = PackedWeight(self.downscale_layers[2 * i].weight, 2)
             pk[f'up{i}'] = PackedWeight(self.upscale_layers[2 * i].weight, 2)
@@ -545,7 +549,7 @@ class NextFramePredictor(nn.Module):
         # ---- standardise + recurrent state (K5, K6)
         if self._state is None or self._state.shape[0] != B:
             self.init_internal_states(B)
-        # XS = [state 64 | x_start 12 | zero pad to 128] lives in a persistent buffer whose padding is zeroed once (a fresh
+        # XS = [state 64 | x_start 12 | zero pad to 80] lives in a persistent buffer whose padding is zeroed once (a fresh
         # torch.zeros of 137 MB per step was pure fill traffic); a detached alias keeps this step's autograd graph off it
         xs = self._xs_buf.detach()
         if not self._has_prev:

@@ -128,3 +128,35 @@ def test_cta_pair_kernel_matches_single_cta_and_reference(B, Ho, Wo, C, N, kind)
         ref = F.relu(acc + bias)
         got = out_pair[b].float()
         assert torch.allclose(got, ref, rtol=2e-2, atol=5e-2), float((got - ref).abs().max())
+
+
+def test_ragged_channel_operand_c80():
+    """The gate / embedding operand has 80 channels (76 used): its second 64-channel TMA box is zero-filled past channel
+    80 and only the valid K=16 steps run; wgrad runs the MMA at N = 80; dgrad writes an 80-channel output through the
+    clipped TMA store.  All three against torch."""
+    from simple_b200.gemm import tap_gemm, tap_wgrad
+    torch.manual_seed(9)
+    B, H, W, C, N = 6, 21, 16, 80, 128
+    x = torch.randn(B, H, W, C, device=_dev()).bfloat16()
+    wt = (torch.randn(N, C, 3, 3, device=_dev()) * 0.05).bfloat16()
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    wp = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = tap_gemm(x, wp, taps, H, W, out_dtype=torch.bfloat16)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.allclose(out.float(), ref, rtol=2e-2, atol=5e-2), float((out.float() - ref).abs().max())
+    # wgrad, A-channel side = 80
+    dy = torch.randn(B, H, W, N, device=_dev()).bfloat16()
+    dw = torch.zeros(N, 9 * C, device=_dev())
+    tap_wgrad(x, dy, taps, dw, splits=2)
+    wref = torch.zeros(N, C, 3, 3, device=_dev(), requires_grad=True)
+    (g,) = torch.autograd.grad(F.conv2d(x.float().permute(0, 3, 1, 2), wref, padding=1), wref, dy.float().permute(0, 3, 1, 2))
+    torch.cuda.synchronize()
+    assert torch.allclose(dw, g.permute(0, 2, 3, 1).reshape(N, 9 * C), rtol=1e-3, atol=5e-2)
+    # 1x1 "dgrad" with an 80-channel output (ragged last 32-column chunk, no bias)
+    w2 = (torch.randn(C, 96, device=_dev()) * 0.1).bfloat16()     # [N_out = 80, K = 96]
+    y = torch.randn(B, H, W, 96, device=_dev()).bfloat16()
+    dx = tap_gemm(y, w2, [(0, 0)], H, W, N=C)
+    torch.cuda.synchronize()
+    ref2 = y.float() @ w2.float().t()
+    assert dx.shape == (B, H, W, C) and torch.allclose(dx.float(), ref2, rtol=2e-2, atol=5e-2)
