@@ -153,9 +153,10 @@ int sb_prep_bwd_reduce(const sb_prep_args* args, sb_stream_t stream);
 int sb_prep_bwd_apply(const sb_prep_args* args, sb_stream_t stream);
 
 /* standardize_frame (simple/utils.py:122-126): in fp32 [B,C,P] -> (x-mean)/max(std_unbiased, 1/sqrt(P)) written to
- * dst_bf16[(b*P+i)*ld + coff + c] and/or out_f32 [B,C,P] (may alias `in`: the reference standardises targets in place). */
+ * dst_bf16[(b*P+i)*ld + coff + c] and/or out_f32 [B,C,P] (may alias `in`: the reference standardises targets in place).
+ * stats_scratch: caller-owned fp32 [B*C*2] (per-plane mean / scale between the statistics and the apply kernel). C <= 16. */
 int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
-                   sb_stream_t stream);
+                   float* stats_scratch, sb_stream_t stream);
 
 /* Scheduled-sampling frame feedback (simple/trainer.py:58-65,125-132), in place on the fp32 frame stack [B,C_stack,HW]:
  * next = gt w.p. *eps_ptr else pred (u8 [B,C_new,HW]); next/255 with each value replaced w.p. p_noise by the frame's lower

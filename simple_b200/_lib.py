@@ -110,7 +110,7 @@ class _Sigs:
     sb_prep = [ctypes.POINTER(PrepArgs), _p]
     sb_prep_bwd_reduce = [ctypes.POINTER(PrepArgs), _p]
     sb_prep_bwd_apply = [ctypes.POINTER(PrepArgs), _p]
-    sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p]
+    sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p]
     sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
     sb_frame_feedback = [_p, _p, _p, _p, _f, _p, ctypes.c_ulonglong, _i, _i, _i, _i, _p]
     sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]

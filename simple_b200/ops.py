@@ -415,8 +415,9 @@ def standardize(x, dst=None, coff=0, out_f32=None):
     """x fp32 [B,C,H,W] -> standardised; writes bf16 into dst[..., coff:coff+C] (NHWC) and/or fp32 `out_f32` (NCHW)."""
     assert x.dtype == torch.float32 and x.is_contiguous()
     B, C, H, W = x.shape
+    scratch = torch.empty(B * C * 2, device=x.device, dtype=torch.float32)
     _lib.check(_lib.lib().sb_standardize(x.data_ptr(), B, C, H * W, _ptr(dst), dst.shape[-1] if dst is not None else 0,
-                                         coff, _ptr(out_f32), _lib.stream_ptr()), 'sb_standardize')
+                                         coff, _ptr(out_f32), scratch.data_ptr(), _lib.stream_ptr()), 'sb_standardize')
 
 
 def frame_feedback(stack, gt_u8, pred_u8, eps, p_noise, seed):
