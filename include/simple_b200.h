@@ -141,6 +141,9 @@ typedef struct {
   void* d_add;             /* grad wrt add (plain) or NULL */
   float* dcol;             /* optional fp32 [C] (caller zeroes): += column sums of d_main over b,y,x = the bias gradient
                               of the convolution that produced `in` (sb_prep_bwd_apply only) */
+  int b_base, b_count;     /* batch-chunked launch: process samples [b_base, b_base+b_count) only (all pointers and B
+                              still describe the WHOLE batch; b_count == 0 = all samples).  Lets a caller run
+                              stats -> prep or reduce -> apply chunk by chunk inside the L2 */
   float* dgb;              /* optional fp32 [C,2] (caller zeroes; sb_prep_bwd_reduce only): += sum over b of bsums[b,c,0..1],
                               i.e. (d beta, d gamma) of the InstanceNorm affine */
 } sb_prep_args;

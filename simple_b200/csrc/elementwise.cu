@@ -73,6 +73,8 @@ __device__ __forceinline__ int fast_div(int n, uint32_t m) { return m ? (int)__u
 
 struct PrepParams {
   int B, H, W, C;
+  int b_base;               // first sample of this launch (grid.y covers b_count samples): batch-chunked launches keep a
+                            // stage's reduce -> apply working set inside the 126 MB L2
   int add_f32;              // `add` holds fp32
   int in_f32;               // main input holds fp32 instead of bf16 (tiny deep layers: InstanceNorm over <= 30 pixels)
   View in;                  // main input
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) prep_fwd_kernel(const __grid_constant_
   iter_space<F, F_OUTS2D>(q.out2, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const int b = blockIdx.y, c = cv * 8;
+  const int b = blockIdx.y + q.b_base, c = cv * 8;
   const int NP = ny * nx;
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(256, (MODE == 0 ? 3 : 2))
   extern __shared__ float sm[];
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y + q.b_base;
   const int c = cv * 8;
   const int P = q.H * q.W;
   const int p_begin = blockIdx.x * pix_per_slab;
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(256, 2)
   iter_space<F, F_INS2D>(q.d_main, q.H, q.W, &y0, &ny, &x0, &nx);
   const int CV = q.C / 8;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  const int b = blockIdx.y, c = cv * 8;
+  const int b = blockIdx.y + q.b_base, c = cv * 8;
   const int NP = ny * nx;
   const int p_begin = blockIdx.x * pix_per_slab;
   const int p_end = min(NP, p_begin + pix_per_slab);
@@ -839,6 +841,8 @@ static uint32_t div_magic(int d) { return d <= 1 ? 0u : (uint32_t)((0x100000000U
 static int fill(PrepParams& q, const sb_prep_args* a) {
   if (!a || a->C % 8 || a->C < 8 || a->C / 8 > 256) return SB_ERR_ARG;
   q.B = a->B; q.H = a->H; q.W = a->W; q.C = a->C;
+  q.b_base = a->b_base;
+  if (a->b_base < 0 || a->b_count < 0 || a->b_base + a->b_count > a->B) return SB_ERR_ARG;
   q.in_f32 = a->in_f32;
   q.add_f32 = a->add_f32;
   q.in = mk_view(&a->in);
@@ -874,12 +878,13 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   if ((q.sc == nullptr) != (q.sh == nullptr)) return SB_ERR_ARG;
   return SB_OK;
 }
-static void reduce_cfg(const PrepParams& q, int* PL, int* slabs, int* pps, int* threads, int P = -1) {
+static int launch_samples(const sb_prep_args* a) { return a->b_count > 0 ? a->b_count : a->B; }
+static void reduce_cfg(const PrepParams& q, int nb, int* PL, int* slabs, int* pps, int* threads, int P = -1) {
   const int CV = q.C / 8;
   *PL = 256 / CV < 1 ? 1 : 256 / CV;
   *threads = CV * (*PL);
   if (P < 0) P = q.H * q.W;
-  int want = (148 * 6 + q.B - 1) / q.B;  // ~6 CTAs per SM over the whole grid
+  int want = (148 * 6 + nb - 1) / nb;  // ~6 CTAs per SM over the whole grid
   if (want < 1) want = 1;
   int per = (P + want - 1) / want;
   if (per < *PL) per = *PL;
@@ -899,9 +904,10 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   if (rc || !sums || !q.in.p) return SB_ERR_ARG;
   q.sums = nullptr;
   int PL, slabs, pps, threads;
-  reduce_cfg(q, &PL, &slabs, &pps, &threads);
+  const int nb = launch_samples(a);
+  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads);
   const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
-  const dim3 grid(slabs, q.B);
+  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
   if (q.in_f32 || q.add_f32) {
     reduce_bc_kernel<0, true, kRT><<<grid, threads, smem, st>>>(q, sums, PL, pps);
@@ -925,10 +931,11 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   int ny, nx;
   if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
   int PL, slabs, pps, threads;
-  reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
+  const int nb = launch_samples(a);
+  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads, ny * nx);
   if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
   q.nx_magic = div_magic(nx);
-  const dim3 grid(slabs, q.B);
+  const dim3 grid(slabs, nb);
   const size_t smem = 8 * q.C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (q.in_f32 || q.add_f32) {
@@ -953,9 +960,10 @@ extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
   int rc = fill(q, a);
   if (rc || !q.in.p || !q.g2.p || !q.bsums) return SB_ERR_ARG;
   int PL, slabs, pps, threads;
-  reduce_cfg(q, &PL, &slabs, &pps, &threads);
+  const int nb = launch_samples(a);
+  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads);
   const size_t smem = ((size_t)threads * 4 * 8 + 8 * (size_t)q.C) * sizeof(float);
-  const dim3 grid(slabs, q.B);
+  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
   if (q.in_f32 || q.add_f32) {
     reduce_bc_kernel<1, true, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
@@ -981,12 +989,13 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   int ny, nx;
   if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
   int PL, slabs, pps, threads;
-  reduce_cfg(q, &PL, &slabs, &pps, &threads, ny * nx);
+  const int nb = launch_samples(a);
+  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads, ny * nx);
   if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
   q.nx_magic = div_magic(nx);
   // shared memory: 8*C per-channel constants, reused as the [PL][CV][8] scratch of the bias-gradient reduction
   const size_t smem = (size_t)(8 * q.C > threads * 8 ? 8 * q.C : threads * 8) * sizeof(float);
-  const dim3 grid(slabs, q.B);
+  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
   if (q.in_f32 || q.add_f32) {
     prep_bwd_apply_kernel<true, kRT><<<grid, threads, smem, st>>>(q, PL, pps);

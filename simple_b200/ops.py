@@ -4,6 +4,7 @@ Every function here launches hand-written sm_100a kernels through `simple_b200._
 the arithmetic (torch is used for allocation, streams and the autograd tape only).
 """
 import ctypes
+import os
 
 import torch
 
@@ -106,6 +107,24 @@ def _prep_args(spec, B, main, add, sums, gamma, beta, sc, sh, out1, out2, seed, 
     return a
 
 
+# Batch chunking (experiment, OFF by default): a stage's two passes (statistics -> apply, backward reduce -> backward
+# apply) read the same tensors; run chunk by chunk, the second pass finds its inputs in the 126 MB L2 instead of HBM.
+# Measured on B200 at B=64: 8.03 ms/step unchunked, 8.35 ms at 40 MB chunks, 8.89 ms at 24 MB -- the smaller grids lose
+# more (tail effects, fewer bytes in flight) than the L2 hits win.  SB_PREP_CHUNK_MB > 0 re-enables it.
+CHUNK_BYTES = int(float(os.environ.get('SB_PREP_CHUNK_MB', '0')) * (1 << 20))
+
+
+def _chunks(B, bytes_per_sample):
+    if CHUNK_BYTES <= 0 or B * bytes_per_sample <= 2 * CHUNK_BYTES:
+        return [(0, 0)]  # one launch over the whole batch
+    nb = max(1, CHUNK_BYTES // max(1, bytes_per_sample))
+    return [(b0, min(nb, B - b0)) for b0 in range(0, B, nb)]
+
+
+def _sample_bytes(*tensors):
+    return sum(t.numel() * t.element_size() // t.shape[0] for t in tensors if t is not None)
+
+
 def stats_raw(spec, main, add=None):
     """Per-(b,c) raw sums [B,C,2] (sum, sum of squares) of relu?(main)+add over the logical H x W pixels."""
     B = main.shape[0]
@@ -122,15 +141,23 @@ class FusedPrep(torch.autograd.Function):
     def forward(ctx, spec, main, add, gamma, beta, sc, sh, seed, keep, dbias_dst=None):
         B = main.shape[0]
         dev = main.device
-        sums = stats_raw(spec, main, add) if spec.norm else None
+        L, st = _lib.lib(), _lib.stream_ptr()
         gamma_f = gamma.detach().float().contiguous() if gamma is not None else None
         beta_f = beta.detach().float().contiguous() if beta is not None else None
         sc_f = sc.detach().float().contiguous() if sc is not None else None
         sh_f = sh.detach().float().contiguous() if sh is not None else None
         out1 = torch.empty((B, spec.H, spec.W, spec.C), device=dev, dtype=torch.bfloat16) if spec.want_out1 else None
         out2 = torch.empty(spec.lay_out.shape(B), device=dev, dtype=torch.bfloat16)
+        sums = torch.zeros(B, spec.C, 2, device=dev, dtype=torch.float32) if spec.norm else None
         a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, out1, out2, seed, keep)
-        _lib.check(_lib.lib().sb_prep(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep')
+        a_st = _prep_args(spec, B, main, add, None, None, None, None, None, None, None, 0, None) if spec.norm else None
+        # (without InstanceNorm there is a single pass: nothing to keep in the L2 between passes)
+        for b0, nb in (_chunks(B, _sample_bytes(main, add)) if spec.norm else [(0, 0)]):
+            if spec.norm:
+                a_st.b_base, a_st.b_count = b0, nb
+                _lib.check(L.sb_stats(ctypes.byref(a_st), sums.data_ptr(), st), 'sb_stats')
+            a.b_base, a.b_count = b0, nb
+            _lib.check(L.sb_prep(ctypes.byref(a), st), 'sb_prep')
         ctx.spec, ctx.seed, ctx.dbias_dst = spec, seed, dbias_dst
         ctx.save_for_backward(main, add, sums, gamma_f, beta_f, sc_f, sh_f, keep)
         ctx.has = (add is not None, gamma is not None, sc is not None)
@@ -156,8 +183,10 @@ class FusedPrep(torch.autograd.Function):
         a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, None, None, ctx.seed, keep)
         a.g2 = spec.lay_out.view(g2)
         a.g1 = _ptr(g1)
+        L, st = _lib.lib(), _lib.stream_ptr()
         bsums = dgb = None
-        if has_norm or has_inj:
+        two_pass = has_norm or has_inj
+        if two_pass:
             # one zero-filled buffer: per-(b,c) sums [B,C,4] + their batch sums for the affine gradients [C,2]
             buf = torch.zeros(B * spec.C * 4 + spec.C * 2, device=dev, dtype=torch.float32)
             bsums = buf[:B * spec.C * 4].view(B, spec.C, 4)
@@ -165,16 +194,20 @@ class FusedPrep(torch.autograd.Function):
             if has_norm:
                 dgb = buf[B * spec.C * 4:].view(spec.C, 2)
                 a.dgb = dgb.data_ptr()
-            _lib.check(_lib.lib().sb_prep_bwd_reduce(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_reduce')
         d_main = torch.empty(main.shape, device=dev, dtype=torch.bfloat16)
         d_add = torch.empty(add.shape, device=dev, dtype=torch.bfloat16) if has_add else None
-        a.d_main = spec.lay_in.view(d_main)
-        a.d_add = _ptr(d_add)
         dcol = None
         if ctx.dbias_dst is not None:  # bias gradient of the conv that produced `main`, fused into this pass
             dcol = torch.zeros(spec.C, device=dev, dtype=torch.float32)
-            a.dcol = dcol.data_ptr()
-        _lib.check(_lib.lib().sb_prep_bwd_apply(ctypes.byref(a), _lib.stream_ptr()), 'sb_prep_bwd_apply')
+        for b0, nb in (_chunks(B, _sample_bytes(main, add, g2, g1)) if two_pass else [(0, 0)]):
+            a.b_base, a.b_count = b0, nb
+            if two_pass:
+                a.d_main, a.d_add, a.dcol = spec.lay_in.view(None), None, None
+                _lib.check(L.sb_prep_bwd_reduce(ctypes.byref(a), st), 'sb_prep_bwd_reduce')
+            a.d_main = spec.lay_in.view(d_main)
+            a.d_add = _ptr(d_add)
+            a.dcol = _ptr(dcol)
+            _lib.check(L.sb_prep_bwd_apply(ctypes.byref(a), st), 'sb_prep_bwd_apply')
         if dcol is not None:
             ctx.dbias_dst['dbias'] = dcol
         dgamma = dgb[:, 1] if has_norm else None
