@@ -70,6 +70,20 @@ static int make_map_out(CUtensorMap* m, const void* ptr, int B, int H, int W, in
   return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
 }
 
+// Same, 64 channels x 128-byte rows / 128B swizzle (CTA-pair kernel): half as many row requests per byte for the TMA
+// store unit, which is request-rate bound on the 64-byte rows above (measured: ~1400 clk per 128-row store).
+static int make_map_out64(CUtensorMap* m, const void* ptr, int B, int H, int W, int N, int ld, int bw, int bh, int bb) {
+  if (((uintptr_t)ptr & 15) || (ld % 8)) return SB_ERR_ARG;
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
+}
+
 struct TapGemmDev {
   int B, Ho, Wo;
   int bw, bh, bb, rows;
@@ -90,6 +104,7 @@ constexpr int kFwdThreads = 320;         // tap GEMM: TMA warp, MMA warp, 8 epil
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr int kStageOutBytes = 128 * 64;  // epilogue staging buffer: 128 rows x 32 bf16
 constexpr int kOutBufs = 4;               // 2 column halves x double buffering
+constexpr int kStageOut2Bytes = 128 * 128;  // CTA-pair kernel: 128 rows x 64 bf16 (128-byte rows)
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -395,7 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kATileBytes;
   uint8_t* sO = sB + STAGES * B_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sO + kOutBufs * kStageOutBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sO + kOutBufs * kStageOut2Bytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -511,50 +526,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
+      for (int c = half * 64; c < BN; c += 128) {  // 64-column chunks, interleaved between the two halves
         if (n0 + c >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c), v);
-        if (issuer) bulk_wait_read<1>();
-        tmem_ld_wait();
-        const int nb = n0 + c;
-        float f[32];
+        if (issuer) bulk_wait_read<1>();  // the store that used this staging buffer two chunks ago has drained
+        named_bar_sync(bar_id, 128);      // ... and every thread of the half knows it
+        uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOut2Bytes;
+        uint8_t* row = buf + r * 128;
+        const int sw = r & 7;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias) {
+        for (int sub = 0; sub < 2; ++sub) {
+          const int nb = n0 + c + sub * 32;
+          if (nb >= p.N) break;  // ragged N (multiple of 32, not of 64): the TMA store clips the rest of the box
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + c + sub * 32), v);
+          tmem_ld_wait();
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-            f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
+            }
           }
-        }
-        if (p.relu) {
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        named_bar_sync(bar_id, 128);
-        uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOutBytes;
-        if (r < p.rows) {
-          uint8_t* row = buf + r * 64;
-          const int sw = (r >> 1) & 3;
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (r < p.rows) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = pk;
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&t0);
+              pk.y = *reinterpret_cast<uint32_t*>(&t1);
+              pk.z = *reinterpret_cast<uint32_t*>(&t2);
+              pk.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(row + (((sub * 4 + j) ^ sw) << 4)) = pk;  // 128B swizzle: chunk ^ (row & 7)
+            }
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, 128);  // all 128 rows staged
         if (issuer) {
-          tma_store_4d(&tmO, buf, nb, x0, y0, b0);  // rows outside the tensor (the odd last M tile) are clipped
+          tma_store_4d(&tmO, buf, n0 + c, x0, y0, b0);  // rows / channels outside the tensor are clipped
           bulk_commit();
         }
         ++ochunk;
@@ -576,7 +595,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 template <int BN, int STAGES>
 static int launch_tap_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TapGemmDev& p,
                             cudaStream_t stream) {
-  constexpr int smem = STAGES * (kATileBytes + (BN / 2) * 128) + kOutBufs * kStageOutBytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (kATileBytes + (BN / 2) * 128) + kOutBufs * kStageOut2Bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "tap_gemm2_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
@@ -801,13 +820,15 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   const bool pair_ok = p.tma_out && p.splits == 1 && a->N % BN == 0 && BN != 96 && rows >= 64 &&
                        ((p.m_tiles + 1) / 2) * p.n_tiles >= 74 && g_pair_mode != 0;
   if (pair_ok) {
-    CUtensorMap tmBh;
+    CUtensorMap tmBh, tmO64;
     rc = make_map_2d(&tmBh, a->w, a->N, a->ntaps * a->C, a->ldw, BN / 2);
     if (rc) return rc;
+    rc = make_map_out64(&tmO64, a->out, a->B, a->Ho, a->Wo, a->N, a->ldo, a->bw, a->bh, a->bb);
+    if (rc) return rc;
     switch (BN) {
-      case 256: return launch_tap_gemm2<256, 6>(tmA, tmBh, tmO, p, stream);
-      case 192: return launch_tap_gemm2<192, 6>(tmA, tmBh, tmO, p, stream);
-      default: return launch_tap_gemm2<128, 6>(tmA, tmBh, tmO, p, stream);
+      case 256: return launch_tap_gemm2<256, 5>(tmA, tmBh, tmO64, p, stream);
+      case 192: return launch_tap_gemm2<192, 5>(tmA, tmBh, tmO64, p, stream);
+      default: return launch_tap_gemm2<128, 6>(tmA, tmBh, tmO64, p, stream);
     }
   }
   switch (BN) {
