@@ -187,8 +187,10 @@ def run_reference(args):
 # own arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_own(args):
-    # keep stdout to the single JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION/INFO
-    os.environ['NCCL_DEBUG'] = os.environ.get('SB_NCCL_DEBUG', 'WARN')
+    # keep stdout to the single JSON line: NCCL prints its version banner there at any NCCL_DEBUG level (VERSION and up)
+    os.environ.pop('NCCL_DEBUG', None)
+    if os.environ.get('SB_NCCL_DEBUG'):
+        os.environ['NCCL_DEBUG'] = os.environ['SB_NCCL_DEBUG']
     import torch.distributed as dist
     from simple_b200 import _lib, profiling
     from simple_b200.next_frame_predictor import NextFramePredictor

@@ -195,6 +195,15 @@ __global__ void __launch_bounds__(256, MINB)
       a1 = ld_stream(g1 + q * 8);
       b1 = ld_stream(g1 + 128 + q * 8);
     }
+    // target logits: the target bytes were prefetched one iteration ago, so these two 2-byte loads are issued together
+    // with the group loads (one more sector of the same lines) instead of a 15-instruction register select + shuffle
+    float xt0 = 0.f, xt1 = 0.f;
+    if (TRAIN) {
+      const unsigned short* r0 = reinterpret_cast<const unsigned short*>(g0);
+      const unsigned short* r1 = reinterpret_cast<const unsigned short*>(g1);
+      if (v0) xt0 = __uint_as_float((uint32_t)__ldg(r0 + t0) << 16);
+      if (v1) xt1 = __uint_as_float((uint32_t)__ldg(r1 + t1) << 16);
+    }
     // next iteration's pixels and target bytes (addresses do not depend on data)
     bool nv0, nv1;
     int np0, np1, no0, no1;
@@ -205,11 +214,9 @@ __global__ void __launch_bounds__(256, MINB)
       if (nv0) nt0 = target[no0];
       if (nv1) nt1 = target[no1];
     }
-    const float xt0 = TRAIN ? target_logit(a0, b0, t0, lane) : 0.f;
     ce_group<TRAIN>(a0, b0, q, t0, xt0, clip, gscale, argmax_out ? argmax_out + o0 : nullptr,
                     TRAIN ? dlogits + (size_t)p0 * 768 + g * 256 : nullptr, (TRAIN && dbias) ? s_db + g * 256 : nullptr, db,
                     loss_acc, v0);
-    const float xt1 = TRAIN ? target_logit(a1, b1, t1, lane) : 0.f;
     ce_group<TRAIN>(a1, b1, q, t1, xt1, clip, gscale, argmax_out ? argmax_out + o1 : nullptr,
                     TRAIN ? dlogits + (size_t)p1 * 768 + g * 256 : nullptr, (TRAIN && dbias) ? s_db + g * 256 : nullptr, db,
                     loss_acc, v1);
