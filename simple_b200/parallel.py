@@ -51,7 +51,7 @@ class FlatGradSync:
         self.group = group
         self.flat = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.n_buckets = n_buckets
+        self.n_buckets = int(os.environ.get('SB_DP_BUCKETS', n_buckets))
         self._layout = None      # overlap mode: dict(name -> (offset, numel)), bucket boundaries, tail offset
         self._comm_stream = None
         self._avg = dist.ReduceOp.AVG if hasattr(dist.ReduceOp, 'AVG') else None

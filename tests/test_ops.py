@@ -489,3 +489,36 @@ def test_frame_feedback_shift_median_noise_and_scheduled_sampling():
     out = ops.frame_feedback(s_big, g_big, p_big, torch.full((), 0.5, device=DEV), 0.0, 3)
     took_gt = int((out[:, 9, 0, 0] > 0.5).sum())
     assert 16 <= took_gt <= 48, took_gt
+
+
+@pytest.mark.parametrize('B', [3, 64])
+def test_teacher_forced_lstm_cluster_kernels_match_lstmcell(B):
+    """sb_lstm_teacher_fwd/bwd (2-CTA cluster, W_hh resident in shared memory, all 16 steps / BPTT in one launch each)
+    vs 16 nn.LSTMCell steps + autograd, fp32: outputs and every gradient (inputs, initial state, W_hh)."""
+    from simple_b200 import ops
+    torch.manual_seed(17)
+    cell = torch.nn.LSTMCell(128, 128).to(DEV)
+    x = torch.randn(B, 16, 128, device=DEV)
+    h0 = torch.randn(B, 128, device=DEV) * 0.5
+    c0 = torch.randn(B, 128, device=DEV) * 0.5
+    gout = torch.randn(B, 16, 128, device=DEV)
+    # reference
+    xr, h0r, c0r = (t.clone().requires_grad_(True) for t in (x, h0, c0))
+    h, c = h0r, c0r
+    outs = []
+    for i in range(16):
+        h, c = cell(xr[:, i], (h, c))
+        outs.append(h)
+    ref = torch.stack(outs, dim=1)
+    ref.backward(gout)
+    ref_g = [xr.grad.clone(), h0r.grad.clone(), c0r.grad.clone(), cell.weight_hh.grad.clone(), cell.weight_ih.grad.clone()]
+    cell.zero_grad()
+    # fused: the input half of the gates is one GEMM over all steps, the recurrence runs in the cluster kernels
+    xf, h0f, c0f = (t.clone().requires_grad_(True) for t in (x, h0, c0))
+    xw = F.linear(xf, cell.weight_ih, cell.bias_ih + cell.bias_hh)
+    got = ops.LstmTeacher.apply(xw, h0f, c0f, cell.weight_hh)
+    got.backward(gout)
+    torch.cuda.synchronize()
+    assert rel(got, ref) < 1e-5, rel(got, ref)
+    for a, b in zip([xf.grad, h0f.grad, c0f.grad, cell.weight_hh.grad, cell.weight_ih.grad], ref_g):
+        assert rel(a, b) < 1e-4, rel(a, b)
