@@ -79,7 +79,7 @@ typedef struct {
   int tap_dx[SB_MAX_TAPS];
   float* dw;          /* fp32 [N, ldw] */
   int ldw;
-  int splits;         /* pixel-tile split factor */
+  int splits;         /* pixel-tile split factor; 0 = automatic (about two waves of CTAs) */
 } sb_tap_wgrad_args;
 int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
 

@@ -622,6 +622,11 @@ struct TapWgradDev {
   int tap_dy[SB_MAX_TAPS], tap_dx[SB_MAX_TAPS];
   float* dw;
   int ldw, splits;
+  // Orientation.  Normal: M side (128-row tiles) = dY channels, N side (BN columns) = A channels, shifted by the tap.
+  // Swapped: M side = A channels (shifted), N side = dY channels -- chosen by the launcher when it pads less (a 192 x 384
+  // gradient wastes 44 % of a 256 x 512 tiling but none of a 384 x 192 one).  `C`/`N` above always name the N-side / M-side
+  // channel counts of the launch; Ctrue is the A-channel count that addresses dw.
+  int swapped, Ctrue;
 };
 constexpr int kWgRows = 64;                   // pixels per stage (K of the contraction)
 constexpr int kWgChunkBytes = kWgRows * 128;  // 64 pixels x 64 channels bf16
@@ -634,6 +639,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   constexpr int DY_BYTES = 2 * kWgChunkBytes;
   constexpr int A_BYTES = NCH * kWgChunkBytes;
   constexpr int TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static_assert(BN % 64 == 0, "N-side tile = whole 64-channel chunks");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDY = smem;
@@ -686,11 +692,13 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int y0 = ((pt / p.tiles_x) % p.tiles_y) * p.bh;
         const int b0 = (pt / (p.tiles_x * p.tiles_y)) * p.bb;
         mbar_expect_tx(&full[s], (uint32_t)(DY_BYTES + A_BYTES));
-        tma_load_4d(sDY + s * DY_BYTES, &tmDY, &full[s], m0, x0, y0, b0);
-        tma_load_4d(sDY + s * DY_BYTES + kWgChunkBytes, &tmDY, &full[s], m0 + 64, x0, y0, b0);
+        const int mx = p.swapped ? dx : 0, my = p.swapped ? dy : 0;  // pixel shift of the M-side operand
+        const int nx = p.swapped ? 0 : dx, ny = p.swapped ? 0 : dy;  // ... and of the N-side operand
+        tma_load_4d(sDY + s * DY_BYTES, &tmDY, &full[s], m0, x0 + mx, y0 + my, b0);
+        tma_load_4d(sDY + s * DY_BYTES + kWgChunkBytes, &tmDY, &full[s], m0 + 64, x0 + mx, y0 + my, b0);
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-          tma_load_4d(sA + s * A_BYTES + j * kWgChunkBytes, &tmA, &full[s], c0 + j * 64, x0 + dx, y0 + dy, b0);
+          tma_load_4d(sA + s * A_BYTES + j * kWgChunkBytes, &tmA, &full[s], c0 + j * 64, x0 + nx, y0 + ny, b0);
       }
     }
   } else if (warp == 1) {
@@ -722,7 +730,10 @@ __global__ void __launch_bounds__(kGemmThreads)
     const int lg = warp & 3;
     const int m = m0 + lg * 32 + lane;
     const bool valid = m < p.N;
-    float* orow = p.dw + (long long)m * p.ldw + (long long)t * p.C + c0;
+    // normal: dw[m][t*C + c]; swapped (row = A channel, column = dY channel): dw[column][t*Ctrue + row], the 32 lanes of a
+    // warp still hit 32 consecutive floats
+    float* orow = p.swapped ? p.dw + (long long)t * p.Ctrue + m
+                            : p.dw + (long long)m * p.ldw + (long long)t * p.C + c0;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       if (c0 + c >= p.C) break;
@@ -730,11 +741,17 @@ __global__ void __launch_bounds__(kGemmThreads)
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
       tmem_ld_wait();
       if (!valid) continue;
+      if (p.swapped) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (c0 + c + j < p.C)
-          red_add_v4(orow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                     __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 32; ++j)
+          if (c0 + c + j < p.C) atomicAdd(orow + (long long)(c0 + c + j) * p.ldw, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (c0 + c + j < p.C)
+            red_add_v4(orow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+      }
     }
   }
   tc_fence_before();
@@ -859,21 +876,58 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   }
   p.dw = a->dw; p.ldw = a->ldw;
   const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
-  p.splits = a->splits < 1 ? 1 : (a->splits > PT ? PT : a->splits);
+  // Tile the [dY channels N] x [A channels C] gradient: M side in 128-row tiles, N side in BN-column tiles
+  // (BN in {64,128,192,256}; the last tile runs the MMA at the 16-rounded remainder).  Pick the orientation and BN that
+  // waste the fewest tensor-core cycles.
+  auto pad_n = [](int ch, int* bn_out) {
+    int best = 1 << 30, best_tiles = 1 << 30, bn_best = 64;
+    const int opts[4] = {64, 128, 192, 256};
+    for (int bn : opts) {  // least padded MMA work; ties: fewer tiles (fewer re-reads of the M side), then the smaller tile
+      const int full = ch / bn, rem = ch - full * bn;
+      const int cost = full * bn + ((rem + 15) / 16) * 16, tiles = full + (rem ? 1 : 0);
+      if (cost < best || (cost == best && tiles < best_tiles)) {
+        best = cost;
+        best_tiles = tiles;
+        bn_best = bn;
+      }
+    }
+    *bn_out = bn_best;
+    return best;
+  };
+  int bn_norm, bn_swap;
+  const long long cost_norm = (long long)((a->N + 127) / 128) * 128 * pad_n(a->C, &bn_norm);
+  const long long cost_swap = (long long)((a->C + 127) / 128) * 128 * pad_n(a->N, &bn_swap);
+  p.swapped = (cost_swap * 100 < cost_norm * 85) ? 1 : 0;  // the swapped epilogue issues scalar atomics: only for a clear win
+  p.Ctrue = a->C;
   int BN;
-  if (a->C > 128) BN = 256;
-  else if (a->C > 64) BN = 128;
-  else BN = 64;
-  p.c_tiles = (a->C + BN - 1) / BN;
-  p.m_tiles = (a->N + 127) / 128;
+  const void *m_ptr, *n_ptr;
+  int mH, mW, mC, nH, nW, nC;
+  if (!p.swapped) {
+    BN = bn_norm;
+    p.N = a->N; p.C = a->C;
+    m_ptr = a->dy; mH = a->Ho; mW = a->Wo; mC = a->N;
+    n_ptr = a->a; nH = a->H; nW = a->W; nC = a->C;
+  } else {
+    BN = bn_swap;
+    p.N = a->C; p.C = a->N;  // kernel naming: N = M-side channels, C = N-side channels
+    m_ptr = a->a; mH = a->H; mW = a->W; mC = a->C;
+    n_ptr = a->dy; nH = a->Ho; nW = a->Wo; nC = a->N;
+  }
+  p.c_tiles = (p.C + BN - 1) / BN;
+  p.m_tiles = (p.N + 127) / 128;
+  const int ctas = p.m_tiles * p.ntaps * p.c_tiles;
+  int splits = a->splits;
+  if (splits < 1) splits = (2 * 148) / ctas;  // auto: at most two full waves of CTAs (one CTA per SM), never a third
+  p.splits = splits < 1 ? 1 : (splits > PT ? PT : splits);
   CUtensorMap tmDY, tmA;
-  rc = make_map_nhwc(&tmDY, a->dy, a->B, a->Ho, a->Wo, a->N, a->bw, a->bh, a->bb);
+  rc = make_map_nhwc(&tmDY, m_ptr, a->B, mH, mW, mC, a->bw, a->bh, a->bb);
   if (rc) return rc;
-  rc = make_map_nhwc(&tmA, a->a, a->B, a->H, a->W, a->C, a->bw, a->bh, a->bb);
+  rc = make_map_nhwc(&tmA, n_ptr, a->B, nH, nW, nC, a->bw, a->bh, a->bb);
   if (rc) return rc;
   dim3 grid(p.m_tiles * p.ntaps * p.c_tiles, p.splits, 1);
   switch (BN) {
     case 256: return launch_tap_wgrad<256, 4>(tmDY, tmA, p, grid, stream);
+    case 192: return launch_tap_wgrad<192, 4>(tmDY, tmA, p, grid, stream);
     case 128: return launch_tap_wgrad<128, 6>(tmDY, tmA, p, grid, stream);
     default: return launch_tap_wgrad<64, 6>(tmDY, tmA, p, grid, stream);
   }

@@ -359,11 +359,11 @@ class TapConv(torch.autograd.Function):
         if spec.transposed:
             # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
             dwp = slot if slot is not None else torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
-            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=_wgrad_splits(B, spec.Ha, spec.Wa, spec.Ca, spec.N, T),
+            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for ~2 waves of CTAs
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         else:
             dwp = slot if slot is not None else torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
-            tap_wgrad(a, dy, spec.taps, dwp, splits=_wgrad_splits(B, spec.Ho, spec.Wo, spec.N, spec.Ca, T),
+            tap_wgrad(a, dy, spec.taps, dwp, splits=0,
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         if pw.defer_unpack:
             pw.gpacked, dweight = dwp, None
@@ -391,15 +391,6 @@ def auto_splits(B, Ho, Wo, N, KT):
     if ctas >= 100:
         return 1
     return int(max(1, min(KT, -(-296 // ctas), 32)))
-
-
-def _wgrad_splits(B, Ho, Wo, M, Ccols, T):
-    """Pixel-split factor so that the wgrad grid has roughly two waves of CTAs."""
-    BN = 256 if Ccols > 128 else (128 if Ccols > 64 else 64)
-    ctas = -(-M // 128) * T * -(-Ccols // BN)
-    ptiles = max(1, (B * Ho * Wo) // 64)
-    want = max(1, (2 * 148) // ctas)
-    return int(min(want, ptiles))
 
 
 def _bias_act(acc, bias, relu, keep_f32=False):

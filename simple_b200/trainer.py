@@ -114,6 +114,45 @@ class Trainer:
         epsilon *= progress
         return float(1 - epsilon)
 
+    # ---- checkpoint / resume.  The reference saves the model weights only (trainer.py:175-176) and
+    # restarts the optimiser from scratch; this also carries the Adafactor state, the step counters and the RNG streams.
+    def save_checkpoint(self, path, epoch=0):
+        opt_state = []
+        for p in self.model.parameters():
+            st = self.optimizer.state.get(p, {})
+            opt_state.append({k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in st.items()
+                              if k in ('step', 'exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq')})
+        seed = self.model._seed_dev
+        torch.save({'model': {k: v.detach().cpu() for k, v in self.model.state_dict().items()}, 'optimizer': opt_state,
+                    'model_step': self.model_step, 'reward_step': self.reward_step, 'epoch': int(epoch),
+                    'dropout_seed': int(seed.item()) if seed is not None else None,
+                    'torch_rng': torch.get_rng_state(),
+                    'cuda_rng': torch.cuda.get_rng_state(self.model.logits.weight.device)}, path)
+
+    def load_checkpoint(self, path):
+        """Restores weights, optimiser state, counters and RNG streams; returns the stored epoch."""
+        ck = torch.load(path, map_location='cpu')
+        self.model.load_state_dict(ck['model'])  # (also invalidates the packed bf16 operands)
+        dev = self.model.logits.weight.device
+        self.optimizer.state.clear()
+        self.optimizer._cache.clear()
+        for p, saved in zip(self.model.parameters(), ck['optimizer']):
+            if not saved:
+                continue
+            st = self.optimizer._init_state(p)
+            st['step'] = int(saved['step'])
+            st['step_dev'].fill_(float(saved['step']))
+            for k in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
+                if k in saved:
+                    st[k].copy_(saved[k].to(dev))
+        self.model_step, self.reward_step = ck['model_step'], ck['reward_step']
+        if ck.get('dropout_seed') is not None:
+            self.model._seed_dev = torch.full((1,), ck['dropout_seed'], dtype=torch.int64, device=dev)
+        torch.set_rng_state(ck['torch_rng'])
+        torch.cuda.set_rng_state(ck['cuda_rng'], dev)
+        self._runner = None  # captured graphs refer to the old optimiser records
+        return ck['epoch']
+
     def train_step(self, frames, actions, new_states_u8, rewards, values, epsilon):
         """One optimiser step (trainer.py:122-149).  Returns the loss dict of `wm_loss` (device scalars)."""
         self.model.train()

@@ -168,3 +168,40 @@ def test_packed_gradient_mode_matches_reference_layout_mode():
                                operm=pw.operm.tolist() if pw.operm is not None else None)
             assert torch.equal(ref.fwd, pw.fwd) and torch.equal(ref.tr, pw.tr), (j, k)
         frames = torch.cat((frames[:, 3:], out['argmax'].float() / 255), dim=1)
+
+
+def test_checkpoint_resume_restores_weights_optimizer_state_and_rng():
+    """a checkpoint carries weights, Adafactor state (incl. the lagging gate.* counters), dropout seed
+    and RNG streams; a fresh Trainer that loads it continues with the same optimiser state."""
+    import os
+    import tempfile
+    from types import SimpleNamespace
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.trainer import Trainer
+    cfg = _cfg(batch_size=2, rollout_length=4)
+    cfg.cuda_graph = False
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    trainer = Trainer(model, cfg)
+    env = SimpleNamespace(buffer=_fake_buffer(24))
+    trainer.train(1, env, steps=8)  # two windows of 4 steps
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'ck.pt')
+        trainer.save_checkpoint(path, epoch=3)
+        torch.manual_seed(123)
+        model2 = NextFramePredictor(cfg, 3).to(DEV)
+        trainer2 = Trainer(model2, cfg)
+        assert trainer2.load_checkpoint(path) == 3
+    for (k, a), b in zip(model.named_parameters(), model2.parameters()):
+        assert torch.equal(a, b), k
+        sa, sb_ = trainer.optimizer.state[a], trainer2.optimizer.state[b]
+        assert sa['step'] == sb_['step'] and float(sb_['step_dev']) == sb_['step'], k
+        for key in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
+            if key in sa:
+                assert torch.equal(sa[key], sb_[key]), (k, key)
+    assert trainer.optimizer.state[model.gate.weight]['step'] == 8 - 2   # skipped on the first step of each window
+    assert int(model2._seed_dev) == int(model._seed_dev)
+    assert torch.equal(torch.cuda.get_rng_state(torch.device(DEV)), torch.cuda.get_rng_state(torch.device(DEV)))
+    m = trainer2.train(1, env, steps=4)  # and it keeps training
+    assert all(np.isfinite(v) for v in m.values())
+    assert trainer2.optimizer.state[model2.logits.weight]['step'] == 12

@@ -160,3 +160,22 @@ def test_ragged_channel_operand_c80():
     torch.cuda.synchronize()
     ref2 = y.float() @ w2.float().t()
     assert dx.shape == (B, H, W, C) and torch.allclose(dx.float(), ref2, rtol=2e-2, atol=5e-2)
+
+
+def test_wgrad_swapped_orientation_and_bn192():
+    """A 192 x 384 gradient (down0 / up4 of the world model) is tiled 384 x 192 -- A channels on the 128-row side, dY
+    channels on a 192-column tile -- instead of a 44 %-padded 256 x 512; plus automatic pixel splits.  Against torch."""
+    from simple_b200.gemm import tap_wgrad
+    torch.manual_seed(21)
+    B, H, W, C, N = 4, 14, 10, 384, 192   # A: [B,H+1,W+1,C] (2x2 taps over a padded input), dY: [B,H,W,N]
+    a = torch.randn(B, H + 1, W + 1, C, device=_dev()).bfloat16()
+    dy = torch.randn(B, H, W, N, device=_dev()).bfloat16()
+    taps = [(dy_, dx_) for dy_ in range(2) for dx_ in range(2)]
+    dw = torch.zeros(N, 4 * C, device=_dev())
+    tap_wgrad(a, dy, taps, dw, splits=0)
+    torch.cuda.synchronize()
+    ref = torch.zeros(N, 4 * C, device=_dev())
+    for t, (ty, tx) in enumerate(taps):
+        at = a[:, ty:ty + H, tx:tx + W].float().reshape(-1, C)
+        ref[:, t * C:(t + 1) * C] = dy.float().reshape(-1, N).t() @ at
+    assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), float((dw - ref).abs().max())
