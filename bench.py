@@ -200,6 +200,7 @@ def run_own(args):
     from simple_b200.trainer import Trainer
     from types import SimpleNamespace
 
+    torch.backends.cudnn.benchmark = True  # (the PyTorch stand-in policy's convolutions: let cuDNN pick its kernels)
     rank, world, local = init_distributed()
     dev = torch.device('cuda', local)
 

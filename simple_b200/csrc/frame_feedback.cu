@@ -28,7 +28,14 @@ __global__ void __launch_bounds__(256)
   if (t < 256) hist[t] = 0u;
   __syncthreads();
   if (p_noise > 0.f) {
-    for (int i = t; i < n; i += blockDim.x) atomicAdd(&hist[src[i]], 1u);
+    // warp-aggregated histogram: Atari frames are mostly one background colour, i.e. every lane hits the same bin and
+    // plain shared-memory atomics serialise 25 k increments on one address (measured: 50 us of this 70 us kernel)
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+      const int i = i0 + t;
+      const int v = i < n ? (int)src[i] : 256 + (t & 31);  // out-of-range lanes get unique pseudo-values
+      const unsigned peers = __match_any_sync(0xffffffffu, v);
+      if (v < 256 && (t & 31) == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned)__popc(peers));
+    }
     __syncthreads();
     if (t == 0) {  // lower median: the value at sorted position (n - 1) / 2
       const unsigned int target = (unsigned int)((n - 1) / 2);

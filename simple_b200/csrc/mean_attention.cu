@@ -68,6 +68,22 @@ __device__ __forceinline__ void ma_row_dots(const MaSmem& sm, const float* w4, i
   out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
 }
 
+// Same four dot products with the channels of the row split over the 32 lanes of a warp (few pixels, many channels: the
+// posterior's second MeanAttention has HW = 30, C = 512 -- one thread per row would leave 480 of 512 threads idle).
+__device__ __forceinline__ void ma_row_dots_warp(const MaSmem& sm, const float* w4, int hw, int C, int lane, float* out) {
+  const __nv_bfloat162* row = reinterpret_cast<const __nv_bfloat162*>(sm.x + (size_t)hw * (C + 2));
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int c2 = lane; c2 < C / 2; c2 += 32) {
+    const float2 v = __bfloat1622float2(row[c2]);
+    const int c = 2 * c2;
+    a0 = fmaf(v.x, w4[c], fmaf(v.y, w4[c + 1], a0));
+    a1 = fmaf(v.x, w4[C + c], fmaf(v.y, w4[C + c + 1], a1));
+    a2 = fmaf(v.x, w4[2 * C + c], fmaf(v.y, w4[2 * C + c + 1], a2));
+    a3 = fmaf(v.x, w4[3 * C + c], fmaf(v.y, w4[3 * C + c + 1], a3));
+  }
+  out[0] = warp_sum(a0); out[1] = warp_sum(a1); out[2] = warp_sum(a2); out[3] = warp_sum(a3);
+}
+
 __global__ void __launch_bounds__(kMaThreads)
     mean_attention_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ We,
                               const float* __restrict__ be, const float* __restrict__ Wd, const float* __restrict__ bd,
@@ -78,11 +94,19 @@ __global__ void __launch_bounds__(kMaThreads)
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   ma_stage(sm, x + (size_t)b * HW * C, We, HW, C);
   __syncthreads();
-  for (int hw = t; hw < HW; hw += kMaThreads) {
-    float d[4];
-    ma_row_dots(sm, sm.we, hw, C, d);
+  if (HW * 4 < kMaThreads) {
+    for (int hw = warp; hw < HW; hw += kMaThreads / 32) {
+      float d[4];
+      ma_row_dots_warp(sm, sm.we, hw, C, lane, d);
+      if (lane < 4) sm.a[lane * HW + hw] = d[lane] + be[lane];
+    }
+  } else {
+    for (int hw = t; hw < HW; hw += kMaThreads) {
+      float d[4];
+      ma_row_dots(sm, sm.we, hw, C, d);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sm.a[k * HW + hw] = d[k] + be[k];
+      for (int k = 0; k < 4; ++k) sm.a[k * HW + hw] = d[k] + be[k];
+    }
   }
   __syncthreads();
   if (warp < 4) {  // softmax group j = warp: flat indices f = 4 i + j
@@ -153,11 +177,19 @@ __global__ void __launch_bounds__(kMaThreads)
     dam[i] = sm.l[c * 5 + k];
   }
   __syncthreads();
-  for (int hw = t; hw < HW; hw += kMaThreads) {
-    float d[4];
-    ma_row_dots(sm, dam, hw, C, d);
+  if (HW * 4 < kMaThreads) {
+    for (int hw = warp; hw < HW; hw += kMaThreads / 32) {
+      float d[4];
+      ma_row_dots_warp(sm, dam, hw, C, lane, d);
+      if (lane < 4) sm.ds[lane * HW + hw] = d[lane] * invP;
+    }
+  } else {
+    for (int hw = t; hw < HW; hw += kMaThreads) {
+      float d[4];
+      ma_row_dots(sm, dam, hw, C, d);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sm.ds[k * HW + hw] = d[k] * invP;
+      for (int k = 0; k < 4; ++k) sm.ds[k * HW + hw] = d[k] * invP;
+    }
   }
   __syncthreads();
   if (warp < 4) {  // softmax backward of group j = warp: da = s * (ds - sum s ds); stored over ds
