@@ -29,6 +29,17 @@ class CnnPolicy(nn.Module):
                 nn.init.orthogonal_(m.weight, nn.init.calculate_gain('relu'))
                 nn.init.zeros_(m.bias)
 
+    def evaluate_actions(self, obs, action):
+        """(value, log pi(action|obs), mean entropy) -- a2c_ppo_acktr/policy.py:120-133."""
+        x = self.main(obs / 255.0)
+        logp_all = torch.log_softmax(self.dist(x), dim=-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1).mean()
+        return self.critic_linear(x), logp_all.gather(1, action), entropy
+
+    @torch.no_grad()
+    def get_value(self, obs):
+        return self.critic_linear(self.main(obs / 255.0))
+
     @torch.no_grad()
     def act(self, obs):
         x = self.main(obs / 255.0)

@@ -89,6 +89,28 @@ class SimulatedVecEnv:
         self._initial.copy_(frames_u8.to(torch.uint8), non_blocking=True)
         self._has_initial = [True] * self.num_envs
 
+    def restart_from_replay(self, obs_u8, valid=None, first_small_rollout=None, flip_first=True):
+        """Restart path of the epoch loop (simple/__main__.py:85-91) as ONE device gather instead of `agents` pickled
+        tensor sends: every agent draws a random record of the real replay (`sample_buffer(1)`: uniformly among the
+        records that already carry a value, atari_utils/atari_utils/envs.py:158-172); with `flip_first`
+        (`simulation_flip_first_random_for_beginning`) the LAST agent starts from `first_small_rollout`
+        (`get_first_small_rollout()`: the first frames of the real episode) instead.
+        obs_u8: u8 [N,12,H,W] replay observations (device or host); valid: optional bool [N]."""
+        obs_u8 = torch.as_tensor(obs_u8)
+        n = obs_u8.shape[0]
+        if valid is None:
+            cand = torch.arange(n, device=self.device)
+        else:
+            cand = torch.nonzero(torch.as_tensor(valid, device=self.device), as_tuple=False).flatten()
+        if cand.numel() == 0:
+            raise ValueError('the replay holds no record with a value yet')
+        pick = cand[torch.randint(cand.numel(), (self.num_envs,), device=self.device)]
+        frames = obs_u8.to(self.device)[pick].to(torch.uint8)
+        if flip_first and first_small_rollout is not None:
+            frames[-1] = torch.as_tensor(first_small_rollout).to(self.device, torch.uint8)
+        self.restart_all(frames)
+        return pick
+
     def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
         idx = range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
         return [getattr(self.envs[i], method_name)(*method_args, **method_kwargs) for i in idx]

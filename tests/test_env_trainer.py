@@ -84,6 +84,15 @@ def test_simulated_env_surface_and_graph_equivalence():
     env2.reset()
     o1, *_ = env2.step(torch.zeros(A, 1, dtype=torch.long))
     assert torch.equal(o1[:, :9].cpu(), init[:, 3:].float())
+    # batched restart from the real replay: valid records only, last agent = first small rollout
+    replay = synth_replay(12, 3, 9)['obs']
+    valid = torch.tensor([i % 3 != 0 for i in range(12)])
+    first = torch.full((12, 105, 80), 7, dtype=torch.uint8)
+    pick = env2.restart_from_replay(replay, valid=valid, first_small_rollout=first)
+    assert bool(valid[pick.cpu()].all())
+    got = env2.reset()
+    assert torch.equal(got[-1].cpu(), first.float())
+    assert torch.equal(got[:-1].cpu(), replay[pick.cpu()[:-1]].float())
 
 
 def test_state_dict_round_trip_with_reference_keys():
@@ -205,3 +214,37 @@ def test_checkpoint_resume_restores_weights_optimizer_state_and_rng():
     m = trainer2.train(1, env, steps=4)  # and it keeps training
     assert all(np.isfinite(v) for v in m.values())
     assert trainer2.optimizer.state[model2.logits.weight]['step'] == 12
+
+
+def test_device_ppo_learns_in_the_simulated_env():
+    """PPO.learn on the device-resident simulated env (rollout storage, GAE, clipped-surrogate update)
+    runs end to end without host round trips and changes the policy."""
+    from bench import synth_replay
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.policy import CnnPolicy
+    from simple_b200.ppo import DevicePPO
+    from simple_b200.simulated_env import Discrete, make_simulated_env
+    A = 4
+    cfg = _cfg(agents=A, rollout_length=6)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    env = make_simulated_env(cfg, model, Discrete(3))
+    env.restart_all(synth_replay(A, 3, 5)['obs'].to(DEV))
+    policy = CnnPolicy((12, 105, 80), 3).to(DEV)
+    before = [p.detach().clone() for p in policy.parameters()]
+    ppo = DevicePPO(env, policy, num_mini_batch=2, ppo_epoch=2)
+    st = ppo.collect()
+    assert st['obs'].dtype == torch.uint8 and st['obs'].shape == (7, A, 12, 105, 80)
+    assert st['returns'].shape == (7, A, 1) and bool(torch.isfinite(st['returns'][:-1]).all())
+    # GAE against the reference recursion on the host
+    v, r, m = st['values'].cpu(), st['rewards'].cpu(), st['masks'].cpu()
+    gae, want = torch.zeros(A, 1), torch.zeros(6, A, 1)
+    for t in reversed(range(6)):
+        delta = r[t] + 0.99 * v[t + 1] * m[t + 1] - v[t]
+        gae = delta + 0.99 * 0.95 * m[t + 1] * gae
+        want[t] = gae + v[t]
+    assert torch.allclose(st['returns'][:-1].cpu(), want, atol=1e-5)
+    metrics = ppo.learn(2 * 6 * A)
+    assert set(metrics) == {'ppo_value_loss', 'ppo_action_loss', 'ppo_entropy'}
+    assert all(np.isfinite(x) for x in metrics.values()) and 0 < metrics['ppo_entropy'] <= np.log(3) + 1e-4
+    assert any(not torch.equal(a, b) for a, b in zip(before, policy.parameters()))
