@@ -3,7 +3,7 @@
 The epoch orchestration of the reference (real-Atari collection, PPO update, evaluation) is OUT OF SCOPE of this
 B200 hot-path build (needs gym/ALE/baselines).  This entry point parses the same flags, builds the
 world model + trainer + simulated env on the GPU and runs a self-contained demonstration on a synthetic replay:
-world-model training followed by simulated rollouts with a CNN policy.
+world-model training followed by PPO iterations in the simulated env (device-resident rollouts + updates).
 """
 import argparse
 from time import strftime
@@ -54,6 +54,7 @@ def build_parser():
     # demo-only
     p.add_argument('--wm-steps', type=int, default=100, help='world-model optimiser steps on the synthetic replay')
     p.add_argument('--n-action', type=int, default=3)
+    p.add_argument('--ppo-iterations', type=int, default=2, help='PPO.learn iterations in the simulated env')
     return p
 
 
@@ -84,14 +85,14 @@ def main():
     print('world model:', metrics)
     env = make_simulated_env(config, model, Discrete(config.n_action))
     policy = CnnPolicy(env.observation_space.shape, config.n_action).to(dev)
-    env.restart_all(d['obs'][:config.agents].to(dev))
-    obs = env.reset()
-    total = torch.zeros(config.agents, 1, device=dev)
-    for _ in range(config.rollout_length):
-        _, action, _ = policy.act(obs)
-        obs, rew, done, _ = env.step(action)
-        total += rew
-    print('simulated rollout returns:', total.flatten().tolist())
+    from .ppo import DevicePPO
+    ppo = DevicePPO(env, policy, gamma=config.ppo_gamma, lr=config.ppo_lr)
+    for it in range(config.ppo_iterations):
+        # restart path of simple/__main__.py:85-91: every agent from a random replay record, the last one from the
+        # first frames of the (synthetic) episode
+        env.restart_from_replay(d['obs'], first_small_rollout=d['obs'][0],
+                                flip_first=config.simulation_flip_first_random_for_beginning)
+        print(f'ppo iteration {it}:', ppo.learn(config.rollout_length * config.agents))
 
 
 if __name__ == '__main__':

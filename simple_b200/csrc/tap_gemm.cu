@@ -834,6 +834,7 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
   p.n_tiles = (a->N + BN - 1) / BN;
   // CTA-pair kernel: bf16 TMA-store outputs, no split-K, enough 256-row tiles to fill the 74 SM pairs, full N tiles
+  // (N = 96 tiles measured slower on the pair kernel: 181 vs 162 us for the logits dgrad, which is HBM-bound anyway)
   const bool pair_ok = p.tma_out && p.splits == 1 && a->N % BN == 0 && BN != 96 && rows >= 64 &&
                        ((p.m_tiles + 1) / 2) * p.n_tiles >= 74 && g_pair_mode != 0;
   if (pair_ok) {
@@ -845,7 +846,8 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
     switch (BN) {
       case 256: return launch_tap_gemm2<256, 5>(tmA, tmBh, tmO64, p, stream);
       case 192: return launch_tap_gemm2<192, 5>(tmA, tmBh, tmO64, p, stream);
-      default: return launch_tap_gemm2<128, 6>(tmA, tmBh, tmO64, p, stream);
+      case 128: return launch_tap_gemm2<128, 6>(tmA, tmBh, tmO64, p, stream);
+      default: return launch_tap_gemm2<96, 6>(tmA, tmBh, tmO64, p, stream);
     }
   }
   switch (BN) {

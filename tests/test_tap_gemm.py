@@ -82,7 +82,7 @@ def test_wgrad(C, N, splits):
     assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), err
 
 
-@pytest.mark.parametrize('B,Ho,Wo,C,N,kind', [(9, 52, 40, 96, 192, 's2d'), (5, 105, 80, 96, 768, '1x1'),
+@pytest.mark.parametrize('B,Ho,Wo,C,N,kind', [(9, 52, 40, 96, 192, 's2d'), (5, 105, 80, 96, 768, '1x1'), (5, 105, 80, 768, 96, '1x1'),
                                                (7, 105, 80, 128, 128, '3x3'), (33, 26, 20, 192, 384, 's2d')])
 def test_cta_pair_kernel_matches_single_cta_and_reference(B, Ho, Wo, C, N, kind):
     """Large bf16-output layers run on the CTA-pair (tcgen05 cta_group::2, M = 256) kernel.  It must agree with the
