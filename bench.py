@@ -24,6 +24,7 @@ import torch
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
+CE_DRAM_BYTES_B64 = 1599.7e6  # dram__bytes_read+write of one pixel_ce_kernel launch at B=64 (ncu, profiles/)
 ALG_GFLOP_PER_FRAME_TRAIN = 36.80  # conv/deconv fwd+bwd per sample (algorithmic)
 
 
@@ -336,7 +337,10 @@ def run_own(args):
             c = summ['pixel_ce_kernel']
             ach = c['work'] / (c['ms'] * 1e-3) / 1e9
             line['roofline_ce'] = {'bound': 'hbm', 'kernel': 'pixel_ce_kernel', 'achieved': ach, 'peak': hbm,
-                                   'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'peak_source': how,
+                                   'unit': 'GB/s', 'frac': ach / hbm,
+                                   'traffic': CE_DRAM_BYTES_B64 if batch == 64 else None,
+                                   'traffic_source': 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
+                                   'peak_source': how,
                                    'ms_per_launch': c['ms'] / c['launches'],
                                    'alg_bytes_per_launch': c['work'] / c['launches']}
     # ---- simulated rollout: agents x 50 steps with a PPO-style CNN policy (configs[2]); agents sharded over ranks
