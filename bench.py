@@ -338,7 +338,7 @@ def run_own(args):
             ach = c['work'] / (c['ms'] * 1e-3) / 1e9
             line['roofline_ce'] = {'bound': 'hbm', 'kernel': 'pixel_ce_kernel', 'achieved': ach, 'peak': hbm,
                                    'unit': 'GB/s', 'frac': ach / hbm,
-                                   'traffic': CE_DRAM_BYTES_B64 if batch == 64 else None,
+                                   'traffic': CE_DRAM_BYTES_B64 if B == 64 else None,
                                    'traffic_source': 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
                                    'peak_source': how,
                                    'ms_per_launch': c['ms'] / c['launches'],
