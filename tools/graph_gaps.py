@@ -11,7 +11,13 @@ from simple_b200.next_frame_predictor import NextFramePredictor  # noqa: E402
 from simple_b200.trainer import StepRunner, Trainer  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-dev = torch.device('cuda:0')
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank, local = 0, 0
+if world > 1:  # under torchrun: data-parallel step with the overlapped gradient all-reduce; rank 0 reports
+    from simple_b200.parallel import FlatGradSync, init_distributed
+    rank, world, local = init_distributed()
+dev = torch.device('cuda', local)
+torch.cuda.set_device(dev)
 cfg = SimpleNamespace(
     agents=16, batch_size=B, bottleneck_bits=128, bottleneck_noise=0.1, clip_grad_norm=1.0, compress_steps=5,
     device=str(dev), done_on_last_rollout_step=True, dropout=0.15, filter_double_steps=3, frame_shape=(3, 105, 80),
@@ -22,7 +28,9 @@ cfg = SimpleNamespace(
 torch.manual_seed(0)
 model = NextFramePredictor(cfg, 3).to(dev)
 trainer = Trainer(model, cfg)
-d = {k: v.to(dev) for k, v in synth_replay(B + 40, 3, 1).items()}
+if world > 1:
+    trainer.grad_sync = FlatGradSync(model)
+d = {k: v.to(dev) for k, v in synth_replay(B + 40, 3, 1 + rank).items()}
 replay = dict(obs=d['obs'], new_obs=d['new_obs'], action=d['action'].float(), reward=d['reward'].long(), value=d['value'])
 r = StepRunner(trainer, replay, B, use_graph=True)
 r.begin(torch.arange(B, device=dev), 0)
@@ -38,6 +46,12 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) a
     e1.record()
     torch.cuda.synchronize()
 wall = e0.elapsed_time(e1) / N
+if world > 1:
+    import torch.distributed as dist
+    dist.barrier()
+    torch.cuda.synchronize()
+    if rank != 0:
+        os._exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 busy = sum(e.device_time_total if hasattr(e, 'device_time_total') else e.cuda_time_total for e in evs) / 1e3 / N
 print(f'B={B}: wall {wall:.3f} ms/step, GPU kernel time {busy:.3f} ms/step, {len(evs) / N:.0f} kernels/step')
@@ -50,3 +64,27 @@ for e in evs:
     a[1] += t
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f'{t:8.3f} ms {n:6.1f}x  {k}')
+# timeline of the last profiled step: idle gaps of the GPU (> 15 us) and where the NCCL kernels sit
+tl = sorted(((e.time_range.start, e.time_range.end, e.name.split('(')[0][:60]) for e in evs), key=lambda x: x[0])
+per = len(tl) // N
+last = tl[-per:]
+t0 = last[0][0]
+print(f'--- last step timeline: {len(last)} kernels, span {(max(x[1] for x in last) - t0) / 1e3:.3f} ms')
+end = last[0][1]
+prev = last[0][2]
+for a, b, n in last[1:]:
+    if a - end > 15:
+        print(f'  gap {a - end:7.1f} us at +{(end - t0) / 1e3:6.3f} ms  after {prev}  before {n}')
+    if b > end:
+        end, prev = b, n
+for a, b, n in last:
+    if 'nccl' in n:
+        print(f'  nccl +{(a - t0) / 1e3:6.3f} .. +{(b - t0) / 1e3:6.3f} ms  ({(b - a):7.1f} us)')
+for key in ('pixel_ce_kernel', 'adafactor_tick', 'grad_sumsq', 'frame_feedback'):
+    for a, b, n in last:
+        if key in n:
+            print(f'  mark {key} +{(a - t0) / 1e3:6.3f} ms')
+            break
+if world > 1:
+    sys.stdout.flush()
+    os._exit(0)
