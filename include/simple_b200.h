@@ -170,11 +170,13 @@ int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t* pred, cons
                       sb_stream_t stream);
 
 /* conv-GRU blend of the recurrent state (simple/next_frame_predictor.py:298-303) and its backward.
- * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld. */
+ * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld.
+ * s_new may alias s_old (in-place update).  The backward reads the old state from a bf16 copy with row stride s_ld
+ * (channels 0..63 of the previous step's gate operand), so the fp32 state need not be kept. */
 int sb_gru_blend(const void* G, const float* s_old, float* s_new, void* xs, int xs_ld, long long npix,
                  sb_stream_t stream);
-int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs_ld, void* dG, long long npix,
-                     sb_stream_t stream);
+int sb_gru_blend_bwd(const void* G, const void* s_old_bf16, int s_ld, const void* dxs, int dxs_ld, void* dG,
+                     long long npix, sb_stream_t stream);
 
 /* fp32 (O,I,KH,KW) master weight -> bf16 GEMM operands (see DESIGN.md "weight packing"). */
 int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, int Opad, const int* iperm,

@@ -114,7 +114,7 @@ class _Sigs:
     sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p]
     sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
     sb_frame_feedback = [_p, _p, _p, _p, _f, _p, ctypes.c_ulonglong, _i, _i, _i, _i, _p]
-    sb_gru_blend_bwd = [_p, _p, _p, _i, _p, _ll, _p]
+    sb_gru_blend_bwd = [_p, _p, _i, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_lstm_sample = [_p] * 13 + [_i, _p, _p, _p]

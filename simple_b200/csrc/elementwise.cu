@@ -635,8 +635,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // dG from d(state_new): d/dgate = sg*(1-sg)*(s - tanh(c)),  d/dcand = (1-sg)*(1-tanh(c)^2).  s_old carries no grad.
+// The old state is read from its bf16 copy inside the previous step's gate operand (row stride s_ld): the fp32 state
+// buffer has already been updated in place by the forward.
 __global__ void __launch_bounds__(256)
-    gru_blend_bwd_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ s_old,
+    gru_blend_bwd_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ s_old, int s_ld,
                          const __nv_bfloat16* __restrict__ dxs, int dxs_ld, __nv_bfloat16* dG, long long npix) {
   const long long total = npix * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256)
     float g[8], cand[8], s[8], d[8], dg[8], dc[8];
     bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + c), g);
     bf8_to_f(*reinterpret_cast<const BF8*>(G + pix * 128 + 64 + c), cand);
-    ld8f(s_old + pix * 64 + c, s);
+    bf8_to_f(*reinterpret_cast<const BF8*>(s_old + pix * s_ld + c), s);
     bf8_to_f(*reinterpret_cast<const BF8*>(dxs + pix * dxs_ld + c), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1046,11 +1048,12 @@ extern "C" int sb_gru_blend(const void* G, const float* s_old, float* s_new, voi
   return SB_OK;
 }
 
-extern "C" int sb_gru_blend_bwd(const void* G, const float* s_old, const void* dxs, int dxs_ld, void* dG,
+extern "C" int sb_gru_blend_bwd(const void* G, const void* s_old_bf16, int s_ld, const void* dxs, int dxs_ld, void* dG,
                                 long long npix, sb_stream_t stream) {
-  if (!G || !s_old || !dxs || !dG || dxs_ld % 8) return SB_ERR_ARG;
+  if (!G || !s_old_bf16 || !dxs || !dG || dxs_ld % 8 || s_ld % 8 || s_ld < 64) return SB_ERR_ARG;
   gru_blend_bwd_kernel<<<grid_for(npix * 8), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)G, s_old, (const __nv_bfloat16*)dxs, dxs_ld, (__nv_bfloat16*)dG, npix);
+      (const __nv_bfloat16*)G, (const __nv_bfloat16*)s_old_bf16, s_ld, (const __nv_bfloat16*)dxs, dxs_ld,
+      (__nv_bfloat16*)dG, npix);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

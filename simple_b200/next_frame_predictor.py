@@ -350,10 +350,7 @@ class NextFramePredictor(nn.Module):
         """Make the state computed by the last forward current (next_frame_predictor.py:303,312 of the reference)."""
         if self._pending is None:
             return
-        xs, s_new = self._pending
-        self._xs_prev.copy_(xs)
-        if s_new is not None:
-            self._state.copy_(s_new)
+        self._xs_prev.copy_(self._pending)
         self._has_prev = True
         self._pending = None
 
@@ -555,11 +552,10 @@ class NextFramePredictor(nn.Module):
         if not self._has_prev:
             xs[..., :64].zero_()  # first step of a window: the recurrent state is zero and the gate conv is skipped
         ops.standardize(x.contiguous().float(), dst=xs, coff=64)
-        s_new = None
         if self._has_prev:
             G = self._conv('gate', P['gate'], self._xs_prev)
-            xs, s_new = ops.GruBlend.apply(G, self._state, xs)
-        self._pending = (xs.detach(), s_new)
+            xs = ops.GruBlend.apply(G, self._state, xs, self._xs_prev)  # fp32 state updated in place
+        self._pending = xs.detach()
         e = self._conv('embed', P['embed'], xs)
         # ---- encoder (K1, K3, K4, K8)
         skips = []

@@ -411,28 +411,30 @@ def tap_conv(spec, a, weight, bias, pw):
 # recurrent state blend, standardisation, loss
 # ---------------------------------------------------------------------------------------------------------------
 class GruBlend(torch.autograd.Function):
-    """xs_state (bf16, written into xs[..., :64]) = s*sigmoid(g) + tanh(c)*(1-sigmoid(g)); returns the new fp32 state."""
+    """state (fp32, updated IN PLACE) = s*sigmoid(g) + tanh(c)*(1-sigmoid(g)); its bf16 copy goes into xs[..., :64].
+    The backward takes the old state from `xs_prev[..., :64]` (the bf16 copy the gate conv just read), so no second
+    fp32 state buffer and no commit copy exist."""
 
     @staticmethod
-    def forward(ctx, G, s_old, xs):
+    def forward(ctx, G, state, xs, xs_prev):
         npix = G.numel() // 128
-        s_new = torch.empty_like(s_old)
-        _lib.check(_lib.lib().sb_gru_blend(G.data_ptr(), s_old.data_ptr(), s_new.data_ptr(), xs.data_ptr(),
+        assert state.dtype == torch.float32 and state.is_contiguous() and xs_prev.dtype == torch.bfloat16
+        _lib.check(_lib.lib().sb_gru_blend(G.data_ptr(), state.data_ptr(), state.data_ptr(), xs.data_ptr(),
                                            xs.shape[-1], npix, _lib.stream_ptr()), 'sb_gru_blend')
-        ctx.save_for_backward(G, s_old)
+        ctx.save_for_backward(G, xs_prev)
         ctx.mark_dirty(xs)
-        ctx.mark_non_differentiable(s_new)
-        return xs, s_new
+        return xs
 
     @staticmethod
-    def backward(ctx, dxs, _):
-        G, s_old = ctx.saved_tensors
+    def backward(ctx, dxs):
+        G, xs_prev = ctx.saved_tensors
         npix = G.numel() // 128
         dxs = dxs.contiguous()
         dG = torch.empty_like(G)
-        _lib.check(_lib.lib().sb_gru_blend_bwd(G.data_ptr(), s_old.data_ptr(), dxs.data_ptr(), dxs.shape[-1],
-                                               dG.data_ptr(), npix, _lib.stream_ptr()), 'sb_gru_blend_bwd')
-        return dG, None, None
+        _lib.check(_lib.lib().sb_gru_blend_bwd(G.data_ptr(), xs_prev.data_ptr(), xs_prev.shape[-1], dxs.data_ptr(),
+                                               dxs.shape[-1], dG.data_ptr(), npix, _lib.stream_ptr()),
+                   'sb_gru_blend_bwd')
+        return dG, None, None, None
 
 
 def standardize(x, dst=None, coff=0, out_f32=None):

@@ -117,7 +117,7 @@ class FlatGradSync:
                 self._all_reduce(self.flat[lo:hi])
             self._launched += 1
 
-    def _finish_overlapped(self, packed):
+    def _finish_overlapped(self, packed, overlap=None):
         L = self._layout
         conv = {id(p): pw for p, pw in packed.items()}
         rest = [p for p in self.params if id(p) not in conv and p.grad is not None]
@@ -128,8 +128,15 @@ class FlatGradSync:
         if rest:
             torch._foreach_copy_(list(views.values()), [p.grad for p in rest])
         lo = L['bounds'][self._launched - 1] if self._launched else 0
-        self._all_reduce(self.flat[lo:off])  # the not-yet-launched buckets + the non-conv tail, on the compute stream
-        torch.cuda.current_stream().wait_stream(self._comm_stream)
+        # the not-yet-launched buckets + the non-conv tail: nothing of the backward pass is left to hide them behind, so
+        # the caller's `overlap` work (frame feedback, state commit: independent of the gradients) runs meanwhile
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            self._all_reduce(self.flat[lo:off])
+        if overlap is not None:
+            overlap()
+        cur.wait_stream(self._comm_stream)
         for p, pw in packed.items():
             if pw.grad_slot is not None and pw.gpacked is not None:
                 views[p] = pw.grad_slot
@@ -137,11 +144,14 @@ class FlatGradSync:
         return views
 
     # ---- entry point -------------------------------------------------------------------------------------------
-    def __call__(self, model, packed=None):
+    def __call__(self, model, packed=None, overlap=None):
         """`packed`: optional {param: ops.PackedWeight}; those parameters contribute their packed-layout gradient
-        (`pw.gpacked`, zero-padded, identical layout on every rank) instead of `p.grad`."""
+        (`pw.gpacked`, zero-padded, identical layout on every rank) instead of `p.grad`.  `overlap`: optional callable
+        with gradient-independent work of the step, run while the last all-reduce is in flight."""
         if packed and self._layout is not None and all(pw.grad_slot is not None for pw in packed.values()):
-            return self._finish_overlapped(packed)
+            return self._finish_overlapped(packed, overlap)
+        if overlap is not None:
+            overlap()
         active = []
         for p in self.params:
             pw = packed.get(p) if packed else None

@@ -153,8 +153,10 @@ class Trainer:
         self._runner = None  # captured graphs refer to the old optimiser records
         return ck['epoch']
 
-    def train_step(self, frames, actions, new_states_u8, rewards, values, epsilon):
-        """One optimiser step (trainer.py:122-149).  Returns the loss dict of `wm_loss` (device scalars)."""
+    def train_step(self, frames, actions, new_states_u8, rewards, values, epsilon, after_backward=None):
+        """One optimiser step (trainer.py:122-149).  Returns the loss dict of `wm_loss` (device scalars).
+        `after_backward(out)`: optional gradient-independent tail work of the caller (frame feedback); it is issued
+        between the backward pass and the optimiser so that it overlaps the last gradient all-reduce."""
         self.model.train()
         out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
         self.optimizer.zero_grad(set_to_none=True)
@@ -162,12 +164,20 @@ class Trainer:
         if self.grad_sync is not None and hasattr(self.grad_sync, 'prepare'):
             self.grad_sync.prepare(self.model, packed)  # gradient arena + bucketed all-reduce overlapped with backward
         out['loss'].backward()
-        grads = self.grad_sync(self.model, packed) if self.grad_sync is not None else None
+
+        def tail():
+            self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous operand
+            if after_backward is not None:
+                after_backward(out)
+        if self.grad_sync is not None:
+            grads = self.grad_sync(self.model, packed, tail)
+        else:
+            grads = None
+            tail()
         self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads, packed=packed)
         if packed:
             for pw in packed.values():
                 pw.gpacked = None
-        self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous state
         return out
 
     def train(self, epoch, env, steps=15000):
@@ -283,11 +293,14 @@ class StepRunner:
         else:
             new_states, action, reward, value = (self.inp['new_obs'], self.inp['action'], self.inp['reward'],
                                                  self.inp['value'])
-        out = tr.train_step(self.frames, action, new_states, reward, value, self.eps)
         # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode; input noise with
-        # the per-frame median; frame-stack shift -- one kernel, in place on the static frame buffer
-        ops.frame_feedback(self.frames, new_states, out['argmax'], self.eps, float(tr.config.input_noise),
-                           tr.model._seed_dev)
+        # the per-frame median; frame-stack shift -- one kernel, in place on the static frame buffer.  Issued right
+        # after the backward pass (nothing later reads the frames): under data parallelism it hides behind the last
+        # gradient all-reduce
+        def feedback(out):
+            ops.frame_feedback(self.frames, new_states, out['argmax'], self.eps, float(tr.config.input_noise),
+                               tr.model._seed_dev)
+        out = tr.train_step(self.frames, action, new_states, reward, value, self.eps, after_backward=feedback)
         self.losses += torch.stack([out[k].detach().float() for k in self.names])
         self.idx += 1
         self.last = {k: v.detach() for k, v in out.items()}  # no reference to this step's autograd graph survives

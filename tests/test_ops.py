@@ -411,21 +411,27 @@ def test_conv_layer_fwd_bwd(kind):
 
 
 def test_gru_blend():
+    """In-place fp32 state update + bf16 copy into the gate operand; the backward reads the old state from the bf16
+    copy inside the previous operand (80-channel rows)."""
     from simple_b200 import ops
     torch.manual_seed(4)
     B, H, W = 2, 9, 8
     G = torch.randn(B, H, W, 128, device=DEV).bfloat16().requires_grad_(True)
-    s_old = torch.randn(B, H, W, 64, device=DEV)
-    xs = torch.zeros(B, H, W, 128, device=DEV, dtype=torch.bfloat16)
+    s_old = torch.randn(B, H, W, 64, device=DEV).bfloat16().float()  # bf16-representable: both copies agree exactly
+    xs_prev = torch.zeros(B, H, W, 80, device=DEV, dtype=torch.bfloat16)
+    xs_prev[..., :64] = s_old.bfloat16()
+    xs_prev[..., 64:] = 7.0
+    state = s_old.clone()
+    xs = torch.zeros(B, H, W, 80, device=DEV, dtype=torch.bfloat16)
     xs[..., 64:76] = 1.0
-    xs2, s_new = ops.GruBlend.apply(G, s_old, xs)
+    xs2 = ops.GruBlend.apply(G, state, xs, xs_prev)
     Gr = G.detach().float().requires_grad_(True)
     g, c = Gr[..., :64], Gr[..., 64:]
     ref = s_old * torch.sigmoid(g) + torch.tanh(c) * (1 - torch.sigmoid(g))
-    assert torch.allclose(s_new, ref, atol=1e-4, rtol=1e-4)
+    assert torch.allclose(state, ref, atol=1e-4, rtol=1e-4)  # updated in place
     assert rel(xs2[..., :64], ref) < 1e-2
     assert float((xs2[..., 64:76] - 1).abs().max()) == 0
-    gout = torch.randn(B, H, W, 128, device=DEV).bfloat16()
+    gout = torch.randn(B, H, W, 80, device=DEV).bfloat16()
     xs2.backward(gout)
     ref.backward(gout[..., :64].float())
     assert rel(G.grad, Gr.grad) < 1.5e-2
