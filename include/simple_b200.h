@@ -30,6 +30,9 @@ const char* sb_version(void);
 /* Debug / A-B switch: 1 (default) lets sb_tap_gemm use the CTA-pair (tcgen05 cta_group::2) kernel for large bf16-output
  * layers, 0 forces the single-CTA kernel.  Returns the previous setting. */
 int sb_set_pair_mode(int enabled);
+/* Same for sb_tap_wgrad's tap groups (3 taps of a 3x3 layer share one dY tile per pipeline stage; used for narrow
+ * layers with many pixels: the gate conv).  0 = one tap per CTA everywhere. */
+int sb_set_wgrad_tap_groups(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores ("tap GEMM").

@@ -87,6 +87,8 @@ def lib():
     L.sb_version.restype = ctypes.c_char_p
     L.sb_set_pair_mode.argtypes = [ctypes.c_int]
     L.sb_set_pair_mode.restype = ctypes.c_int
+    L.sb_set_wgrad_tap_groups.argtypes = [ctypes.c_int]
+    L.sb_set_wgrad_tap_groups.restype = ctypes.c_int
     L.sb_set_ce_tma.argtypes = [ctypes.c_int]
     L.sb_set_ce_tma.restype = ctypes.c_int
     L.sb_set_prep_specialize.argtypes = [ctypes.c_int]
@@ -134,7 +136,7 @@ class _Sigs:
     sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
 
 
-EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
 
 
 def check(rc, what):

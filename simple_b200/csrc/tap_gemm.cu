@@ -14,6 +14,7 @@
 namespace sb {
 
 long long g_launches = 0;
+int g_wgrad_tap_groups = 1;  // 1: 3-tap groups in the weight-gradient kernel where eligible (A/B switch for tests)
 int g_pair_mode = 1;  // 1: use the CTA-pair (cta_group::2) tap GEMM where eligible; 0: single-CTA kernel only
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -631,20 +632,24 @@ struct TapWgradDev {
 constexpr int kWgRows = 64;                   // pixels per stage (K of the contraction)
 constexpr int kWgChunkBytes = kWgRows * 128;  // 64 pixels x 64 channels bf16
 
-template <int BN, int STAGES>
+// TG = taps per CTA: one dY tile per stage feeds TG shifted A tiles and TG accumulators (TMEM columns j*BN).  A 3x3
+// layer with few channels (the gate conv: 128 x 80 per tap) is bound by re-reading dY once per tap; TG = 3 reads it 3x
+// instead of 9x.  TG > 1 needs the normal orientation (the shift is on the N-side operand).
+template <int BN, int STAGES, int TG>
 __global__ void __launch_bounds__(kGemmThreads)
     tap_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ TapWgradDev p) {
   constexpr int NCH = BN / 64;
   constexpr int DY_BYTES = 2 * kWgChunkBytes;
-  constexpr int A_BYTES = NCH * kWgChunkBytes;
-  constexpr int TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr int A_BYTES = NCH * kWgChunkBytes;  // per tap
+  constexpr int TMEM_COLS = TG * BN <= 64 ? 64 : TG * BN <= 128 ? 128 : TG * BN <= 256 ? 256 : 512;
   static_assert(BN % 64 == 0, "N-side tile = whole 64-channel chunks");
+  static_assert(TG * BN <= 512, "accumulators of one tap group must fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDY = smem;
   uint8_t* sA = smem + STAGES * DY_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + STAGES * A_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + STAGES * TG * A_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -653,8 +658,10 @@ __global__ void __launch_bounds__(kGemmThreads)
   int w = blockIdx.x;
   const int ct = w % p.c_tiles;
   w /= p.c_tiles;
-  const int t = w % p.ntaps;
-  const int mtile = w / p.ntaps;
+  const int groups = (p.ntaps + TG - 1) / TG;
+  const int t = (w % groups) * TG;             // first tap of this CTA's group
+  const int ntg = min(TG, p.ntaps - t);        // taps in the group
+  const int mtile = w / groups;
   const int m0 = mtile * 128, c0 = ct * BN;
   const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
   const int pt_begin = (int)((long long)PT * blockIdx.y / p.splits);
@@ -691,14 +698,20 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int x0 = (pt % p.tiles_x) * p.bw;
         const int y0 = ((pt / p.tiles_x) % p.tiles_y) * p.bh;
         const int b0 = (pt / (p.tiles_x * p.tiles_y)) * p.bb;
-        mbar_expect_tx(&full[s], (uint32_t)(DY_BYTES + A_BYTES));
-        const int mx = p.swapped ? dx : 0, my = p.swapped ? dy : 0;  // pixel shift of the M-side operand
-        const int nx = p.swapped ? 0 : dx, ny = p.swapped ? 0 : dy;  // ... and of the N-side operand
+        mbar_expect_tx(&full[s], (uint32_t)(DY_BYTES + ntg * A_BYTES));
+        const int mx = (TG == 1 && p.swapped) ? dx : 0, my = (TG == 1 && p.swapped) ? dy : 0;  // M-side pixel shift
         tma_load_4d(sDY + s * DY_BYTES, &tmDY, &full[s], m0, x0 + mx, y0 + my, b0);
         tma_load_4d(sDY + s * DY_BYTES + kWgChunkBytes, &tmDY, &full[s], m0 + 64, x0 + mx, y0 + my, b0);
 #pragma unroll
-        for (int j = 0; j < NCH; ++j)
-          tma_load_4d(sA + s * A_BYTES + j * kWgChunkBytes, &tmA, &full[s], c0 + j * 64, x0 + nx, y0 + ny, b0);
+        for (int g = 0; g < TG; ++g) {
+          if (g >= ntg) break;
+          // pixel shift of the N-side operand (normal orientation)
+          const int nx = (TG == 1 && p.swapped) ? 0 : p.tap_dx[t + g], ny = (TG == 1 && p.swapped) ? 0 : p.tap_dy[t + g];
+#pragma unroll
+          for (int j = 0; j < NCH; ++j)
+            tma_load_4d(sA + (s * TG + g) * A_BYTES + j * kWgChunkBytes, &tmA, &full[s], c0 + j * 64, x0 + nx, y0 + ny,
+                        b0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -712,13 +725,17 @@ __global__ void __launch_bounds__(kGemmThreads)
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sDY + s * DY_BYTES);
-        const uint32_t b_addr = smem_u32(sA + s * A_BYTES);
 #pragma unroll
-        for (int k = 0; k < kWgRows / 16; ++k) {
-          // MN-major, SW128: LBO = byte stride between 64-channel chunks, SBO = byte stride between 8-pixel groups
-          const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
-          const uint64_t bd = make_smem_desc_sw128(b_addr + k * 16 * 128, kWgChunkBytes, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+        for (int g = 0; g < TG; ++g) {
+          if (g >= ntg) break;
+          const uint32_t b_addr = smem_u32(sA + (s * TG + g) * A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kWgRows / 16; ++k) {
+            // MN-major, SW128: LBO = byte stride between 64-channel chunks, SBO = byte stride between 8-pixel groups
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 16 * 128, kWgChunkBytes, 1024);
+            umma_bf16(tmem_base + (uint32_t)(g * BN), ad, bd, idesc, (uint32_t)((i | k) != 0));
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -732,13 +749,14 @@ __global__ void __launch_bounds__(kGemmThreads)
     const bool valid = m < p.N;
     // normal: dw[m][t*C + c]; swapped (row = A channel, column = dY channel): dw[column][t*Ctrue + row], the 32 lanes of a
     // warp still hit 32 consecutive floats
-    float* orow = p.swapped ? p.dw + (long long)t * p.Ctrue + m
-                            : p.dw + (long long)m * p.ldw + (long long)t * p.C + c0;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      if (c0 + c >= p.C) break;
+    for (int gc = 0; gc < ntg * BN; gc += 32) {
+      const int g = gc / BN, c = gc - g * BN;  // tap of the group, column inside its accumulator
+      if (c0 + c >= p.C) continue;
+      float* orow = p.swapped ? p.dw + (long long)(t + g) * p.Ctrue + m
+                              : p.dw + (long long)m * p.ldw + (long long)(t + g) * p.C + c0;
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)gc, v);
       tmem_ld_wait();
       if (!valid) continue;
       if (p.swapped) {
@@ -759,18 +777,19 @@ __global__ void __launch_bounds__(kGemmThreads)
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TG = 1>
 static int launch_tap_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmA, const TapWgradDev& p, dim3 grid,
                             cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 + BN / 64) * kWgChunkBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (2 + TG * (BN / 64)) * kWgChunkBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "tap_wgrad_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tap_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+    if (cudaFuncSetAttribute(tap_wgrad_kernel<BN, STAGES, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return SB_ERR_CUDA;
     configured = true;
   }
-  tap_wgrad_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmDY, tmA, p);
+  tap_wgrad_kernel<BN, STAGES, TG><<<grid, kGemmThreads, smem, stream>>>(tmDY, tmA, p);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -917,7 +936,11 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   }
   p.c_tiles = (p.C + BN - 1) / BN;
   p.m_tiles = (p.N + 127) / 128;
-  const int ctas = p.m_tiles * p.ntaps * p.c_tiles;
+  // tap groups (3 taps share one dY tile): multi-tap layers with one narrow N-side tile and many pixels -- the gate conv
+  const bool grouped = g_wgrad_tap_groups != 0 && !p.swapped && BN == 128 && p.c_tiles == 1 && p.ntaps % 3 == 0 &&
+                       PT >= 1024;
+  const int groups = grouped ? p.ntaps / 3 : p.ntaps;
+  const int ctas = p.m_tiles * groups * p.c_tiles;
   int splits = a->splits;
   if (splits < 1) splits = (2 * 148) / ctas;  // auto: at most two full waves of CTAs (one CTA per SM), never a third
   p.splits = splits < 1 ? 1 : (splits > PT ? PT : splits);
@@ -926,7 +949,8 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   if (rc) return rc;
   rc = make_map_nhwc(&tmA, n_ptr, a->B, nH, nW, nC, a->bw, a->bh, a->bb);
   if (rc) return rc;
-  dim3 grid(p.m_tiles * p.ntaps * p.c_tiles, p.splits, 1);
+  dim3 grid(ctas, p.splits, 1);
+  if (grouped) return launch_tap_wgrad<128, 3, 3>(tmDY, tmA, p, grid, stream);
   switch (BN) {
     case 256: return launch_tap_wgrad<256, 4>(tmDY, tmA, p, grid, stream);
     case 192: return launch_tap_wgrad<192, 4>(tmDY, tmA, p, grid, stream);
@@ -942,6 +966,11 @@ extern "C" int sb_init(int device) {
   return load_driver_entry();
 }
 extern "C" long long sb_launch_count(void) { return sb::g_launches; }
+extern "C" int sb_set_wgrad_tap_groups(int enabled) {
+  const int prev = sb::g_wgrad_tap_groups;
+  sb::g_wgrad_tap_groups = enabled ? 1 : 0;
+  return prev;
+}
 extern "C" int sb_set_pair_mode(int enabled) {
   const int prev = sb::g_pair_mode;
   sb::g_pair_mode = enabled ? 1 : 0;

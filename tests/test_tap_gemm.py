@@ -179,3 +179,36 @@ def test_wgrad_swapped_orientation_and_bn192():
         at = a[:, ty:ty + H, tx:tx + W].float().reshape(-1, C)
         ref[:, t * C:(t + 1) * C] = dy.float().reshape(-1, N).t() @ at
     assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), float((dw - ref).abs().max())
+
+
+def test_wgrad_tap_groups_match_single_tap_kernel_and_torch():
+    """The gate conv's weight gradient (3x3 taps, 128 x 80 per tap, half a million pixels) runs with THREE taps per CTA:
+    one dY tile per pipeline stage feeds three shifted A tiles and three TMEM accumulators.  Same result as the
+    one-tap-per-CTA kernel (up to the order of the fp32 split reductions) and as torch; the image border exercises the
+    TMA zero fill of every shifted tile."""
+    from simple_b200 import _lib
+    from simple_b200.gemm import tap_wgrad
+    torch.manual_seed(31)
+    B, H, W, C, N = 8, 105, 80, 80, 128
+    x = torch.randn(B, H, W, C, device=_dev()).bfloat16()
+    x[..., 76:] = 0
+    dy = (torch.randn(B, H, W, N, device=_dev()) * 0.1).bfloat16()
+    taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
+    L = _lib.lib()
+    dw_g = torch.zeros(N, 9 * C, device=_dev())
+    dw_1 = torch.zeros(N, 9 * C, device=_dev())
+    prev = L.sb_set_wgrad_tap_groups(1)
+    try:
+        tap_wgrad(x, dy, taps, dw_g, splits=0)
+        L.sb_set_wgrad_tap_groups(0)
+        tap_wgrad(x, dy, taps, dw_1, splits=0)
+    finally:
+        L.sb_set_wgrad_tap_groups(prev)
+    wref = torch.zeros(N, C, 3, 3, device=_dev(), requires_grad=True)
+    (g,) = torch.autograd.grad(F.conv2d(x.float().permute(0, 3, 1, 2), wref, padding=1), wref,
+                               dy.float().permute(0, 3, 1, 2))
+    ref = g.permute(0, 2, 3, 1).reshape(N, 9 * C)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((dw_g - dw_1).abs().max()) <= 2e-5 * scale
+    assert float((dw_g - ref).abs().max()) <= 2e-3 * scale, float((dw_g - ref).abs().max()) / scale
