@@ -7,6 +7,9 @@
 //  * sb_prep_bwd_*       the matching backward
 //  * sb_gru_blend[_bwd]  next_frame_predictor.py:298-303
 //  * sb_pack_conv        fp32 (O,I,kh,kw) master weights -> bf16 K-major GEMM operands
+#include <cstdlib>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "../../include/simple_b200.h"
 
@@ -881,17 +884,51 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   return SB_OK;
 }
 static int launch_samples(const sb_prep_args* a) { return a->b_count > 0 ? a->b_count : a->B; }
-static void reduce_cfg(const PrepParams& q, int nb, int* PL, int* slabs, int* pps, int* threads, int P = -1) {
+// Grid sizing.  A launch is (slabs, samples) CTAs; what matters is how that count sits against the number of CTAs the
+// chip holds at once (`cap` per SM x 148 slots).  Measured on the training step (B = 64, ms per step): a fixed
+// "6 CTAs per SM" rule gave 14 x 64 = 896 CTAs on 296 slots -- three full waves plus eight CTAs alone in a fourth --
+// 7.86; grids cut to whole waves: 6 waves 8.03, 4 waves 7.86, 3 waves 7.76, 2 waves 7.63, ONE wave 7.61.  Every CTA
+// pays a prologue (per-channel constants into shared memory) and an epilogue (block reduction + atomics), so the
+// fewest, longest CTAs win: the slab count is the largest that keeps the whole grid co-resident.
+// SB_PREP_WAVES=n forces n waves (experiments).
+static int g_prep_waves = 0;
+static void reduce_cfg(const PrepParams& q, int nb, int cap, int* PL, int* slabs, int* pps, int* threads, int P = -1) {
   const int CV = q.C / 8;
   *PL = 256 / CV < 1 ? 1 : 256 / CV;
   *threads = CV * (*PL);
   if (P < 0) P = q.H * q.W;
-  int want = (148 * 6 + nb - 1) / nb;  // ~6 CTAs per SM over the whole grid
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("SB_PREP_WAVES");
+    if (e) g_prep_waves = atoi(e);
+    env_read = true;
+  }
+  if (cap < 1) cap = 2;
+  const int slots = cap * 148;
+  int want = slots * (g_prep_waves > 0 ? g_prep_waves : 1) / nb;
   if (want < 1) want = 1;
   int per = (P + want - 1) / want;
   if (per < *PL) per = *PL;
   *pps = per;
   *slabs = (P + per - 1) / per;
+}
+// resident CTAs per SM of one kernel instance at this block size / dynamic shared memory (cached per instance)
+template <typename K>
+static int resident_ctas(K kernel, int threads, size_t smem) {
+  struct Entry { int threads; size_t smem; int n; };
+  static std::unordered_map<const void*, Entry> cache;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  auto it = cache.find(key);
+  if (it != cache.end() && it->second.threads == threads && it->second.smem == smem) return it->second.n;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 2;
+  cache[key] = Entry{threads, smem, n};
+  return n;
+}
+static void block_cfg(const PrepParams& q, int* PL, int* threads) {
+  const int CV = q.C / 8;
+  *PL = 256 / CV < 1 ? 1 : 256 / CV;
+  *threads = CV * (*PL);
 }
 
 extern "C" int sb_set_prep_specialize(int enabled) {
@@ -907,18 +944,21 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   q.sums = nullptr;
   int PL, slabs, pps, threads;
   const int nb = launch_samples(a);
-  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads);
+  block_cfg(q, &PL, &threads);
   const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
-  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern) {
+    reduce_cfg(q, nb, resident_ctas(kern, threads, smem), &PL, &slabs, &pps, &threads);
+    kern<<<dim3(slabs, nb), threads, smem, st>>>(q, sums, PL, pps);
+  };
   if (q.in_f32 || q.add_f32) {
-    reduce_bc_kernel<0, true, kRT><<<grid, threads, smem, st>>>(q, sums, PL, pps);
+    go(reduce_bc_kernel<0, true, kRT>);
   } else {
     switch (feat_mask(q, kStatsBits)) {
-#define SB_CASE(M) case (M): reduce_bc_kernel<0, false, (M)><<<grid, threads, smem, st>>>(q, sums, PL, pps); break;
+#define SB_CASE(M) case (M): go(reduce_bc_kernel<0, false, (M)>); break;
       SB_STATS_MASKS(SB_CASE)
 #undef SB_CASE
-      default: reduce_bc_kernel<0, false, kRT><<<grid, threads, smem, st>>>(q, sums, PL, pps);
+      default: go(reduce_bc_kernel<0, false, kRT>);
     }
   }
   ++g_launches;
@@ -934,22 +974,25 @@ extern "C" int sb_prep(const sb_prep_args* a, sb_stream_t stream) {
   if (q.out2.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.out2.s * q.out2.H2; nx = q.out2.s * q.out2.W2; }
   int PL, slabs, pps, threads;
   const int nb = launch_samples(a);
-  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads, ny * nx);
+  block_cfg(q, &PL, &threads);
   if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
   q.nx_magic = div_magic(nx);
-  const dim3 grid(slabs, nb);
   const size_t smem = 8 * q.C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern) {
+    reduce_cfg(q, nb, resident_ctas(kern, threads, smem), &PL, &slabs, &pps, &threads, ny * nx);
+    kern<<<dim3(slabs, nb), threads, smem, st>>>(q, PL, pps);
+  };
   if (q.in_f32 || q.add_f32) {
-    prep_fwd_kernel<true, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    go(prep_fwd_kernel<true, kRT>);
   } else if (q.keep) {
-    prep_fwd_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    go(prep_fwd_kernel<false, kRT>);
   } else {
     switch (feat_mask(q, kFwdBits)) {
-#define SB_CASE(M) case (M): prep_fwd_kernel<false, (M)><<<grid, threads, smem, st>>>(q, PL, pps); break;
+#define SB_CASE(M) case (M): go(prep_fwd_kernel<false, (M)>); break;
       SB_FWD_MASKS(SB_CASE)
 #undef SB_CASE
-      default: prep_fwd_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+      default: go(prep_fwd_kernel<false, kRT>);
     }
   }
   ++g_launches;
@@ -963,20 +1006,23 @@ extern "C" int sb_prep_bwd_reduce(const sb_prep_args* a, sb_stream_t stream) {
   if (rc || !q.in.p || !q.g2.p || !q.bsums) return SB_ERR_ARG;
   int PL, slabs, pps, threads;
   const int nb = launch_samples(a);
-  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads);
+  block_cfg(q, &PL, &threads);
   const size_t smem = ((size_t)threads * 4 * 8 + 8 * (size_t)q.C) * sizeof(float);
-  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern) {
+    reduce_cfg(q, nb, resident_ctas(kern, threads, smem), &PL, &slabs, &pps, &threads);
+    kern<<<dim3(slabs, nb), threads, smem, st>>>(q, q.bsums, PL, pps);
+  };
   if (q.in_f32 || q.add_f32) {
-    reduce_bc_kernel<1, true, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+    go(reduce_bc_kernel<1, true, kRT>);
   } else if (q.keep) {
-    reduce_bc_kernel<1, false, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+    go(reduce_bc_kernel<1, false, kRT>);
   } else {
     switch (feat_mask(q, kRed1Bits)) {
-#define SB_CASE(M) case (M): reduce_bc_kernel<1, false, (M)><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps); break;
+#define SB_CASE(M) case (M): go(reduce_bc_kernel<1, false, (M)>); break;
       SB_RED1_MASKS(SB_CASE)
 #undef SB_CASE
-      default: reduce_bc_kernel<1, false, kRT><<<grid, threads, smem, st>>>(q, q.bsums, PL, pps);
+      default: go(reduce_bc_kernel<1, false, kRT>);
     }
   }
   ++g_launches;
@@ -992,23 +1038,26 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
   if (q.d_main.kind == 0) { ny = q.H; nx = q.W; } else { ny = q.d_main.s * q.d_main.H2; nx = q.d_main.s * q.d_main.W2; }
   int PL, slabs, pps, threads;
   const int nb = launch_samples(a);
-  reduce_cfg(q, nb, &PL, &slabs, &pps, &threads, ny * nx);
+  block_cfg(q, &PL, &threads);
   if (nx >= 300 || ny * nx >= (1 << 17)) return SB_ERR_ARG;
   q.nx_magic = div_magic(nx);
   // shared memory: 8*C per-channel constants, reused as the [PL][CV][8] scratch of the bias-gradient reduction
   const size_t smem = (size_t)(8 * q.C > threads * 8 ? 8 * q.C : threads * 8) * sizeof(float);
-  const dim3 grid(slabs, nb);
   cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern) {
+    reduce_cfg(q, nb, resident_ctas(kern, threads, smem), &PL, &slabs, &pps, &threads, ny * nx);
+    kern<<<dim3(slabs, nb), threads, smem, st>>>(q, PL, pps);
+  };
   if (q.in_f32 || q.add_f32) {
-    prep_bwd_apply_kernel<true, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    go(prep_bwd_apply_kernel<true, kRT>);
   } else if (q.keep) {
-    prep_bwd_apply_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+    go(prep_bwd_apply_kernel<false, kRT>);
   } else {
     switch (feat_mask(q, kApplyBits)) {
-#define SB_CASE(M) case (M): prep_bwd_apply_kernel<false, (M)><<<grid, threads, smem, st>>>(q, PL, pps); break;
+#define SB_CASE(M) case (M): go(prep_bwd_apply_kernel<false, (M)>); break;
       SB_APPLY_MASKS(SB_CASE)
 #undef SB_CASE
-      default: prep_bwd_apply_kernel<false, kRT><<<grid, threads, smem, st>>>(q, PL, pps);
+      default: go(prep_bwd_apply_kernel<false, kRT>);
     }
   }
   ++g_launches;
