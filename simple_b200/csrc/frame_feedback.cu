@@ -1,4 +1,5 @@
-// Scheduled-sampling frame feedback of the world-model trainer (simple/trainer.py:58-65,125-132), one CTA per sample:
+// Scheduled-sampling frame feedback of the world-model trainer (simple/trainer.py:58-65,125-132), one 4-CTA cluster per
+// sample:
 //   next  = ground-truth frame w.p. epsilon, else the model's own arg-max decode            (u8 [3,HW])
 //   next  = next / 255, each value replaced w.p. input_noise by the frame's (lower) median  (torch.median semantics)
 //   stack = cat(stack[3:], next)                                                            (fp32 [12,HW], in place)
@@ -11,13 +12,26 @@
 namespace sb {
 extern long long g_launches;
 
-__global__ void __launch_bounds__(256)
+constexpr int kFfCluster = 4;  // CTAs per sample: each histograms and rewrites a quarter of the frame
+
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t cluster_addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
+// grid = (kFfCluster, B), one 4-CTA cluster per sample.  Each CTA histograms a quarter of the sample's bytes, the four
+// partial histograms are summed through distributed shared memory, the median is found with a block-wide scan, and
+// each CTA rewrites its quarter of the pixels.
+__global__ void __cluster_dims__(kFfCluster, 1, 1) __launch_bounds__(256)
     frame_feedback_kernel(float* __restrict__ stack, const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred,
                           const float* __restrict__ eps_ptr, float p_noise, const unsigned long long* seed_ptr,
                           unsigned long long seed, int C_stack, int C_new, int HW) {
   __shared__ unsigned int hist[256];
+  __shared__ unsigned int warp_tot[8];
   __shared__ int s_median;
-  const int b = blockIdx.x, t = threadIdx.x;
+  const int b = blockIdx.y, t = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
   const unsigned long long sd = seed_ptr ? seed + *seed_ptr : seed;
   const uint2 key = hash_key(sd, 0x46454544u);
   // scheduled sampling: one uniform per sample
@@ -25,51 +39,64 @@ __global__ void __launch_bounds__(256)
   const bool use_gt = u01(hash4x32(0x7fffff00u + (uint32_t)b, key).x) < eps;
   const uint8_t* src = (use_gt ? gt : pred) + (size_t)b * C_new * HW;
   const int n = C_new * HW;
-  if (t < 256) hist[t] = 0u;
+  hist[t] = 0u;
+  if (t == 0) s_median = 0;
   __syncthreads();
-  if (p_noise > 0.f) {
-    // Histogram of the frame's bytes.  16 bytes per thread and load (a 1-byte load per iteration was a chain of ~100
-    // dependent global round trips), warp-aggregated increments: Atari frames are mostly one background colour, so
-    // every lane hits the same bin and plain shared-memory atomics would serialise 25 k increments on one address.
-    const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? n / 16 : 0;
+  if (p_noise > 0.f) {  // (uniform over the grid: every CTA takes the same branch, cluster barriers included)
+    // Histogram of this CTA's share of the frame's bytes.  16 bytes per thread and load, warp-aggregated increments:
+    // Atari frames are mostly one background colour, so every lane hits the same bin and plain shared-memory atomics
+    // would serialise on one address.
     const int lane = t & 31;
-    for (int i0 = 0; i0 < nvec; i0 += blockDim.x) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    const int nvec = aligned ? n / 16 : 0;
+    const int vper = (nvec + kFfCluster - 1) / kFfCluster;
+    const int v_begin = (int)rank * vper, v_end = min(nvec, v_begin + vper);
+    for (int i0 = v_begin; i0 < v_end; i0 += blockDim.x) {
       const int i = i0 + t;
       uint4 q = make_uint4(0, 0, 0, 0);
-      if (i < nvec) q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      if (i < v_end) q = __ldg(reinterpret_cast<const uint4*>(src) + i);
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
-        const int v = i < nvec ? (int)((w[k >> 2] >> (8 * (k & 3))) & 0xffu) : 256 + lane;  // idle lanes: unique values
+        const int v = i < v_end ? (int)((w[k >> 2] >> (8 * (k & 3))) & 0xffu) : 256 + lane;  // idle lanes: unique values
         const unsigned peers = __match_any_sync(0xffffffffu, v);
         if (v < 256 && lane == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned)__popc(peers));
       }
     }
-    for (int i0 = nvec * 16; i0 < n; i0 += blockDim.x) {  // tail / unaligned fallback
-      const int i = i0 + t;
-      const int v = i < n ? (int)src[i] : 256 + lane;
-      const unsigned peers = __match_any_sync(0xffffffffu, v);
-      if (v < 256 && lane == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned)__popc(peers));
-    }
-    __syncthreads();
-    if (t == 0) {  // lower median: the value at sorted position (n - 1) / 2
-      const unsigned int target = (unsigned int)((n - 1) / 2);
-      unsigned int cum = 0;
-      int v = 0;
-      for (; v < 256; ++v) {
-        cum += hist[v];
-        if (cum > target) break;
+    if (rank == 0) {  // tail / unaligned fallback
+      for (int i0 = nvec * 16; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + t;
+        const int v = i < n ? (int)src[i] : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, v);
+        if (v < 256 && lane == __ffs(peers) - 1) atomicAdd(&hist[v], (unsigned)__popc(peers));
       }
-      s_median = v;
     }
+    cluster_sync_all();  // all four partial histograms complete and visible
+    unsigned int cnt = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < kFfCluster; ++r) cnt += ld_cluster_u32(mapa_u32(&hist[t], r));
+    // lower median = value at sorted position (n - 1) / 2: first bin whose inclusive prefix count exceeds it
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[t >> 5] = incl;
     __syncthreads();
+    unsigned int base = 0;
+    for (int wi = 0; wi < (t >> 5); ++wi) base += warp_tot[wi];
+    incl += base;
+    const unsigned int target = (unsigned int)((n - 1) / 2);
+    if (incl > target && incl - cnt <= target) s_median = t;  // exactly one bin satisfies this
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves (or reuses hist) while a peer may still read its partial histogram
   }
   const float med = (float)s_median / 255.0f;
   float* st = stack + (size_t)b * C_stack * HW;
   const uint32_t thr = (uint32_t)(p_noise * 65536.0f);
-  // the pixels of a sample are split over gridDim.y CTAs (each recomputes the 25 KB histogram: cheaper than a second pass)
-  const int per = (HW + gridDim.y - 1) / gridDim.y;
-  const int hw_begin = blockIdx.y * per, hw_end = min(HW, hw_begin + per);
+  const int per = (HW + kFfCluster - 1) / kFfCluster;
+  const int hw_begin = (int)rank * per, hw_end = min(HW, hw_begin + per);
   for (int hw = hw_begin + t; hw < hw_end; hw += blockDim.x) {
     // shift: channel c <- channel c + C_new, ascending c (each element is read before this thread overwrites it)
     for (int c = 0; c < C_stack - C_new; ++c) st[(size_t)c * HW + hw] = st[(size_t)(c + C_new) * HW + hw];
@@ -93,11 +120,8 @@ extern "C" int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t*
                                  float p_noise, const unsigned long long* seed_ptr, unsigned long long seed, int B,
                                  int C_stack, int C_new, int HW, sb_stream_t stream) {
   if (!stack || !gt || !pred || B < 1 || C_new < 1 || C_new > 8 || C_stack <= C_new || HW < 1) return SB_ERR_ARG;
-  int split = (2 * 148 + B - 1) / B;  // ~2 CTAs per SM over the whole grid
-  if (split < 1) split = 1;
-  if (split > 16) split = 16;
-  frame_feedback_kernel<<<dim3(B, split), 256, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr, seed, C_stack,
-                                                            C_new, HW);
+  frame_feedback_kernel<<<dim3(kFfCluster, B), 256, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr,
+                                                                               seed, C_stack, C_new, HW);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -487,6 +487,19 @@ def test_frame_feedback_shift_median_noise_and_scheduled_sampling():
     assert 0.04 < rate < 0.06, rate  # (a few replaced values coincide with the median and do not count as changed)
     st2 = ops.frame_feedback(stack0.clone(), gt, pred, one, 0.05, 8)
     assert not torch.equal(st2, st)  # another seed, another mask
+    # Atari-like frames (mostly one background value: the warp-aggregated histogram path) and a frame size whose byte
+    # count is not a multiple of 16 (scalar tail), median still exact
+    for (h2, w2) in ((105, 80), (21, 13)):
+        g2 = torch.where(torch.rand(B, 3, h2, w2, device=DEV) < 0.9, torch.full((), 87, device=DEV),
+                         torch.randint(0, 256, (B, 3, h2, w2), device=DEV)).to(torch.uint8)
+        g2[1] = torch.randint(0, 3, (3, h2, w2), device=DEV, dtype=torch.uint8)  # median decided between close bins
+        s0 = torch.rand(B, 12, h2, w2, device=DEV)
+        out2 = ops.frame_feedback(s0.clone(), g2, g2, one, 0.3, 11)
+        want2 = g2.float() / 255
+        med2 = want2.reshape(B, -1).median(dim=1).values.reshape(B, 1, 1, 1)
+        ch2 = out2[:, 9:] != want2
+        assert torch.equal(out2[:, 9:][ch2], med2.expand_as(want2)[ch2])
+        assert torch.equal(out2[:, :9], s0[:, 3:])
     # epsilon = 0.5: roughly half of the samples take the ground truth
     Bb = 64
     s_big = torch.zeros(Bb, 12, 8, 8, device=DEV)
