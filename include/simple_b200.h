@@ -172,6 +172,12 @@ int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t* pred, cons
                       const unsigned long long* seed_ptr, unsigned long long seed, int B, int C_stack, int C_new, int HW,
                       sb_stream_t stream);
 
+/* Epilogue of a split-K sb_tap_gemm (fp32 partial sums [rows, N]): out = act(acc + bias[N]) as fp32 (out may alias acc)
+ * or bf16 -- the bias add + ReLU of the reference's conv layers (next_frame_predictor.py:37-63,320-350) for the deep,
+ * tiny feature maps whose GEMMs are split over K. */
+int sb_bias_act(const float* acc, const float* bias, int relu, void* out, int out_is_f32, long long rows, int N,
+                sb_stream_t stream);
+
 /* conv-GRU blend of the recurrent state (simple/next_frame_predictor.py:298-303) and its backward.
  * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld.
  * s_new may alias s_old (in-place update).  The backward reads the old state from a bf16 copy with row stride s_ld

@@ -595,18 +595,53 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// thread = one pixel of one sample; C <= 16 channels
+// thread = one pixel of one sample, all CT channels: CT independent coalesced plane loads in flight, the CT bf16 results
+// written with 16/8-byte stores when the destination allows (12 channels at channel offset 64: one 16 B + one 8 B
+// store instead of twelve scattered 2-byte stores).  CT = 0: runtime channel count (<= 16), scalar stores.
+template <int CT>
 __global__ void __launch_bounds__(256)
     standardize_apply_kernel(const float* __restrict__ in, const float2* __restrict__ stats, int C, int P,
                              __nv_bfloat16* dst, int ld, int coff, float* out_f32) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  for (int c = 0; c < C; ++c) {
-    const float2 st = stats[b * C + c];
-    const float v = (in[((long long)b * C + c) * P + i] - st.x) * st.y;  // coalesced across the pixels of a plane
-    if (dst) dst[((long long)b * P + i) * ld + coff + c] = __float2bfloat16_rn(v);  // C consecutive halves per thread
-    if (out_f32) out_f32[((long long)b * C + c) * P + i] = v;
+  if (CT == 0) {
+    for (int c = 0; c < C; ++c) {
+      const float2 st = stats[b * C + c];
+      const float v = (in[((long long)b * C + c) * P + i] - st.x) * st.y;  // coalesced across the pixels of a plane
+      if (dst) dst[((long long)b * P + i) * ld + coff + c] = __float2bfloat16_rn(v);
+      if (out_f32) out_f32[((long long)b * C + c) * P + i] = v;
+    }
+    return;
+  }
+  constexpr int CC = CT == 0 ? 1 : CT;
+  float v[CC];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) v[c] = in[((long long)b * CC + c) * P + i];
+#pragma unroll
+  for (int c = 0; c < CC; ++c) {
+    const float2 st = stats[b * CC + c];
+    v[c] = (v[c] - st.x) * st.y;
+  }
+  if (out_f32) {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) out_f32[((long long)b * CC + c) * P + i] = v[c];
+  }
+  if (dst) {
+    __nv_bfloat16* o = dst + ((long long)b * P + i) * ld + coff;
+    if (CC % 4 == 0 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+#pragma unroll
+      for (int c = 0; c < CC; c += 4) {
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[c], v[c + 1]), t1 = __floats2bfloat162_rn(v[c + 2], v[c + 3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&t0);
+        pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        *reinterpret_cast<uint2*>(o + c) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CC; ++c) o[c] = __float2bfloat16_rn(v[c]);
+    }
   }
 }
 
@@ -773,6 +808,32 @@ __global__ void __launch_bounds__(256)
         for (int j = 0; j < 8; ++j)
           if (r + j < Opad) dst[(long long)c * ldd + r + j] = v[j];
       }
+    }
+  }
+}
+
+// epilogue of a split-K tap GEMM (tiny deep-layer outputs): fp32 partial sums + bias -> ReLU -> bf16 or fp32 (in place
+// allowed).  One launch instead of an ATen add / relu / cast chain.
+__global__ void __launch_bounds__(256)
+    bias_act_kernel(const float* acc, const float* __restrict__ bias, int relu, float* out_f32, __nv_bfloat16* out_bf16,
+                    long long nvec, int N) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(acc)[i];
+    if (bias) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % N));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+    }
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if (out_f32) {
+      reinterpret_cast<float4*>(out_f32)[i] = v;
+    } else {
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      reinterpret_cast<uint2*>(out_bf16)[i] = pk;
     }
   }
 }
@@ -1080,8 +1141,24 @@ extern "C" int sb_standardize(const float* in, int B, int C, int P, void* dst_bf
   standardize_stats_kernel<<<B * C, 256, P * sizeof(float), st>>>(in, P, stats);
   ++g_launches;
   SB_CHECK_LAUNCH();
-  standardize_apply_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff,
-                                                                     out_f32);
+  const dim3 grid((P + 255) / 256, B);
+  if (C == 12)
+    standardize_apply_kernel<12><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+  else if (C == 3)
+    standardize_apply_kernel<3><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+  else
+    standardize_apply_kernel<0><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_bias_act(const float* acc, const float* bias, int relu, void* out, int out_is_f32, long long rows,
+                           int N, sb_stream_t stream) {
+  if (!acc || !out || rows < 1 || N < 4 || N % 4) return SB_ERR_ARG;
+  const long long nvec = rows * N / 4;
+  bias_act_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>(acc, bias, relu, out_is_f32 ? (float*)out : nullptr,
+                                                                   out_is_f32 ? nullptr : (__nv_bfloat16*)out, nvec, N);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -394,13 +394,12 @@ def auto_splits(B, Ho, Wo, N, KT):
 
 
 def _bias_act(acc, bias, relu, keep_f32=False):
-    """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16 (or fp32)."""
-    y = acc
-    if bias is not None:
-        y = y + bias
-    if relu:
-        y = torch.relu(y)
-    return y if keep_f32 else y.bfloat16()
+    """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16 (or fp32, in place)."""
+    N = acc.shape[-1]
+    out = acc if keep_f32 else torch.empty(acc.shape, device=acc.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().sb_bias_act(acc.data_ptr(), _ptr(bias), int(bool(relu)), out.data_ptr(), int(keep_f32),
+                                      acc.numel() // N, N, _lib.stream_ptr()), 'sb_bias_act')
+    return out
 
 
 def tap_conv(spec, a, weight, bias, pw):
