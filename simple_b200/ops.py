@@ -382,7 +382,8 @@ class TapConv(torch.autograd.Function):
 
 
 def auto_splits(B, Ho, Wo, N, KT):
-    """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed."""
+    """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed
+    (one co-resident wave: 148 slots measured a shade faster than two, and halves the fp32 atomics)."""
     from .gemm import choose_box
     bw, bh, bb = choose_box(Wo, Ho, B)
     m_tiles = -(-Wo // bw) * -(-Ho // bh) * -(-B // bb)
@@ -390,7 +391,7 @@ def auto_splits(B, Ho, Wo, N, KT):
     ctas = m_tiles * -(-N // BN)
     if ctas >= 100:
         return 1
-    return int(max(1, min(KT, -(-296 // ctas), 32)))
+    return int(max(1, min(KT, -(-int(os.environ.get('SB_SPLIT_SLOTS', '148')) // ctas), 32)))
 
 
 def _bias_act(acc, bias, relu, keep_f32=False):
