@@ -359,7 +359,7 @@ class TapConv(torch.autograd.Function):
         if spec.transposed:
             # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
             dwp = slot if slot is not None else torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
-            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for ~2 waves of CTAs
+            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for one wave of CTAs
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         else:
             dwp = slot if slot is not None else torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
