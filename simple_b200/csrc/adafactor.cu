@@ -34,19 +34,32 @@ __device__ __forceinline__ float clip_coef(const float* total_sumsq, float max_n
 }
 
 // ---- 1. global gradient norm ------------------------------------------------------------------------------------
+// Persistent: a resident grid walks the (tensor, 4096-element chunk) list, 16-byte loads, one atomic per CTA (the
+// one-CTA-per-chunk version issued 16.7 k atomics on the same address).
 __global__ void __launch_bounds__(256)
     grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const long long* __restrict__ glen,
-                      const int2* __restrict__ block_map, float* total) {
+                      const int2* __restrict__ block_map, int nblocks, float* total) {
   __shared__ float red[8];
-  const int2 bm = block_map[blockIdx.x];  // (tensor, first element)
-  const sb_tensor_desc d = descs[bm.x];
-  const long long n = glen ? glen[bm.x] : d.n;  // a packed gradient buffer is longer than its parameter (zero padding)
-  const long long begin = (long long)bm.y * 4096;
-  const long long end = begin + 4096 < n ? begin + 4096 : n;
   float s = 0.f;
-  for (long long i = begin + threadIdx.x; i < end; i += 256) {
-    const float g = d.g[i];
-    s += g * g;
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int2 bm = block_map[blk];  // (tensor, chunk)
+    const float* g = descs[bm.x].g;
+    const long long n = glen ? glen[bm.x] : descs[bm.x].n;  // a packed gradient buffer is longer than its parameter
+    const long long begin = (long long)bm.y * 4096;
+    const long long end = begin + 4096 < n ? begin + 4096 : n;
+    if (end - begin == 4096 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+      const float4* g4 = reinterpret_cast<const float4*>(g + begin);
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(g4 + threadIdx.x + 256 * k);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    } else {
+      for (long long i = begin + threadIdx.x; i < end; i += 256) {
+        const float x = g[i];
+        s += x * x;
+      }
+    }
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(total, s);
@@ -421,7 +434,9 @@ extern "C" int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, 
 extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev,
                              int nblocks, float* total, sb_stream_t stream) {
   if (!descs_dev || !block_map_dev || nblocks < 1 || !total) return SB_ERR_ARG;
-  grad_sumsq_kernel<<<nblocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, glen_dev, (const int2*)block_map_dev, total);
+  const int grid = nblocks < 148 * 8 ? nblocks : 148 * 8;  // 8 CTAs of 256 threads per SM: one resident wave
+  grad_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, glen_dev, (const int2*)block_map_dev, nblocks,
+                                                            total);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
