@@ -193,6 +193,14 @@ int sb_pack_conv(const float* w, int O, int I, int KH, int KW, int s, int Ipad, 
 /* tr[:, t*Opad:(t+1)*Opad] = fwd[:, t*PHI:(t+1)*PHI]^T per tap (the second half of sb_pack_conv, for operands whose
  * `fwd` was refreshed in place by sb_adafactor_conv_packed).  PHI = s*s*Ipad. */
 int sb_transpose_taps(const void* fwd, void* tr, int Opad, int PHI, int T, sb_stream_t stream);
+/* The same for a list of layers in one launch.  first_tile = prefix sum of ceil(PHI/64) * ceil(Opad/64) * T over the
+ * preceding entries; total_tiles = the sum over all entries.  descs_dev: device array. */
+typedef struct sb_transpose_desc {
+  const void* fwd;
+  void* tr;
+  int Opad, PHI, T, first_tile;
+} sb_transpose_desc;
+int sb_transpose_taps_multi(const sb_transpose_desc* descs_dev, int n, int total_tiles, sb_stream_t stream);
 /* inverse map for gradients: fp32 packed [Opad, T*s*s*Ipad] (layout of `fwd`) -> reference layout (O,I,KH,KW). */
 int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s, int Ipad, int Opad,
                         const int* iperm, const int* operm, float* out, sb_stream_t stream);

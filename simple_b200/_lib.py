@@ -134,6 +134,7 @@ class _Sigs:
     sb_adafactor_conv_packed = [_p, _p, _p, _i, _i, _i, _p, _f, _i, _p]
     sb_transpose_taps = [_p, _p, _i, _i, _i, _p]
     sb_bias_act = [_p, _p, _i, _p, _i, _ll, _i, _p]
+    sb_transpose_taps_multi = [_p, _i, _i, _p]
     sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
 
 

@@ -128,9 +128,8 @@ class Adafactor(torch.optim.Optimizer):
                 k['O'], k['I'], k['s'], k['Ipad'], k['Opad'] = pw.O, pw.I, pw.s, pw.Ipad, pw.Opad
             st['RMS'] = _LazyRMS(acc, i, p.numel())
         self._launch(rec, n, max_grad_norm)
-        for _, _, pw in active:
-            if pw is not None:
-                pw.refresh_transposed()  # `fwd` was rewritten by the update: re-derive the per-tap transpose
+        from .ops import refresh_transposed_all
+        refresh_transposed_all([pw for _, _, pw in active])  # `fwd` was rewritten: re-derive the per-tap transposes
         self.last_key = key
         return loss
 

@@ -761,15 +761,13 @@ __global__ void __launch_bounds__(256) unpack_conv_kernel(const __grid_constant_
 // tr[:, t*Opad:(t+1)*Opad] = fwd[:, t*PHI:(t+1)*PHI]^T for every tap t.  64x64 bf16 tiles through shared memory, 16-byte
 // global accesses on both sides (full 128-byte row segments per 8 threads); the previous 32x32 / 2-byte version moved
 // 64-byte segments and ran at ~1.1 TB/s over the 137 MB of operands.
-__global__ void __launch_bounds__(256)
-    transpose_taps_kernel(const __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ tr, int Opad, int PHI,
-                          int T) {
-  __shared__ unsigned short tile[64][66];  // [source row][source col], pitch 66 halves = 33 words (odd: conflict-free)
-  const int t = blockIdx.z;
+__device__ __forceinline__ void transpose_tile(unsigned short (*tile)[66], const __nv_bfloat16* __restrict__ fwd,
+                                               __nv_bfloat16* __restrict__ tr, int Opad, int PHI, int T, int bx, int by,
+                                               int t) {
   const unsigned short* src = reinterpret_cast<const unsigned short*>(fwd) + (long long)t * PHI;
   unsigned short* dst = reinterpret_cast<unsigned short*>(tr) + (long long)t * Opad;
   const long long lds = (long long)T * PHI, ldd = (long long)T * Opad;
-  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int c0 = bx * 64, r0 = by * 64;
   const int cv = (threadIdx.x & 7) * 8, rr = threadIdx.x >> 3;  // 8 threads x 8 halves per 64-wide row, 32 rows per pass
   const bool vec_ok = (PHI % 8 == 0) && (Opad % 8 == 0);
 #pragma unroll
@@ -810,6 +808,28 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+    transpose_taps_kernel(const __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ tr, int Opad, int PHI,
+                          int T) {
+  __shared__ unsigned short tile[64][66];  // [source row][source col], pitch 66 halves = 33 words (odd: conflict-free)
+  transpose_tile(tile, fwd, tr, Opad, PHI, T, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+// All layers of the network in ONE launch (the per-layer launches of the small layers were 2..24 CTAs each): CTA ->
+// (layer, tile) through the prefix sums of the layers' tile counts.
+__global__ void __launch_bounds__(256)
+    transpose_taps_multi_kernel(const sb_transpose_desc* __restrict__ descs, int n) {
+  __shared__ unsigned short tile[64][66];
+  int l = 0;
+  while (l + 1 < n && (int)blockIdx.x >= descs[l + 1].first_tile) ++l;
+  const sb_transpose_desc d = descs[l];
+  int w = blockIdx.x - d.first_tile;
+  const int nx = (d.PHI + 63) / 64, ny = (d.Opad + 63) / 64;
+  const int bx = w % nx;
+  w /= nx;
+  const int by = w % ny, t = w / ny;
+  transpose_tile(tile, (const __nv_bfloat16*)d.fwd, (__nv_bfloat16*)d.tr, d.Opad, d.PHI, d.T, bx, by, t);
 }
 
 // epilogue of a split-K tap GEMM (tiny deep-layer outputs): fp32 partial sums + bias -> ReLU -> bf16 or fp32 (in place
@@ -1217,6 +1237,14 @@ extern "C" int sb_transpose_taps(const void* fwd, void* tr, int Opad, int PHI, i
   dim3 grid((PHI + 63) / 64, (Opad + 63) / 64, T);
   transpose_taps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)fwd, (__nv_bfloat16*)tr, Opad,
                                                                 PHI, T);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_transpose_taps_multi(const sb_transpose_desc* descs_dev, int n, int total_tiles, sb_stream_t stream) {
+  if (!descs_dev || n < 1 || total_tiles < 1) return SB_ERR_ARG;
+  transpose_taps_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(descs_dev, n);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -381,6 +381,36 @@ class TapConv(torch.autograd.Function):
         return None, da, dweight, dbias, None
 
 
+_TRANSPOSE_TABLES = {}
+
+
+def refresh_transposed_all(pws):
+    """`fwd` of every PackedWeight in `pws` was rewritten by the optimiser: re-derive all `tr` operands in ONE launch.
+    The descriptor table holds static device pointers and is built once per set of layers."""
+    pws = [pw for pw in pws if pw is not None]
+    if not pws:
+        return
+    key = tuple(id(pw) for pw in pws)
+    rec = _TRANSPOSE_TABLES.get(key)
+    if rec is None:
+        import numpy as np
+        dt = np.dtype([('fwd', np.uint64), ('tr', np.uint64), ('Opad', np.int32), ('PHI', np.int32), ('T', np.int32),
+                       ('first_tile', np.int32)])
+        assert dt.itemsize == 32
+        tab = np.zeros(len(pws), dtype=dt)
+        first = 0
+        for i, pw in enumerate(pws):
+            phi = pw.PH * pw.Ipad
+            tab[i] = (pw.fwd.data_ptr(), pw.tr.data_ptr(), pw.Opad, phi, pw.T, first)
+            first += -(-phi // 64) * -(-pw.Opad // 64) * pw.T
+        dev = torch.from_numpy(tab.view(np.uint8).copy()).to(pws[0].fwd.device)
+        rec = _TRANSPOSE_TABLES[key] = (dev, len(pws), first, pws)  # (keeps the PackedWeights alive: ids stay unique)
+    dev, n, total, _ = rec
+    _lib.check(_lib.lib().sb_transpose_taps_multi(dev.data_ptr(), n, total, _lib.stream_ptr()), 'sb_transpose_taps_multi')
+    for pw in pws:
+        pw.fresh = True
+
+
 def auto_splits(B, Ho, Wo, N, KT):
     """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed
     (one co-resident wave: 148 slots measured a shade faster than two, and halves the fp32 atomics)."""
