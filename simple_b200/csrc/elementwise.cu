@@ -818,6 +818,7 @@ __global__ void __launch_bounds__(256)
 }
 // All layers of the network in ONE launch (the per-layer launches of the small layers were 2..24 CTAs each): CTA ->
 // (layer, tile) through the prefix sums of the layers' tile counts.
+static_assert(sizeof(sb_transpose_desc) == 32, "sb_transpose_desc: the Python side builds 32-byte records");
 __global__ void __launch_bounds__(256)
     transpose_taps_multi_kernel(const sb_transpose_desc* __restrict__ descs, int n) {
   __shared__ unsigned short tile[64][66];
