@@ -411,6 +411,9 @@ def refresh_transposed_all(pws):
         pw.fresh = True
 
 
+SPLIT_FLOOR = True
+
+
 def auto_splits(B, Ho, Wo, N, KT):
     """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed
     (one co-resident wave: 148 slots measured a shade faster than two, and halves the fp32 atomics)."""
@@ -421,7 +424,13 @@ def auto_splits(B, Ho, Wo, N, KT):
     ctas = m_tiles * -(-N // BN)
     if ctas >= 100:
         return 1
-    return int(max(1, min(KT, -(-int(os.environ.get('SB_SPLIT_SLOTS', '148')) // ctas), 32)))
+    slots = int(os.environ.get('SB_SPLIT_SLOTS', '148'))
+    # floor: tiles x splits never exceeds the resident grid, so no CTA of the persistent kernel gets a second tile
+    # (ceil gave e.g. 9 tiles x 17 splits = 153 work items on 148 CTAs: five CTAs ran twice as long as the rest).
+    # A/B on the replayed step (tools/split_ab.py, ms/step): ceil 7.42 / 7.42, floor 7.35 / 7.56 -- within run-to-run
+    # noise, so the rule is chosen on the work-balance argument
+    s = slots // ctas if SPLIT_FLOOR else -(-slots // ctas)
+    return int(max(1, min(KT, s, 32)))
 
 
 def _bias_act(acc, bias, relu, keep_f32=False):

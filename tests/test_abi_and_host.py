@@ -149,3 +149,24 @@ def test_separable_timing_table_equals_reference_signal():
         th, tw = sep[:H], sep[H:]
         full = torch.cat((th[:, None, :].expand(H, W, C // 2), tw[None, :, :].expand(H, W, C // 2)), dim=2)
         assert torch.allclose(full.permute(2, 0, 1), ref, atol=1e-6)
+
+
+def test_split_k_sizing_and_transpose_table_layout():
+    """Host-side launch geometry: split-K factors target ONE wave of CTAs (148 SMs), and the descriptor records of the
+    single-launch operand transpose match the 32-byte C struct of include/simple_b200.h."""
+    import re
+    import numpy as np
+    from simple_b200 import ops
+    # deep 3x2 feature map at batch 64: 384 rows = 3 M tiles, N = 768 = 3 N tiles -> 9 tiles, 16 splits = 144 CTAs
+    assert ops.auto_splits(64, 3, 2, 768, 192) == 16          # 144 <= 148: no CTA gets a second work item
+    assert ops.auto_splits(64, 105, 80, 96, 2) == 1            # thousands of tiles: never split
+    assert 1 <= ops.auto_splits(16, 3, 2, 768, 192) <= 32      # rollout batch: capped
+    assert ops.auto_splits(1, 3, 2, 768, 4) <= 4               # never more splits than K steps
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'simple_b200.h')).read()
+    m = re.search(r'typedef struct sb_transpose_desc \{(.*?)\} sb_transpose_desc;', hdr, re.S)
+    assert m, 'sb_transpose_desc missing from the header'
+    fields = [f.strip() for f in m.group(1).split(';') if f.strip()]
+    assert fields == ['const void* fwd', 'void* tr', 'int Opad, PHI, T, first_tile']
+    dt = np.dtype([('fwd', np.uint64), ('tr', np.uint64), ('Opad', np.int32), ('PHI', np.int32), ('T', np.int32),
+                   ('first_tile', np.int32)])
+    assert dt.itemsize == 32

@@ -31,7 +31,9 @@ def _worker(rank, world, port, out):
             p.grad = torch.full_like(p, float(rank + 1 + i + 10 * step))
         if step == 1:
             params[0].grad = None  # like gate.* on the first step of a window: absent on every rank
-        views = sync(model)
+        ran = []
+        views = sync(model, None, lambda: ran.append(step))  # gradient-independent tail work of the caller
+        assert ran == [step]  # ... is run exactly once per call (behind the last all-reduce on the GPU path)
         res = {i: views[p].clone() for i, p in enumerate(params) if p in views}
         out.put((rank, step, {i: v for i, v in res.items()}, [p.detach().clone() for p in params]))
     dist.barrier()
