@@ -126,19 +126,6 @@ __device__ __forceinline__ void ce_group(const uint4 ra, const uint4 rb, int q, 
   }
 }
 
-// target logit out of the registers of the owning lane (no dependent global load): element t of the group lives in lane
-// (t >> 3) & 15 of the half-warp, packed word ((t & 7) >> 1) + 4 * (t >> 7), low or high half by t & 1
-__device__ __forceinline__ float target_logit(const uint4 ra, const uint4 rb, int t, int lane) {
-  const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-  const int widx = ((t & 7) >> 1) + ((t >> 7) << 2);
-  uint32_t sel = w[0];
-#pragma unroll
-  for (int k = 1; k < 8; ++k) sel = (widx == k) ? w[k] : sel;
-  const uint32_t bits = (t & 1) ? (sel & 0xffff0000u) : (sel << 16);
-  const int src = (lane & 16) | ((t >> 3) & 15);
-  return __uint_as_float(__shfl_sync(0xffffffffu, bits, src));
-}
-
 // Register-staged kernel.  A warp keeps ONE colour (fixed bias-gradient columns per lane) and walks the pixels
 // wslot, wslot + nws, ...; each iteration gives two pixels to each half-warp (four independent 16-byte loads per thread
 // in flight), with the target bytes of the NEXT iteration prefetched so that no dependent load sits on the critical path.
