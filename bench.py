@@ -28,30 +28,7 @@ CE_DRAM_BYTES_B64 = 1599.7e6  # dram__bytes_read+write of one pixel_ce_kernel la
 ALG_GFLOP_PER_FRAME_TRAIN = 36.80  # conv/deconv fwd+bwd per sample (algorithmic)
 
 
-# ----------------------------------------------------------------------------------------------------------------
-# synthetic "Atari-like" replay: constant background + moving sprites from a 16-colour palette
-# ----------------------------------------------------------------------------------------------------------------
-def synth_replay(n, n_action, seed, device='cpu'):
-    g = torch.Generator().manual_seed(seed)
-    H, W = 105, 80
-    palette = torch.randint(0, 256, (16, 3), generator=g, dtype=torch.uint8)
-    frames = palette[0].view(1, 3, 1, 1).repeat(n + 4, 1, H, W)
-    pos = torch.randint(0, 60, (10, 2), generator=g)
-    vel = torch.randint(-2, 3, (10, 2), generator=g)
-    col = torch.randint(1, 16, (10,), generator=g)
-    for t in range(n + 4):
-        for s in range(10):
-            y = int((pos[s, 0] + vel[s, 0] * t) % (H - 8))
-            x = int((pos[s, 1] + vel[s, 1] * t) % (W - 8))
-            frames[t, :, y:y + 8, x:x + 8] = palette[col[s]].view(3, 1, 1)
-    obs = torch.stack([frames[t:t + 4].reshape(12, H, W) for t in range(n)])
-    new_obs = frames[4:n + 4].clone()
-    a = torch.randint(0, n_action, (n,), generator=g)
-    action = torch.nn.functional.one_hot(a, n_action).to(torch.uint8)
-    reward = torch.randint(0, 3, (n,), generator=g, dtype=torch.uint8)
-    value = torch.randn(n, generator=g)
-    return dict(obs=obs.to(device), new_obs=new_obs.to(device), action=action.to(device), reward=reward.to(device),
-                value=value.to(device))
+from simple_b200.synthetic import synth_replay  # noqa: E402  (synthetic "Atari-like" replay)
 
 
 class ClockSampler(threading.Thread):
@@ -188,10 +165,8 @@ def run_reference(args):
 # own arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_own(args):
-    # keep stdout to the single JSON line: NCCL prints its version banner there at any NCCL_DEBUG level (VERSION and up)
-    os.environ.pop('NCCL_DEBUG', None)
-    if os.environ.get('SB_NCCL_DEBUG'):
-        os.environ['NCCL_DEBUG'] = os.environ['SB_NCCL_DEBUG']
+    # stdout carries the single JSON line; NCCL's log (whatever NCCL_DEBUG level the caller chose) goes to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     import torch.distributed as dist
     from simple_b200 import _lib, profiling
     from simple_b200.next_frame_predictor import NextFramePredictor

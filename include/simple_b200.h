@@ -82,7 +82,7 @@ typedef struct {
   int tap_dx[SB_MAX_TAPS];
   float* dw;          /* fp32 [N, ldw] */
   int ldw;
-  int splits;         /* pixel-tile split factor; 0 = automatic (about two waves of CTAs) */
+  int splits;         /* pixel-tile split factor; 0 = automatic (one co-resident wave of CTAs) */
 } sb_tap_wgrad_args;
 int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
 
@@ -255,18 +255,6 @@ int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, const int* index_dev, in
                        const float* total_sumsq, float max_norm, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Latent-bit predictor (simple/next_frame_predictor.py:66-121; K11/K12).
- * sb_lstm_sample: the 16-step LSTM sampling pass in one launch (one CTA per sample, fp32):
- *   x0,h0,c0 [B,128]; LSTMCell weights w_ih,w_hh [512,128], b_ih,b_hh [512]; dense5 w5 [256,128], b5 [256];
- *   dense4 w4 [128,256], b4 [128]; noise [B,16,256] Exp(1) draws or NULL (then Philox with *seed_ptr);
- *   out: bits [B,128] in {-1,+1} (LSB first per byte), ints [B,16].
- * sb_lstm_cell_fwd/bwd: fused pointwise part of one teacher-forced LSTMCell step.
- * --------------------------------------------------------------------------------------------------------- */
-int sb_lstm_sample(const float* x0, const float* h0, const float* c0, const float* w_ih, const float* w_hh,
-                   const float* b_ih, const float* b_hh, const float* w5, const float* b5, const float* w4,
-                   const float* b4, const float* noise, const unsigned long long* seed_ptr, int B, float* bits,
-                   int* ints, sb_stream_t stream);
-/* ---------------------------------------------------------------------------------------------------------
  * MeanAttention of the posterior encoder (simple/utils.py:72-88), one CTA per sample, activations staged in shared memory.
  * x: bf16 NHWC conv output [B, HW, C]; We [4,C], be [4]: the 1x1 conv; Wd [O, 5C], bd [O]: the dense layer on
  * cat(am, m) laid out c*5+k.  The softmax follows the reference's memory reinterpretation (groups = flat index mod 4).
@@ -278,7 +266,7 @@ int sb_mean_attention_fwd(const void* x, const float* We, const float* be, const
 int sb_mean_attention_bwd(const void* x, const float* We, const float* Wd, const float* s_save, const float* dy, int B,
                           int HW, int C, int O, void* dx, float* dWe_part, float* dbe_part, sb_stream_t stream);
 
-/* Second-generation latent-bit kernels: transposed weights (whhT [128,512] = W_hh^T, w5T [128,256] = W5^T), input-gate
+/* Latent-bit predictor (simple/next_frame_predictor.py:66-121; K11/K12): transposed weights (whhT [128,512] = W_hh^T, w5T [128,256] = W5^T), input-gate
  * pre-activations by table lookup (E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh; G0 [B,512] for the first step), one
  * or two samples per CTA.  sb_lstm_teacher_fwd/bwd run all 16 teacher-forced LSTMCell steps and their backward through
  * time in one launch each: xw [B,16,512] input-gate pre-activations -> hs [B,16,128]; saved act [B,16,512], cs [B,16,128];
@@ -290,9 +278,6 @@ int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const
                         float* act, float* cs, sb_stream_t stream);
 int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, const float* c0, const float* whh, int B,
                         float* dpre, float* dh0, float* dc0, sb_stream_t stream);
-int sb_lstm_cell_fwd(const float* pre, const float* c_prev, float* act, float* c, float* h, int B, sb_stream_t stream);
-int sb_lstm_cell_bwd(const float* act, const float* c_prev, const float* c, const float* dh, const float* dc,
-                     float* dpre, float* dc_prev, int B, sb_stream_t stream);
 
 #ifdef __cplusplus
 }

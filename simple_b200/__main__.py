@@ -62,9 +62,7 @@ def main():
     config = build_parser().parse_args()
     from types import SimpleNamespace
     import os
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from bench import synth_replay
+    from .synthetic import synth_replay
     from .next_frame_predictor import NextFramePredictor
     from .policy import CnnPolicy
     from .simulated_env import Discrete, make_simulated_env

@@ -15,18 +15,34 @@ _LIB = None
 SB_MAX_TAPS = 16
 
 
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math',
+              '-Xcompiler', '-fPIC']
+
+
 def build(verbose=False, force=False):
-    """Compile every CUDA source for sm_100a into csrc/libsimple_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a into csrc/libsimple_b200.so (nvcc cross-compiles without a GPU).
+    One object file per source (compiled in parallel, only when stale), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = sorted(glob.glob(os.path.join(_CSRC, '*.cu')))
-    deps = srcs + glob.glob(os.path.join(_CSRC, '*.cuh')) + [os.path.join(_HERE, '..', 'include', 'simple_b200.h')]
-    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
-        return _SO
-    cmd = ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-           '--use_fast_math', '-shared', '-Xcompiler', '-fPIC', '-o', _SO] + srcs
-    if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-    subprocess.run(cmd, check=True, cwd=_CSRC)
+    common = glob.glob(os.path.join(_CSRC, '*.cuh')) + [os.path.join(_HERE, '..', 'include', 'simple_b200.h')]
+    newest_common = max(os.path.getmtime(d) for d in common)
+    objdir = os.path.join(_CSRC, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    jobs, objs = [], []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_common):
+            cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            jobs.append(cmd)
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            for r in ex.map(lambda c: subprocess.run(c, cwd=_CSRC, capture_output=not verbose, text=True), jobs):
+                if r.returncode != 0:
+                    raise RuntimeError('nvcc failed:\n' + (r.stderr or '') + (r.stdout or ''))
+    if jobs or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(o) for o in objs):
+        subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', _SO] + objs, check=True,
+                       cwd=_CSRC)
     return _SO
 
 
@@ -119,14 +135,11 @@ class _Sigs:
     sb_gru_blend_bwd = [_p, _p, _i, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
-    sb_lstm_sample = [_p] * 13 + [_i, _p, _p, _p]
-    sb_lstm_cell_fwd = [_p, _p, _p, _p, _p, _i, _p]
     sb_mean_attention_fwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_mean_attention_bwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_lstm_sample2 = [_p] * 9 + [_i, _p, _p, _p]
     sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
     sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
-    sb_lstm_cell_bwd = [_p, _p, _p, _p, _p, _p, _p, _i, _p]
     sb_grad_sumsq = [_p, _p, _p, _i, _p, _p]
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]

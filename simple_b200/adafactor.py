@@ -129,7 +129,7 @@ class Adafactor(torch.optim.Optimizer):
             st['RMS'] = _LazyRMS(acc, i, p.numel())
         self._launch(rec, n, max_grad_norm)
         from .ops import refresh_transposed_all
-        refresh_transposed_all([pw for _, _, pw in active])  # `fwd` was rewritten: re-derive the per-tap transposes
+        refresh_transposed_all([pw for _, _, pw in active], rec)  # `fwd` was rewritten: re-derive the per-tap transposes
         self.last_key = key
         return loss
 

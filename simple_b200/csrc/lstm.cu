@@ -1,12 +1,12 @@
 // Latent-bit predictor kernels -- K11/K12 of SURVEY 2.3 (simple/next_frame_predictor.py:66-121).
 //
-//  * sb_lstm_sample: the whole 16-step autoregressive sampling pass of BitsPredictor.forward (:109-121) in ONE launch:
+//  * sb_lstm_sample2: the whole 16-step autoregressive sampling pass of BitsPredictor.forward (:109-121) in ONE launch:
 //    LSTMCell(128) -> Linear 128->256 -> multinomial(exp(logits)) -> one-hot -> Linear 256->128, then ints -> bits
-//    (LSB first, simple/utils.py:115-119) -> {-1,+1}.  One CTA per sample, fp32, state in shared memory; the reference
-//    issues ~20 ATen kernels per step (320 per forward).  multinomial(w, 1) == argmax(w / q), q ~ Exp(1)
-//    (ATen's implementation for one sample): q is either supplied (parity mode) or drawn in-kernel with Philox.
-//  * sb_lstm_cell_fwd / _bwd: fused pointwise part of one teacher-forced LSTMCell step (:97-100) and its backward; the
-//    two GEMMs per step stay plain library calls on [B,128] x [128,512].
+//    (LSB first, simple/utils.py:115-119) -> {-1,+1}; fp32, state in shared memory; the reference issues ~20 ATen
+//    kernels per step (320 per forward).  multinomial(w, 1) == argmax(w / q), q ~ Exp(1) (ATen's implementation for one
+//    sample): q is either supplied (parity mode) or drawn in-kernel with Philox.
+//  * sb_lstm_teacher_fwd / _bwd: all 16 teacher-forced LSTMCell steps (:97-100) and their backward through time, one
+//    launch each.
 #include "common.cuh"
 #include "../../include/simple_b200.h"
 
@@ -30,106 +30,6 @@ __device__ __forceinline__ float tanh_acc(float x) {
 __device__ __forceinline__ float row_dot(const float* __restrict__ w_row, const float4 v, int lane) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(w_row) + lane);
   return a.x * v.x + a.y * v.y + a.z * v.z + a.w * v.w;
-}
-
-__global__ void __launch_bounds__(512)
-    lstm_sample_kernel(const float* __restrict__ x0, const float* __restrict__ h0, const float* __restrict__ c0,
-                       const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                       const float* __restrict__ b_hh, const float* __restrict__ w5, const float* __restrict__ b5,
-                       const float* __restrict__ w4, const float* __restrict__ b4, const float* __restrict__ noise,
-                       const unsigned long long* seed_ptr, float* __restrict__ bits, int* __restrict__ ints) {
-  __shared__ __align__(16) float x[kH], h[kH];
-  __shared__ float c[kH], gates[4 * kH], score[kV];
-  __shared__ int sym[kSteps];
-  __shared__ float red_v[8];
-  __shared__ int red_i[8];
-  const int b = blockIdx.x, t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;  // 16 warps
-  if (t < kH) {
-    x[t] = x0[b * kH + t];
-    h[t] = h0[b * kH + t];
-    c[t] = c0[b * kH + t];
-  }
-  __syncthreads();
-  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
-  for (int step = 0; step < kSteps; ++step) {
-    // gates = W_ih x + b_ih + W_hh h + b_hh   (PyTorch LSTMCell order: i, f, g, o); warp w owns rows 32w .. 32w+31
-    {
-      const float4 xv = reinterpret_cast<const float4*>(x)[lane];
-      const float4 hv = reinterpret_cast<const float4*>(h)[lane];
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int row = warp * 32 + r;
-        float s = row_dot(w_ih + (size_t)row * kH, xv, lane) + row_dot(w_hh + (size_t)row * kH, hv, lane);
-        s = warp_sum(s);
-        if (lane == 0) gates[row] = s + b_ih[row] + b_hh[row];
-      }
-    }
-    __syncthreads();
-    if (t < kH) {
-      const float ig = sigmoidf_(gates[t]), fg = sigmoidf_(gates[kH + t]);
-      const float gg = tanh_acc(gates[2 * kH + t]), og = sigmoidf_(gates[3 * kH + t]);
-      const float cn = fg * c[t] + ig * gg;
-      c[t] = cn;
-      h[t] = og * tanh_acc(cn);
-    }
-    __syncthreads();
-    {
-      const float4 hv = reinterpret_cast<const float4*>(h)[lane];
-#pragma unroll 8
-      for (int r = 0; r < 16; ++r) {  // 256 logits: warp w owns rows 16w .. 16w+15
-        const int row = warp * 16 + r;
-        float s = warp_sum(row_dot(w5 + (size_t)row * kH, hv, lane));
-        if (lane == 0) {
-          const float logit = s + b5[row];
-          float q;
-          if (noise) {
-            q = noise[((size_t)b * kSteps + step) * kV + row];
-          } else {
-            const uint4 rr = philox4x32(make_uint4((uint32_t)row, (uint32_t)step, (uint32_t)b, 0x4c53544du),
-                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            q = -logf(((float)(rr.x >> 8) + 0.5f) * (1.0f / 16777216.0f));
-          }
-          score[row] = expf(logit) / q;  // sample_with_temperature(T=1): multinomial(exp(logits))
-        }
-      }
-    }
-    __syncthreads();
-    // argmax over 256 scores, first index on ties
-    if (t < kV) {
-      float v = score[t];
-      int i = t;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        if (ov > v || (ov == v && oi < i)) {
-          v = ov;
-          i = oi;
-        }
-      }
-      if ((t & 31) == 0) {
-        red_v[t >> 5] = v;
-        red_i[t >> 5] = i;
-      }
-    }
-    __syncthreads();
-    if (t == 0) {
-      float v = red_v[0];
-      int i = red_i[0];
-      for (int wv = 1; wv < 8; ++wv)
-        if (red_v[wv] > v || (red_v[wv] == v && red_i[wv] < i)) {
-          v = red_v[wv];
-          i = red_i[wv];
-        }
-      sym[step] = i;
-    }
-    __syncthreads();
-    if (t < kH) x[t] = w4[(size_t)t * kV + sym[step]] + b4[t];  // dense4(one_hot(s)) = W4[:, s] + b4
-    __syncthreads();
-  }
-  if (t < kSteps) ints[b * kSteps + t] = sym[t];
-  if (t < kSteps * 8) bits[(size_t)b * (kSteps * 8) + t] = ((sym[t >> 3] >> (t & 7)) & 1) ? 1.0f : -1.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -314,42 +214,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
   }
 }
 
-// pre [B,4H] (i|f|g|o pre-activations), c_prev [B,H] -> act [B,4H] (post-activation gates, saved), c, h [B,H]
-__global__ void __launch_bounds__(256)
-    lstm_cell_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ c_prev, float* __restrict__ act,
-                         float* __restrict__ c, float* __restrict__ h, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * kH) return;
-  const int b = i / kH, j = i - b * kH;
-  const float* p = pre + (size_t)b * 4 * kH;
-  const float ig = sigmoidf_(p[j]), fg = sigmoidf_(p[kH + j]), gg = tanh_acc(p[2 * kH + j]), og = sigmoidf_(p[3 * kH + j]);
-  const float cn = fg * c_prev[i] + ig * gg;
-  float* a = act + (size_t)b * 4 * kH;
-  a[j] = ig; a[kH + j] = fg; a[2 * kH + j] = gg; a[3 * kH + j] = og;
-  c[i] = cn;
-  h[i] = og * tanh_acc(cn);
-}
-
-__global__ void __launch_bounds__(256)
-    lstm_cell_bwd_kernel(const float* __restrict__ act, const float* __restrict__ c_prev, const float* __restrict__ c,
-                         const float* __restrict__ dh, const float* __restrict__ dc, float* __restrict__ dpre,
-                         float* __restrict__ dc_prev, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * kH) return;
-  const int b = i / kH, j = i - b * kH;
-  const float* a = act + (size_t)b * 4 * kH;
-  const float ig = a[j], fg = a[kH + j], gg = a[2 * kH + j], og = a[3 * kH + j];
-  const float tc = tanh_acc(c[i]);
-  const float dhi = dh ? dh[i] : 0.f;
-  const float dct = (dc ? dc[i] : 0.f) + dhi * og * (1.0f - tc * tc);
-  float* d = dpre + (size_t)b * 4 * kH;
-  d[j] = dct * gg * ig * (1.0f - ig);
-  d[kH + j] = dct * c_prev[i] * fg * (1.0f - fg);
-  d[2 * kH + j] = dct * ig * (1.0f - gg * gg);
-  d[3 * kH + j] = dhi * tc * og * (1.0f - og);
-  dc_prev[i] = dct * fg;
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // Cluster versions of the teacher-forced pass and its backward through time (same split as lstm_sample3_kernel: CTA r
 // of the pair owns hidden units [64r, 64r+64) and keeps the 256 matching rows of W_hh resident in shared memory).
@@ -499,37 +363,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
 }  // namespace sb
 
 using namespace sb;
-
-extern "C" int sb_lstm_sample(const float* x0, const float* h0, const float* c0, const float* w_ih, const float* w_hh,
-                              const float* b_ih, const float* b_hh, const float* w5, const float* b5, const float* w4,
-                              const float* b4, const float* noise, const unsigned long long* seed_ptr, int B,
-                              float* bits, int* ints, sb_stream_t stream) {
-  if (!x0 || !h0 || !c0 || !w_ih || !w_hh || !b_ih || !b_hh || !w5 || !b5 || !w4 || !b4 || !bits || !ints || B < 1)
-    return SB_ERR_ARG;
-  lstm_sample_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(x0, h0, c0, w_ih, w_hh, b_ih, b_hh, w5, b5, w4, b4, noise,
-                                                          seed_ptr, bits, ints);
-  ++g_launches;
-  SB_CHECK_LAUNCH();
-  return SB_OK;
-}
-
-extern "C" int sb_lstm_cell_fwd(const float* pre, const float* c_prev, float* act, float* c, float* h, int B,
-                                sb_stream_t stream) {
-  if (!pre || !c_prev || !act || !c || !h || B < 1) return SB_ERR_ARG;
-  lstm_cell_fwd_kernel<<<(B * kH + 255) / 256, 256, 0, (cudaStream_t)stream>>>(pre, c_prev, act, c, h, B);
-  ++g_launches;
-  SB_CHECK_LAUNCH();
-  return SB_OK;
-}
-
-extern "C" int sb_lstm_cell_bwd(const float* act, const float* c_prev, const float* c, const float* dh, const float* dc,
-                                float* dpre, float* dc_prev, int B, sb_stream_t stream) {
-  if (!act || !c_prev || !c || !dpre || !dc_prev || B < 1) return SB_ERR_ARG;
-  lstm_cell_bwd_kernel<<<(B * kH + 255) / 256, 256, 0, (cudaStream_t)stream>>>(act, c_prev, c, dh, dc, dpre, dc_prev, B);
-  ++g_launches;
-  SB_CHECK_LAUNCH();
-  return SB_OK;
-}
 
 template <int S>
 static int launch_sample3(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,

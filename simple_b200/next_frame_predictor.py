@@ -94,6 +94,10 @@ class BitsPredictor(nn.Module):  # :66-121
         self._sampler_tables = None
         self.cache_sampler_tables = False  # set while the weights are known to be static (NextFramePredictor.repack)
 
+    def refresh_sampler_tables(self):
+        """(Re)compute the sampling kernel's weight-only operands INTO the persistent table tensors (same addresses)."""
+        self._sampler_tables = ops.lstm_sampler_tables(self.lstm, self.dense5, self.dense4, out=self._sampler_tables)
+
     def project(self, x):
         """dense1..3 share their input: one [B,4608] x [4608,384] GEMM instead of three -> (first_input, h0, c0).
         The training forward calls the predictor twice on the same input (teacher pass, sampling pass): project once."""
@@ -115,7 +119,7 @@ class BitsPredictor(nn.Module):  # :66-121
             emb = emb * (rand.keep_mask(emb.shape, 0.1) / 0.9)
             tin = torch.cat((first.unsqueeze(1), emb), dim=1)[:, :n]
             # teacher forcing: every LSTM input is known up front, so the input half of the gates is ONE GEMM over
-            # all 16 steps; only the recurrent half stays sequential, with the pointwise cell fused (sb_lstm_cell_*)
+            # all 16 steps; only the recurrent half stays sequential, in one launch (sb_lstm_teacher_fwd)
             xw = F.linear(tin, self.lstm.weight_ih, self.lstm.bias_ih + self.lstm.bias_hh)  # [B,16,512]
             outs = ops.LstmTeacher.apply(xw, h, c, self.lstm.weight_hh)  # one launch for the 16 recurrent steps
             outs = outs * (rand.keep_mask(outs.shape, 0.1) / 0.9)
@@ -124,11 +128,12 @@ class BitsPredictor(nn.Module):  # :66-121
             return pred, loss / self.config.rollout_length
         # sampling: integer outputs, nothing to differentiate -> one persistent kernel for all 16 steps
         noise = rand.sample_noise(B, n) if hasattr(rand, 'sample_noise') else None
-        tables = self._sampler_tables  # weight-only operands, cached while the weights are static (rollouts)
-        if tables is None:
+        # weight-only operands.  While the weights are static (rollouts) they live in PERSISTENT tensors that
+        # `refresh_sampler_tables` rewrites in place: a captured rollout graph keeps reading valid, current memory
+        if self.cache_sampler_tables and self._sampler_tables is not None:
+            tables = self._sampler_tables
+        else:
             tables = ops.lstm_sampler_tables(self.lstm, self.dense5, self.dense4)
-            if self.cache_sampler_tables:
-                self._sampler_tables = tables
         bits, _ = ops.lstm_sample(first, h, c, self.lstm, self.dense5, self.dense4, noise=noise,
                                   seed=getattr(rand, 'seed', None) if noise is None else None, tables=tables)
         return bits, 0.0
@@ -320,10 +325,16 @@ class NextFramePredictor(nn.Module):
         # new state in `_pending` and `commit_state()` copies it in (after the backward pass, which still needs the old
         # gate operand).  A forward auto-commits a pending state first, so plain `model(x, a)` loops behave like the
         # reference.
+        # One buffer set PER BATCH SIZE, never freed (`_bufs`): CUDA graphs captured for the trainer (B = batch_size) and
+        # for the simulated env (B = agents) both keep valid addresses when the two alternate on one model.
+        self._bufs = {}           # B -> dict(state, xs_prev, xs_buf, ps)
         self._state = None        # fp32 [B,H,W,64] recurrent state (detached)
-        self._xs_prev = None      # bf16 [B,H,W,128]: previous step's (state | x_start | 0) operand of the gate conv
-        self._xs_buf = None       # bf16 [B,H,W,128]: this step's operand (persistent: the zero padding is written once)
+        self._xs_prev = None      # bf16 [B,H,W,80]: previous step's (state | x_start | 0) operand of the gate conv
+        self._xs_buf = None       # bf16 [B,H,W,80]: this step's operand (persistent: the zero padding is written once)
         self._ps_buf = None       # bf16 [B,H,W,64]: posterior input (x_start 12 | target 3 | zero pad)
+        # bumped whenever memory that a captured graph may have baked in is re-allocated (device move, operand rebuild):
+        # StepRunner / SimulatedVecEnv compare it with the value they captured under and re-capture on mismatch
+        self._generation = 0
         self._has_prev = False
         self._pending = None
         self._seed_dev = None
@@ -337,14 +348,27 @@ class NextFramePredictor(nn.Module):
     def init_internal_states(self, batch_size):
         dev = self.logits.weight.device
         H, W = self.config.frame_shape[1:]
-        if self._state is not None and self._state.shape[0] == batch_size and self._state.device == dev:
-            self._state.zero_()  # keep the buffers (and their addresses)
+        bufs = self._bufs.get(batch_size)
+        if bufs is None or bufs['state'].device != dev:
+            bufs = self._bufs[batch_size] = dict(
+                state=torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev),
+                xs_prev=torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16),
+                xs_buf=torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16),
+                ps=torch.zeros(batch_size, H, W, 64, device=dev, dtype=torch.bfloat16))  # channels 15..63 stay zero
         else:
-            self._state = torch.zeros(batch_size, H, W, self.config.recurrent_state_size, device=dev)
-            self._xs_prev = torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16)
-            self._xs_buf = torch.zeros(batch_size, H, W, XS_C, device=dev, dtype=torch.bfloat16)
+            bufs['state'].zero_()  # keep the buffers (and their addresses)
+        self._state, self._xs_prev, self._xs_buf, self._ps_buf = (bufs['state'], bufs['xs_prev'], bufs['xs_buf'],
+                                                                  bufs['ps'])
         self._has_prev = False
         self._pending = None
+
+    def capture_key(self):
+        """Identity of every buffer a captured CUDA graph of this model bakes in.  A holder of such a graph compares the
+        key it captured under with the current one and re-captures on mismatch (stale-graph hazards)."""
+        t = self.stochastic_model.bits_predictor._sampler_tables
+        ptr = lambda x: None if x is None else x.data_ptr()
+        return (self._generation, ptr(self._state), ptr(self._xs_prev), ptr(self._xs_buf), ptr(self._ps_buf),
+                ptr(self._seed_dev), None if t is None else t['E'].data_ptr())
 
     def commit_state(self):
         """Make the state computed by the last forward current (next_frame_predictor.py:303,312 of the reference)."""
@@ -366,13 +390,25 @@ class NextFramePredictor(nn.Module):
 
     def load_state_dict(self, *a, **kw):
         r = super().load_state_dict(*a, **kw)
-        self._packed = None
+        # same shapes, new values: re-pack INTO the existing bf16 operands / sampler tables (addresses survive, so
+        # captured graphs stay valid)
+        if self._packed is not None and self.logits.weight.is_cuda:
+            for pw in self._packed.values():
+                pw.fresh = False
+            bp = self.stochastic_model.bits_predictor
+            self.repack(static=bp.cache_sampler_tables)
         return r
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)
+        # device / dtype move: every derived buffer is rebuilt at new addresses
         self._packed = None
         self._plan = None
+        self._bufs = {}
+        self._state = self._xs_prev = self._xs_buf = self._ps_buf = None
+        self._has_prev, self._pending, self._seed_dev = False, None, None
+        self.stochastic_model.bits_predictor._sampler_tables = None
+        self._generation += 1
         return r
 
     # ------------------------------------------------------------------ static plan (layouts, specs, timing tables)
@@ -488,10 +524,12 @@ class NextFramePredictor(nn.Module):
     def repack(self, names=None, static=False):
         """Refresh the bf16 GEMM operands from the fp32 master weights (after an optimiser step / load)."""
         bp = self.stochastic_model.bits_predictor
-        bp._sampler_tables = None
         bp.cache_sampler_tables = bool(static)  # static=True: the caller promises frozen weights until the next repack
+        if static:
+            bp.refresh_sampler_tables()
         if self._packed is None:
             self._packed = self._build_packed()
+            self._generation += 1
             return
         mods = self._weights()
         for k in (names or self._packed.keys()):
@@ -544,7 +582,7 @@ class NextFramePredictor(nn.Module):
             return rand.big_keep_mask(spec_shape_nchw, p)
 
         # ---- standardise + recurrent state (K5, K6)
-        if self._state is None or self._state.shape[0] != B:
+        if self._state is None or self._state.shape[0] != B or self._state.device != dev:
             self.init_internal_states(B)
         # XS = [state 64 | x_start 12 | zero pad to 80] lives in a persistent buffer whose padding is zeroed once (a fresh
         # torch.zeros of 137 MB per step was pure fill traffic); a detached alias keeps this step's autograd graph off it
@@ -579,9 +617,7 @@ class NextFramePredictor(nn.Module):
         sc0, sh0 = inj[0]
         h = h * sc0[:, :, None, None] + sh0[:, :, None, None]
         if target is not None:
-            if self._ps_buf is None or self._ps_buf.shape[0] != B or self._ps_buf.device != dev:
-                self._ps_buf = torch.zeros(B, H, W, 64, device=dev, dtype=torch.bfloat16)  # channels 15..63 stay zero
-            ps = self._ps_buf.detach()
+            ps = self._ps_buf.detach()  # persistent per batch size (init_internal_states); channels 15..63 stay zero
             ops.standardize(target, dst=ps, coff=12, out_f32=target)  # in place, like the reference (:332-334)
         sm = self.stochastic_model
         if training:
@@ -678,6 +714,7 @@ class NextFramePredictor(nn.Module):
             self._plan = self._build_plan(dev)
         if self._packed is None:
             self._packed = self._build_packed()
+            self._generation += 1
         elif self._auto_repack:
             self.repack()
         self._weights_cache = self._weights()

@@ -1,7 +1,7 @@
 """Host-side operators of the world-model hot path: thin autograd wrappers over the C-ABI CUDA kernels.
 
-Every function here launches hand-written sm_100a kernels through `simple_b200._lib`; nothing falls back to ATen for
-the arithmetic (torch is used for allocation, streams and the autograd tape only).
+Every operator here launches hand-written sm_100a kernels through `simple_b200._lib` and raises if the library is
+missing (no CPU / ATen fallback for the kernels).  torch supplies allocation, streams and the autograd tape.
 """
 import ctypes
 import os
@@ -381,17 +381,17 @@ class TapConv(torch.autograd.Function):
         return None, da, dweight, dbias, None
 
 
-_TRANSPOSE_TABLES = {}
-
-
-def refresh_transposed_all(pws):
+def refresh_transposed_all(pws, cache):
     """`fwd` of every PackedWeight in `pws` was rewritten by the optimiser: re-derive all `tr` operands in ONE launch.
-    The descriptor table holds static device pointers and is built once per set of layers."""
+    The descriptor table holds device pointers; it lives in `cache` (a dict owned by the caller, e.g. the optimiser's
+    per-parameter-set record) and is rebuilt when any operand address changed, so nothing outlives its owner."""
     pws = [pw for pw in pws if pw is not None]
     if not pws:
         return
-    key = tuple(id(pw) for pw in pws)
-    rec = _TRANSPOSE_TABLES.get(key)
+    key = tuple((pw.fwd.data_ptr(), pw.tr.data_ptr()) for pw in pws)
+    rec = cache.get('transpose_table')
+    if rec is not None and rec[0] != key:
+        rec = None
     if rec is None:
         import numpy as np
         dt = np.dtype([('fwd', np.uint64), ('tr', np.uint64), ('Opad', np.int32), ('PHI', np.int32), ('T', np.int32),
@@ -404,8 +404,8 @@ def refresh_transposed_all(pws):
             tab[i] = (pw.fwd.data_ptr(), pw.tr.data_ptr(), pw.Opad, phi, pw.T, first)
             first += -(-phi // 64) * -(-pw.Opad // 64) * pw.T
         dev = torch.from_numpy(tab.view(np.uint8).copy()).to(pws[0].fwd.device)
-        rec = _TRANSPOSE_TABLES[key] = (dev, len(pws), first, pws)  # (keeps the PackedWeights alive: ids stay unique)
-    dev, n, total, _ = rec
+        rec = cache['transpose_table'] = (key, dev, len(pws), first)
+    _, dev, n, total = rec
     _lib.check(_lib.lib().sb_transpose_taps_multi(dev.data_ptr(), n, total, _lib.stream_ptr()), 'sb_transpose_taps_multi')
     for pw in pws:
         pw.fresh = True
@@ -593,15 +593,22 @@ def mean_attention(x_nhwc_bf16, module):
                                  module.dense.weight, module.dense.bias)
 
 
-def lstm_sampler_tables(lstm, dense5, dense4):
+def lstm_sampler_tables(lstm, dense5, dense4, out=None):
     """Weight-only operands of the sampling kernel (refresh whenever the weights change):
-    whhT [128,512], w5T [128,256], E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh, bias = b_ih + b_hh."""
+    whhT [128,512], w5T [128,256], E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh, bias = b_ih + b_hh,
+    wihT [128,512] = W_ih^T (first-step input gates).  `out`: a dict returned earlier -- rewritten IN PLACE (same device
+    addresses: a captured rollout graph keeps reading current values)."""
     with torch.no_grad():
         bias = (lstm.bias_ih + lstm.bias_hh).float()
         emb = dense4.weight.t().float() + dense4.bias.float()  # [256,128]: dense4(one_hot(s)) for every symbol s
-        return dict(whhT=lstm.weight_hh.t().contiguous().float(), w5T=dense5.weight.t().contiguous().float(),
-                    E=torch.addmm(bias, emb, lstm.weight_ih.t().float()).contiguous(), bias=bias,
-                    b5=dense5.bias.detach().float().contiguous())
+        new = dict(whhT=lstm.weight_hh.t().contiguous().float(), w5T=dense5.weight.t().contiguous().float(),
+                   E=torch.addmm(bias, emb, lstm.weight_ih.t().float()).contiguous(), bias=bias,
+                   b5=dense5.bias.detach().float().contiguous(), wihT=lstm.weight_ih.t().contiguous().float())
+        if out is None or any(out[k].device != v.device for k, v in new.items()):
+            return new
+        for k, v in new.items():
+            out[k].copy_(v)
+        return out
 
 
 def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None, tables=None):
@@ -611,7 +618,7 @@ def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None, tables=
     f = lambda t: t.detach().float().contiguous()
     tb = tables if tables is not None else lstm_sampler_tables(lstm, dense5, dense4)
     with torch.no_grad():
-        G0 = torch.addmm(tb['bias'], f(x0), lstm.weight_ih.t().float())  # [B,512]
+        G0 = torch.addmm(tb['bias'], f(x0), tb['wihT'])  # [B,512]
     h0, c0 = f(h0), f(c0)
     bits = torch.empty(B, 128, device=x0.device, dtype=torch.float32)
     ints = torch.empty(B, 16, device=x0.device, dtype=torch.int32)
@@ -656,32 +663,3 @@ class LstmTeacher(torch.autograd.Function):
         h_prev = torch.cat((h0.unsqueeze(1), hs[:, :-1]), dim=1).reshape(-1, 128)
         dw_hh = dpre.reshape(-1, 512).t() @ h_prev  # [512,128]
         return dpre, dh0, dc0, dw_hh
-
-
-class LstmCell(torch.autograd.Function):
-    """Pointwise part of nn.LSTMCell: (pre-activations [B,512], c_prev [B,128]) -> (h, c)."""
-
-    @staticmethod
-    def forward(ctx, pre, c_prev):
-        B = pre.shape[0]
-        pre, c_prev = pre.contiguous(), c_prev.contiguous()
-        act = torch.empty_like(pre)
-        c = torch.empty_like(c_prev)
-        h = torch.empty_like(c_prev)
-        _lib.check(_lib.lib().sb_lstm_cell_fwd(pre.data_ptr(), c_prev.data_ptr(), act.data_ptr(), c.data_ptr(),
-                                               h.data_ptr(), B, _lib.stream_ptr()), 'sb_lstm_cell_fwd')
-        ctx.save_for_backward(act, c_prev, c)
-        return h, c
-
-    @staticmethod
-    def backward(ctx, dh, dc):
-        act, c_prev, c = ctx.saved_tensors
-        B = act.shape[0]
-        dh = dh.contiguous() if dh is not None else None
-        dc = dc.contiguous() if dc is not None else None
-        dpre = torch.empty_like(act)
-        dc_prev = torch.empty_like(c)
-        _lib.check(_lib.lib().sb_lstm_cell_bwd(act.data_ptr(), c_prev.data_ptr(), c.data_ptr(), _ptr(dh), _ptr(dc),
-                                               dpre.data_ptr(), dc_prev.data_ptr(), B, _lib.stream_ptr()),
-                   'sb_lstm_cell_bwd')
-        return dpre, dc_prev

@@ -144,6 +144,7 @@ class SimulatedVecEnv:
         self._rew = torch.zeros(A, device=dev)
         self._val = torch.zeros(A, device=dev)
         self._graph = None
+        self._graph_key = None
         self._warm = 0
         self._policy = None
 
@@ -174,6 +175,8 @@ class SimulatedVecEnv:
         model._auto_repack = False
         try:
             first = not model._has_prev
+            if self._graph is not None and self._graph_key != model.capture_key():
+                self._graph, self._warm = None, 0  # a buffer the graph baked in was re-allocated: capture again
             if first or not self.use_graph:
                 self._core()
             elif self._graph is None and self._warm < 2:
@@ -184,7 +187,7 @@ class SimulatedVecEnv:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._core()
-                self._graph = g
+                self._graph, self._graph_key = g, model.capture_key()
                 g.replay()
             else:
                 self._graph.replay()

@@ -77,8 +77,10 @@ class Trainer:
         self.config = config
         self.logger = None
         if self.config.use_wandb:
-            from atari_utils.logger import WandBLogger  # optional dependency of the reference
-            self.logger = WandBLogger()
+            # The reference logs through its own atari_utils.logger (out of scope here): any object with `.log(dict)` can
+            # be assigned to `trainer.logger`; nothing of the reference is imported by this package.
+            raise ValueError('simple_b200.Trainer: use_wandb is not supported; assign an object with .log(dict) to '
+                             'trainer.logger instead')
         self.optimizer = Adafactor(self.model.parameters())
         self.model_step = 1
         self.reward_step = 1
@@ -147,7 +149,10 @@ class Trainer:
                     st[k].copy_(saved[k].to(dev))
         self.model_step, self.reward_step = ck['model_step'], ck['reward_step']
         if ck.get('dropout_seed') is not None:
-            self.model._seed_dev = torch.full((1,), ck['dropout_seed'], dtype=torch.int64, device=dev)
+            if self.model._seed_dev is not None and self.model._seed_dev.device == dev:
+                self.model._seed_dev.fill_(ck['dropout_seed'])  # in place: captured graphs read this address
+            else:
+                self.model._seed_dev = torch.full((1,), ck['dropout_seed'], dtype=torch.int64, device=dev)
         torch.set_rng_state(ck['torch_rng'])
         torch.cuda.set_rng_state(ck['cuda_rng'], dev)
         self._runner = None  # captured graphs refer to the old optimiser records
@@ -262,6 +267,7 @@ class StepRunner:
                         reward=torch.zeros(B, dtype=torch.long, device=dev), value=torch.zeros(B, device=dev))
         self.graph = None
         self.graph_key = None
+        self.model_key = None
         self.graph_kernels = 0  # kernels of this library recorded in the captured step
         self.replays = 0
         self.warm = 0
@@ -307,6 +313,9 @@ class StepRunner:
 
     def step(self):
         opt = self.trainer.optimizer
+        model = self.trainer.model
+        if self.graph is not None and self.model_key != model.capture_key():
+            self.graph, self.warm = None, 0  # a buffer the graph baked in was re-allocated: capture again
         if self.j == 0 or not self.use_graph:
             self._body()
         elif self.graph is None and self.warm < 2:
@@ -324,7 +333,7 @@ class StepRunner:
             with torch.cuda.graph(g):
                 self._body()
             self.graph_kernels = int(_lib.lib().sb_launch_count() - l0)
-            self.graph, self.graph_key = g, opt.last_key
+            self.graph, self.graph_key, self.model_key = g, opt.last_key, model.capture_key()
             g.replay()  # capture only records: run the step that was just captured
             self.replays += 1
             if os.environ.get('SB_BENCH_DEBUG'):
