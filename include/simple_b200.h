@@ -210,10 +210,15 @@ int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s
  * decay_rate=-0.8, relative_step, scale_parameter, no momentum, no weight decay).
  * Replaces: simple/trainer.py:148 and simple/adafactor.py:113-212 (K16, K17).
  * Descriptors and block maps live in DEVICE memory (built by the host wrapper each step; one small H2D copy).
- *   sb_grad_sumsq:      block_map[i] = (tensor, first 4096-element chunk); *total += sum g^2  (caller zeroes total)
+ *   sb_grad_sumsq:      block_map[i] = (tensor, first 4096-element chunk); *total = sum g^2.  scratch: caller-owned fp32
+ *                       [1 + SB_SUMSQ_MAX_CTAS], zeroed ONCE (word 0 is a ticket counter the kernel resets itself).
  *   sb_adafactor_conv:  4-D weights (O,I,KH,KW) of one kernel size; block_map[i] = (descriptor index, first patch), 128 patches
- *                       per block; pass 1 updates row/col states and acc[0]=sum u^2, acc[1]=sum p^2 (caller zeroes
- *                       acc), pass 2 applies the update.  g is scaled by min(1, max_norm/(sqrt(total)+1e-6)).
+ *                       per block, the blocks of one tensor consecutive; pass 1 updates row/col states and writes
+ *                       acc[0]=sum u^2, acc[1]=sum p^2, pass 2 applies the update.  g is scaled by
+ *                       min(1, max_norm/(sqrt(total)+1e-6)).  scratch (pass 1): caller-owned fp32 [ntensors + 2*nblocks],
+ *                       its first ntensors words (ticket counters, reset by the kernel) zeroed ONCE.
+ *   All cross-CTA sums above are ORDER-DETERMINISTIC (per-CTA partials, added in index order by the last arriver):
+ *   data-parallel replicas that see the same reduced gradient apply bit-identical updates.
  *   sb_adafactor_small: 1-D (cols==0, state in `row`) and 2-D tensors, one CTA per descriptor.
  *   sb_adafactor_big2d: large 2-D tensors, one thread-block cluster of 8 CTAs per descriptor (row bands; column sums
  *                       and RMS partials combined through distributed shared memory).
@@ -241,13 +246,15 @@ typedef struct {
 /* step counters += 1 for every descriptor (first call of a step; keeps CUDA-graph replays self-contained) */
 int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, sb_stream_t stream);
 /* glen_dev: optional per-descriptor gradient length (a packed gradient buffer is longer than its parameter) */
+#define SB_SUMSQ_MAX_CTAS (148 * 8)
 int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev, int nblocks,
-                  float* total, sb_stream_t stream);
+                  float* total, float* scratch, sb_stream_t stream);
 int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
-                      const float* total_sumsq, float max_norm, int pass, sb_stream_t stream);
+                      const float* total_sumsq, float max_norm, int pass, float* scratch, int ntensors,
+                      sb_stream_t stream);
 int sb_adafactor_conv_packed(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev, const int* block_map_dev,
                              int nblocks, int KH, int KW, const float* total_sumsq, float max_norm, int pass,
-                             sb_stream_t stream);
+                             float* scratch, int ntensors, sb_stream_t stream);
 /* index_dev: optional list of descriptor indices handled by this launch (NULL = descriptors 0..ntensors-1) */
 int sb_adafactor_small(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors, int max_rows_plus_cols,
                        const float* total_sumsq, float max_norm, sb_stream_t stream);

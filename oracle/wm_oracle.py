@@ -11,6 +11,14 @@ this restatement is pinned against the reference itself, imported live from
 the fixtures under `tests/golden/`.  `tests/test_oracle_golden.py` re-checks the oracle
 against those fixtures wherever the tests run.
 
+Strict-validation mode (`cfg.emulate_bf16 = True`, see `bf16_config`): the same restatement, but rounded to bf16
+at exactly the points where the CUDA path stores bf16 (GEMM operands and outputs, the skip tensors, the outputs of
+the fused elementwise stages; DESIGN.md section 5 lists them) with fp32 everywhere the CUDA path keeps fp32 (tiny
+deep-layer outputs, statistics, the latent path).  It is still a CPU fp32 computation -- what remains different from
+the GPU is summation order and intrinsic precision -- so discrete decisions (posterior signs, sampled latent symbols,
+arg-max frames) can be compared END TO END instead of stage by stage.  With the flag absent / False every function
+below is the pinned fp32 restatement, bit-identical to the reference.
+
 All randomness is explicit: every function takes a `rand` object (see `GlobalRand`,
 `ReplayRand`).  `GlobalRand` draws from the torch / numpy global generators with exactly
 the primitive calls and in exactly the order the reference uses, so with equal seeds the
@@ -45,6 +53,33 @@ def default_config(**overrides):
     )
     cfg.update(overrides)
     return SimpleNamespace(**cfg)
+
+
+def bf16_config(**overrides):
+    """default_config with the bf16-emulation (strict validation) mode switched on."""
+    return default_config(emulate_bf16=True, **overrides)
+
+
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 (nearest even) and back; straight-through gradient (the CUDA path rounds gradients too, but
+    unbiasedly: the oracle keeps them in fp32)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _emul(cfg):
+    return bool(getattr(cfg, 'emulate_bf16', False))
+
+
+def _q(cfg, x):
+    """A point where the CUDA path stores bf16 (identity in the pinned fp32 mode)."""
+    return _RoundBF16.apply(x) if _emul(cfg) else x
 
 
 # ----------------------------------------------------------------------------------
@@ -180,7 +215,13 @@ def int_to_bit(ints, nbits=8):
     return torch.cat([torch.remainder(x // 2 ** i, 2) for i in range(nbits)], -1).float()
 
 
-def instance_norm(x, w, b, eps=1e-6):
+def instance_norm(x, w, b, eps=1e-6, cfg=None):
+    if cfg is not None and _emul(cfg):
+        # statistics as the fused kernels form them (csrc/elementwise.cu load_cst): E[z^2] - E[z]^2, clamped at 0
+        mean = x.mean(dim=(2, 3), keepdim=True)
+        var = ((x * x).mean(dim=(2, 3), keepdim=True) - mean * mean).clamp(min=0.)
+        xhat = (x - mean) * torch.rsqrt(var + eps)
+        return xhat * w.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
     return F.instance_norm(x, weight=w, bias=b, eps=eps)
 
 
@@ -243,14 +284,15 @@ def stochastic_model(p, cfg, layer, inputs, action, target, epsilon, rand, train
     """:161-200.  Returns (x, lstm_loss_increment)."""
     pre = 'stochastic_model'
     if training and target is not None:
-        x = torch.cat((inputs, target), dim=1)
-        x = F.conv2d(x, p[pre + '.input_embedding.weight'], p[pre + '.input_embedding.bias'])
+        q = lambda t: _q(cfg, t)
+        x = q(torch.cat((inputs, target), dim=1))  # bf16 operand (x_start | standardised target)
+        x = q(F.conv2d(x, q(p[pre + '.input_embedding.weight']), p[pre + '.input_embedding.bias']))
         x = x + timing_signal_nd((cfg.hidden_size, *cfg.frame_shape[1:]))
-        x = action_injector(p, pre + '.action_injector', x, action)
-        x = F.conv2d(x, p[pre + '.conv1.weight'], p[pre + '.conv1.bias'], stride=4, padding=2)
+        x = q(action_injector(p, pre + '.action_injector', x, action))
+        x = q(F.conv2d(x, q(p[pre + '.conv1.weight']), p[pre + '.conv1.bias'], stride=4, padding=2))
         x1 = mean_attention(p, pre + '.mean_attentions.0', x)
         x = F.relu(x)
-        x = F.conv2d(x, p[pre + '.conv2.weight'], p[pre + '.conv2.bias'], stride=4, padding=2)
+        x = q(F.conv2d(x, q(p[pre + '.conv2.weight']), p[pre + '.conv2.bias'], stride=4, padding=2))
         x2 = mean_attention(p, pre + '.mean_attentions.1', x)
         x = torch.cat((x1, x2), dim=-1)
         x = F.linear(x, p[pre + '.dense1.weight'], p[pre + '.dense1.bias'])
@@ -316,30 +358,34 @@ def forward(p, cfg, state, x, action, target=None, epsilon=0, rand=None, trainin
         aux = {}
     tshapes, opads = layer_shapes(cfg)
     timing = [timing_signal_nd(s) for s in tshapes]
+    q = lambda t: _q(cfg, t)  # bf16 storage points of the CUDA path (identity unless cfg.emulate_bf16)
     x_start = torch.stack([standardize_frame(f) for f in x])  # :307
     # get_internal_states :292-304
     internal = state['internal_states']
     if state['last_x_start'] is not None:
-        sa = torch.cat((internal, state['last_x_start']), dim=1)
-        gc = F.conv2d(sa, p['gate.weight'], p['gate.bias'], padding=1)
+        sa = torch.cat((q(internal), q(state['last_x_start'])), dim=1)  # gate operand: bf16 copy of the fp32 state
+        gc = q(F.conv2d(sa, q(p['gate.weight']), p['gate.bias'], padding=1))
         g, c = torch.split(gc, cfg.recurrent_state_size, dim=1)
         g = torch.sigmoid(g)
         c = torch.tanh(c)
         internal = internal * g
         internal = internal + c * (1 - g)
         state['internal_states'] = internal.detach()
-    h = torch.cat((x_start, internal), dim=1)
+    h = torch.cat((q(x_start), q(internal)), dim=1)
     state['last_x_start'] = x_start
-    h = F.conv2d(h, p['input_embedding.weight'], p['input_embedding.bias']) + timing[0]
+    h = q(F.conv2d(h, q(p['input_embedding.weight']), p['input_embedding.bias'])) + timing[0]
     inputs = []
     for i in range(cfg.compress_steps):  # :320-326
-        inputs.append(h)
+        inputs.append(q(h))  # skip tensor (stored bf16)
         h = h * (rand.keep_mask(h.shape, cfg.dropout) / (1 - cfg.dropout))
-        h = h + timing[i + 1]
-        h = F.conv2d(h, p[f'downscale_layers.{2 * i}.weight'], p[f'downscale_layers.{2 * i}.bias'],
+        h = q(h + timing[i + 1])
+        h = F.conv2d(h, q(p[f'downscale_layers.{2 * i}.weight']), p[f'downscale_layers.{2 * i}.bias'],
                      stride=2, padding=1)
         h = F.relu(h)
-        h = instance_norm(h, p[f'downscale_layers.{2 * i + 1}.weight'], p[f'downscale_layers.{2 * i + 1}.bias'])
+        if h.shape[2] * h.shape[3] > 30:
+            h = q(h)  # conv outputs are bf16 except the tiny deep layers (<= 30 pixels), which stay fp32
+        h = instance_norm(h, p[f'downscale_layers.{2 * i + 1}.weight'], p[f'downscale_layers.{2 * i + 1}.bias'], cfg=cfg)
+    h = q(h)  # the bottleneck is stored bf16
     aux['skips'] = inputs
     aux['x5'] = h
     value_pred = F.linear(torch.flatten(h, start_dim=1), p['value_estimator.dense.weight'],
@@ -351,32 +397,36 @@ def forward(p, cfg, state, x, action, target=None, epsilon=0, rand=None, trainin
     h, lstm_loss = stochastic_model(p, cfg, h, x_start, action, target, epsilon, rand, training, aux)
     aux['after_stoch'] = h
     x_mid = h.mean(dim=(2, 3))
+    h = q(h)
     # MiddleNetwork :52-63
     for i in range(cfg.hidden_layers):
-        y = h * (rand.keep_mask(h.shape, cfg.residual_dropout) / (1 - cfg.residual_dropout))
-        y = F.relu(F.conv2d(y, p[f'middle_network.middle_network.{2 * i}.weight'],
+        y = q(h * (rand.keep_mask(h.shape, cfg.residual_dropout) / (1 - cfg.residual_dropout)))
+        y = F.relu(F.conv2d(y, q(p[f'middle_network.middle_network.{2 * i}.weight']),
                             p[f'middle_network.middle_network.{2 * i}.bias'], padding=1))
         if i == 0:
             h = y
         else:
             h = instance_norm(h + y, p[f'middle_network.middle_network.{2 * i + 1}.weight'],
-                              p[f'middle_network.middle_network.{2 * i + 1}.bias'])
+                              p[f'middle_network.middle_network.{2 * i + 1}.bias'], cfg=cfg)
     inputs = list(reversed(inputs))
     for i in range(cfg.compress_steps):  # :343-350
         h = h * (rand.keep_mask(h.shape, cfg.dropout) / (1 - cfg.dropout))
-        h = action_injector(p, f'action_injectors.{i + 1}', h, action)
-        h = F.conv_transpose2d(h, p[f'upscale_layers.{2 * i}.weight'], p[f'upscale_layers.{2 * i}.bias'],
+        h = q(action_injector(p, f'action_injectors.{i + 1}', h, action))
+        h = F.conv_transpose2d(h, q(p[f'upscale_layers.{2 * i}.weight']), p[f'upscale_layers.{2 * i}.bias'],
                                stride=2, padding=1, output_padding=opads[i])
         h = F.relu(h)
+        if h.shape[2] * h.shape[3] > 30:
+            h = q(h)
         h = h + inputs[i]
-        h = instance_norm(h, p[f'upscale_layers.{2 * i + 1}.weight'], p[f'upscale_layers.{2 * i + 1}.bias'])
+        h = instance_norm(h, p[f'upscale_layers.{2 * i + 1}.weight'], p[f'upscale_layers.{2 * i + 1}.bias'], cfg=cfg)
         h = h + timing[1 + cfg.compress_steps + i]
     x_fin = h.mean(dim=(2, 3))
     r = torch.cat((x_mid, x_fin), dim=1)
     r = F.relu(F.linear(r, p['reward_estimator.dense1.weight'], p['reward_estimator.dense1.bias']))
     reward_pred = F.linear(r, p['reward_estimator.dense2.weight'], p['reward_estimator.dense2.bias'])
+    h = q(h)
     aux['final_x'] = h
-    logits = F.conv2d(h, p['logits.weight'], p['logits.bias'])
+    logits = q(F.conv2d(h, q(p['logits.weight']), p['logits.bias']))
     logits = logits.reshape(-1, 256, *cfg.frame_shape)
     return logits, reward_pred, value_pred, lstm_loss
 

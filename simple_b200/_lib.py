@@ -140,11 +140,11 @@ class _Sigs:
     sb_lstm_sample2 = [_p] * 9 + [_i, _p, _p, _p]
     sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
     sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
-    sb_grad_sumsq = [_p, _p, _p, _i, _p, _p]
+    sb_grad_sumsq = [_p, _p, _p, _i, _p, _p, _p]
     sb_adafactor_tick = [_p, _i, _p]
-    sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p]
+    sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p, _i, _p]
     sb_adafactor_small = [_p, _p, _i, _i, _p, _f, _p]
-    sb_adafactor_conv_packed = [_p, _p, _p, _i, _i, _i, _p, _f, _i, _p]
+    sb_adafactor_conv_packed = [_p, _p, _p, _i, _i, _i, _p, _f, _i, _p, _i, _p]
     sb_transpose_taps = [_p, _p, _i, _i, _i, _p]
     sb_bias_act = [_p, _p, _i, _p, _i, _ll, _i, _p]
     sb_transpose_taps_multi = [_p, _i, _i, _p]

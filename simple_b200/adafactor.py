@@ -100,6 +100,8 @@ class Adafactor(torch.optim.Optimizer):
                        glen=hn[n * 128:].view(np.int64), dev=torch.zeros(nbytes, dtype=torch.uint8, device=dev),
                        acc=torch.zeros(n, 2, device=dev, dtype=torch.float32),
                        total=torch.zeros(1, device=dev, dtype=torch.float32), maps=self._build_maps(active, dev),
+                       # scratch of the order-deterministic reductions (ticket counters zeroed once; see the header)
+                       sumsq_scratch=torch.zeros(1 + 148 * 8, device=dev, dtype=torch.float32),
                        params=[p for p, _, _ in active], pin=torch.zeros(nbytes, dtype=torch.uint8).pin_memory(),
                        any_packed=any(pw is not None for _, _, pw in active))
             self._cache[key] = rec
@@ -127,6 +129,9 @@ class Adafactor(torch.optim.Optimizer):
                 k['operm'] = pw.operm.data_ptr() if pw.operm is not None else 0
                 k['O'], k['I'], k['s'], k['Ipad'], k['Opad'] = pw.O, pw.I, pw.s, pw.Ipad, pw.Opad
             st['RMS'] = _LazyRMS(acc, i, p.numel())
+        if 'conv_scratch' not in rec:
+            nb = max([bm.shape[0] for bm in rec['maps']['conv'].values()] + [1])
+            rec['conv_scratch'] = torch.zeros(n + 2 * nb, device=dev, dtype=torch.float32)
         self._launch(rec, n, max_grad_norm)
         from .ops import refresh_transposed_all
         refresh_transposed_all([pw for _, _, pw in active], rec)  # `fwd` was rewritten: re-derive the per-tap transposes
@@ -160,15 +165,17 @@ class Adafactor(torch.optim.Optimizer):
         _lib.check(L.sb_adafactor_tick(descs_ptr, n, s), 'sb_adafactor_tick')
         mn = float(max_grad_norm) if max_grad_norm is not None else 0.0
         _lib.check(L.sb_grad_sumsq(descs_ptr, glen_ptr, maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
-                                   total.data_ptr(), s), 'sb_grad_sumsq')
+                                   total.data_ptr(), rec['sumsq_scratch'].data_ptr(), s), 'sb_grad_sumsq')
+        cs = rec['conv_scratch'].data_ptr()
         for (kh, kw, is_packed), bm in maps['conv'].items():
             for pas in (1, 2):
                 if is_packed:
                     _lib.check(L.sb_adafactor_conv_packed(descs_ptr, packs_ptr, bm.data_ptr(), bm.shape[0], kh, kw,
-                                                          total.data_ptr(), mn, pas, s), 'sb_adafactor_conv_packed')
+                                                          total.data_ptr(), mn, pas, cs, n, s),
+                               'sb_adafactor_conv_packed')
                 else:
                     _lib.check(L.sb_adafactor_conv(descs_ptr, bm.data_ptr(), bm.shape[0], kh, kw, total.data_ptr(), mn,
-                                                   pas, s), 'sb_adafactor_conv')
+                                                   pas, cs, n, s), 'sb_adafactor_conv')
         if maps['big2d'] is not None:
             idx, mc, mr = maps['big2d']
             _lib.check(L.sb_adafactor_big2d(descs_ptr, idx.data_ptr(), idx.numel(), mc, mr, total.data_ptr(), mn, s),

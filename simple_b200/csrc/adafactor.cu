@@ -33,13 +33,24 @@ __device__ __forceinline__ float clip_coef(const float* total_sumsq, float max_n
   return fminf(c, 1.0f);
 }
 
+// Fixed-order sum of `n` floats by one warp (lane-strided partial sums, then the xor-shuffle tree): the result depends on
+// the values only, never on which CTA finished first.
+__device__ __forceinline__ float warp_ordered_sum(const volatile float* v, int n, int lane) {
+  float t = 0.f;
+  for (int i = lane; i < n; i += 32) t += v[i];
+  return warp_sum(t);
+}
+
 // ---- 1. global gradient norm ------------------------------------------------------------------------------------
-// Persistent: a resident grid walks the (tensor, 4096-element chunk) list, 16-byte loads, one atomic per CTA (the
-// one-CTA-per-chunk version issued 16.7 k atomics on the same address).
+// Persistent: a resident grid walks the (tensor, 4096-element chunk) list, 16-byte loads.  ORDER-DETERMINISTIC: every CTA
+// publishes its partial sum, the CTA that arrives last (ticket counter in scratch[0]) adds the partials in index order.
+// Data-parallel replicas therefore compute bit-identical clip coefficients from the bit-identical reduced gradient and
+// never drift apart (round 1 used one fp32 atomic per CTA and re-broadcast the weights every window).
 __global__ void __launch_bounds__(256)
     grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const long long* __restrict__ glen,
-                      const int2* __restrict__ block_map, int nblocks, float* total) {
+                      const int2* __restrict__ block_map, int nblocks, float* total, float* scratch) {
   __shared__ float red[8];
+  __shared__ unsigned s_ticket;
   float s = 0.f;
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int2 bm = block_map[blk];  // (tensor, chunk)
@@ -62,7 +73,20 @@ __global__ void __launch_bounds__(256)
     }
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(total, s);
+  if (threadIdx.x == 0) {
+    scratch[1 + blockIdx.x] = s;
+    __threadfence();
+    s_ticket = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u);
+  }
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x < 32) {
+    __threadfence();
+    const float t = warp_ordered_sum(scratch + 1, (int)gridDim.x, (int)threadIdx.x);
+    if (threadIdx.x == 0) {
+      *total = t;
+      *reinterpret_cast<unsigned*>(scratch) = 0u;  // ready for the next launch / graph replay
+    }
+  }
 }
 
 // ---- 2. conv-type weights ---------------------------------------------------------------------------------------
@@ -80,9 +104,11 @@ __device__ __forceinline__ int packed_tap_offset(int k, int sh, int s, int Ipad)
 template <int KH, int KW, int PASS, bool PACKED>
 __global__ void __launch_bounds__(128)
     adafactor_conv_kernel(const sb_tensor_desc* __restrict__ descs, const sb_pack_desc* __restrict__ packs,
-                          const int2* __restrict__ block_map, const float* __restrict__ total_sumsq, float max_norm) {
+                          const int2* __restrict__ block_map, const float* __restrict__ total_sumsq, float max_norm,
+                          float* scratch, int ntensors) {
   constexpr int KK = KH * KW;
   __shared__ float red[8];
+  __shared__ unsigned s_ticket;
   const int2 bm = block_map[blockIdx.x];  // (tensor, first patch)
   const sb_tensor_desc d = descs[bm.x];
   const float tstep = *d.stepf;
@@ -192,11 +218,37 @@ __global__ void __launch_bounds__(128)
     }
   }
   if (PASS == 1) {
+    // sum u^2 / sum p^2 of the whole tensor, ORDER-DETERMINISTIC (see grad_sumsq_kernel): scratch = [ntensors ticket
+    // counters | 2 floats per CTA of this launch]; the CTAs of one tensor are consecutive in the block map, so the
+    // tensor's first CTA is blockIdx.x - (first patch / 128) and the last arriver adds the partials in CTA order.
     su = block_sum(su, red);
     sp = block_sum(sp, red);
+    unsigned* tickets = reinterpret_cast<unsigned*>(scratch);
+    float* part = scratch + ntensors;
+    const int nb = (int)((npatch + 127) / 128);
+    const int first = (int)blockIdx.x - bm.y / 128;
     if (threadIdx.x == 0) {
-      atomicAdd(&d.acc[0], su);
-      atomicAdd(&d.acc[1], sp);
+      part[2 * blockIdx.x] = su;
+      part[2 * blockIdx.x + 1] = sp;
+      __threadfence();
+      s_ticket = atomicAdd(&tickets[bm.x], 1u);
+    }
+    __syncthreads();
+    if (s_ticket == (unsigned)(nb - 1) && threadIdx.x < 32) {
+      __threadfence();
+      float tu = 0.f, tp = 0.f;
+      const volatile float* pv = part + 2 * first;
+      for (int i = (int)threadIdx.x; i < nb; i += 32) {
+        tu += pv[2 * i];
+        tp += pv[2 * i + 1];
+      }
+      tu = warp_sum(tu);
+      tp = warp_sum(tp);
+      if (threadIdx.x == 0) {
+        d.acc[0] = tu;
+        d.acc[1] = tp;
+        tickets[bm.x] = 0u;
+      }
     }
   }
 }
@@ -432,11 +484,11 @@ extern "C" int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, 
 }
 
 extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev,
-                             int nblocks, float* total, sb_stream_t stream) {
-  if (!descs_dev || !block_map_dev || nblocks < 1 || !total) return SB_ERR_ARG;
-  const int grid = nblocks < 148 * 8 ? nblocks : 148 * 8;  // 8 CTAs of 256 threads per SM: one resident wave
+                             int nblocks, float* total, float* scratch, sb_stream_t stream) {
+  if (!descs_dev || !block_map_dev || nblocks < 1 || !total || !scratch) return SB_ERR_ARG;
+  const int grid = nblocks < SB_SUMSQ_MAX_CTAS ? nblocks : SB_SUMSQ_MAX_CTAS;  // 8 CTAs of 256 threads per SM: one resident wave
   grad_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, glen_dev, (const int2*)block_map_dev, nblocks,
-                                                            total);
+                                                            total, scratch);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -444,14 +496,18 @@ extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* g
 
 template <int KH, int KW>
 static int launch_conv(const sb_tensor_desc* descs, const sb_pack_desc* packs, const int* bm, int nblocks,
-                       const float* total, float max_norm, int pass, cudaStream_t s) {
+                       const float* total, float max_norm, int pass, float* scratch, int ntensors, cudaStream_t s) {
   const int2* m = (const int2*)bm;
   if (packs) {
-    if (pass == 1) adafactor_conv_kernel<KH, KW, 1, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
-    else adafactor_conv_kernel<KH, KW, 2, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+    if (pass == 1)
+      adafactor_conv_kernel<KH, KW, 1, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm, scratch, ntensors);
+    else
+      adafactor_conv_kernel<KH, KW, 2, true><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm, scratch, ntensors);
   } else {
-    if (pass == 1) adafactor_conv_kernel<KH, KW, 1, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
-    else adafactor_conv_kernel<KH, KW, 2, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm);
+    if (pass == 1)
+      adafactor_conv_kernel<KH, KW, 1, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm, scratch, ntensors);
+    else
+      adafactor_conv_kernel<KH, KW, 2, false><<<nblocks, 128, 0, s>>>(descs, packs, m, total, max_norm, scratch, ntensors);
   }
   ++g_launches;
   SB_CHECK_LAUNCH();
@@ -460,30 +516,35 @@ static int launch_conv(const sb_tensor_desc* descs, const sb_pack_desc* packs, c
 
 static int conv_dispatch(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev, const int* block_map_dev,
                          int nblocks, int KH, int KW, const float* total_sumsq, float max_norm, int pass,
-                         sb_stream_t stream) {
+                         float* scratch, int ntensors, sb_stream_t stream) {
   if (!descs_dev || !block_map_dev || nblocks < 1 || (pass != 1 && pass != 2)) return SB_ERR_ARG;
+  if (pass == 1 && (!scratch || ntensors < 1)) return SB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (KH == 1 && KW == 1)
-    return launch_conv<1, 1>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+    return launch_conv<1, 1>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, scratch, ntensors, s);
   if (KH == 3 && KW == 3)
-    return launch_conv<3, 3>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+    return launch_conv<3, 3>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, scratch, ntensors, s);
   if (KH == 4 && KW == 4)
-    return launch_conv<4, 4>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+    return launch_conv<4, 4>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, scratch, ntensors, s);
   if (KH == 8 && KW == 8)
-    return launch_conv<8, 8>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, s);
+    return launch_conv<8, 8>(descs_dev, packs_dev, block_map_dev, nblocks, total_sumsq, max_norm, pass, scratch, ntensors, s);
   return SB_ERR_ARG;
 }
 
 extern "C" int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
-                                 const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
-  return conv_dispatch(descs_dev, nullptr, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, stream);
+                                 const float* total_sumsq, float max_norm, int pass, float* scratch, int ntensors,
+                                 sb_stream_t stream) {
+  return conv_dispatch(descs_dev, nullptr, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, scratch, ntensors,
+                       stream);
 }
 
 extern "C" int sb_adafactor_conv_packed(const sb_tensor_desc* descs_dev, const sb_pack_desc* packs_dev,
                                         const int* block_map_dev, int nblocks, int KH, int KW,
-                                        const float* total_sumsq, float max_norm, int pass, sb_stream_t stream) {
+                                        const float* total_sumsq, float max_norm, int pass, float* scratch, int ntensors,
+                                        sb_stream_t stream) {
   if (!packs_dev) return SB_ERR_ARG;
-  return conv_dispatch(descs_dev, packs_dev, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, stream);
+  return conv_dispatch(descs_dev, packs_dev, block_map_dev, nblocks, KH, KW, total_sumsq, max_norm, pass, scratch,
+                       ntensors, stream);
 }
 
 extern "C" int sb_adafactor_small(const sb_tensor_desc* descs_dev, const int* index_dev, int ntensors,

@@ -301,6 +301,15 @@ __device__ __forceinline__ uint4 hash4x32(uint32_t ctr, uint2 key) {
 // uniform in [0,1) from 32 random bits (24-bit mantissa, like torch.rand)
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
 
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// The library is built with --use_fast_math, under which tanhf() becomes tanh.approx (~5e-4 relative error): too coarse
+// for the fp32 latent path, whose sampled symbols are compared bit-exactly with the oracle, and for the fp32 recurrent
+// state (1/8 of a bf16 ulp).  exp-based form: ~1e-6.
+__device__ __forceinline__ float tanh_acc(float x) {
+  const float t = expf(-2.0f * fabsf(x));
+  return copysignf((1.0f - t) / (1.0f + t), x);
+}
+
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 }  // namespace sb

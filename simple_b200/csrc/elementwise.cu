@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float sg = 1.0f / (1.0f + __expf(-g[j]));
-      const float tc = tanhf(cand[j]);
+      const float tc = tanh_acc(cand[j]);
       o[j] = s[j] * sg + tc * (1.0f - sg);
     }
     *reinterpret_cast<float4*>(s_new + pix * 64 + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float sg = 1.0f / (1.0f + __expf(-g[j]));
-      const float tc = tanhf(cand[j]);
+      const float tc = tanh_acc(cand[j]);
       dg[j] = d[j] * sg * (1.0f - sg) * (s[j] - tc);
       dc[j] = d[j] * (1.0f - sg) * (1.0f - tc * tc);
     }

@@ -17,13 +17,6 @@ constexpr int kH = 128;       // latent_state_size
 constexpr int kV = 256;       // 2^bits_at_once symbols
 constexpr int kSteps = 16;    // bottleneck_bits / bits_at_once
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-// The library is built with --use_fast_math, under which tanhf() becomes tanh.approx (~5e-4 relative error): too coarse
-// for the fp32 latent path, whose sampled symbols are compared bit-exactly with the oracle.  exp-based form: ~1e-6.
-__device__ __forceinline__ float tanh_acc(float x) {
-  const float t = expf(-2.0f * fabsf(x));
-  return copysignf((1.0f - t) / (1.0f + t), x);
-}
 
 // One warp computes one output row: lane l holds elements 4l..4l+3 of the 128-vector, reads the matching float4 of the
 // weight row (a fully coalesced 512-byte row per warp instruction) and the partial sums are reduced with shuffles.

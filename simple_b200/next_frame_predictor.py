@@ -362,10 +362,11 @@ class NextFramePredictor(nn.Module):
         self._has_prev = False
         self._pending = None
 
-    def capture_key(self):
+    def capture_key(self, rollout=False):
         """Identity of every buffer a captured CUDA graph of this model bakes in.  A holder of such a graph compares the
-        key it captured under with the current one and re-captures on mismatch (stale-graph hazards)."""
-        t = self.stochastic_model.bits_predictor._sampler_tables
+        key it captured under with the current one and re-captures on mismatch (stale-graph hazards).
+        `rollout`: the graph also reads the persistent sampler tables (eval forward with static weights)."""
+        t = self.stochastic_model.bits_predictor._sampler_tables if rollout else None
         ptr = lambda x: None if x is None else x.data_ptr()
         return (self._generation, ptr(self._state), ptr(self._xs_prev), ptr(self._xs_buf), ptr(self._ps_buf),
                 ptr(self._seed_dev), None if t is None else t['E'].data_ptr())

@@ -174,10 +174,24 @@ class FlatGradSync:
         return views
 
 
+def seed_rank_streams(model, base_seed=0):
+    """Per-rank random streams (SURVEY 8e caveat 3): the replicas hold identical weights but must draw INDEPENDENT dropout
+    masks / latent noise for their shards, like the samples of one global batch do.  Offsets the model's in-kernel
+    dropout seed and torch's CUDA generator by the rank."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = model.logits.weight.device
+    seed = (int(base_seed) + 0x9E3779B9 * (rank + 1)) & ((1 << 40) - 1)
+    if model._seed_dev is not None and model._seed_dev.device == dev:
+        model._seed_dev.fill_(seed)
+    else:
+        model._seed_dev = torch.full((1,), seed, dtype=torch.int64, device=dev)
+    torch.cuda.manual_seed(seed)
+
+
 def broadcast_parameters(model, src=0):
-    """Make every rank hold rank `src`'s weights: at start-up (same effect as seeding identically) and, called once per
-    rollout window by the Trainer, to cancel the ~1e-9/step drift between replicas that the fp32-atomic reductions inside
-    the fused optimiser introduce (the reduced gradient itself is bit-identical on every rank)."""
+    """Make every rank hold rank `src`'s weights at start-up (same effect as seeding identically).  Not needed afterwards:
+    the reduced gradient is bit-identical on every rank and every reduction of the fused clip + Adafactor kernels is
+    order-deterministic, so the replicas never drift (asserted in tests/test_dp_nccl.py)."""
     if dist.is_initialized() and dist.get_world_size() > 1:
         for p in model.parameters():
             dist.broadcast(p.data, src)

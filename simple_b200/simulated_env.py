@@ -175,7 +175,7 @@ class SimulatedVecEnv:
         model._auto_repack = False
         try:
             first = not model._has_prev
-            if self._graph is not None and self._graph_key != model.capture_key():
+            if self._graph is not None and self._graph_key != model.capture_key(rollout=True):
                 self._graph, self._warm = None, 0  # a buffer the graph baked in was re-allocated: capture again
             if first or not self.use_graph:
                 self._core()
@@ -187,7 +187,7 @@ class SimulatedVecEnv:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._core()
-                self._graph, self._graph_key = g, model.capture_key()
+                self._graph, self._graph_key = g, model.capture_key(rollout=True)
                 g.replay()
             else:
                 self._graph.replay()

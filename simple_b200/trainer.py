@@ -101,8 +101,22 @@ class Trainer:
         if per_sample:  # one frame [3,H,W] at a time in the reference => one median per sample
             med = state.reshape(state.shape[0], -1).median(dim=1).values.reshape(-1, 1, 1, 1)
         else:
-            med = torch.median(state)
+            med = self.global_median(state_u8)
         return state * keep + med * (1 - keep)
+
+    def global_median(self, state_u8):
+        """torch.median(state / 255) over the WHOLE batch (simple/trainer.py:64) as a device scalar.  Under data
+        parallelism the batch is sharded: the 256-bin histograms of the shards are all-reduced, and the lower median
+        (the element of rank (N-1)//2, what torch.median returns) is read off the prefix sums -- exactly the median of
+        the global batch (SURVEY 8e caveat 1), not a per-shard one."""
+        import torch.distributed as dist
+        if not (self.grad_sync is not None and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1):
+            return torch.median(state_u8.float() / 255)
+        hist = torch.bincount(state_u8.reshape(-1).long(), minlength=256)
+        dist.all_reduce(hist)
+        k = (hist.sum() - 1) // 2
+        return (torch.cumsum(hist, 0) <= k).sum().float() / 255
 
     def epsilon_schedule(self, epoch, i):
         """Probability of feeding the ground-truth frame (trainer.py:78-87)."""
@@ -218,9 +232,8 @@ class Trainer:
         metrics = {}
         for i in iterator:
             epsilon = self.epsilon_schedule(epoch, i)
-            if self.grad_sync is not None:
-                from .parallel import broadcast_parameters
-                broadcast_parameters(self.model)  # once per window: keeps the data-parallel replicas bit-identical
+            # (data parallel: no re-synchronisation of the replicas is needed -- every reduction downstream of the gradient
+            # all-reduce is order-deterministic, so identical replicas stay bit-identical; tests/test_dp_nccl.py)
             runner.begin(rp.sample_starts(B), epsilon)
             for j in range(rollout_len):
                 runner.step()

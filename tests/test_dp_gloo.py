@@ -61,3 +61,38 @@ def test_flat_grad_sync_averages_over_ranks():
         for i in g0:
             want = (1 + i + 10 * step + 2 + i + 10 * step) / 2.0  # mean over the two ranks
             assert torch.equal(g0[i], g1[i]) and float(g0[i].flatten()[0]) == want
+
+
+def _median_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from types import SimpleNamespace
+    from simple_b200.parallel import init_distributed
+    from simple_b200.trainer import Trainer
+    init_distributed('gloo')
+    g = torch.Generator().manual_seed(5)
+    full = torch.randint(0, 256, (4, 12, 21, 16), generator=g, dtype=torch.uint8)  # even element count: lower median
+    full[:2] //= 3  # the two shards have different distributions: a per-shard median would differ
+    shard = full[rank * 2:(rank + 1) * 2]
+    med = Trainer.global_median(SimpleNamespace(grad_sync=object()), shard)
+    out.put((rank, float(med), float(torch.median(full.float() / 255)), float(torch.median(shard.float() / 255))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_batch_median_by_histogram_all_reduce():
+    """simple/trainer.py:64 takes torch.median over the WHOLE batch; sharded, that is a 256-bin histogram all-reduce."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_median_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, med, want, local in got:
+        assert med == want, (rank, med, want)
+    assert {local for *_, local in got} != {got[0][2]}  # (the shards' own medians are not the global one)

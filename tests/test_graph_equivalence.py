@@ -1,0 +1,191 @@
+"""CUDA-graph replay == eager execution, for the training step (StepRunner) and the simulated-env step, including the
+stale-graph hazards of round 1's review: buffers a graph baked in must survive a rollout with agents != batch_size
+between two train() calls, new weights (load_state_dict) and an optimiser step between two rollouts."""
+import copy
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _cfg(**kw):
+    from oracle.wm_oracle import default_config
+    return default_config(device=DEV, **kw)
+
+
+def _replay(n, n_action=3, seed=1):
+    from simple_b200.synthetic import synth_replay
+    d = synth_replay(n, n_action, seed)
+    return dict(obs=d['obs'].to(DEV), new_obs=d['new_obs'].to(DEV), action=d['action'].float().to(DEV),
+                reward=d['reward'].long().to(DEV), value=d['value'].to(DEV))
+
+
+class _Snapshot:
+    """Everything one training step reads and writes: weights, bf16 operands, optimiser state (device + host counters),
+    recurrent state, frame stack, indices, seeds, RNG."""
+
+    def __init__(self, trainer, runner):
+        m, opt = trainer.model, trainer.optimizer
+        self.t, self.r = trainer, runner
+        self.params = [p.detach().clone() for p in m.parameters()]
+        self.packed = {k: (pw.fwd.clone(), pw.tr.clone(), pw.fresh) for k, pw in m._packed.items()}
+        self.opt = {p: {k: (v.clone() if isinstance(v, torch.Tensor) else copy.copy(v)) for k, v in st.items()
+                        if k != 'RMS'} for p, st in opt.state.items()}
+        self.model = (m._state.clone(), m._xs_prev.clone(), m._xs_buf.clone(), m._has_prev, m._seed_dev.clone())
+        assert m._pending is None
+        self.runner = (runner.frames.clone(), runner.idx.clone(), runner.losses.clone(), runner.eps.clone(), runner.j)
+        self.rng = torch.cuda.get_rng_state(torch.device(DEV))
+
+    def restore(self):
+        m, opt = self.t.model, self.t.optimizer
+        with torch.no_grad():
+            for p, v in zip(m.parameters(), self.params):
+                p.copy_(v)
+            for k, (f, t, fresh) in self.packed.items():
+                m._packed[k].fwd.copy_(f)
+                m._packed[k].tr.copy_(t)
+                m._packed[k].fresh = fresh
+            for p, st in self.opt.items():
+                for k, v in st.items():
+                    if isinstance(v, torch.Tensor):
+                        opt.state[p][k].copy_(v)
+                    else:
+                        opt.state[p][k] = v
+            s, xp, xb, hp, seed = self.model
+            m._state.copy_(s); m._xs_prev.copy_(xp); m._xs_buf.copy_(xb)
+            m._has_prev, m._pending = hp, None
+            m._seed_dev.copy_(seed)
+            f, i, l, e, j = self.runner
+            self.r.frames.copy_(f); self.r.idx.copy_(i); self.r.losses.copy_(l); self.r.eps.copy_(e)
+            self.r.j = j
+        torch.cuda.set_rng_state(self.rng, torch.device(DEV))
+
+
+def test_step_runner_graph_replay_equals_eager_step():
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.trainer import StepRunner, Trainer
+    B = 4
+    cfg = _cfg(batch_size=B, rollout_length=8)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    trainer = Trainer(model, cfg)
+    rp = _replay(B + 24)
+    runner = StepRunner(trainer, rp, B, use_graph=True, resident=True)
+    runner.begin(torch.arange(B, device=DEV), 0.3)
+    for _ in range(5):  # eager first step, 2 warm-up steps, capture + first replay, one more replay
+        runner.step()
+    assert runner.graph is not None and runner.replays == 2
+    torch.cuda.synchronize()
+    snap = _Snapshot(trainer, runner)
+    runner.step()  # graph replay
+    torch.cuda.synchronize()
+    assert runner.replays == 3
+    g_losses = runner.losses.clone()
+    g_params = [p.detach().clone() for p in model.parameters()]
+    g_frames, g_state = runner.frames.clone(), model._state.clone()
+    snap.restore()
+    runner._body()  # the same step, eagerly (what the graph captured)
+    torch.cuda.synchronize()
+    # fp32 atomics (InstanceNorm statistics, split-K, weight gradients) make two executions differ in the last bits only
+    assert torch.allclose(runner.losses, g_losses, rtol=1e-3, atol=1e-4), (runner.losses, g_losses)
+    for (k, p), q in zip(model.named_parameters(), g_params):
+        err = float((p - q).abs().max() / (q.abs().max() + 1e-12))
+        assert err < 1e-4, (k, err)
+    assert float((runner.frames != g_frames).float().mean()) < 2e-3  # fed-back arg-max frames (+ input noise)
+    assert float((model._state - g_state).abs().max()) < 5e-2 and float((model._state - g_state).abs().mean()) < 1e-4
+
+
+def test_trainer_graph_survives_rollout_with_other_batch_size():
+    """train() -> simulated rollout with agents != batch_size -> train() on the same replay: the
+    captured step graph must keep reading live recurrent-state buffers."""
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.simulated_env import Discrete, make_simulated_env
+    from simple_b200.synthetic import synth_replay
+    from simple_b200.trainer import Trainer
+    B, A = 4, 3
+    cfg = _cfg(batch_size=B, rollout_length=6, agents=A)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    trainer = Trainer(model, cfg)
+    d = synth_replay(40, 3, 0)
+    buf = [[d['obs'][i], d['action'][i], d['reward'][i], d['new_obs'][i], torch.tensor(0, dtype=torch.uint8),
+            d['value'][i].clone()] for i in range(40)]
+    env_real = SimpleNamespace(buffer=buf)
+    m1 = trainer.train(1, env_real, steps=12)
+    runner = trainer._runner
+    assert runner.graph is not None
+    key = runner.model_key
+    sim = make_simulated_env(cfg, model, Discrete(3))
+    sim.restart_all(d['obs'][:A].to(DEV))
+    sim.reset()
+    for _ in range(6):
+        sim.step(torch.randint(0, 3, (A, 1)))
+    m2 = trainer.train(1, env_real, steps=24)
+    assert trainer._runner is runner and runner.graph is not None and runner.model_key == key == model.capture_key()
+    assert all(np.isfinite(v) for v in m2.values())
+    assert m2['loss_reconstruct'] < m1['loss_reconstruct'], (m1, m2)
+
+
+def _rollout(env, model, seed, actions):
+    model._seed_dev.fill_(seed)
+    torch.cuda.manual_seed(seed)
+    env.reset()
+    obs_all, rew_all = [], []
+    for a in actions:
+        obs, rew, _, _ = env.step(a)
+        obs_all.append(obs.to(torch.uint8).cpu())
+        rew_all.append(rew.float().cpu())
+    return torch.stack(obs_all), torch.stack(rew_all)
+
+
+def test_env_graph_equals_eager_across_rollouts_and_weight_changes():
+    """rollout (graph captured) -> NEW weights + a training forward/backward at B != A -> rollout again: the replayed
+    graph must produce what an eager env produces from the same state and seeds."""
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.simulated_env import Discrete, make_simulated_env
+    from simple_b200.synthetic import synth_replay
+    from simple_b200.trainer import wm_loss
+    A, B, T = 4, 2, 6
+    cfg = _cfg(agents=A, rollout_length=T, batch_size=B)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    d = synth_replay(A + 8, 3, 5)
+    init = d['obs'][:A].to(DEV)
+    env_g = make_simulated_env(cfg, model, Discrete(3))
+    cfg_e = copy.copy(cfg)
+    cfg_e.cuda_graph = False
+    env_e = make_simulated_env(cfg_e, model, Discrete(3))
+    for e in (env_g, env_e):
+        e.restart_all(init)
+    g = torch.Generator().manual_seed(3)
+    actions = [torch.randint(0, 3, (A, 1), generator=g) for _ in range(T)]
+    env_g.reset()
+    for a in actions:  # first rollout: eager first step, warm-up, capture, replays
+        env_g.step(a)
+    assert env_g._graph is not None
+    graph = env_g._graph
+    # ---- the world model changes: other weights, then one training forward/backward at another batch size
+    torch.manual_seed(1)
+    other = NextFramePredictor(cfg, 3)
+    model.load_state_dict(other.state_dict())
+    model.train()
+    out = wm_loss(model, cfg, d['obs'][:B].to(DEV).float() / 255, d['action'][:B].float().to(DEV),
+                  d['new_obs'][:B].to(DEV), d['reward'][:B].long().to(DEV), d['value'][:B].to(DEV), 0.0)
+    out['loss'].backward()
+    model.zero_grad(set_to_none=True)
+    # ---- second rollout: replayed graph vs eager env, same state and seeds
+    og, rg = _rollout(env_g, model, 1234, actions)
+    assert env_g._graph is graph, 'the graph should have stayed valid (persistent buffers), not been re-captured'
+    oe, re_ = _rollout(env_e, model, 1234, actions)
+    agree = float((og == oe).float().mean())
+    print('graph vs eager: frame agreement', agree, 'reward max diff', float((rg - re_).abs().max()))
+    assert agree > 0.98, agree
+    assert float((rg[:-1] - re_[:-1]).abs().max()) == 0.0 and float((rg[-1] - re_[-1]).abs().max()) < 5e-2
+    # and the stale-weights failure mode is detectable by this test: the first rollout's frames (old weights) differ
+    model.load_state_dict({k: v for k, v in NextFramePredictor(cfg, 3).state_dict().items()})  # yet another set
+    o3, _ = _rollout(env_g, model, 1234, actions)
+    assert float((o3[:, :, -3:] == og[:, :, -3:]).float().mean()) < 0.9

@@ -1,0 +1,193 @@
+"""Strict end-to-end parity: the CUDA path, UNFORCED, against the bf16-emulating oracle (oracle.wm_oracle with
+`emulate_bf16`: the pinned fp32 restatement of the reference, rounded to bf16 exactly where the CUDA path stores
+bf16).  Same weights, same inputs, same injected randomness; nothing is forced to the oracle's decisions.
+
+north_star bars, asserted here on full windows at the BASELINE shapes (B = 16, n_action = 3; n_action = 9):
+  * sampled latent bits and posterior signs: bit-exact (flip rate 0 on these seeds, asserted);
+  * logits within 1e-2 relative; total / reconstruction / reward / lstm losses and reward_pred within 1e-3;
+  * arg-max decoded frames: agreement measured END TO END against the oracle's arg-max and asserted; the decode itself is
+    bit-exact given identical logits (stage-isolated test in test_ops.py) -- with an untrained network the 256 bf16
+    logits of a pixel are nearly flat, so a 1-ulp difference of one logit (summation order inside the tensor core) moves
+    a tie; the agreement bound is therefore a measured number, written next to the assertion;
+  * encoder gradients on the REFERENCE init: cosine >= 0.99 against the emulating oracle (they agree only to 0.80-0.90
+    with the fp32 oracle -- and so does the emulating oracle itself, see DESIGN.md section 5: that gap is bf16 storage,
+    not a kernel defect).
+Measured flip / agreement rates are written to gpurun_out/strict_parity_*.json (committed under profiles/).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _setup(B, n_action, steps, seed=0):
+    from oracle import wm_oracle as O
+    from oracle.make_golden import make_inputs
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    cfg = O.default_config(device=DEV, batch_size=B)
+    torch.manual_seed(seed)
+    model = NextFramePredictor(cfg, n_action)
+    p0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    frames_u8, per_step = make_inputs(1 + seed, B, n_action, steps)
+    return O, cfg, model, p0, frames_u8, per_step
+
+
+def _dump(name, rows):
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open(os.path.join('gpurun_out', name), 'w') as f:
+        json.dump(rows, f, indent=1)
+
+
+@pytest.mark.parametrize('B,n_action,steps', [(16, 3, 5), (4, 9, 3)])
+def test_train_window_unforced_vs_emulating_oracle(B, n_action, steps):
+    """A window of `steps` training forwards + backwards (recurrent state carried, gate conv live from step 1) on the
+    reference init.  Both sides are fed the ORACLE's scheduled-sampling frames so that step j compares like with like;
+    the recurrent state is each side's own."""
+    torch.set_num_threads(os.cpu_count())
+    eps = 0.3
+    O, cfg, model, p0, frames_u8, per_step = _setup(B, n_action, steps)
+    from simple_b200.next_frame_predictor import InjectedRand
+    from simple_b200.trainer import wm_loss
+    ocfg = O.bf16_config(device='cpu', batch_size=B)
+    p = {k: v.clone().requires_grad_(True) for k, v in p0.items()}
+    state = O.init_state(ocfg, B)
+    frames = frames_u8.float() / 255
+    model.train()
+    model.init_internal_states(B)
+    torch.manual_seed(123)
+    np.random.seed(123)
+    rows = []
+    for j in range(steps):
+        s = per_step[j]
+        rand = O.GlobalRand()
+        aux = {}
+        tgt = s['new_state'].float() / 255
+        logits, rew, val, lstm = O.forward(p, ocfg, state, frames, s['action'], tgt, eps, rand, training=True, aux=aux)
+        loss, lrec, lval, lrew = O.wm_losses(ocfg, logits, rew, val, lstm, s['new_state'].long(), s['reward'], s['value'])
+        names = list(p)
+        ograd = dict(zip(names, torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)))
+
+        model.parity_rand = InjectedRand(rand.log, DEV)  # randomness as input; NO forced decisions
+        model.zero_grad(set_to_none=True)
+        out = wm_loss(model, cfg, frames.to(DEV), s['action'].to(DEV), s['new_state'].to(DEV), s['reward'].to(DEV),
+                      s['value'].to(DEV), eps, keep_logits=True)
+        out['loss'].backward()
+        torch.cuda.synchronize()
+        assert model.parity_rand.pos == len(rand.log), 'not all injected draws were consumed'
+        la = model.last_aux
+        sign_flip = float(((la['posterior_pre'].cpu() > 0) != (aux['posterior_pre'] > 0)).float().mean())
+        bit_flip = float((la['bits_pred'].cpu() != aux['bits_pred']).float().mean())
+        latent_err = float((la['bits'].cpu() - aux['bits'].detach()).abs().max())
+        oam = torch.argmax(logits, dim=1)
+        am_agree = float((out['argmax'].cpu().long() == oam).float().mean())
+        row = dict(step=j, B=B, n_action=n_action, posterior_sign_flip=sign_flip, sampled_bit_flip=bit_flip,
+                   latent_max_abs_err=latent_err, argmax_agreement=am_agree,
+                   logits_rel=_rel(out['logits_ref'], logits), reward_rel=_rel(out['reward_pred'], rew),
+                   value_abs=float((out['value_pred'].cpu() - val.detach()).abs().max()),
+                   posterior_pre_rel=_rel(la['posterior_pre'], aux['posterior_pre']))
+        for k, ref in (('loss', loss), ('loss_reconstruct', lrec), ('loss_value', lval), ('loss_reward', lrew),
+                       ('loss_lstm', lstm)):
+            row[k + '_abs'] = abs(float(out[k]) - float(ref))
+            row[k + '_ref'] = float(ref)
+        grads = {}
+        for k, prm in model.named_parameters():
+            og = ograd[k]
+            if og is None:
+                assert prm.grad is None or float(prm.grad.abs().max()) == 0, k
+                continue
+            assert prm.grad is not None, k
+            gg = prm.grad.detach().float().cpu()
+            grads[k] = (float((gg - og).norm() / (og.norm() + 1e-30)),
+                        float((gg * og).sum() / (gg.norm() * og.norm() + 1e-30)), float(og.norm()))
+        row['grad_min_cos'] = min(c for _, c, n in grads.values() if n > 1e-9)
+        row['grad_worst'] = min(((c, k) for k, (_, c, n) in grads.items() if n > 1e-9))[1]
+        row['grad_max_rel_l2'] = max(r for r, _, n in grads.values() if n > 1e-9)
+        rows.append(row)
+        print(json.dumps(row))
+        with open('gpurun_out/strict_grad_B%d_a%d_step%d.txt' % (B, n_action, j), 'w') as f:
+            for k, (r, c, n) in grads.items():
+                f.write('%-60s relL2=%.4g cos=%.5f |g|=%.4g\n' % (k, r, c, n))
+        _dump('strict_parity_train_B%d_a%d.json' % (B, n_action), rows)
+        # ---- north_star bars
+        assert sign_flip == 0.0 and bit_flip == 0.0, row      # latent decisions bit-exact end to end
+        assert latent_err < 1e-3, row
+        assert row['logits_rel'] < 1e-2, row
+        assert row['reward_rel'] < 1e-3 or float((out['reward_pred'].cpu() - rew.detach()).abs().max()) < 1e-3, row
+        for k in ('loss', 'loss_reconstruct', 'loss_reward', 'loss_lstm'):
+            assert row[k + '_abs'] < 1e-3 * max(1.0, abs(row[k + '_ref'])), (k, row)
+        # value head: 4608-wide dot product over the bf16 bottleneck right behind a 6-pixel InstanceNorm:
+        # written bound 2e-2 absolute on outputs of O(1)
+        assert row['value_abs'] < 2e-2 and row['loss_value_abs'] < 2e-2, row
+        assert am_agree > 0.97, row   # measured 0.99+ (profiles/r2_strict_parity.md); decode itself bit-exact
+        assert row['grad_min_cos'] > 0.99, row
+        frames = torch.cat((frames[:, 3:], oam.float() / 255), dim=1)
+    model.parity_rand = None
+
+
+@pytest.mark.parametrize('A,n_action,steps', [(16, 3, 5), (4, 9, 5), (2, 3, 50)])
+def test_rollout_vs_emulating_oracle(A, n_action, steps):
+    """SimulatedVecEnv.step (eager, injected randomness) against O.rollout_step for a whole rollout: every side feeds
+    back ITS OWN arg-max frames and carries its own recurrent state (subproc_vec_env.py:409-445), incl. the value-head
+    bonus on the last step.  Sampled bits bit-exact; frame agreement per step reported and bounded."""
+    torch.set_num_threads(os.cpu_count())
+    O, cfg, model, p0, frames_u8, per_step = _setup(A, n_action, steps, seed=2)
+    from simple_b200.next_frame_predictor import InjectedRand
+    from simple_b200.simulated_env import Discrete, make_simulated_env
+    cfg.agents, cfg.rollout_length, cfg.cuda_graph = A, steps, False
+    ocfg = O.bf16_config(device='cpu', batch_size=A, agents=A, rollout_length=steps)
+    env = make_simulated_env(cfg, model, Discrete(n_action))
+    env.restart_all(frames_u8.to(DEV))
+    obs = env.reset()
+    state = O.init_state(ocfg, A)
+    frames = frames_u8.float() / 255
+    torch.manual_seed(7)
+    rows = []
+    for j in range(steps):
+        act = per_step[j]['action']  # one-hot [A,n]
+        rand = O.GlobalRand()
+        aux = {}
+        # (rollout_step wraps forward; call forward here to also get the latent bits)
+        with torch.no_grad():
+            logits, rewards, values, _ = O.forward(p0, ocfg, state, frames, act.unsqueeze(1), None, 0, rand,
+                                                   training=False, aux=aux)
+        new_states = torch.argmax(logits, dim=1)
+        frames = torch.cat((frames[:, 3:], new_states.float() / 255), dim=1)
+        o_obs = (frames * 255).byte()
+        o_rew = (torch.argmax(rewards, dim=1) - 1).double()
+        if j == steps - 1:
+            o_rew = o_rew + values.double()
+        model.parity_rand = InjectedRand(rand.log, DEV)
+        obs, rew, done, _ = env.step(act.argmax(dim=1, keepdim=True))
+        torch.cuda.synchronize()
+        assert model.parity_rand.pos == len(rand.log)
+        bit_flip = float((model.last_aux['bits'].cpu() != aux['bits']).float().mean())
+        agree = float((obs.cpu().to(torch.uint8)[:, -3:] == o_obs[:, -3:]).float().mean())
+        rew_err = float((rew.cpu().double().reshape(-1) - o_rew).abs().max())
+        row = dict(step=j, A=A, n_action=n_action, sampled_bit_flip=bit_flip, new_frame_agreement=agree,
+                   reward_abs_err=rew_err)
+        rows.append(row)
+        _dump('strict_parity_rollout_A%d_a%d_T%d.json' % (A, n_action, steps), rows)
+        assert not done.any()
+    model.parity_rand = None
+    print(json.dumps(rows[0]), json.dumps(rows[-1]))
+    flips = [r['sampled_bit_flip'] for r in rows]
+    agrees = [r['new_frame_agreement'] for r in rows]
+    # bits: bit-exact on the first step (identical inputs); later steps see frames that differ in the few pixels where
+    # the two arg-max decodes disagreed, so a flip there is a consequence, not a cause: bounded, and reported per step
+    assert flips[0] == 0.0, rows[0]
+    assert max(flips) <= 0.02, max(flips)
+    assert agrees[0] > 0.97 and min(agrees) > 0.90, (agrees[0], min(agrees))
+    # rewards are arg-max decodes of a 3-way head (+ the value bonus on the last step)
+    assert max(r['reward_abs_err'] for r in rows[:-1]) == 0.0
+    assert rows[-1]['reward_abs_err'] < 5e-2, rows[-1]
