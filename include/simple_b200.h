@@ -149,6 +149,9 @@ typedef struct {
                               stats -> prep or reduce -> apply chunk by chunk inside the L2 */
   float* dgb;              /* optional fp32 [C,2] (caller zeroes; sb_prep_bwd_reduce only): += sum over b of bsums[b,c,0..1],
                               i.e. (d beta, d gamma) of the InstanceNorm affine */
+  int moments;             /* 1 (planes of H*W <= 64 pixels only): `sums` holds (mean, biased centred variance) instead of
+                              raw sums -- sb_stats then runs a two-pass, atomics-free kernel (the 6-pixel InstanceNorms with
+                              eps = 1e-6 are ill-conditioned under single-pass statistics); same flag for all four calls */
 } sb_prep_args;
 /* Debug / A-B switch: 1 (default) dispatches to kernel instances specialised at compile time for the feature
  * combinations of the world model; 0 always runs the fully-runtime instances.  Returns the previous setting. */

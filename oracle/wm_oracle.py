@@ -215,13 +215,35 @@ def int_to_bit(ints, nbits=8):
     return torch.cat([torch.remainder(x // 2 ** i, 2) for i in range(nbits)], -1).float()
 
 
+class _InstanceNormEmul(torch.autograd.Function):
+    """InstanceNorm as the fused CUDA stages compute it (csrc/elementwise.cu): statistics single-pass (E[z^2] - E[z]^2,
+    clamped at 0) for the streaming kernel, two-pass for planes of <= 64 pixels (stats_small_kernel); backward by the
+    analytic formula rstd * gamma * (g - mean(g) - xhat * mean(g * xhat))."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        mean = x.mean(dim=(2, 3), keepdim=True)
+        if x.shape[2] * x.shape[3] <= 64:
+            var = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True)
+        else:
+            var = ((x * x).mean(dim=(2, 3), keepdim=True) - mean * mean).clamp(min=0.)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        xhat = (x - mean) * rstd
+        ctx.save_for_backward(xhat, rstd, w)
+        return xhat * w.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        xhat, rstd, w = ctx.saved_tensors
+        gx = g * w.reshape(1, -1, 1, 1)
+        m1 = gx.mean(dim=(2, 3), keepdim=True)
+        m2 = (gx * xhat).mean(dim=(2, 3), keepdim=True)
+        return rstd * (gx - m1 - xhat * m2), (g * xhat).sum(dim=(0, 2, 3)), g.sum(dim=(0, 2, 3)), None
+
+
 def instance_norm(x, w, b, eps=1e-6, cfg=None):
     if cfg is not None and _emul(cfg):
-        # statistics as the fused kernels form them (csrc/elementwise.cu load_cst): E[z^2] - E[z]^2, clamped at 0
-        mean = x.mean(dim=(2, 3), keepdim=True)
-        var = ((x * x).mean(dim=(2, 3), keepdim=True) - mean * mean).clamp(min=0.)
-        xhat = (x - mean) * torch.rsqrt(var + eps)
-        return xhat * w.reshape(1, -1, 1, 1) + b.reshape(1, -1, 1, 1)
+        return _InstanceNormEmul.apply(x, w, b, eps)
     return F.instance_norm(x, weight=w, bias=b, eps=eps)
 
 

@@ -83,7 +83,7 @@ class PrepArgs(ctypes.Structure):
         ('keep', ctypes.c_void_p), ('Tb', ctypes.c_void_p), ('sc', ctypes.c_void_p), ('sh', ctypes.c_void_p),
         ('out2', SbView), ('g2', SbView), ('g1', ctypes.c_void_p), ('bsums', ctypes.c_void_p),
         ('d_main', SbView), ('d_add', ctypes.c_void_p), ('dcol', ctypes.c_void_p),
-        ('b_base', ctypes.c_int), ('b_count', ctypes.c_int), ('dgb', ctypes.c_void_p),
+        ('b_base', ctypes.c_int), ('b_count', ctypes.c_int), ('dgb', ctypes.c_void_p), ('moments', ctypes.c_int),
     ]
 
 

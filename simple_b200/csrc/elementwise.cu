@@ -109,6 +109,7 @@ struct PrepParams {
   // host-precomputed
   uint32_t w_magic;         // fast_div magic of W
   uint32_t nx_magic;        // fast_div magic of the iteration-space width (see iter_space)
+  int moments;              // `sums` holds (mean, biased centred variance) from the two-pass small-plane kernel
 };
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -209,9 +210,15 @@ __device__ __forceinline__ ChanCst load_cst(const PrepParams& q, int b, float* s
     float mean = 0.f, rstd = 1.f, g = 1.f, bt = 0.f, m1 = 0.f, m2 = 0.f;
     if (q.sums) {
       const float s1 = q.sums[((long long)b * C + c) * 2], s2 = q.sums[((long long)b * C + c) * 2 + 1];
-      mean = s1 * invP;
-      const float var = fmaxf(s2 * invP - mean * mean, 0.f);
-      rstd = rsqrtf(var + q.eps);
+      float var;
+      if (q.moments) {  // two-pass statistics of a tiny plane (stats_small_kernel)
+        mean = s1;
+        var = s2;
+      } else {
+        mean = s1 * invP;
+        var = fmaxf(s2 * invP - mean * mean, 0.f);
+      }
+      rstd = 1.0f / __fsqrt_rn(var + q.eps);
       g = q.gamma[c];
       bt = q.beta[c];
       if (bwd && q.bsums) {
@@ -545,6 +552,51 @@ __global__ void __launch_bounds__(256, 2)
   if (has_dcol) {
     __syncthreads();  // the per-channel constants in shared memory are dead: reuse the space as reduction scratch
     lane_reduce_atomic<1>(dsum, sm, CV, PL, cv, pl, q.dcol, 0, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// InstanceNorm statistics of TINY planes (H*W <= 64: the 6x5 / 3x2 bottleneck layers).  eps = 1e-6 and planes of 6
+// pixels make these norms ill-conditioned: a ReLU-sparse channel has a variance of 1e-8..1e-6, where the single-pass
+// E[z^2] - E[z]^2 of the streaming kernel (fp32 atomics over pixel lanes) is mostly cancellation noise -- and rstd ~ 1000
+// turns that noise into O(1e-2) errors of the normalised values the value head reads.  Here one thread owns 8 channels of
+// one sample and makes TWO passes over the <= 64 pixels (mean, then centred sum of squares), like ATen's instance norm:
+// out[b,c] = (mean, biased variance).  No atomics: run-to-run deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stats_small_kernel(const __grid_constant__ PrepParams q, float* out, int nb) {
+  const int CV = q.C / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb * CV) return;
+  const int b = i / CV + q.b_base, c = (i % CV) * 8;
+  const int P = q.H * q.W;
+  float mean[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean[j] = m2[j] = 0.f;
+  RawZ raw;
+  for (int pix = 0; pix < P; ++pix) {
+    const int y = pix / q.W, x = pix - y * q.W;
+    float z[8], mainv[8];
+    finish_z<true, kRT>(q, raw, b, y, x, c, z, mainv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mean[j] += z[j];
+  }
+  const float invP = 1.0f / (float)P;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean[j] *= invP;
+  for (int pix = 0; pix < P; ++pix) {
+    const int y = pix / q.W, x = pix - y * q.W;
+    float z[8], mainv[8];
+    finish_z<true, kRT>(q, raw, b, y, x, c, z, mainv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = z[j] - mean[j];
+      m2[j] += d * d;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    out[((long long)b * q.C + c + j) * 2] = mean[j];
+    out[((long long)b * q.C + c + j) * 2 + 1] = m2[j] * invP;
   }
 }
 
@@ -947,6 +999,8 @@ static int fill(PrepParams& q, const sb_prep_args* a) {
   q.d_add = (__nv_bfloat16*)a->d_add;
   q.dcol = a->dcol;
   q.dgb = a->dgb;
+  q.moments = a->moments;
+  if (q.moments && (long long)q.H * q.W > 64) return SB_ERR_ARG;
   if (!view_ok(q.in) || !view_ok(q.out2) || !view_ok(q.g2) || !view_ok(q.d_main)) return SB_ERR_ARG;
   {  // 32-bit element offsets: the largest view (padded space-to-depth extent included) must stay below 2^31 elements
     long long worst = (long long)q.B * q.H * q.W * q.C;
@@ -1026,9 +1080,16 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   q.sums = nullptr;
   int PL, slabs, pps, threads;
   const int nb = launch_samples(a);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (q.moments) {
+    const int total = nb * (q.C / 8);
+    stats_small_kernel<<<(total + 127) / 128, 128, 0, st>>>(q, sums, nb);
+    ++g_launches;
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+  }
   block_cfg(q, &PL, &threads);
   const size_t smem = (size_t)threads * 2 * 8 * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
   auto go = [&](auto kern) {
     reduce_cfg(q, nb, resident_ctas(kern, threads, smem), &PL, &slabs, &pps, &threads);
     kern<<<dim3(slabs, nb), threads, smem, st>>>(q, sums, PL, pps);

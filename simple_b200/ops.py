@@ -104,6 +104,8 @@ def _prep_args(spec, B, main, add, sums, gamma, beta, sc, sh, out1, out2, seed, 
     a.Tb = _ptr(spec.Tb)
     a.sc, a.sh = _ptr(sc), _ptr(sh)
     a.out2 = spec.lay_out.view(out2)
+    # tiny planes (the 6x5 / 3x2 bottleneck InstanceNorms): two-pass (mean, variance) statistics, see sb_prep_args
+    a.moments = int(bool(spec.norm) and spec.H * spec.W <= 64)
     return a
 
 

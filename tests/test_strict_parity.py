@@ -43,6 +43,16 @@ def _setup(B, n_action, steps, seed=0):
     return O, cfg, model, p0, frames_u8, per_step
 
 
+def _tie_consistent(ologits, choice):
+    """Fraction of (sample, colour, pixel) positions where the CUDA arg-max `choice` (long [B,3,H,W]) is a maximum of the
+    ORACLE's logits [B,256,3,H,W] up to bf16 resolution: oracle_logit[choice] >= max - 2 bf16 ulps of the maximum.  A
+    wrong decode (any logit that is not a near-tie of the maximum) counts as inconsistent."""
+    mx = ologits.max(dim=1).values
+    got = ologits.gather(1, choice.unsqueeze(1)).squeeze(1)
+    ulp = torch.exp2(torch.floor(torch.log2(mx.abs().clamp(min=1e-30))) - 7)
+    return float((got >= mx - 2 * ulp).float().mean())
+
+
 def _dump(name, rows):
     os.makedirs('gpurun_out', exist_ok=True)
     with open(os.path.join('gpurun_out', name), 'w') as f:
@@ -93,6 +103,7 @@ def test_train_window_unforced_vs_emulating_oracle(B, n_action, steps):
         am_agree = float((out['argmax'].cpu().long() == oam).float().mean())
         row = dict(step=j, B=B, n_action=n_action, posterior_sign_flip=sign_flip, sampled_bit_flip=bit_flip,
                    latent_max_abs_err=latent_err, argmax_agreement=am_agree,
+                   argmax_tie_consistent=_tie_consistent(logits.detach(), out['argmax'].cpu().long()),
                    logits_rel=_rel(out['logits_ref'], logits), reward_rel=_rel(out['reward_pred'], rew),
                    value_abs=float((out['value_pred'].cpu() - val.detach()).abs().max()),
                    posterior_pre_rel=_rel(la['posterior_pre'], aux['posterior_pre']))
@@ -129,22 +140,49 @@ def test_train_window_unforced_vs_emulating_oracle(B, n_action, steps):
         # value head: 4608-wide dot product over the bf16 bottleneck right behind a 6-pixel InstanceNorm:
         # written bound 2e-2 absolute on outputs of O(1)
         assert row['value_abs'] < 2e-2 and row['loss_value_abs'] < 2e-2, row
-        assert am_agree > 0.97, row   # measured 0.99+ (profiles/r2_strict_parity.md); decode itself bit-exact
+        # arg-max frames: every CUDA decode is a maximum of the oracle's logits up to bf16 resolution (ties of the bf16
+        # logits are the only disagreements), and the plain agreement is what that leaves: measured 0.998
+        assert row['argmax_tie_consistent'] >= 0.9999, row
+        assert am_agree > 0.99, row
         assert row['grad_min_cos'] > 0.99, row
         frames = torch.cat((frames[:, 3:], oam.float() / 255), dim=1)
     model.parity_rand = None
 
 
-@pytest.mark.parametrize('A,n_action,steps', [(16, 3, 5), (4, 9, 5), (2, 3, 50)])
-def test_rollout_vs_emulating_oracle(A, n_action, steps):
-    """SimulatedVecEnv.step (eager, injected randomness) against O.rollout_step for a whole rollout: every side feeds
-    back ITS OWN arg-max frames and carries its own recurrent state (subproc_vec_env.py:409-445), incl. the value-head
-    bonus on the last step.  Sampled bits bit-exact; frame agreement per step reported and bounded."""
+def _trained_weights(cfg, n_action, steps=150):
+    """Weights after `steps` optimiser steps of the CUDA trainer on the synthetic sprite replay: a model whose pixel
+    distributions are PEAKED (like any trained world model), unlike the nearly flat logits of the random init."""
+    from types import SimpleNamespace
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    from simple_b200.synthetic import synth_replay
+    from simple_b200.trainer import Trainer
+    tcfg = SimpleNamespace(**{**vars(cfg), 'batch_size': 8, 'rollout_length': 25})
+    torch.manual_seed(0)
+    model = NextFramePredictor(tcfg, n_action).to(DEV)
+    d = synth_replay(80, n_action, 4)
+    buf = [[d['obs'][i], d['action'][i], d['reward'][i], d['new_obs'][i], torch.tensor(0, dtype=torch.uint8),
+            d['value'][i].clone()] for i in range(80)]
+    m = Trainer(model, tcfg).train(1, SimpleNamespace(buffer=buf), steps=steps)
+    print('trained:', m)
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, d['obs']
+
+
+@pytest.mark.parametrize('A,n_action,steps,trained', [(16, 3, 5, False), (4, 9, 5, False), (4, 3, 50, True)])
+def test_rollout_vs_emulating_oracle(A, n_action, steps, trained):
+    """SimulatedVecEnv.step (eager, injected randomness) against the oracle's rollout step (subproc_vec_env.py:409-445)
+    for a whole rollout, recurrent state carried on both sides, incl. the value-head bonus on the last step.
+      * random init: the frame stacks are re-synchronised to the oracle's after every step (each step is compared on
+        identical input frames; an untrained model turns every bf16 arg-max tie into a different input and diverges);
+      * trained weights: FREE-RUNNING for the reference's full 50-step horizon -- both sides feed back their own decodes."""
     torch.set_num_threads(os.cpu_count())
     O, cfg, model, p0, frames_u8, per_step = _setup(A, n_action, steps, seed=2)
     from simple_b200.next_frame_predictor import InjectedRand
     from simple_b200.simulated_env import Discrete, make_simulated_env
     cfg.agents, cfg.rollout_length, cfg.cuda_graph = A, steps, False
+    if trained:
+        p0, obs0 = _trained_weights(cfg, n_action)
+        model.load_state_dict(p0)
+        frames_u8 = obs0[10:10 + A].clone()
     ocfg = O.bf16_config(device='cpu', batch_size=A, agents=A, rollout_length=steps)
     env = make_simulated_env(cfg, model, Discrete(n_action))
     env.restart_all(frames_u8.to(DEV))
@@ -157,7 +195,6 @@ def test_rollout_vs_emulating_oracle(A, n_action, steps):
         act = per_step[j]['action']  # one-hot [A,n]
         rand = O.GlobalRand()
         aux = {}
-        # (rollout_step wraps forward; call forward here to also get the latent bits)
         with torch.no_grad():
             logits, rewards, values, _ = O.forward(p0, ocfg, state, frames, act.unsqueeze(1), None, 0, rand,
                                                    training=False, aux=aux)
@@ -171,23 +208,28 @@ def test_rollout_vs_emulating_oracle(A, n_action, steps):
         obs, rew, done, _ = env.step(act.argmax(dim=1, keepdim=True))
         torch.cuda.synchronize()
         assert model.parity_rand.pos == len(rand.log)
-        bit_flip = float((model.last_aux['bits'].cpu() != aux['bits']).float().mean())
-        agree = float((obs.cpu().to(torch.uint8)[:, -3:] == o_obs[:, -3:]).float().mean())
-        rew_err = float((rew.cpu().double().reshape(-1) - o_rew).abs().max())
-        row = dict(step=j, A=A, n_action=n_action, sampled_bit_flip=bit_flip, new_frame_agreement=agree,
-                   reward_abs_err=rew_err)
+        new = obs.cpu().to(torch.uint8)[:, -3:]
+        row = dict(step=j, A=A, n_action=n_action, trained=trained,
+                   sampled_bit_flip=float((model.last_aux['bits'].cpu() != aux['bits']).float().mean()),
+                   new_frame_agreement=float((new == o_obs[:, -3:]).float().mean()),
+                   new_frame_tie_consistent=_tie_consistent(logits, new.long()),
+                   reward_abs_err=float((rew.cpu().double().reshape(-1) - o_rew).abs().max()))
         rows.append(row)
         _dump('strict_parity_rollout_A%d_a%d_T%d.json' % (A, n_action, steps), rows)
         assert not done.any()
+        if not trained and j < steps - 1:  # re-synchronise the input frames (the recurrent states stay each side's own)
+            env.frames.copy_(o_obs.to(DEV))
+            env._obs.copy_(env.frames)
     model.parity_rand = None
     print(json.dumps(rows[0]), json.dumps(rows[-1]))
     flips = [r['sampled_bit_flip'] for r in rows]
     agrees = [r['new_frame_agreement'] for r in rows]
-    # bits: bit-exact on the first step (identical inputs); later steps see frames that differ in the few pixels where
-    # the two arg-max decodes disagreed, so a flip there is a consequence, not a cause: bounded, and reported per step
-    assert flips[0] == 0.0, rows[0]
-    assert max(flips) <= 0.02, max(flips)
-    assert agrees[0] > 0.97 and min(agrees) > 0.90, (agrees[0], min(agrees))
+    assert max(flips) == 0.0, flips                     # sampled latent bits: bit-exact over the whole rollout
+    if trained:
+        assert min(agrees) > 0.99, min(agrees)          # free-running 50 steps (measured: see profiles/r2_strict_parity.md)
+    else:
+        assert min(agrees) > 0.99, min(agrees)          # measured 0.998 per step on identical inputs (bf16 logit ties)
+        assert min(r['new_frame_tie_consistent'] for r in rows) >= 0.9999
     # rewards are arg-max decodes of a 3-way head (+ the value bonus on the last step)
     assert max(r['reward_abs_err'] for r in rows[:-1]) == 0.0
-    assert rows[-1]['reward_abs_err'] < 5e-2, rows[-1]
+    assert rows[-1]['reward_abs_err'] < 2e-2, rows[-1]
