@@ -146,7 +146,6 @@ class StochasticModel(nn.Module):  # :124-206
         channels = config.frame_shape[0] * (int(config.stacking) + 1)
         filters = [128, 512]
         self.lstm_loss = None
-        self.get_lstm_loss()
         self.input_embedding = nn.Conv2d(channels, config.hidden_size, 1)
         self.conv1 = nn.Conv2d(config.hidden_size, filters[0], 8, 4, padding=2)
         self.conv2 = nn.Conv2d(filters[0], filters[1], 8, 4, padding=2)
@@ -164,10 +163,15 @@ class StochasticModel(nn.Module):  # :124-206
         return layer * z_mul + z_add
 
     def get_lstm_loss(self, reset=True):
+        """Accumulated teacher-forcing loss since the last reset (next_frame_predictor.py:202-206 of the reference).
+        The accumulator is `None` while empty: no device tensor outlives a step, so a captured CUDA graph never bakes
+        in the address of a tensor that eager code later frees (round 1 kept a zeros() tensor here; every replay of
+        the step graph then added whatever had since been allocated at that address to the reported loss)."""
         res = self.lstm_loss
+        if res is None:
+            res = torch.zeros((), device=self.dense1.weight.device)
         if reset:
-            dev = res.device if isinstance(res, torch.Tensor) else None
-            self.lstm_loss = torch.zeros((), device=dev)  # (no host->device copy: CUDA-graph capturable)
+            self.lstm_loss = None
         return res
 
 
@@ -684,7 +688,7 @@ class NextFramePredictor(nn.Module):
         flat = layer.reshape(B, -1)
         proj = sm.bits_predictor.project(flat)
         _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean, proj=proj)
-        sm.lstm_loss = sm.lstm_loss.to(lstm_loss.device) + lstm_loss
+        sm.lstm_loss = lstm_loss if sm.lstm_loss is None else sm.lstm_loss + lstm_loss
         bits_pred, _ = sm.bits_predictor(flat, rand, proj=[t.detach() for t in proj])
         bits_pred = self._forced(rand, 'sampled_bits', bits_pred)
         aux['bits_pred'] = bits_pred.detach()

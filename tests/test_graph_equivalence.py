@@ -71,7 +71,15 @@ def test_step_runner_graph_replay_equals_eager_step():
     B = 4
     cfg = _cfg(batch_size=B, rollout_length=8)
     torch.manual_seed(0)
-    model = NextFramePredictor(cfg, 3).to(DEV)
+    model = NextFramePredictor(cfg, 3)
+    # well-conditioned variant (see tests/test_strict_parity.py::_setup): on the reference init the global gradient norm
+    # -- hence every update, through the clip coefficient -- moves by tens of percent between two executions of the SAME
+    # step (fp32 atomics + the 1000x gain of the 6-pixel InstanceNorms), which would drown a graph-vs-eager comparison
+    with torch.no_grad():
+        for k in ('downscale_layers.6.bias', 'downscale_layers.8.bias', 'middle_network.middle_network.0.bias',
+                  'middle_network.middle_network.2.bias', 'upscale_layers.0.bias'):
+            dict(model.named_parameters())[k].add_(1.0)
+    model = model.to(DEV)
     trainer = Trainer(model, cfg)
     rp = _replay(B + 24)
     runner = StepRunner(trainer, rp, B, use_graph=True, resident=True)
@@ -93,10 +101,13 @@ def test_step_runner_graph_replay_equals_eager_step():
         return dict(losses=runner.losses.clone(), params=[p.detach().clone() for p in model.parameters()],
                     frames=runner.frames.clone(), state=model._state.clone())
 
+    before = [v.clone() for v in snap.params]
+
     def worst(a, b):
+        """largest difference between the two runs' UPDATES, relative to the update itself"""
         rows = []
-        for (k, _), x, y in zip(model.named_parameters(), a['params'], b['params']):
-            rows.append((float((x - y).abs().max() / (y.abs().max() + 1e-12)), k))
+        for (k, _), x, y, w0 in zip(model.named_parameters(), a['params'], b['params'], before):
+            rows.append((float((x - y).norm() / ((y - w0).norm() + 1e-30)), k))
         return sorted(rows, reverse=True)
 
     g1, g2, e1, e2 = run('graph'), run('graph'), run('eager'), run('eager')
@@ -107,7 +118,8 @@ def test_step_runner_graph_replay_equals_eager_step():
     ge = worst(g1, e1)
     print('noise floor (same kind twice): %.3e; graph vs eager worst: %s' % (floor, ge[:3]))
     assert torch.allclose(e1['losses'], g1['losses'], rtol=1e-3, atol=1e-4), (e1['losses'], g1['losses'])
-    assert ge[0][0] < max(1e-4, 3 * floor), (ge[:5], floor)
+    assert floor < 2e-2, floor
+    assert ge[0][0] < max(1e-3, 3 * floor), (ge[:5], floor)
     assert float((e1['frames'] != g1['frames']).float().mean()) < 5e-3  # fed-back arg-max frames (+ input noise)
     assert float((e1['state'] - g1['state']).abs().mean()) < 1e-4
 
