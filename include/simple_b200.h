@@ -281,14 +281,86 @@ int sb_mean_attention_bwd(const void* x, const float* We, const float* Wd, const
  * or two samples per CTA.  sb_lstm_teacher_fwd/bwd run all 16 teacher-forced LSTMCell steps and their backward through
  * time in one launch each: xw [B,16,512] input-gate pre-activations -> hs [B,16,128]; saved act [B,16,512], cs [B,16,128];
  * backward emits dpre [B,16,512] (= d xw; dW_hh = dpre^T h_prev on the host side), dh0, dc0 [B,128]. */
+/* hc_ld: row stride (floats, >= 128) of h0 / c0 / dh0 / dc0 -- they may be column slices of the [B,384] output of the
+ * fused dense1|dense2|dense3 projection. */
 int sb_lstm_sample2(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
                     const float* w5T, const float* b5, const float* noise, const unsigned long long* seed_ptr, int B,
-                    float* bits, int* ints, sb_stream_t stream);
-int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B, float* hs,
-                        float* act, float* cs, sb_stream_t stream);
+                    int hc_ld, float* bits, int* ints, sb_stream_t stream);
+int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B, int hc_ld,
+                        float* hs, float* act, float* cs, sb_stream_t stream);
 int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, const float* c0, const float* whh, int B,
-                        float* dpre, float* dh0, float* dc0, sb_stream_t stream);
+                        int hc_ld, float* dpre, float* dh0, float* dc0, sb_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Latent / heads block (csrc/latent.cu): every elementwise, reduction, gather and scatter piece between the bottleneck
+ * and the middle network, forward and backward; the dense layers between them are plain library GEMMs issued by the
+ * caller.  "flat" = the reference's flatten order of the [768,3,2] bottleneck (index c*6 + h*2 + w).  Optional explicit
+ * randomness pointers (NULL = drawn in-kernel from a counter hash of seed + *seed_ptr; the backward regenerates it).
+ * Replaces: simple/next_frame_predictor.py:328 (value head), simple/utils.py:98-105 (ActionInjector scale/shift, all
+ * injectors at once), next_frame_predictor.py:176-197 (posterior bits, straight-through, the three mix() calls of
+ * simple/utils.py:157-163), :87-107 (teacher forcing: bytes, dense4 lookup, dropouts, CE), :153-159 (add_bits),
+ * :11-24,352-354 + simple/trainer.py:138-141 (reward MLP tail, reward CE, value MSE).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* dsc[9];   /* grad w.r.t. sigmoid(dense1(a)) of injector i (NULL = none); element (b,c) at b*sc_sb + c*sc_sc */
+  const float* dsh[9];   /* grad w.r.t. dense2(a); element (b,c) at b*sh_sb + c*sh_sc */
+  int sc_sb[9], sc_sc[9], sh_sb[9], sh_sc[9];
+} sb_inj_grads;
+/* x5: bf16 NHWC [B,3,2,768]; bank [B, 2S] = (dense1 pre-activations | dense2 outputs) of the `ninj` injectors (widths[i]
+ * channels each, widths[0] == 768, S = sum); wv [4608] flat, bv [1].  Outputs: sc_flat / sh_flat (injector i: contiguous
+ * [B, widths[i]] block at element offset B * sum(widths[:i])), h_flat [B,4608] = x5 * sc_0 + sh_0 (may be NULL), value [B]. */
+int sb_heads_fwd(const void* x5, const float* bank, const int* widths, int ninj, const float* wv, const float* bv, int B,
+                 float* sc_flat, float* sh_flat, float* h_flat, float* value, sb_stream_t stream);
+/* dx5 bf16 NHWC; dbank [B,2S]; dwv [4608], dbv [1], dbank_b [2S]: accumulated (+=), caller zeroes. */
+int sb_heads_bwd(const void* x5, const float* bank, const int* widths, int ninj, const sb_inj_grads* grads,
+                 const float* wv, const float* dvalue, const float* dh_flat, int B, void* dx5, float* dbank, float* dwv,
+                 float* dbv, float* dbank_b, sb_stream_t stream);
+/* pre [B,128] -> x = tanh(pre + truncnorm), bits2 = mix(sign(x) * flip, x, 1 - eps), bits_clean = sign(pre),
+ * flags u8 [B,128] (bit0 flip = -1, bit1 first mix took x), tints int32 [B,16] (bytes of bits_clean, LSB first). */
+int sb_posterior_bits_fwd(const float* pre, const float* tn, const float* u_flip, const float* u_mix1,
+                          const float* eps_ptr, float eps_val, float noise_p, const unsigned long long* seed_ptr,
+                          unsigned long long seed, int B, float* x, float* bits2, float* bits_clean, uint8_t* flags,
+                          int* tints, sb_stream_t stream);
+/* bits3 = mix(bits_pred, bits2, 1 - (1 - eps) * max_sampling); sets flags bit2 where bits2 was taken. */
+int sb_mix_bits(const float* bits_pred, const float* bits2, const float* u_mix2, const float* eps_ptr, float eps_val,
+                float max_sampling, const unsigned long long* seed_ptr, unsigned long long seed, int B, float* bits3,
+                uint8_t* flags, sb_stream_t stream);
+/* dpre = dbits3 * m2 * ((1-m1)*flip + m1) * (1 - x^2); db1 [128] += column sums (caller zeroes). */
+int sb_posterior_bits_bwd(const float* dbits3, const float* x, const uint8_t* flags, int B, float* dpre, float* db1,
+                          sb_stream_t stream);
+/* tin [B,16,128]: step 0 = proj[b, :128] (row stride proj_ld), step t = dropout(w4[:, byte_{t-1}] + b4; keep [B,16,128] or
+ * hash, p); optionally bsum [512] = b_ih + b_hh.  Backward: dproj[b, :128] = dtin[:, 0]; dw4 [128,256], db4 [128] += scatter. */
+int sb_teacher_embed_fwd(const float* proj, int proj_ld, const int* tints, const float* w4, const float* b4,
+                         const float* keep, float p, const unsigned long long* seed_ptr, unsigned long long seed,
+                         const float* b_ih, const float* b_hh, float* bsum, int B, float* tin, sb_stream_t stream);
+int sb_teacher_embed_bwd(const float* dtin, const int* tints, const float* keep, float p,
+                         const unsigned long long* seed_ptr, unsigned long long seed, int B, float* dproj, int dproj_ld,
+                         float* dw4, float* db4, sb_stream_t stream);
+/* out = x * keep / (1 - p) over n elements (keep: explicit 0/1 floats, or NULL = hash stream `stream_id`). */
+int sb_drop_scale(const float* x, const float* keep, float p, const unsigned long long* seed_ptr, unsigned long long seed,
+                  unsigned int stream_id, float* out, long long n, sb_stream_t stream);
+/* Row-wise softmax CE (N <= 256): *loss_sum += sum_r (lse - x[r,t_r]); dlogits = (softmax - onehot) * gscale;
+ * dbias [N] += column sums of dlogits (optional).  Caller zeroes loss_sum / dbias. */
+int sb_softmax_ce_rows(const float* logits, const int* targets, int R, int N, float gscale, float* loss_sum,
+                       float* dlogits, float* dbias, sb_stream_t stream);
+/* zz [B,1536] = (dense2(bits) | dense3(bits)); out = mix(h*sigmoid(z_mul)+z_add, h, 1-(1-eps)*use_max_p) when train, else
+ * h*sigmoid(z_mul)+z_add.  hm: bf16 NHWC [B,3,2,768]; x_mid [B,768] = mean over the 6 pixels; m3 u8 [B,4608] (train). */
+int sb_latent_out_fwd(const float* h_flat, const float* zz, const float* u_mix3, int train, const float* eps_ptr,
+                      float eps_val, float use_max_p, const unsigned long long* seed_ptr, unsigned long long seed, int B,
+                      void* hm, float* x_mid, uint8_t* m3, sb_stream_t stream);
+/* dx_mid: [B,768] with row stride dxm_ld (a column slice of the reward MLP's input gradient), or NULL. */
+int sb_latent_out_bwd(const void* dhm, const float* dx_mid, int dxm_ld, const float* h_flat, const float* zz,
+                      const uint8_t* m3, int B, float* dh_flat, float* dzz, float* db23, sb_stream_t stream);
+/* whhT [128,512], wihT [128,512], w5T [128,256], emb [256,128] = w4^T + b4 (operands of sb_lstm_sample2) in one launch. */
+int sb_sampler_tables(const float* w_hh, const float* w_ih, const float* w5, const float* w4, const float* b4, float* whhT,
+                      float* wihT, float* w5T, float* emb, sb_stream_t stream);
+/* hid_pre [B,128]; reward_pred [B,3] = w2 relu(hid_pre) + b2.  With rewards (int64 [B]): loss_out[0] += CE / B,
+ * loss_out[1] += mean (value_pred - values)^2, dhid_pre, dw2 [3,128] / db2 [3] (+=), dvalue [B].  rewards == NULL: forward only. */
+int sb_reward_value(const float* hid_pre, const float* w2, const float* b2, const long long* rewards,
+                    const float* value_pred, const float* values, int B, float* reward_pred, float* loss_out,
+                    float* dhid_pre, float* dw2, float* db2, float* dvalue, sb_stream_t stream);
+/* out[N] += column sums of x [M,N] (row stride ld): bias gradients of the dense layers. */
+int sb_colsum_f32(const float* x, int M, int N, int ld, float* out, sb_stream_t stream);
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,11 @@ class TapWgradArgs(ctypes.Structure):
     ]
 
 
+class InjGrads(ctypes.Structure):
+    _fields_ = [('dsc', ctypes.c_void_p * 9), ('dsh', ctypes.c_void_p * 9), ('sc_sb', ctypes.c_int * 9),
+                ('sc_sc', ctypes.c_int * 9), ('sh_sb', ctypes.c_int * 9), ('sh_sc', ctypes.c_int * 9)]
+
+
 class SbView(ctypes.Structure):
     _fields_ = [('p', ctypes.c_void_p), ('kind', ctypes.c_int), ('s', ctypes.c_int), ('pad', ctypes.c_int),
                 ('H2', ctypes.c_int), ('W2', ctypes.c_int)]
@@ -137,9 +142,9 @@ class _Sigs:
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_mean_attention_fwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_mean_attention_bwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
-    sb_lstm_sample2 = [_p] * 9 + [_i, _p, _p, _p]
-    sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
-    sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]
+    sb_lstm_sample2 = [_p] * 9 + [_i, _i, _p, _p, _p]
+    sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
+    sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_grad_sumsq = [_p, _p, _p, _i, _p, _p, _p]
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p, _i, _p]
@@ -149,6 +154,21 @@ class _Sigs:
     sb_bias_act = [_p, _p, _i, _p, _i, _ll, _i, _p]
     sb_transpose_taps_multi = [_p, _i, _i, _p]
     sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
+    # latent / heads block (csrc/latent.cu)
+    sb_heads_fwd = [_p, _p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p]
+    sb_heads_bwd = [_p, _p, _p, _i, ctypes.POINTER(InjGrads), _p, _p, _p, _i, _p, _p, _p, _p, _p, _p]
+    sb_posterior_bits_fwd = [_p, _p, _p, _p, _p, _f, _f, _p, ctypes.c_ulonglong, _i, _p, _p, _p, _p, _p, _p]
+    sb_mix_bits = [_p, _p, _p, _p, _f, _f, _p, ctypes.c_ulonglong, _i, _p, _p, _p]
+    sb_posterior_bits_bwd = [_p, _p, _p, _i, _p, _p, _p]
+    sb_teacher_embed_fwd = [_p, _i, _p, _p, _p, _p, _f, _p, ctypes.c_ulonglong, _p, _p, _p, _i, _p, _p]
+    sb_teacher_embed_bwd = [_p, _p, _p, _f, _p, ctypes.c_ulonglong, _i, _p, _i, _p, _p, _p]
+    sb_drop_scale = [_p, _p, _f, _p, ctypes.c_ulonglong, ctypes.c_uint, _p, _ll, _p]
+    sb_softmax_ce_rows = [_p, _p, _i, _i, _f, _p, _p, _p, _p]
+    sb_latent_out_fwd = [_p, _p, _p, _i, _p, _f, _f, _p, ctypes.c_ulonglong, _i, _p, _p, _p, _p]
+    sb_latent_out_bwd = [_p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p]
+    sb_sampler_tables = [_p] * 10
+    sb_reward_value = [_p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p]
+    sb_colsum_f32 = [_p, _i, _i, _i, _p, _p]
 
 
 EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]

@@ -52,7 +52,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
     lstm_sample3_kernel(const float* __restrict__ G0, const float* __restrict__ h0, const float* __restrict__ c0,
                         const float* __restrict__ E, const float* __restrict__ whhT, const float* __restrict__ w5T,
                         const float* __restrict__ b5, const float* __restrict__ noise,
-                        const unsigned long long* seed_ptr, int B, float* __restrict__ bits, int* __restrict__ ints) {
+                        const unsigned long long* seed_ptr, int B, int hc_ld, float* __restrict__ bits, int* __restrict__ ints) {
   extern __shared__ float wsm[];
   float* wh = wsm;                    // [128 k][256 local gate rows]: local row g*64+jl <-> global row g*128 + 64r + jl
   float* w5 = wsm + kH * 256;         // [128 k][128 local logits]:    local ln <-> global logit 128r + ln
@@ -73,11 +73,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
   }
   for (int i = t; i < S * kH; i += 512) {
     const int s = i / kH, j = i - s * kH;
-    hbuf[0][s][j] = h0[min(b0 + s, B - 1) * kH + j];
+    hbuf[0][s][j] = h0[(size_t)min(b0 + s, B - 1) * hc_ld + j];
   }
   for (int i = t; i < S * 64; i += 512) {
     const int s = i >> 6, jl = i & 63;
-    c[s][jl] = c0[min(b0 + s, B - 1) * kH + 64 * (int)rank + jl];
+    c[s][jl] = c0[(size_t)min(b0 + s, B - 1) * hc_ld + 64 * (int)rank + jl];
   }
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   cluster_sync_all();  // both CTAs are running (remote shared-memory writes below) and the local weights are staged
@@ -214,7 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
 template <int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
     lstm_teacher_fwd2_kernel(const float* __restrict__ xw, const float* __restrict__ h0, const float* __restrict__ c0,
-                             const float* __restrict__ whhT, int B, float* __restrict__ hs, float* __restrict__ act,
+                             const float* __restrict__ whhT, int B, int hc_ld, float* __restrict__ hs, float* __restrict__ act,
                              float* __restrict__ cs) {
   extern __shared__ float wsm[];
   float* wh = wsm;  // [128 k][256 local gate rows]
@@ -226,8 +226,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
     const int k = i >> 8, lr = i & 255;
     wh[i] = __ldg(whhT + k * (4 * kH) + (lr >> 6) * kH + 64 * (int)rank + (lr & 63));
   }
-  for (int i = t; i < S * kH; i += 512) hbuf[0][i / kH][i % kH] = h0[min(b0 + i / kH, B - 1) * kH + i % kH];
-  for (int i = t; i < S * 64; i += 512) c[i >> 6][i & 63] = c0[min(b0 + (i >> 6), B - 1) * kH + 64 * (int)rank + (i & 63)];
+  for (int i = t; i < S * kH; i += 512) hbuf[0][i / kH][i % kH] = h0[(size_t)min(b0 + i / kH, B - 1) * hc_ld + i % kH];
+  for (int i = t; i < S * 64; i += 512) c[i >> 6][i & 63] = c0[(size_t)min(b0 + (i >> 6), B - 1) * hc_ld + 64 * (int)rank + (i & 63)];
   cluster_sync_all();
   for (int step = 0; step < kSteps; ++step) {
     const float (*h_old)[kH] = hbuf[step & 1];
@@ -281,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
 template <int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
     lstm_teacher_bwd2_kernel(const float* __restrict__ dhs, const float* __restrict__ act, const float* __restrict__ cs,
-                             const float* __restrict__ c0, const float* __restrict__ whh, int B,
+                             const float* __restrict__ c0, const float* __restrict__ whh, int B, int hc_ld,
                              float* __restrict__ dpre_all, float* __restrict__ dh0, float* __restrict__ dc0) {
   extern __shared__ float wsm[];
   float* wr = wsm;  // [256 local rows][128 j]: the W_hh rows of this CTA's hidden units (gate-major local order)
@@ -305,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
       const size_t row = (size_t)b * kSteps + step;
       const float* a = act + row * 4 * kH;
       const float ig = a[j], fg = a[kH + j], gg = a[2 * kH + j], og = a[3 * kH + j];
-      const float cprev = step > 0 ? cs[(row - 1) * kH + j] : c0[b * kH + j];
+      const float cprev = step > 0 ? cs[(row - 1) * kH + j] : c0[(size_t)b * hc_ld + j];
       const float tc = tanh_acc(cs[row * kH + j]);
       const float dhi = dhs[row * kH + j] + dh[s][jl];
       const float dct = dc[s][jl] + dhi * og * (1.0f - tc * tc);
@@ -347,8 +347,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512)
   for (int i = t; i < S * 64; i += 512) {
     const int s = i >> 6, jl = i & 63;
     if (b0 + s < B) {
-      dh0[(b0 + s) * kH + 64 * (int)rank + jl] = dh[s][jl];
-      dc0[(b0 + s) * kH + 64 * (int)rank + jl] = dc[s][jl];
+      dh0[(size_t)(b0 + s) * hc_ld + 64 * (int)rank + jl] = dh[s][jl];
+      dc0[(size_t)(b0 + s) * hc_ld + 64 * (int)rank + jl] = dc[s][jl];
     }
   }
 }
@@ -360,7 +360,7 @@ using namespace sb;
 template <int S>
 static int launch_sample3(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
                           const float* w5T, const float* b5, const float* noise, const unsigned long long* seed_ptr, int B,
-                          float* bits, int* ints, cudaStream_t st) {
+                          int hc_ld, float* bits, int* ints, cudaStream_t st) {
   constexpr int smem = (kH * 256 + kH * 128) * sizeof(float);  // resident weight slices: 192 KB
   static bool configured = false;
   if (!configured) {
@@ -369,7 +369,8 @@ static int launch_sample3(const float* G0, const float* h0, const float* c0, con
     configured = true;
   }
   const int groups = (B + S - 1) / S;
-  lstm_sample3_kernel<S><<<2 * groups, 512, smem, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints);
+  lstm_sample3_kernel<S><<<2 * groups, 512, smem, st>>>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, hc_ld, bits,
+                                                        ints);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -377,17 +378,18 @@ static int launch_sample3(const float* G0, const float* h0, const float* c0, con
 
 extern "C" int sb_lstm_sample2(const float* G0, const float* h0, const float* c0, const float* E, const float* whhT,
                                const float* w5T, const float* b5, const float* noise,
-                               const unsigned long long* seed_ptr, int B, float* bits, int* ints, sb_stream_t stream) {
-  if (!G0 || !h0 || !c0 || !E || !whhT || !w5T || !b5 || !bits || !ints || B < 1) return SB_ERR_ARG;
+                               const unsigned long long* seed_ptr, int B, int hc_ld, float* bits, int* ints,
+                               sb_stream_t stream) {
+  if (!G0 || !h0 || !c0 || !E || !whhT || !w5T || !b5 || !bits || !ints || B < 1 || hc_ld < kH) return SB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   // one CTA pair (cluster) per one or two samples, recurrent weights resident in the pair's shared memory
-  if (B >= 64 && B % 2 == 0) return launch_sample3<2>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints, st);
-  return launch_sample3<1>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, bits, ints, st);
+  if (B >= 64 && B % 2 == 0) return launch_sample3<2>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, hc_ld, bits, ints, st);
+  return launch_sample3<1>(G0, h0, c0, E, whhT, w5T, b5, noise, seed_ptr, B, hc_ld, bits, ints, st);
 }
 
 template <int S>
 static int launch_teacher(bool bwd, const float* p0, const float* p1, const float* p2, const float* p3, const float* p4,
-                          int B, float* o0, float* o1, float* o2, cudaStream_t st) {
+                          int B, int hc_ld, float* o0, float* o1, float* o2, cudaStream_t st) {
   constexpr int smem = kH * 256 * sizeof(float);  // resident W_hh slice: 128 KB
   static bool configured = false;
   if (!configured) {
@@ -399,25 +401,26 @@ static int launch_teacher(bool bwd, const float* p0, const float* p1, const floa
     configured = true;
   }
   const int groups = (B + S - 1) / S;
-  if (!bwd) lstm_teacher_fwd2_kernel<S><<<2 * groups, 512, smem, st>>>(p0, p1, p2, p3, B, o0, o1, o2);
-  else lstm_teacher_bwd2_kernel<S><<<2 * groups, 512, smem, st>>>(p0, p1, p2, p3, p4, B, o0, o1, o2);
+  if (!bwd) lstm_teacher_fwd2_kernel<S><<<2 * groups, 512, smem, st>>>(p0, p1, p2, p3, B, hc_ld, o0, o1, o2);
+  else lstm_teacher_bwd2_kernel<S><<<2 * groups, 512, smem, st>>>(p0, p1, p2, p3, p4, B, hc_ld, o0, o1, o2);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
 
-extern "C" int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B,
+extern "C" int sb_lstm_teacher_fwd(const float* xw, const float* h0, const float* c0, const float* whhT, int B, int hc_ld,
                                    float* hs, float* act, float* cs, sb_stream_t stream) {
-  if (!xw || !h0 || !c0 || !whhT || !hs || !act || !cs || B < 1) return SB_ERR_ARG;
+  if (!xw || !h0 || !c0 || !whhT || !hs || !act || !cs || B < 1 || hc_ld < kH) return SB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B >= 64 && B % 2 == 0) return launch_teacher<2>(false, xw, h0, c0, whhT, nullptr, B, hs, act, cs, st);
-  return launch_teacher<1>(false, xw, h0, c0, whhT, nullptr, B, hs, act, cs, st);
+  if (B >= 64 && B % 2 == 0) return launch_teacher<2>(false, xw, h0, c0, whhT, nullptr, B, hc_ld, hs, act, cs, st);
+  return launch_teacher<1>(false, xw, h0, c0, whhT, nullptr, B, hc_ld, hs, act, cs, st);
 }
 
 extern "C" int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, const float* c0,
-                                   const float* whh, int B, float* dpre, float* dh0, float* dc0, sb_stream_t stream) {
-  if (!dhs || !act || !cs || !c0 || !whh || !dpre || !dh0 || !dc0 || B < 1) return SB_ERR_ARG;
+                                   const float* whh, int B, int hc_ld, float* dpre, float* dh0, float* dc0,
+                                   sb_stream_t stream) {
+  if (!dhs || !act || !cs || !c0 || !whh || !dpre || !dh0 || !dc0 || B < 1 || hc_ld < kH) return SB_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B >= 64 && B % 2 == 0) return launch_teacher<2>(true, dhs, act, cs, c0, whh, B, dpre, dh0, dc0, st);
-  return launch_teacher<1>(true, dhs, act, cs, c0, whh, B, dpre, dh0, dc0, st);
+  if (B >= 64 && B % 2 == 0) return launch_teacher<2>(true, dhs, act, cs, c0, whh, B, hc_ld, dpre, dh0, dc0, st);
+  return launch_teacher<1>(true, dhs, act, cs, c0, whh, B, hc_ld, dpre, dh0, dc0, st);
 }

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import latent, ops
 from .ops import ConvSpec, PackedWeight, PrepSpec, fused_prep, plain, s2d_in, s2d_out, tap_conv
 
 # channels of the gate / embedding operand XS = [recurrent state 64 | x_start 12 | zero pad]: 76 rounded up to the tcgen05
@@ -30,10 +30,7 @@ class ActionInjector(nn.Module):  # simple/utils.py:91-96
         self.dense1 = nn.Linear(n_action, size)
         self.dense2 = nn.Linear(n_action, size)
 
-    def scale_shift(self, action):
-        """sigmoid(dense1(a)), dense2(a) as [B,C] (the broadcast over H,W happens inside the fused kernels)."""
-        a = action.reshape(action.shape[0], -1)
-        return torch.sigmoid(self.dense1(a)), self.dense2(a)
+    # (all seven injectors are evaluated at once by latent.HeadsIn; the broadcast multiply-add runs inside sb_prep)
 
 
 class MeanAttention(nn.Module):  # simple/utils.py:72-88
@@ -98,35 +95,16 @@ class BitsPredictor(nn.Module):  # :66-121
         """(Re)compute the sampling kernel's weight-only operands INTO the persistent table tensors (same addresses)."""
         self._sampler_tables = ops.lstm_sampler_tables(self.lstm, self.dense5, self.dense4, out=self._sampler_tables)
 
-    def project(self, x):
-        """dense1..3 share their input: one [B,4608] x [4608,384] GEMM instead of three -> (first_input, h0, c0).
-        The training forward calls the predictor twice on the same input (teacher pass, sampling pass): project once."""
-        w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
-        b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
-        return F.linear(x, w123, b123).chunk(3, dim=1)
-
-    def forward(self, x, rand, target_bits=None, proj=None):
-        """x: [B,4608] (C,H,W order).  Teacher-forced loss when target_bits is given, else sampled bits in {-1,+1}."""
+    def forward(self, x, rand, target_bits=None):
+        """Sampling pass on a flattened [B,4608] (C,H,W order) bottleneck: bits in {-1,+1} (stand-alone surface; the
+        model itself runs both passes of the predictor inside latent.LatentTrain / latent.latent_eval)."""
+        if target_bits is not None:
+            raise NotImplementedError('the teacher-forced pass is part of simple_b200.latent.LatentTrain')
         n = self.total_number_bits // self.bits_at_once
         B = x.shape[0]
-        first, h, c = proj if proj is not None else self.project(x)
-        if target_bits is not None:
-            tb = target_bits.reshape(-1, n, self.bits_at_once).clamp(min=0.)
-            w = (2 ** torch.arange(self.bits_at_once, device=x.device)).float()
-            tints = (tb * w).sum(-1).long()  # LSB first, on device (the reference round-trips through the host)
-            # dense4(one_hot(t)) == W4[:, t] + b4: an embedding lookup instead of a 256-wide matmul
-            emb = F.embedding(tints, self.dense4.weight.t()) + self.dense4.bias
-            emb = emb * (rand.keep_mask(emb.shape, 0.1) / 0.9)
-            tin = torch.cat((first.unsqueeze(1), emb), dim=1)[:, :n]
-            # teacher forcing: every LSTM input is known up front, so the input half of the gates is ONE GEMM over
-            # all 16 steps; only the recurrent half stays sequential, in one launch (sb_lstm_teacher_fwd)
-            xw = F.linear(tin, self.lstm.weight_ih, self.lstm.bias_ih + self.lstm.bias_hh)  # [B,16,512]
-            outs = ops.LstmTeacher.apply(xw, h, c, self.lstm.weight_hh)  # one launch for the 16 recurrent steps
-            outs = outs * (rand.keep_mask(outs.shape, 0.1) / 0.9)
-            pred = self.dense5(outs)
-            loss = F.cross_entropy(pred.permute(0, 2, 1), tints)
-            return pred, loss / self.config.rollout_length
-        # sampling: integer outputs, nothing to differentiate (SURVEY 9.8) -> one persistent kernel for all 16 steps
+        w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
+        b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
+        first, h, c = F.linear(x, w123, b123).chunk(3, dim=1)
         noise = rand.sample_noise(B, n) if hasattr(rand, 'sample_noise') else None
         # weight-only operands.  While the weights are static (rollouts) they live in PERSISTENT tensors that
         # `refresh_sampler_tables` rewrites in place: a captured rollout graph keeps reading valid, current memory
@@ -156,11 +134,6 @@ class StochasticModel(nn.Module):  # :124-206
         self.mean_attentions = nn.ModuleList([MeanAttention(f, 2 * channels) for f in filters])
         self.bits_predictor = BitsPredictor(config, layer_shape[0] * layer_shape[1] * layer_shape[2],
                                             config.latent_state_size, config.bottleneck_bits)
-
-    def add_bits(self, layer, bits):
-        z_mul = torch.sigmoid(self.dense2(bits))[:, :, None, None]
-        z_add = self.dense3(bits)[:, :, None, None]
-        return layer * z_mul + z_add
 
     def get_lstm_loss(self, reset=True):
         """Accumulated teacher-forcing loss since the last reset (next_frame_predictor.py:202-206 of the reference).
@@ -198,30 +171,26 @@ def timing_signal_nhwc(C, H, W, min_timescale=1.0, max_timescale=1.0e4):
 
 
 class DeviceRand:
-    """Fast-path randomness for the small latent tensors (torch's CUDA generator); the big dropout masks are Philox
-    streams generated inside the fused kernels from (seed, stream_id, element index)."""
+    """Fast-path randomness: every draw of the forward pass is generated INSIDE the kernels from a counter-based hash of
+    (seed, stream id, element index) -- the dropout masks in the fused elementwise stages, the latent noise / mix masks
+    in csrc/latent.cu, Philox in the LSTM sampler -- and regenerated by the backward kernels.  Returning None tells the
+    operators to do that; `seed` is an int64 DEVICE tensor so that CUDA-graph replays draw fresh numbers."""
 
     def __init__(self, device, seed):
         self.device = device
-        self.seed = seed  # int64 device tensor: read by the kernels at run time (CUDA-graph safe)
+        self.seed = seed
 
     def keep_mask(self, shape, p):
-        return (torch.rand(shape, device=self.device) >= p).float()
+        return None
 
     def big_keep_mask(self, shape, p):
-        return None  # generated in-kernel
+        return None
 
     def uniform(self, shape):
-        return torch.rand(shape, device=self.device)
-
-    def exponential(self, shape):
-        return torch.empty(shape, device=self.device).exponential_(1)
+        return None
 
     def truncnorm(self, shape):
-        # truncated normal on [-2,2] sigma, sigma = 0.2, by inverse CDF (the reference calls scipy on the host)
-        lo, hi = 0.5 * (1 + math.erf(-2 / math.sqrt(2))), 0.5 * (1 + math.erf(2 / math.sqrt(2)))
-        u = torch.rand(shape, device=self.device) * (hi - lo) + lo
-        return 0.2 * math.sqrt(2) * torch.erfinv(2 * u - 1)
+        return None
 
 
 class InjectedRand:
@@ -264,12 +233,6 @@ class InjectedRand:
 
     def truncnorm(self, shape):
         return self._next('truncnorm', shape)
-
-
-def mix(x1, x2, eps, rand):
-    """simple/utils.py:157-163 -- x2 where rand < eps."""
-    mask = (rand.uniform(x1.shape) < eps).float()
-    return (1 - mask) * x1 + mask * x2
 
 
 class NextFramePredictor(nn.Module):
@@ -346,6 +309,8 @@ class NextFramePredictor(nn.Module):
         self._packed = None
         self._auto_repack = True
         self.parity_rand = None   # set to an InjectedRand to run with explicit randomness
+        self._head_targets = None
+        self._lp = None
         self.last_aux = {}
 
     # ------------------------------------------------------------------ reference surface
@@ -554,19 +519,12 @@ class NextFramePredictor(nn.Module):
                 pw.on_ready = None
         return {mods[k].weight: pw for k, pw in self._packed.items()}
 
-    def _injector_bank(self, action, with_posterior):
-        """sigmoid(dense1(a)) and dense2(a) of ALL ActionInjectors (6 trunk + the posterior's) as two GEMMs on the
-        concatenated weights instead of 14 tiny ones (simple/utils.py:98-105; K = n_action)."""
-        mods = list(self.action_injectors) + ([self.stochastic_model.action_injector] if with_posterior else [])
-        a = action.reshape(action.shape[0], -1)
-        w1 = torch.cat([m.dense1.weight for m in mods], dim=0)
-        b1 = torch.cat([m.dense1.bias for m in mods], dim=0)
-        w2 = torch.cat([m.dense2.weight for m in mods], dim=0)
-        b2 = torch.cat([m.dense2.bias for m in mods], dim=0)
-        sc = torch.sigmoid(F.linear(a, w1, b1))
-        sh = F.linear(a, w2, b2)
-        sizes = [m.dense1.weight.shape[0] for m in mods]
-        return list(zip(sc.split(sizes, dim=1), sh.split(sizes, dim=1)))
+    def _latent_params(self):
+        """Flat parameter groups of the latent / heads block (rebuilt after a device move)."""
+        lp = getattr(self, '_lp', None)
+        if lp is None or not lp.valid():
+            lp = self._lp = latent.LatentParams(self)
+        return lp
 
     def _conv(self, name, spec, a, need_weight_grad=True):
         m = self._weights_cache[name]
@@ -614,27 +572,22 @@ class NextFramePredictor(nn.Module):
             main = self._conv(f'down{i}', P['down'][i], A)
         nrm = self.downscale_layers[9]
         _, x5 = fused_prep(P['prep_x5'], main, gamma=nrm.weight, beta=nrm.bias, dbias_dst=P['down'][4].dbias_src)
-        # ---- bottleneck heads and latent (tiny tensors; fp32, NCHW semantics of the reference)
-        h = x5.float().permute(0, 3, 1, 2)  # [B,768,3,2]
-        value_pred = F.linear(h.reshape(B, -1), self.value_estimator.dense.weight,
-                              self.value_estimator.dense.bias).squeeze(-1)
-        inj = self._injector_bank(action, training)
-        sc0, sh0 = inj[0]
-        h = h * sc0[:, :, None, None] + sh0[:, :, None, None]
+        # ---- bottleneck heads and latent (csrc/latent.cu around plain GEMMs; flatten order of the reference: C,H,W)
+        lp = self._latent_params()
+        outs = latent.HeadsIn.apply(x5, action, lp)
+        value_pred, h_flat = outs[0], outs[1]
+        inj = [(outs[2 + 2 * i], outs[3 + 2 * i]) for i in range(6)]  # decoder injectors 1..5, then the posterior's
         if target is not None:
             ps = self._ps_buf.detach()  # persistent per batch size (init_internal_states); channels 15..63 stay zero
             ops.standardize(target, dst=ps, coff=12, out_f32=target)  # in place, like the reference (:332-334)
         sm = self.stochastic_model
         if training:
             ps[..., :12] = xs.detach()[..., 64:76]
-            h = self._posterior(h, ps, inj[-1], epsilon, rand, aux)
+            x12 = self._posterior_features(ps, inj[5])
+            hm, x_mid, lstm_loss = latent.LatentTrain.apply(h_flat, x12, lp, epsilon, rand, c, aux)
+            sm.lstm_loss = lstm_loss if sm.lstm_loss is None else sm.lstm_loss + lstm_loss
         else:
-            bits, _ = sm.bits_predictor(h.reshape(B, -1), rand)
-            bits = self._forced(rand, 'sampled_bits', bits)
-            aux['bits'] = bits.detach()
-            h = sm.add_bits(h, bits)
-        x_mid = h.mean(dim=(2, 3))
-        hm = h.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+            hm, x_mid = latent.latent_eval(h_flat.detach(), lp, rand, aux)
         # ---- middle network (:52-63)
         mn = self.middle_network.middle_network
         sp = P['prep_m0']
@@ -647,7 +600,7 @@ class NextFramePredictor(nn.Module):
         main, add, nrm = y2, y1, mn[3]
         for i in range(5):
             sp = P['prep_dec'][i]
-            sc, sh = inj[i + 1]
+            sc, sh = inj[i]
             km = keep((B, sp.C, sp.H, sp.W), sp.p)
             _, A = fused_prep(sp, main, add=add, gamma=nrm.weight, beta=nrm.bias, sc=sc, sh=sh, seed=seed, keep=km,
                               dbias_dst=(P['mid'][1] if i == 0 else P['up'][i - 1]).dbias_src)
@@ -657,17 +610,23 @@ class NextFramePredictor(nn.Module):
         _, hf = fused_prep(P['prep_final'], main, add=add, gamma=nrm.weight, beta=nrm.bias,
                            dbias_dst=P['up'][4].dbias_src)
         # x_fin = mean_hw(IN(z)*gamma + beta + timing) == beta + mean_hw(timing): the normalised part has zero mean
-        x_fin = (nrm.bias + P['tmean10']).unsqueeze(0).expand(B, -1)
-        reward_pred = self.reward_estimator(torch.cat((x_mid, x_fin), dim=1))
+        x_fin = nrm.bias + P['tmean10']
+        tg = self._head_targets
+        if tg is not None or not torch.is_grad_enabled():
+            # fused tail: reward MLP (+ reward CE, value MSE and all their gradients when the targets are known)
+            reward_pred, l_rew, l_val = latent.HeadsOut.apply(x_mid, x_fin, value_pred, tg[0] if tg else None,
+                                                              tg[1] if tg else None, self)
+            aux['loss_reward'], aux['loss_value'] = l_rew, l_val
+        else:  # plain `model(x, a, target)` under autograd with the losses taken outside: differentiable library ops
+            reward_pred = self.reward_estimator(torch.cat((x_mid, x_fin.unsqueeze(0).expand(B, -1)), dim=1))
         logits = self._conv('logits', P['logits'], hf)  # bf16 [B,H,W,768], channel = colour*256 + value
         return logits, reward_pred, value_pred
 
-    def _posterior(self, layer, ps, inj_s, epsilon, rand, aux):
-        """StochasticModel.forward, training branch (next_frame_predictor.py:162-197)."""
-        c = self.config
+    def _posterior_features(self, ps, inj_s):
+        """Convolutional part of StochasticModel.forward's training branch (next_frame_predictor.py:163-174): the two
+        8x8/4 convs and their MeanAttention read-outs -> [B,60]."""
         P = self._plan
         sm = self.stochastic_model
-        B = layer.shape[0]
         e = self._conv('s_embed', P['s_embed'], ps)
         sc, sh = inj_s
         _, A = fused_prep(P['prep_s0'], e, sc=sc, sh=sh, dbias_dst=P['s_embed'].dbias_src)
@@ -676,42 +635,13 @@ class NextFramePredictor(nn.Module):
         _, A = fused_prep(P['prep_s1'], c1)
         c2 = self._conv('s_conv2', P['s_conv2'], A)  # [B,6,5,512]
         x2 = ops.mean_attention(c2, sm.mean_attentions[1])
-        x = sm.dense1(torch.cat((x1, x2), dim=-1))
-        aux['posterior_pre'] = x.detach()
-        x = x + (self._forced(rand, 'posterior_pre', x.detach()) - x.detach())
-        bits_clean = (2 * (0 < x).float()).detach() - 1
-        x = torch.tanh(x + rand.truncnorm(x.shape))
-        bits = x + (2 * (0 < x).float() - 1 - x).detach()
-        noise = 2 * (c.bottleneck_noise < rand.uniform(x.shape)).float() - 1
-        bits = bits * noise
-        bits = mix(bits, x, 1 - epsilon, rand)
-        flat = layer.reshape(B, -1)
-        proj = sm.bits_predictor.project(flat)
-        _, lstm_loss = sm.bits_predictor(flat, rand, bits_clean, proj=proj)
-        sm.lstm_loss = lstm_loss if sm.lstm_loss is None else sm.lstm_loss + lstm_loss
-        bits_pred, _ = sm.bits_predictor(flat, rand, proj=[t.detach() for t in proj])
-        bits_pred = self._forced(rand, 'sampled_bits', bits_pred)
-        aux['bits_pred'] = bits_pred.detach()
-        bits_pred = bits_clean + (bits_pred - bits_clean).detach()
-        bits = mix(bits_pred, bits, 1 - (1 - epsilon) * c.latent_rnn_max_sampling, rand)
-        aux['bits'] = bits.detach()  # (detached: nothing may keep last step's autograd graph alive)
-        res = sm.add_bits(layer, bits)
-        return mix(res, layer, 1 - (1 - epsilon) * c.latent_use_max_probability, rand)
+        return torch.cat((x1, x2), dim=-1)
 
-    @staticmethod
-    def _forced(rand, key, value):
-        force = getattr(rand, 'force', None)
-        if not force or key not in force:
-            return value
-        f = force[key].to(value.device)
-        if key == 'posterior_pre':
-            rand.mismatch[key] = float(((f > 0) != (value > 0)).float().mean())
-        else:
-            rand.mismatch[key] = float((f != value).float().mean())
-        return f
-
-    def forward_internal(self, x, action, target=None, epsilon=0):
-        """Runs the network and returns the INTERNAL logits (bf16 [B,H,W,768], colour-major) + reward + value."""
+    def forward_internal(self, x, action, target=None, epsilon=0, rewards=None, values=None):
+        """Runs the network and returns the INTERNAL logits (bf16 [B,H,W,768], colour-major) + reward + value.
+        `rewards` (long [B]) / `values` (f32 [B]): when given, the reward CE and value MSE of simple/trainer.py:138-141
+        are produced by the fused heads kernel and left in `last_aux['loss_reward' / 'loss_value']`."""
+        self._head_targets = (rewards, values) if rewards is not None else None
         dev = x.device
         if dev.type != 'cuda':
             raise RuntimeError('simple_b200.NextFramePredictor runs on CUDA (sm_100a) only; there is no CPU fallback')

@@ -627,7 +627,8 @@ def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None, tables=
     noise = f(noise) if noise is not None else None
     _lib.check(_lib.lib().sb_lstm_sample2(G0.data_ptr(), h0.data_ptr(), c0.data_ptr(), tb['E'].data_ptr(),
                                           tb['whhT'].data_ptr(), tb['w5T'].data_ptr(), tb['b5'].data_ptr(), _ptr(noise),
-                                          _ptr(seed), B, bits.data_ptr(), ints.data_ptr(), _lib.stream_ptr()),
+                                          _ptr(seed), B, h0.stride(0), bits.data_ptr(), ints.data_ptr(),
+                                          _lib.stream_ptr()),
                'sb_lstm_sample2')
     return bits, ints
 
@@ -644,7 +645,7 @@ class LstmTeacher(torch.autograd.Function):
         hs = torch.empty(B, 16, 128, device=xw.device, dtype=torch.float32)
         act = torch.empty(B, 16, 512, device=xw.device, dtype=torch.float32)
         cs = torch.empty(B, 16, 128, device=xw.device, dtype=torch.float32)
-        _lib.check(_lib.lib().sb_lstm_teacher_fwd(xw.data_ptr(), h0.data_ptr(), c0.data_ptr(), whhT.data_ptr(), B,
+        _lib.check(_lib.lib().sb_lstm_teacher_fwd(xw.data_ptr(), h0.data_ptr(), c0.data_ptr(), whhT.data_ptr(), B, 128,
                                                   hs.data_ptr(), act.data_ptr(), cs.data_ptr(), _lib.stream_ptr()),
                    'sb_lstm_teacher_fwd')
         ctx.save_for_backward(act, cs, hs, h0, c0, w_hh)
@@ -660,7 +661,7 @@ class LstmTeacher(torch.autograd.Function):
         dh0 = torch.empty_like(h0)
         dc0 = torch.empty_like(c0)
         _lib.check(_lib.lib().sb_lstm_teacher_bwd(dhs.data_ptr(), act.data_ptr(), cs.data_ptr(), c0.data_ptr(),
-                                                  whh.data_ptr(), B, dpre.data_ptr(), dh0.data_ptr(), dc0.data_ptr(),
+                                                  whh.data_ptr(), B, 128, dpre.data_ptr(), dh0.data_ptr(), dc0.data_ptr(),
                                                   _lib.stream_ptr()), 'sb_lstm_teacher_bwd')
         h_prev = torch.cat((h0.unsqueeze(1), hs[:, :-1]), dim=1).reshape(-1, 128)
         dw_hh = dpre.reshape(-1, 512).t() @ h_prev  # [512,128]

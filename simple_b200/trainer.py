@@ -8,7 +8,6 @@ losses are accumulated on the device and read back once per window, and clip+Ada
 import os
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from .adafactor import Adafactor
@@ -22,15 +21,16 @@ def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsi
     bf16 logits (ops.PixelCE); `argmax` is the u8 frame the reference obtains with torch.argmax (trainer.py:130).
     """
     target = new_states_u8.float() / 255
-    logits, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon)
+    logits, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon, rewards=rewards,
+                                                             values=values)
     out = {}
     if keep_logits:  # tests only: the fused loss overwrites the logits with their gradient
         B, H, W, _ = logits.shape
         out['logits_ref'] = logits.detach().reshape(B, H, W, 3, 256).permute(0, 4, 3, 1, 2).float().clone()
     loss_reconstruct, argmax = ops.PixelCE.apply(logits, new_states_u8.contiguous(), float(config.target_loss_clipping),
                                                  True, True, getattr(model, 'logits_dbias', None))
-    loss_value = F.mse_loss(value_pred, values)
-    loss_reward = F.cross_entropy(reward_pred, rewards)
+    # value MSE and reward CE (trainer.py:138-139) come out of the fused heads kernel together with their gradients
+    loss_value, loss_reward = model.last_aux['loss_value'], model.last_aux['loss_reward']
     loss = loss_reconstruct + loss_value + loss_reward
     if config.use_stochastic_model:
         loss_lstm = model.stochastic_model.get_lstm_loss()

@@ -1,0 +1,210 @@
+"""The fused latent / heads block (simple_b200/latent.py + csrc/latent.cu: hand-written forward AND backward) against a
+plain PyTorch-autograd restatement of the reference arithmetic (next_frame_predictor.py:153-200, :66-121, :11-34,
+utils.py:91-105,157-163, trainer.py:138-141) on identical inputs, weights and explicit randomness."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+class _Rand:
+    """Explicit draws in the order the block asks for them (the order of the reference)."""
+
+    def __init__(self, B, seed):
+        g = torch.Generator().manual_seed(seed)
+        u = lambda *s: torch.rand(*s, generator=g).to(DEV)
+        self.tn = (0.2 * torch.randn(B, 128, generator=g)).clamp(-0.4, 0.4).to(DEV)
+        self.u_flip, self.u1, self.u2, self.u3 = u(B, 128), u(B, 128), u(B, 128), u(B, 768, 3, 2)
+        self.keep1 = (u(B, 16, 128) >= 0.1).float()
+        self.keep2 = (u(B, 16, 128) >= 0.1).float()
+        self.noise = torch.empty(B, 16, 256).exponential_(1, generator=g).to(DEV)
+        self.seed, self.force, self.mismatch = 0, {}, {}
+        self._u = iter([self.u_flip, self.u1, self.u2, self.u3])
+        self._k = iter([self.keep1, self.keep2])
+
+    def truncnorm(self, shape):
+        return self.tn
+
+    def uniform(self, shape):
+        t = next(self._u)
+        assert tuple(t.shape) == tuple(shape)
+        return t
+
+    def keep_mask(self, shape, p):
+        return next(self._k)
+
+    def sample_noise(self, B, n):
+        return self.noise
+
+
+def _mix(x1, x2, eps, u):
+    m = (u < eps).float()
+    return (1 - m) * x1 + m * x2
+
+
+def _reference(model, cfg, x5, action, x12, eps, R, bits_pred, rewards, values, x_fin):
+    """Autograd restatement; x5: fp32 NHWC [B,3,2,768] leaf."""
+    sm, bp = model.stochastic_model, model.stochastic_model.bits_predictor
+    B = x5.shape[0]
+    h = x5.permute(0, 3, 1, 2)
+    value = F.linear(h.reshape(B, -1), model.value_estimator.dense.weight, model.value_estimator.dense.bias).squeeze(-1)
+    mods = list(model.action_injectors) + [sm.action_injector]
+    scsh = [(torch.sigmoid(m.dense1(action)), m.dense2(action)) for m in mods]
+    h = h * scsh[0][0][:, :, None, None] + scsh[0][1][:, :, None, None]
+    pre = sm.dense1(x12)
+    bits_clean = (2 * (0 < pre).float()).detach() - 1
+    x = torch.tanh(pre + R.tn)
+    bits = x + (2 * (0 < x).float() - 1 - x).detach()
+    bits = bits * (2 * (cfg.bottleneck_noise < R.u_flip).float() - 1)
+    bits = _mix(bits, x, 1 - eps, R.u1)
+    flat = h.reshape(B, -1)
+    first, h0, c0 = bp.dense1(flat), bp.dense2(flat), bp.dense3(flat)
+    tb = bits_clean.reshape(B, 16, 8).clamp(min=0.)
+    tints = (tb * (2 ** torch.arange(8, device=DEV)).float()).sum(-1).long()
+    emb = F.embedding(tints, bp.dense4.weight.t()) + bp.dense4.bias
+    emb = emb * (R.keep1 / 0.9)
+    tin = torch.cat((first.unsqueeze(1), emb), dim=1)[:, :16]
+    hh, cc, outs = h0, c0, []
+    for t in range(16):
+        gates = F.linear(tin[:, t], bp.lstm.weight_ih, bp.lstm.bias_ih) + F.linear(hh, bp.lstm.weight_hh, bp.lstm.bias_hh)
+        i, f, g, o = gates.chunk(4, dim=1)
+        cc = torch.sigmoid(f) * cc + torch.sigmoid(i) * torch.tanh(g)
+        hh = torch.sigmoid(o) * torch.tanh(cc)
+        outs.append(hh)
+    outs = torch.stack(outs, dim=1) * (R.keep2 / 0.9)
+    pred = bp.dense5(outs)
+    lstm_loss = F.cross_entropy(pred.permute(0, 2, 1), tints) / cfg.rollout_length
+    bp_st = bits_clean + (bits_pred - bits_clean).detach()
+    bits3 = _mix(bp_st, bits, 1 - (1 - eps) * cfg.latent_rnn_max_sampling, R.u2)
+    res = h * torch.sigmoid(sm.dense2(bits3))[:, :, None, None] + sm.dense3(bits3)[:, :, None, None]
+    out = _mix(res, h, 1 - (1 - eps) * cfg.latent_use_max_probability, R.u3)
+    x_mid = out.mean(dim=(2, 3))
+    hm = out.permute(0, 2, 3, 1)
+    reward = model.reward_estimator(torch.cat((x_mid, x_fin.unsqueeze(0).expand(B, -1)), dim=1))
+    l_rew = F.cross_entropy(reward, rewards)
+    l_val = F.mse_loss(value, values)
+    return dict(value=value, scsh=scsh, pre=pre, bits3=bits3, lstm_loss=lstm_loss, hm=hm, x_mid=x_mid, reward=reward,
+                l_rew=l_rew, l_val=l_val, tints=tints)
+
+
+@pytest.mark.parametrize('B,n_action', [(4, 3), (64, 9)])
+def test_fused_latent_block_forward_and_backward_match_autograd(B, n_action):
+    from oracle.wm_oracle import default_config
+    from simple_b200 import latent
+    from simple_b200.next_frame_predictor import NextFramePredictor
+    cfg = default_config(device=DEV, batch_size=B)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, n_action).to(DEV)
+    with torch.no_grad():  # zero-initialised affine / bias parameters would hide errors
+        for p in model.parameters():
+            if float(p.abs().max()) == 0:
+                p.normal_(0, 0.1)
+    g = torch.Generator().manual_seed(1)
+    x5 = torch.randn(B, 3, 2, 768, generator=g).to(DEV).bfloat16()
+    action = F.one_hot(torch.randint(0, n_action, (B,), generator=g), n_action).float().to(DEV)
+    x12 = torch.randn(B, 60, generator=g).to(DEV)
+    rewards = torch.randint(0, 3, (B,), generator=g).to(DEV)
+    values = torch.randn(B, generator=g).to(DEV)
+    x_fin0 = torch.randn(96, generator=g).to(DEV)
+    G_hm = torch.randn(B, 3, 2, 768, generator=g).to(DEV)
+    G_sc = [torch.randn(B, C, generator=g).to(DEV) for C in latent.INJ_WIDTHS[1:]]
+    G_sh = [torch.randn(B, C, generator=g).to(DEV) for C in latent.INJ_WIDTHS[1:]]
+    eps = 0.3
+    # ---- fused path
+    lp = model._latent_params()
+    assert lp.valid()
+    R = _Rand(B, 5)
+    x5_f = x5.clone().requires_grad_(True)
+    x12_f = x12.clone().requires_grad_(True)
+    xfin_f = x_fin0.clone().requires_grad_(True)
+    model.zero_grad(set_to_none=True)
+    aux = {}
+    outs = latent.HeadsIn.apply(x5_f, action, lp)
+    value, h_flat = outs[0], outs[1]
+    hm, x_mid, lstm_loss = latent.LatentTrain.apply(h_flat, x12_f, lp, eps, R, cfg, aux)
+    reward, l_rew, l_val = latent.HeadsOut.apply(x_mid, xfin_f, value, rewards, values, model)
+    total = (hm.float() * G_hm).sum() + lstm_loss + l_rew + l_val
+    for i in range(6):
+        total = total + (outs[2 + 2 * i] * G_sc[i]).sum() + (outs[3 + 2 * i] * G_sh[i]).sum()
+    total.backward()
+    torch.cuda.synchronize()
+    fused_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    # ---- autograd restatement on the same bf16-rounded bottleneck, same randomness, same sampled bits
+    model.zero_grad(set_to_none=True)
+    x5_r = x5.float().clone().requires_grad_(True)
+    x12_r = x12.clone().requires_grad_(True)
+    xfin_r = x_fin0.clone().requires_grad_(True)
+    ref = _reference(model, cfg, x5_r, action, x12_r, eps, R, aux['bits_pred'], rewards, values, xfin_r)
+    hm_r = ref['hm'].bfloat16().float() + (ref['hm'] - ref['hm'].detach())  # the fused block emits bf16 (straight-through)
+    total_r = (hm_r * G_hm).sum() + ref['lstm_loss'] + ref['l_rew'] + ref['l_val']
+    for i in range(6):
+        total_r = total_r + (ref['scsh'][i + 1][0] * G_sc[i]).sum() + (ref['scsh'][i + 1][1] * G_sh[i]).sum()
+    total_r.backward()
+    rel = lambda a, b: float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+    # forward
+    assert rel(value, ref['value']) < 1e-4
+    assert rel(aux['posterior_pre'], ref['pre']) < 1e-5
+    assert torch.equal(aux['bits'], ref['bits3']) or rel(aux['bits'], ref['bits3']) < 1e-5
+    assert rel(lstm_loss, ref['lstm_loss']) < 1e-4
+    assert float((hm.float() - ref['hm'].bfloat16().float()).abs().max()) <= 0.02  # <= 1 bf16 ulp at |x| < 4
+    assert rel(x_mid, ref['x_mid']) < 1e-4
+    assert rel(reward, ref['reward']) < 1e-4 and rel(l_rew, ref['l_rew']) < 1e-4 and rel(l_val, ref['l_val']) < 1e-4
+    for i in range(6):
+        assert rel(outs[2 + 2 * i], ref['scsh'][i + 1][0]) < 1e-5 and rel(outs[3 + 2 * i], ref['scsh'][i + 1][1]) < 1e-5
+    # backward: inputs
+    assert rel(x5_f.grad, x5_r.grad) < 1e-2          # emitted as bf16
+    assert rel(x12_f.grad, x12_r.grad) < 1e-3
+    assert rel(xfin_f.grad, xfin_r.grad) < 1e-3
+    # backward: every parameter of the block
+    expected = ['value_estimator.', 'action_injectors.', 'stochastic_model.action_injector.', 'stochastic_model.dense',
+                'stochastic_model.bits_predictor.', 'reward_estimator.']
+    checked = 0
+    for k, p in model.named_parameters():
+        if not k.startswith(tuple(expected)):
+            continue
+        assert p.grad is not None and k in fused_grads, k
+        r = rel(fused_grads[k], p.grad)
+        assert r < 2e-3, (k, r)
+        checked += 1
+    assert checked == 54, checked  # value 2, injectors 28, stochastic dense1-3 6, bits predictor 14, reward 4
+
+
+def test_fused_latent_block_in_kernel_randomness_is_regenerated_by_backward_and_has_the_right_rates():
+    """Fast path (no explicit draws): masks come from the counter hash.  Check the empirical rates of the three mixes,
+    the flip noise and the two dropouts, and that two calls with the same seed agree while another seed differs."""
+    from oracle.wm_oracle import default_config
+    from simple_b200 import latent
+    from simple_b200.next_frame_predictor import DeviceRand, NextFramePredictor
+    B = 256
+    cfg = default_config(device=DEV, batch_size=B)
+    torch.manual_seed(0)
+    model = NextFramePredictor(cfg, 3).to(DEV)
+    lp = model._latent_params()
+    g = torch.Generator().manual_seed(1)
+    x5 = torch.randn(B, 3, 2, 768, generator=g).to(DEV).bfloat16()
+    action = F.one_hot(torch.randint(0, 3, (B,), generator=g), 3).float().to(DEV)
+    x12 = (3 * torch.randn(B, 60, generator=g)).to(DEV)
+
+    def run(seed):
+        rand = DeviceRand(DEV, torch.full((1,), seed, dtype=torch.int64, device=DEV))
+        aux = {}
+        with torch.no_grad():
+            outs = latent.HeadsIn.apply(x5, action, lp)
+            hm, x_mid, _ = latent.LatentTrain.apply(outs[1], x12, lp, 0.3, rand, cfg, aux)
+        return hm.float(), aux['bits'], aux['bits_pred'], outs[1]
+
+    hm_a, bits_a, bp_a, h_flat = run(11)
+    hm_b, bits_b, _, _ = run(11)
+    hm_c, bits_c, _, _ = run(12)
+    assert torch.equal(hm_a, hm_b) and torch.equal(bits_a, bits_b)
+    assert not torch.equal(bits_a, bits_c)
+    # third mix keeps the layer with probability 1 - (1 - eps) * 0.8 = 0.44
+    h_nhwc = h_flat.reshape(B, 768, 6).permute(0, 2, 1).reshape(B, 3, 2, 768)
+    kept = (hm_a == h_nhwc.bfloat16().float()).float().mean()
+    assert abs(float(kept) - 0.44) < 0.01, float(kept)
+    # second mix takes the sampled bits with probability (1 - eps) * 0.5 = 0.35: elsewhere the entries are +-1 or tanh values
+    took_pred = ((bits_a == bp_a) & (bits_a.abs() == 1)).float().mean()
+    assert 0.30 < float(took_pred) < 0.75
+    assert float((bits_a.abs() < 1).float().mean()) > 0.3  # first mix passes tanh values with probability 0.7 * 0.65
