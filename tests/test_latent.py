@@ -137,7 +137,7 @@ def test_fused_latent_block_forward_and_backward_match_autograd(B, n_action):
     x12_r = x12.clone().requires_grad_(True)
     xfin_r = x_fin0.clone().requires_grad_(True)
     ref = _reference(model, cfg, x5_r, action, x12_r, eps, R, aux['bits_pred'], rewards, values, xfin_r)
-    hm_r = ref['hm'].bfloat16().float() + (ref['hm'] - ref['hm'].detach())  # the fused block emits bf16 (straight-through)
+    hm_r = ref['hm'] + (ref['hm'].bfloat16().float() - ref['hm']).detach()  # the fused block emits bf16 (straight-through)
     total_r = (hm_r * G_hm).sum() + ref['lstm_loss'] + ref['l_rew'] + ref['l_val']
     for i in range(6):
         total_r = total_r + (ref['scsh'][i + 1][0] * G_sc[i]).sum() + (ref['scsh'][i + 1][1] * G_sh[i]).sum()
