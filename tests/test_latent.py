@@ -108,7 +108,7 @@ def test_fused_latent_block_forward_and_backward_match_autograd(B, n_action):
     rewards = torch.randint(0, 3, (B,), generator=g).to(DEV)
     values = torch.randn(B, generator=g).to(DEV)
     x_fin0 = torch.randn(96, generator=g).to(DEV)
-    G_hm = torch.randn(B, 3, 2, 768, generator=g).to(DEV)
+    G_hm = torch.randn(B, 3, 2, 768, generator=g).to(DEV).bfloat16().float()  # (the gradient w.r.t. hm travels as bf16)
     G_sc = [torch.randn(B, C, generator=g).to(DEV) for C in latent.INJ_WIDTHS[1:]]
     G_sh = [torch.randn(B, C, generator=g).to(DEV) for C in latent.INJ_WIDTHS[1:]]
     eps = 0.3
