@@ -62,6 +62,8 @@ typedef struct {
   int relu;
   int splits;         /* split-K factor; >1 forces fp32 red.add accumulation into `out` (caller zeroes it) */
   int accumulate;     /* 1: red.add into fp32 `out` even when splits == 1 */
+  int bias_mod;       /* 0: bias has N entries; else bias[column % bias_mod] (a multiple of 32 dividing N): transposed
+                         convolutions run with N = (phase, channel) and share one bias per channel */
 } sb_tap_gemm_args;
 int sb_tap_gemm(const sb_tap_gemm_args* args, sb_stream_t stream);
 
@@ -147,8 +149,8 @@ typedef struct {
   int b_base, b_count;     /* batch-chunked launch: process samples [b_base, b_base+b_count) only (all pointers and B
                               still describe the WHOLE batch; b_count == 0 = all samples).  Lets a caller run
                               stats -> prep or reduce -> apply chunk by chunk inside the L2 */
-  float* dgb;              /* optional fp32 [C,2] (caller zeroes; sb_prep_bwd_reduce only): += sum over b of bsums[b,c,0..1],
-                              i.e. (d beta, d gamma) of the InstanceNorm affine */
+  float* dgb;              /* optional fp32 [2,C] (caller zeroes; sb_prep_bwd_reduce only): row 0 += sum over b of bsums[b,c,0]
+                              (d beta), row 1 += sum over b of bsums[b,c,1] (d gamma) of the InstanceNorm affine */
   int moments;             /* 1 (planes of H*W <= 64 pixels only): `sums` holds (mean, biased centred variance) instead of
                               raw sums -- sb_stats then runs a two-pass, atomics-free kernel (the 6-pixel InstanceNorms with
                               eps = 1e-6 are ill-conditioned under single-pass statistics); same flag for all four calls */
@@ -163,9 +165,10 @@ int sb_prep_bwd_apply(const sb_prep_args* args, sb_stream_t stream);
 
 /* standardize_frame (simple/utils.py:122-126): in fp32 [B,C,P] -> (x-mean)/max(std_unbiased, 1/sqrt(P)) written to
  * dst_bf16[(b*P+i)*ld + coff + c] and/or out_f32 [B,C,P] (may alias `in`: the reference standardises targets in place).
- * stats_scratch: caller-owned fp32 [B*C*2] (per-plane mean / scale between the statistics and the apply kernel). C <= 16. */
+ * stats_scratch: caller-owned fp32 [B*C*2] (per-plane mean / scale between the statistics and the apply kernel). C <= 16.
+ * dst2_bf16 (optional): a second NHWC destination of the same values (the posterior's input operand). */
 int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
-                   float* stats_scratch, sb_stream_t stream);
+                   float* stats_scratch, void* dst2_bf16, int ld2, int coff2, sb_stream_t stream);
 
 /* Scheduled-sampling frame feedback (simple/trainer.py:58-65,125-132), in place on the fp32 frame stack [B,C_stack,HW]:
  * next = gt w.p. *eps_ptr else pred (u8 [B,C_new,HW]); next/255 with each value replaced w.p. p_noise by the frame's lower
@@ -178,8 +181,8 @@ int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t* pred, cons
 /* Epilogue of a split-K sb_tap_gemm (fp32 partial sums [rows, N]): out = act(acc + bias[N]) as fp32 (out may alias acc)
  * or bf16 -- the bias add + ReLU of the reference's conv layers (next_frame_predictor.py:37-63,320-350) for the deep,
  * tiny feature maps whose GEMMs are split over K. */
-int sb_bias_act(const float* acc, const float* bias, int relu, void* out, int out_is_f32, long long rows, int N,
-                sb_stream_t stream);
+int sb_bias_act(const float* acc, const float* bias, int bias_mod, int relu, void* out, int out_is_f32, long long rows,
+                int N, sb_stream_t stream);
 
 /* conv-GRU blend of the recurrent state (simple/next_frame_predictor.py:298-303) and its backward.
  * G bf16 [npix,128] (gate | candidate pre-activations), state fp32 [npix,64], xs/dxs bf16 with row stride ld.
@@ -273,8 +276,10 @@ int sb_adafactor_big2d(const sb_tensor_desc* descs_dev, const int* index_dev, in
  * --------------------------------------------------------------------------------------------------------- */
 int sb_mean_attention_fwd(const void* x, const float* We, const float* be, const float* Wd, const float* bd, int B,
                           int HW, int C, int O, float* y, float* s_save, float* l_save, sb_stream_t stream);
+/* accumulate = 1: dWe_part [4,C] / dbe_part [4] receive the batch SUM through atomics (caller zeroes) instead of per-sample parts. */
 int sb_mean_attention_bwd(const void* x, const float* We, const float* Wd, const float* s_save, const float* dy, int B,
-                          int HW, int C, int O, void* dx, float* dWe_part, float* dbe_part, sb_stream_t stream);
+                          int HW, int C, int O, void* dx, float* dWe_part, float* dbe_part, int accumulate,
+                          sb_stream_t stream);
 
 /* Latent-bit predictor (simple/next_frame_predictor.py:66-121; K11/K12): transposed weights (whhT [128,512] = W_hh^T, w5T [128,256] = W5^T), input-gate
  * pre-activations by table lookup (E [256,512] = W_ih (W4[:,s] + b4) + b_ih + b_hh; G0 [B,512] for the first step), one

@@ -55,6 +55,7 @@ class TapGemmArgs(ctypes.Structure):
         ('w', ctypes.c_void_p), ('N', ctypes.c_int), ('ldw', ctypes.c_int),
         ('out', ctypes.c_void_p), ('out_f32', ctypes.c_int), ('ldo', ctypes.c_int),
         ('bias', ctypes.c_void_p), ('relu', ctypes.c_int), ('splits', ctypes.c_int), ('accumulate', ctypes.c_int),
+        ('bias_mod', ctypes.c_int),
     ]
 
 
@@ -134,14 +135,14 @@ class _Sigs:
     sb_prep = [ctypes.POINTER(PrepArgs), _p]
     sb_prep_bwd_reduce = [ctypes.POINTER(PrepArgs), _p]
     sb_prep_bwd_apply = [ctypes.POINTER(PrepArgs), _p]
-    sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p]
+    sb_standardize = [_p, _i, _i, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p]
     sb_gru_blend = [_p, _p, _p, _p, _i, _ll, _p]
     sb_frame_feedback = [_p, _p, _p, _p, _f, _p, ctypes.c_ulonglong, _i, _i, _i, _i, _p]
     sb_gru_blend_bwd = [_p, _p, _i, _p, _i, _p, _ll, _p]
     sb_pack_conv = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]
     sb_unpack_conv_grad = [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]
     sb_mean_attention_fwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
-    sb_mean_attention_bwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]
+    sb_mean_attention_bwd = [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]
     sb_lstm_sample2 = [_p] * 9 + [_i, _i, _p, _p, _p]
     sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
@@ -151,7 +152,7 @@ class _Sigs:
     sb_adafactor_small = [_p, _p, _i, _i, _p, _f, _p]
     sb_adafactor_conv_packed = [_p, _p, _p, _i, _i, _i, _p, _f, _i, _p, _i, _p]
     sb_transpose_taps = [_p, _p, _i, _i, _i, _p]
-    sb_bias_act = [_p, _p, _i, _p, _i, _ll, _i, _p]
+    sb_bias_act = [_p, _p, _i, _i, _p, _i, _ll, _i, _p]
     sb_transpose_taps_multi = [_p, _i, _i, _p]
     sb_adafactor_big2d = [_p, _p, _i, _i, _i, _p, _f, _p]
     # latent / heads block (csrc/latent.cu)

@@ -105,7 +105,7 @@ struct PrepParams {
   View d_main;              // grad wrt main (same layout as in)
   __nv_bfloat16* d_add;     // grad wrt add (plain) or NULL
   float* dcol;              // optional [C]: += column sums of d_main (the producing conv's bias gradient)
-  float* dgb;               // optional [C,2] (backward reduce): += sum over b of bsums[b,c,0..1] = (d beta, d gamma)
+  float* dgb;               // optional [2,C] (backward reduce): += sum over b of bsums[b,c,0..1] = (d beta | d gamma)
   // host-precomputed
   uint32_t w_magic;         // fast_div magic of W
   uint32_t nx_magic;        // fast_div magic of the iteration-space width (see iter_space)
@@ -393,7 +393,7 @@ __device__ __forceinline__ void lane_reduce_atomic(float (*acc)[8], float* scrat
     float s = 0.f;
     for (int l = 0; l < PL; ++l) s += scratch[((size_t)l * CV + cvv) * (NV * 8) + rem];
     atomicAdd(out + out_base + (long long)(cvv * 8 + j) * out_stride_c + v, s);
-    if (out2 && v < 2) atomicAdd(out2 + (cvv * 8 + j) * 2 + v, s);  // batch-summed affine gradients
+    if (out2 && v < 2) atomicAdd(out2 + v * (CV * 8) + cvv * 8 + j, s);  // batch-summed affine gradients [2][C]
   }
 }
 
@@ -653,7 +653,8 @@ __global__ void __launch_bounds__(256)
 template <int CT>
 __global__ void __launch_bounds__(256)
     standardize_apply_kernel(const float* __restrict__ in, const float2* __restrict__ stats, int C, int P,
-                             __nv_bfloat16* dst, int ld, int coff, float* out_f32) {
+                             __nv_bfloat16* dst, int ld, int coff, float* out_f32, __nv_bfloat16* dst2, int ld2,
+                             int coff2) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
@@ -662,6 +663,7 @@ __global__ void __launch_bounds__(256)
       const float2 st = stats[b * C + c];
       const float v = (in[((long long)b * C + c) * P + i] - st.x) * st.y;  // coalesced across the pixels of a plane
       if (dst) dst[((long long)b * P + i) * ld + coff + c] = __float2bfloat16_rn(v);
+      if (dst2) dst2[((long long)b * P + i) * ld2 + coff2 + c] = __float2bfloat16_rn(v);
       if (out_f32) out_f32[((long long)b * C + c) * P + i] = v;
     }
     return;
@@ -679,8 +681,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int c = 0; c < CC; ++c) out_f32[((long long)b * CC + c) * P + i] = v[c];
   }
-  if (dst) {
-    __nv_bfloat16* o = dst + ((long long)b * P + i) * ld + coff;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    __nv_bfloat16* base = which == 0 ? dst : dst2;
+    if (!base) continue;
+    __nv_bfloat16* o = base + ((long long)b * P + i) * (which == 0 ? ld : ld2) + (which == 0 ? coff : coff2);
     if (CC % 4 == 0 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
 #pragma unroll
       for (int c = 0; c < CC; c += 4) {
@@ -888,12 +893,12 @@ __global__ void __launch_bounds__(256)
 // epilogue of a split-K tap GEMM (tiny deep-layer outputs): fp32 partial sums + bias -> ReLU -> bf16 or fp32 (in place
 // allowed).  One launch instead of an ATen add / relu / cast chain.
 __global__ void __launch_bounds__(256)
-    bias_act_kernel(const float* acc, const float* __restrict__ bias, int relu, float* out_f32, __nv_bfloat16* out_bf16,
-                    long long nvec, int N) {
+    bias_act_kernel(const float* acc, const float* __restrict__ bias, int bias_mod, int relu, float* out_f32,
+                    __nv_bfloat16* out_bf16, long long nvec) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(acc)[i];
     if (bias) {
-      const float4 bv = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % N));
+      const float4 bv = *reinterpret_cast<const float4*>(bias + (int)((i * 4) % bias_mod));
       v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
     }
     if (relu) {
@@ -1209,7 +1214,7 @@ extern "C" int sb_prep_bwd_apply(const sb_prep_args* a, sb_stream_t stream) {
 }
 
 extern "C" int sb_standardize(const float* in, int B, int C, int P, void* dst_bf16, int ld, int coff, float* out_f32,
-                              float* stats_scratch, sb_stream_t stream) {
+                              float* stats_scratch, void* dst2_bf16, int ld2, int coff2, sb_stream_t stream) {
   if (!in || !stats_scratch || B < 1 || C < 1 || C > 16 || P < 2 || P * sizeof(float) > 200 * 1024) return SB_ERR_ARG;
   static bool configured = false;
   if (!configured) {
@@ -1225,22 +1230,28 @@ extern "C" int sb_standardize(const float* in, int B, int C, int P, void* dst_bf
   SB_CHECK_LAUNCH();
   const dim3 grid((P + 255) / 256, B);
   if (C == 12)
-    standardize_apply_kernel<12><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+    standardize_apply_kernel<12><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32,
+                                                         (__nv_bfloat16*)dst2_bf16, ld2, coff2);
   else if (C == 3)
-    standardize_apply_kernel<3><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+    standardize_apply_kernel<3><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32,
+                                                         (__nv_bfloat16*)dst2_bf16, ld2, coff2);
   else
-    standardize_apply_kernel<0><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32);
+    standardize_apply_kernel<0><<<grid, 256, 0, st>>>(in, stats, C, P, (__nv_bfloat16*)dst_bf16, ld, coff, out_f32,
+                                                         (__nv_bfloat16*)dst2_bf16, ld2, coff2);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
 }
 
-extern "C" int sb_bias_act(const float* acc, const float* bias, int relu, void* out, int out_is_f32, long long rows,
-                           int N, sb_stream_t stream) {
+extern "C" int sb_bias_act(const float* acc, const float* bias, int bias_mod, int relu, void* out, int out_is_f32,
+                           long long rows, int N, sb_stream_t stream) {
   if (!acc || !out || rows < 1 || N < 4 || N % 4) return SB_ERR_ARG;
+  if (bias_mod <= 0) bias_mod = N;
+  if (bias_mod % 4 || N % bias_mod) return SB_ERR_ARG;
   const long long nvec = rows * N / 4;
-  bias_act_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>(acc, bias, relu, out_is_f32 ? (float*)out : nullptr,
-                                                                   out_is_f32 ? nullptr : (__nv_bfloat16*)out, nvec, N);
+  bias_act_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>(acc, bias, bias_mod, relu,
+                                                                   out_is_f32 ? (float*)out : nullptr,
+                                                                   out_is_f32 ? nullptr : (__nv_bfloat16*)out, nvec);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kMaThreads)
     mean_attention_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ We,
                               const float* __restrict__ Wd, const float* __restrict__ s_save,
                               const float* __restrict__ dy, int HW, int C, int O, __nv_bfloat16* __restrict__ dx,
-                              float* __restrict__ dWe_part, float* __restrict__ dbe_part) {
+                              float* dWe_part, float* dbe_part, int accumulate) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const MaSmem sm = ma_carve(smem_raw, HW, C);
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -211,13 +211,19 @@ __global__ void __launch_bounds__(kMaThreads)
       acc[3] = fmaf(v, sm.ds[3 * HW + hw], acc[3]);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dWe_part[((size_t)b * 4 + k) * C + c] = acc[k];
+    for (int k = 0; k < 4; ++k) {
+      if (accumulate) atomicAdd(dWe_part + (size_t)k * C + c, acc[k]);  // batch sum [4,C] (caller zeroes)
+      else dWe_part[((size_t)b * 4 + k) * C + c] = acc[k];
+    }
   }
   if (warp < 4) {
     float s = 0.f;
     for (int hw = lane; hw < HW; hw += 32) s += sm.ds[warp * HW + hw];
     s = warp_sum(s);
-    if (lane == 0) dbe_part[b * 4 + warp] = s;
+    if (lane == 0) {
+      if (accumulate) atomicAdd(dbe_part + warp, s);
+      else dbe_part[b * 4 + warp] = s;
+    }
   }
   // dx[hw,c] = (dm[c] + sum_k dam[c,k] s[k,hw]) / HW + sum_k da[k,hw] We[k,c]
   const int CV = C / 8;
@@ -275,7 +281,7 @@ extern "C" int sb_mean_attention_fwd(const void* x, const float* We, const float
 
 extern "C" int sb_mean_attention_bwd(const void* x, const float* We, const float* Wd, const float* s_save,
                                      const float* dy, int B, int HW, int C, int O, void* dx, float* dWe_part,
-                                     float* dbe_part, sb_stream_t stream) {
+                                     float* dbe_part, int accumulate, sb_stream_t stream) {
   if (!x || !We || !Wd || !s_save || !dy || !dx || !dWe_part || !dbe_part || B < 1 || HW < 1 || C % 8 || C < 8 || O < 1)
     return SB_ERR_ARG;
   const size_t smem = ma_smem_bytes(HW, C) + (size_t)4 * C * 4;  // + the [4][C] gather of d(am) after `red`
@@ -288,7 +294,7 @@ extern "C" int sb_mean_attention_bwd(const void* x, const float* We, const float
     configured = smem;
   }
   mean_attention_bwd_kernel<<<B, kMaThreads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, We, Wd, s_save, dy, HW,
-                                                                          C, O, (__nv_bfloat16*)dx, dWe_part, dbe_part);
+                                                                          C, O, (__nv_bfloat16*)dx, dWe_part, dbe_part, accumulate);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -98,6 +98,7 @@ struct TapGemmDev {
   void* out;
   int out_f32, ldo;
   const float* bias;
+  int bias_mod;  // bias index = column % bias_mod (transposed convs: N = (phase, channel), one bias per channel)
   int relu, atomic;
   int tma_out;  // bf16 output through the shared-memory staged TMA store path
 };
@@ -265,9 +266,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
+            const int nbm = nb % p.bias_mod;  // (bias_mod is a multiple of 32: a 32-column chunk never wraps)
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nbm + j));
               f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
             }
           }
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
             if (p.bias) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+                if (nb + j < p.N) f[j] += __ldg(p.bias + (nb + j) % p.bias_mod);
             }
             if (p.relu) {
 #pragma unroll
@@ -547,9 +549,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
+            const int nbm = nb % p.bias_mod;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nbm + j));
               f[j] += bv.x; f[j + 1] += bv.y; f[j + 2] += bv.z; f[j + 3] += bv.w;
             }
           }
@@ -830,6 +833,8 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   p.splits = a->splits < 1 ? 1 : (a->splits > KT ? KT : a->splits);
   p.out = a->out; p.out_f32 = a->out_f32; p.ldo = a->ldo;
   p.bias = a->bias; p.relu = a->relu; p.atomic = atomic ? 1 : 0;
+  p.bias_mod = a->bias_mod > 0 ? a->bias_mod : a->N;
+  if (a->bias && (p.bias_mod % 32 || a->N % p.bias_mod)) return SB_ERR_ARG;
 
   // N tile: 256 when it divides N (fewer A re-reads), else 192 / 128 / 96
   int BN;

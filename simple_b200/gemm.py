@@ -40,7 +40,7 @@ def _taps(args, taps):
 
 
 def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bias=None, relu=False, splits=1,
-             accumulate=False, box=None, tag=None, flops=0.0):
+             accumulate=False, box=None, tag=None, flops=0.0, bias_mod=0):
     """out[b,y,x,n] (+)= sum_t sum_c a[b,y+dy_t,x+dx_t,c] * w[n, t*C+c].  a: bf16 [B,H,W,C]; w: bf16 [N, >=T*C]."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and a.is_contiguous() and a.dim() == 4
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.dim() == 2
@@ -49,7 +49,11 @@ def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bia
     atomic = splits > 1 or accumulate
     if out is None:
         dt = torch.float32 if atomic else out_dtype
-        out = (torch.zeros if atomic else torch.empty)((B, Ho, Wo, N), device=a.device, dtype=dt)
+        if atomic:
+            from .ops import zeros
+            out = zeros((B, Ho, Wo, N), a.device, dt)
+        else:
+            out = torch.empty((B, Ho, Wo, N), device=a.device, dtype=dt)
     assert out.is_contiguous() and out.shape[:3] == (B, Ho, Wo)
     bw, bh, bb = box or choose_box(Wo, Ho, B)
     args = _lib.TapGemmArgs()
@@ -60,6 +64,7 @@ def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bia
     args.w = w.data_ptr(); args.N = N; args.ldw = w.shape[1]
     args.out = out.data_ptr(); args.out_f32 = int(out.dtype == torch.float32); args.ldo = out.shape[3]
     args.bias = bias.data_ptr() if bias is not None else None
+    args.bias_mod = int(bias_mod)
     args.relu = int(relu); args.splits = splits; args.accumulate = int(accumulate)
     rec = profiling.RECORDER
     ev0 = rec.start() if rec is not None else None

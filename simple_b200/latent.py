@@ -18,6 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
+from .ops import zeros as _zeros
 
 INJ_WIDTHS = (768, 768, 768, 768, 384, 192, 96)  # action_injectors.0-5, stochastic_model.action_injector
 INJ_S = sum(INJ_WIDTHS)
@@ -154,7 +155,7 @@ class HeadsIn(torch.autograd.Function):
         ve = lp.model.value_estimator.dense
         dx5 = torch.empty_like(x5)
         dbank = torch.empty(B, 2 * INJ_S, device=dev)
-        small = torch.zeros(4608 + 1 + 2 * INJ_S, device=dev)  # dwv | dbv | dbank_b
+        small = _zeros((4608 + 1 + 2 * INJ_S,), dev)  # dwv | dbv | dbank_b
         dwv, dbv, dbank_b = small[:4608], small[4608:4609], small[4609:]
         _lib.check(L.sb_heads_bwd(x5.data_ptr(), bank.data_ptr(), lp.widths, len(INJ_WIDTHS), ctypes.byref(g),
                                   ve.weight.data_ptr(), _ptr(dvalue), _ptr(dh), B, dx5.data_ptr(), dbank.data_ptr(),
@@ -239,7 +240,7 @@ class LatentTrain(torch.autograd.Function):
         _lib.check(L.sb_drop_scale(hs.data_ptr(), _ptr(keep2), 0.1, seed_ptr, seed_val, 107, outs_d.data_ptr(),
                                    B * 16 * 128, st), 'sb_drop_scale')
         pred = torch.addmm(bp.dense5.bias, outs_d, w5T)  # [16B,256]
-        zbuf = torch.zeros(1 + 256 + 128 + 1536 + 128 * 256 + 128, **f32)  # loss | db5 | db1 | db23 | dw4 | db4
+        zbuf = _zeros((1 + 256 + 128 + 1536 + 128 * 256 + 128,), dev)  # loss | db5 | db1 | db23 | dw4 | db4
         loss_sum, db5, db1 = zbuf[0:1], zbuf[1:257], zbuf[257:385]
         dpred = torch.empty(B * 16, 256, **f32)
         gscale = 1.0 / (B * 16 * cfg.rollout_length)
@@ -323,7 +324,7 @@ class LatentTrain(torch.autograd.Function):
         h_prev = torch.cat((proj[:, 128:256].unsqueeze(1), hs[:, :-1]), dim=1).reshape(B * 16, 128)
         _acc_grad(bp.lstm.weight_hh, dxw.t() @ h_prev)
         _acc_grad(bp.lstm.weight_ih, dxw.t() @ tin.view(B * 16, 128))
-        dbg = torch.zeros(512 + 384, **f32)
+        dbg = _zeros((512 + 384,), dev)
         _lib.check(L.sb_colsum_f32(dxw.data_ptr(), B * 16, 512, 512, dbg.data_ptr(), st), 'sb_colsum_f32')
         _acc_grad(bp.lstm.bias_ih, dbg[:512])
         _acc_grad(bp.lstm.bias_hh, dbg[:512])
@@ -392,7 +393,7 @@ class HeadsOut(torch.autograd.Function):
                        'sb_reward_value')
             z = torch.zeros(2, device=dev)
             return reward_pred, z[0], z[1]
-        z = torch.zeros(2 + 3 * 128 + 3 + 128, device=dev)  # losses | dw2 | db2 | db1
+        z = torch.zeros(2 + 3 * 128 + 3 + 128, device=dev)  # losses | dw2 | db2 | db1 (own buffer: the losses are returned)
         losses, dw2, db2 = z[:2], z[2:386].view(3, 128), z[386:389]
         dhid = torch.empty(B, 128, device=dev)
         dvalue = torch.empty(B, device=dev)
@@ -419,6 +420,6 @@ class HeadsOut(torch.autograd.Function):
         _lib.check(L.sb_colsum_f32(dhid.data_ptr(), B, 128, 128, db1.data_ptr(), st), 'sb_colsum_f32')
         _acc_grad(re.dense1.bias, db1)
         dr_in = dhid @ re.dense1.weight  # [B,864]
-        dx_fin = torch.zeros(96, device=r_in.device)
+        dx_fin = _zeros((96,), r_in.device)
         _lib.check(L.sb_colsum_f32(dr_in[:, 768:].data_ptr(), B, 96, 864, dx_fin.data_ptr(), st), 'sb_colsum_f32')
         return dr_in[:, :768], dx_fin, dvalue, None, None, None

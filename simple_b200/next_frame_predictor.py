@@ -552,7 +552,9 @@ class NextFramePredictor(nn.Module):
         xs = self._xs_buf.detach()
         if not self._has_prev:
             xs[..., :64].zero_()  # first step of a window: the recurrent state is zero and the gate conv is skipped
-        ops.standardize(x.contiguous().float(), dst=xs, coff=64)
+        # x_start goes into the gate / embedding operand and, in the training branch, into the posterior's operand
+        ps = self._ps_buf.detach() if target is not None else None  # channels 15..63 stay zero (init_internal_states)
+        ops.standardize(x.contiguous().float(), dst=xs, coff=64, dst2=ps if training else None, coff2=0)
         if self._has_prev:
             G = self._conv('gate', P['gate'], self._xs_prev)
             xs = ops.GruBlend.apply(G, self._state, xs, self._xs_prev)  # fp32 state updated in place
@@ -578,11 +580,9 @@ class NextFramePredictor(nn.Module):
         value_pred, h_flat = outs[0], outs[1]
         inj = [(outs[2 + 2 * i], outs[3 + 2 * i]) for i in range(6)]  # decoder injectors 1..5, then the posterior's
         if target is not None:
-            ps = self._ps_buf.detach()  # persistent per batch size (init_internal_states); channels 15..63 stay zero
             ops.standardize(target, dst=ps, coff=12, out_f32=target)  # in place, like the reference (:332-334)
         sm = self.stochastic_model
         if training:
-            ps[..., :12] = xs.detach()[..., 64:76]
             x12 = self._posterior_features(ps, inj[5])
             hm, x_mid, lstm_loss = latent.LatentTrain.apply(h_flat, x12, lp, epsilon, rand, c, aux)
             sm.lstm_loss = lstm_loss if sm.lstm_loss is None else sm.lstm_loss + lstm_loss

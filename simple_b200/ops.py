@@ -66,6 +66,49 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+class ZeroArena:
+    """All zero-initialised scratch of one training step (InstanceNorm sums, split-K / weight-gradient accumulators,
+    bias-gradient and loss accumulators: ~80 buffers, 280 MB at B = 64) carved from ONE buffer that a single memset
+    clears at the start of the step, instead of one fill kernel per buffer.  `begin()` .. `end()` brackets a step; the
+    first bracketed step measures the demand (requests fall back to torch.zeros), later steps are served from the arena.
+    Tensors handed out stay valid until the next `begin()`."""
+
+    def __init__(self):
+        self.buf, self.off, self.need, self.active = None, 0, 0, False
+
+    def begin(self, device):
+        want = self.need + (self.need >> 3)
+        if want > 0 and (self.buf is None or self.buf.numel() < want or self.buf.device != torch.device(device)):
+            self.buf = torch.empty(want, dtype=torch.uint8, device=device)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off, self.active, self._demand = 0, True, 0
+
+    def end(self):
+        self.active = False
+        self.need = max(self.need, getattr(self, '_demand', 0))
+
+    def zeros(self, shape, dtype, device):
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+            n *= int(d)
+        nbytes = (n * torch.empty(0, dtype=dtype).element_size() + 255) & ~255
+        if self.active:
+            self._demand += nbytes
+            if self.buf is not None and self.off + nbytes <= self.buf.numel() and self.buf.device == torch.device(device):
+                t = self.buf[self.off:self.off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(shape)
+                self.off += nbytes
+                return t
+        return torch.zeros(shape, dtype=dtype, device=device)
+
+
+ARENA = ZeroArena()
+
+
+def zeros(shape, device, dtype=torch.float32):
+    return ARENA.zeros(shape, dtype, device)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # raw kernel wrappers
 # ---------------------------------------------------------------------------------------------------------------
@@ -130,7 +173,7 @@ def _sample_bytes(*tensors):
 def stats_raw(spec, main, add=None):
     """Per-(b,c) raw sums [B,C,2] (sum, sum of squares) of relu?(main)+add over the logical H x W pixels."""
     B = main.shape[0]
-    sums = torch.zeros(B, spec.C, 2, device=main.device, dtype=torch.float32)
+    sums = zeros((B, spec.C, 2), main.device)
     a = _prep_args(spec, B, main, add, None, None, None, None, None, None, None, 0, None)
     _lib.check(_lib.lib().sb_stats(ctypes.byref(a), sums.data_ptr(), _lib.stream_ptr()), 'sb_stats')
     return sums
@@ -150,7 +193,7 @@ class FusedPrep(torch.autograd.Function):
         sh_f = sh.detach().float().contiguous() if sh is not None else None
         out1 = torch.empty((B, spec.H, spec.W, spec.C), device=dev, dtype=torch.bfloat16) if spec.want_out1 else None
         out2 = torch.empty(spec.lay_out.shape(B), device=dev, dtype=torch.bfloat16)
-        sums = torch.zeros(B, spec.C, 2, device=dev, dtype=torch.float32) if spec.norm else None
+        sums = zeros((B, spec.C, 2), dev) if spec.norm else None
         a = _prep_args(spec, B, main, add, sums, gamma_f, beta_f, sc_f, sh_f, out1, out2, seed, keep)
         a_st = _prep_args(spec, B, main, add, None, None, None, None, None, None, None, 0, None) if spec.norm else None
         # (without InstanceNorm there is a single pass: nothing to keep in the L2 between passes)
@@ -190,17 +233,17 @@ class FusedPrep(torch.autograd.Function):
         two_pass = has_norm or has_inj
         if two_pass:
             # one zero-filled buffer: per-(b,c) sums [B,C,4] + their batch sums for the affine gradients [C,2]
-            buf = torch.zeros(B * spec.C * 4 + spec.C * 2, device=dev, dtype=torch.float32)
+            buf = zeros((B * spec.C * 4 + spec.C * 2,), dev)
             bsums = buf[:B * spec.C * 4].view(B, spec.C, 4)
             a.bsums = bsums.data_ptr()
             if has_norm:
-                dgb = buf[B * spec.C * 4:].view(spec.C, 2)
+                dgb = buf[B * spec.C * 4:].view(2, spec.C)  # rows: d beta | d gamma (contiguous: no copy in AccumulateGrad)
                 a.dgb = dgb.data_ptr()
         d_main = torch.empty(main.shape, device=dev, dtype=torch.bfloat16)
         d_add = torch.empty(add.shape, device=dev, dtype=torch.bfloat16) if has_add else None
         dcol = None
         if ctx.dbias_dst is not None:  # bias gradient of the conv that produced `main`, fused into this pass
-            dcol = torch.zeros(spec.C, device=dev, dtype=torch.float32)
+            dcol = zeros((spec.C,), dev)
         for b0, nb in (_chunks(B, _sample_bytes(main, add, g2, g1)) if two_pass else [(0, 0)]):
             a.b_base, a.b_count = b0, nb
             if two_pass:
@@ -212,8 +255,8 @@ class FusedPrep(torch.autograd.Function):
             _lib.check(L.sb_prep_bwd_apply(ctypes.byref(a), st), 'sb_prep_bwd_apply')
         if dcol is not None:
             ctx.dbias_dst['dbias'] = dcol
-        dgamma = dgb[:, 1] if has_norm else None
-        dbeta = dgb[:, 0] if has_norm else None
+        dgamma = dgb[1] if has_norm else None
+        dbeta = dgb[0] if has_norm else None
         dsc = bsums[:, :, 2] if has_inj else None
         dsh = bsums[:, :, 3] if has_inj else None
         return None, d_main, d_add, dgamma, dbeta, dsc, dsh, None, None, None
@@ -266,6 +309,8 @@ class PackedWeight:
         dev = weight.device
         self.iperm = torch.tensor(iperm, dtype=torch.int32, device=dev) if iperm is not None else None
         self.operm = torch.tensor(operm, dtype=torch.int32, device=dev) if operm is not None else None
+        self.operm_long = self.operm.long() if operm is not None else None            # reference index -> physical index
+        self.operm_inv = torch.argsort(self.operm_long) if operm is not None else None  # physical -> reference
         self.fwd = torch.zeros(self.Opad, self.T * self.PH * self.Ipad, device=dev, dtype=torch.bfloat16)
         self.tr = torch.zeros(self.PH * self.Ipad, self.T * self.Opad, device=dev, dtype=torch.bfloat16)
         # packed-gradient mode (set by the Trainer fast path): backward leaves the fp32 gradient in the packed layout in
@@ -313,26 +358,23 @@ class TapConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec, a, weight, bias, pw):
         w_op = pw.tr if spec.transposed else pw.fwd
-        bias_f = None
+        bias_f, bias_mod = None, 0
         if bias is not None:
-            bias_f = bias.detach().float()
+            bias_f = bias.detach().float().contiguous()
             if pw.operm is not None:  # output channels are stored permuted: physical[operm[o]] = reference[o]
-                bp = torch.empty_like(bias_f)
-                bp[pw.operm.long()] = bias_f
-                bias_f = bp
-            if spec.bias_tile > 1:
-                bias_f = bias_f.repeat(spec.bias_tile)
-            bias_f = bias_f.contiguous()
+                bias_f = bias_f[pw.operm_inv]  # one gather
+            if spec.bias_tile > 1:  # N = (phase, channel): the epilogue indexes the bias by column % channels
+                bias_mod = spec.N // spec.bias_tile
         B = a.shape[0]
         splits = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
         if splits > 1:
             acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits, tag=spec.name + '.fwd',
                            flops=spec.flops * B)
-            y = _bias_act(acc, bias_f, spec.relu, spec.out_f32)
+            y = _bias_act(acc, bias_f, spec.relu, spec.out_f32, bias_mod)
         else:
             y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu,
                          out_dtype=torch.float32 if spec.out_f32 else torch.bfloat16, tag=spec.name + '.fwd',
-                         flops=spec.flops * B)
+                         flops=spec.flops * B, bias_mod=bias_mod)
         ctx.spec, ctx.pw = spec, pw
         ctx.has_bias = bias is not None
         ctx.save_for_backward(a, y if spec.bwd_mask else None)
@@ -351,8 +393,8 @@ class TapConv(torch.autograd.Function):
             w_op = pw.fwd if spec.transposed else pw.tr
             splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
             if splits > 1:
-                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits, tag=spec.name + '.dgrad',
-                              flops=spec.flops * B).bfloat16()
+                da = _bias_act(tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits,
+                                        tag=spec.name + '.dgrad', flops=spec.flops * B), None, False)
             else:
                 da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
                               flops=spec.flops * B)
@@ -360,11 +402,11 @@ class TapConv(torch.autograd.Function):
         slot = pw.grad_slot if pw.defer_unpack else None
         if spec.transposed:
             # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
-            dwp = slot if slot is not None else torch.zeros(spec.Ca, T * spec.N, device=a.device, dtype=torch.float32)
+            dwp = slot if slot is not None else zeros((spec.Ca, T * spec.N), a.device)
             tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for one wave of CTAs
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         else:
-            dwp = slot if slot is not None else torch.zeros(spec.N, T * spec.Ca, device=a.device, dtype=torch.float32)
+            dwp = slot if slot is not None else zeros((spec.N, T * spec.Ca), a.device)
             tap_wgrad(a, dy, spec.taps, dwp, splits=0,
                       tag=spec.name + '.wgrad', flops=spec.flops * B)
         if pw.defer_unpack:
@@ -379,7 +421,7 @@ class TapConv(torch.autograd.Function):
             # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
             dbias = ext if ext is not None else colsum(dy.reshape(-1, spec.N // spec.bias_tile))
             if pw.operm is not None:
-                dbias = dbias[pw.operm.long()]
+                dbias = dbias[pw.operm_long]
         return None, da, dweight, dbias, None
 
 
@@ -435,12 +477,12 @@ def auto_splits(B, Ho, Wo, N, KT):
     return int(max(1, min(KT, s, 32)))
 
 
-def _bias_act(acc, bias, relu, keep_f32=False):
+def _bias_act(acc, bias, relu, keep_f32=False, bias_mod=0):
     """Epilogue of a split-K GEMM (tiny tensors only): fp32 partial sums -> +bias, ReLU, bf16 (or fp32, in place)."""
     N = acc.shape[-1]
     out = acc if keep_f32 else torch.empty(acc.shape, device=acc.device, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().sb_bias_act(acc.data_ptr(), _ptr(bias), int(bool(relu)), out.data_ptr(), int(keep_f32),
-                                      acc.numel() // N, N, _lib.stream_ptr()), 'sb_bias_act')
+    _lib.check(_lib.lib().sb_bias_act(acc.data_ptr(), _ptr(bias), int(bias_mod), int(bool(relu)), out.data_ptr(),
+                                      int(keep_f32), acc.numel() // N, N, _lib.stream_ptr()), 'sb_bias_act')
     return out
 
 
@@ -478,13 +520,16 @@ class GruBlend(torch.autograd.Function):
         return dG, None, None, None
 
 
-def standardize(x, dst=None, coff=0, out_f32=None):
-    """x fp32 [B,C,H,W] -> standardised; writes bf16 into dst[..., coff:coff+C] (NHWC) and/or fp32 `out_f32` (NCHW)."""
+def standardize(x, dst=None, coff=0, out_f32=None, dst2=None, coff2=0):
+    """x fp32 [B,C,H,W] -> standardised; writes bf16 into dst[..., coff:coff+C] (NHWC), optionally also into
+    dst2[..., coff2:coff2+C], and/or fp32 `out_f32` (NCHW)."""
     assert x.dtype == torch.float32 and x.is_contiguous()
     B, C, H, W = x.shape
     scratch = torch.empty(B * C * 2, device=x.device, dtype=torch.float32)
     _lib.check(_lib.lib().sb_standardize(x.data_ptr(), B, C, H * W, _ptr(dst), dst.shape[-1] if dst is not None else 0,
-                                         coff, _ptr(out_f32), scratch.data_ptr(), _lib.stream_ptr()), 'sb_standardize')
+                                         coff, _ptr(out_f32), scratch.data_ptr(), _ptr(dst2),
+                                         dst2.shape[-1] if dst2 is not None else 0, coff2, _lib.stream_ptr()),
+               'sb_standardize')
 
 
 def frame_feedback(stack, gt_u8, pred_u8, eps, p_noise, seed):
@@ -511,8 +556,8 @@ class PixelCE(torch.autograd.Function):
     def forward(ctx, logits, target_u8, clip, want_argmax, unit_grad, dbias_dst=None):
         B, H, W, _ = logits.shape
         HW = H * W
-        loss_sum = torch.zeros(1, device=logits.device, dtype=torch.float64)
-        dbias = torch.zeros(768, device=logits.device, dtype=torch.float32)
+        loss_sum = zeros((1,), logits.device, torch.float64)
+        dbias = zeros((768,), logits.device)
         amax = torch.empty(B, 3, H, W, device=logits.device, dtype=torch.uint8) if want_argmax else None
         n = float(B * 3 * HW)
         dl = logits.detach()
@@ -581,12 +626,14 @@ class MeanAttentionFn(torch.autograd.Function):
         HW, O = H * W, wd_.shape[0]
         dy = dy.contiguous().float()
         dx = torch.empty_like(x)
-        dwe_part = torch.empty(B, 4, C, device=x.device, dtype=torch.float32)
-        dbe_part = torch.empty(B, 4, device=x.device, dtype=torch.float32)
-        _lib.check(_lib.lib().sb_mean_attention_bwd(x.data_ptr(), we2.data_ptr(), wd_.data_ptr(), s_save.data_ptr(),
-                                                    dy.data_ptr(), B, HW, C, O, dx.data_ptr(), dwe_part.data_ptr(),
-                                                    dbe_part.data_ptr(), _lib.stream_ptr()), 'sb_mean_attention_bwd')
-        return dx, dwe_part.sum(0).reshape(ctx.we_shape), dbe_part.sum(0), dy.t() @ l_save, dy.sum(0)
+        acc = zeros((4 * C + 4 + O,), x.device)  # dWe [4,C] | dbe [4] | dbd [O]: batch sums accumulated by the kernels
+        dwe, dbe, dbd = acc[:4 * C], acc[4 * C:4 * C + 4], acc[4 * C + 4:]
+        L = _lib.lib()
+        _lib.check(L.sb_mean_attention_bwd(x.data_ptr(), we2.data_ptr(), wd_.data_ptr(), s_save.data_ptr(), dy.data_ptr(),
+                                           B, HW, C, O, dx.data_ptr(), dwe.data_ptr(), dbe.data_ptr(), 1,
+                                           _lib.stream_ptr()), 'sb_mean_attention_bwd')
+        _lib.check(L.sb_colsum_f32(dy.data_ptr(), B, O, O, dbd.data_ptr(), _lib.stream_ptr()), 'sb_colsum_f32')
+        return dx, dwe.reshape(ctx.we_shape), dbe, dy.t() @ l_save, dbd
 
 
 def mean_attention(x_nhwc_bf16, module):

@@ -177,6 +177,7 @@ class Trainer:
         `after_backward(out)`: optional gradient-independent tail work of the caller (frame feedback); it is issued
         between the backward pass and the optimiser so that it overlaps the last gradient all-reduce."""
         self.model.train()
+        ops.ARENA.begin(frames.device)  # one memset for all zero-initialised scratch of the step
         out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
         self.optimizer.zero_grad(set_to_none=True)
         packed = self.model.packed_weight_map(defer_unpack=self.packed_grads) if self.packed_grads else None
@@ -197,6 +198,7 @@ class Trainer:
         if packed:
             for pw in packed.values():
                 pw.gpacked = None
+        ops.ARENA.end()
         return out
 
     def train(self, epoch, env, steps=15000):
