@@ -308,16 +308,23 @@ def run_own(args):
             line['roofline_by_layer'] = {
                 t: {'ms': v[0] / 3, 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None}
                 for g in gem for t, v in sorted(g['by_tag'].items())}
-        if 'pixel_ce_kernel' in summ:
-            c = summ['pixel_ce_kernel']
+        ce_key = 'logits_ce_kernel' if 'logits_ce_kernel' in summ else 'pixel_ce_kernel'
+        if ce_key in summ:
+            c = summ[ce_key]
             ach = c['work'] / (c['ms'] * 1e-3) / 1e9
-            line['roofline_ce'] = {'bound': 'hbm', 'kernel': 'pixel_ce_kernel', 'achieved': ach, 'peak': hbm,
-                                   'unit': 'GB/s', 'frac': ach / hbm,
-                                   'traffic': CE_DRAM_BYTES_B64 if B == 64 else None,
-                                   'traffic_source': 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
-                                   'peak_source': how,
-                                   'ms_per_launch': c['ms'] / c['launches'],
-                                   'alg_bytes_per_launch': c['work'] / c['launches']}
+            fused = ce_key == 'logits_ce_kernel'
+            line['roofline_ce'] = {
+                'bound': 'hbm',
+                'kernel': ('tap_gemm2_kernel<256,4,1>: logits GEMM + softmax-CE epilogue (the logits never reach HBM)'
+                           if fused else 'pixel_ce_kernel'),
+                'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
+                'traffic': None if fused else (CE_DRAM_BYTES_B64 if B == 64 else None),
+                'traffic_source': None if fused else 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
+                'peak_source': how, 'ms_per_launch': c['ms'] / c['launches'],
+                'alg_bytes_per_launch': c['work'] / c['launches'],
+                'alg_bytes_definition': ('read hf (bf16 x 96) + write dlogits (bf16 x 768) + targets + arg-max per pixel; '
+                                         'the unfused pair (logits GEMM, pixel_ce_kernel) moved 3 x 768 bf16 per pixel')
+                if fused else 'read logits + write dlogits (bf16 x 768 each) + targets + arg-max per pixel'}
     # ---- simulated rollout: agents x 50 steps with a PPO-style CNN policy (configs[2]); agents sharded over ranks
     A = args.agents
     cfg_env = SimpleNamespace(**{**vars(cfg), 'agents': A})

@@ -102,6 +102,14 @@ int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
 int sb_set_ce_tma(int enabled);
 int sb_pixel_ce(const void* logits, const uint8_t* target, int B, int HW, float clip, float gscale, void* dlogits,
                 uint8_t* argmax_out, double* loss_sum, float* dbias, sb_stream_t stream);
+/* The logits layer (1x1 conv 96 -> 3 x 256, simple/next_frame_predictor.py:356-357) FUSED with the loss above: the
+ * softmax-CE runs in the epilogue of the tcgen05 CTA-pair GEMM (one N tile = one colour = one softmax group per TMEM
+ * lane), so the [B*HW, 768] logits tensor is never written to HBM.  `args` describes the GEMM like sb_tap_gemm (N = 768,
+ * one tap, bias required); args->out = dlogits bf16 [B,Ho,Wo,768] (training: the only large tensor that leaves the SM)
+ * or NULL (rollout: only argmax_out is produced).  Same results as sb_tap_gemm followed by sb_pixel_ce up to the
+ * summation order of the fp32 exp-sums (arg-max identical). */
+int sb_logits_ce(const sb_tap_gemm_args* args, const uint8_t* target, float clip, float gscale, uint8_t* argmax_out,
+                 double* loss_sum, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused elementwise stage between two tap GEMMs ("prep"), its statistics and its backward.

@@ -131,6 +131,7 @@ class _Sigs:
     sb_tap_gemm = [ctypes.POINTER(TapGemmArgs), _p]
     sb_tap_wgrad = [ctypes.POINTER(TapWgradArgs), _p]
     sb_pixel_ce = [_p, _p, _i, _i, _f, _f, _p, _p, _p, _p, _p]
+    sb_logits_ce = [ctypes.POINTER(TapGemmArgs), _p, _f, _f, _p, _p, _p]
     sb_stats = [ctypes.POINTER(PrepArgs), _p, _p]
     sb_prep = [ctypes.POINTER(PrepArgs), _p]
     sb_prep_bwd_reduce = [ctypes.POINTER(PrepArgs), _p]

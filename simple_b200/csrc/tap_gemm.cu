@@ -403,10 +403,27 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 // are signalled in BOTH CTAs by one multicast tcgen05.commit; tempty[a] lives in the leader (16 arrivals: the 8
 // epilogue warps of each CTA, the peer's remotely).
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+// EPI = 1 / 2: fused softmax-CE epilogue of the LOGITS layer (N = 3 x 256, colour-major: an N tile IS one softmax group).
+// Reference: simple/next_frame_predictor.py:356-357 (logits conv) + simple/trainer.py:130,134-137 (CE, clip, arg-max).
+// The 826 MB logits tensor of a B = 64 step is never written: every epilogue thread owns half of one pixel's 256 logits
+// (its two interleaved 64-column chunks, rounded to bf16 exactly like the materialised path), the two halves of a row
+// meet through shared memory for the max / first arg-max / exp-sum, and what leaves the SM is the GRADIENT tile
+// (EPI = 1: training) through the usual swizzled staging + TMA store, or nothing but the arg-max byte (EPI = 2: rollout).
+struct CeParams {
+  const uint8_t* target;  // u8 [B,3,HW] (EPI = 1)
+  uint8_t* amax;          // u8 [B,3,HW] or NULL
+  double* loss_sum;       // += sum max(ce, clip) (EPI = 1)
+  float clip, gscale;
+  int HW;
+};
+constexpr int kCeExchangeBytes = 128 * 11 * 4;  // per row: max[2][2], argmax[2][2] (tile parity), sum[2], target logit
+
+template <int BN, int STAGES, int EPI = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
     tap_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmDev p) {
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmDev p,
+                     const __grid_constant__ CeParams ce) {
+  static_assert(EPI == 0 || BN == 256, "the CE epilogue needs one 256-way softmax group per N tile");
   constexpr int BH = BN / 2;           // weight-tile rows held by each CTA of the pair
   constexpr int B_BYTES = BH * 128;
   constexpr int TMEM_COLS = 2 * BN <= 256 ? 256 : 512;
@@ -512,6 +529,160 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
         umma_commit_2cta(&tfull[as], 3);
       }
     }
+  } else if (EPI != 0) {
+    // ---------------- fused softmax-CE epilogue ----------------
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const int e = warp - 2;
+    const int lg = warp & 3;
+    const int half = e >> 2;           // half 0 owns columns [0,64) u [128,192), half 1 owns [64,128) u [192,256)
+    const int r = lg * 32 + lane;      // row of the 128-row tile = TMEM lane
+    const bool issuer = ((e & 3) == 0) && lane == 0;
+    const uint32_t bar_id = 1u + (uint32_t)half;
+    // exchange area of the two column halves of a row; max / arg-max are double-buffered by tile parity because the
+    // rollout variant has a single barrier per tile (a fast thread may already write tile i+1 while its partner reads i)
+    float* ex_m_all = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parity][2 halves][128] row maxima
+    int* ex_i_all = reinterpret_cast<int*>(ex_m_all + 512);     // [2][2][128] first arg-max columns
+    float* ex_s = reinterpret_cast<float*>(ex_i_all + 512);     // [2][128] exp-sums
+    float* ex_t = ex_s + 256;                                   // [128] target logit
+    const int xl = r % p.bw, yl = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
+    uint32_t ochunk = 0;
+    float loss_acc = 0.f;
+    int tcount = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
+      const int nt = tile % p.n_tiles;  // colour
+      const int mt = 2 * (tile / p.n_tiles) + (int)rank;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * BN;
+      const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
+      const bool valid = (r < p.rows) && (x < p.Wo) && (y < p.Ho) && (b < p.B) && (mt < p.m_tiles);
+      const long long toff = ((long long)b * 3 + nt) * ce.HW + (long long)y * p.Wo + x;  // u8 [B,3,HW] offset
+      int t = 0;
+      if (EPI == 1 && valid) t = ce.target[toff];  // issued before the wait: overlaps the MMA of this tile
+      const int as = tcount & 1;
+      const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      // ---- pass 1: my 128 logits -> +bias -> bf16 (the rounding of the materialised path), packed in 64 registers
+      uint32_t xr[64];
+      __nv_bfloat162 m2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int col = half * 64 + (q4 >> 1) * 128 + (q4 & 1) * 32;  // first column of this 32-column piece
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + col), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + j));
+          const __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(v[j]) + bv.x, __uint_as_float(v[j + 1]) + bv.y);
+          const __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) + bv.z, __uint_as_float(v[j + 3]) + bv.w);
+          xr[q4 * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&a0);
+          xr[q4 * 16 + (j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&a1);
+          m2 = __hmax2(m2, __hmax2(a0, a1));
+        }
+      }
+      // all TMEM reads of this tile are done: hand the accumulator stage back, the next tile's MMAs overlap the rest
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty[as]);
+        else mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+      }
+      const float2 mf = __bfloat1622float2(m2);
+      const float lm = fmaxf(mf.x, mf.y);
+      // first column (in this thread's ascending column order) holding the local maximum
+      int first = 256;
+      {
+        const __nv_bfloat162 g2 = __float2bfloat162_rn(lm);
+#pragma unroll
+        for (int k = 63; k >= 0; --k) {
+          const uint32_t eq = __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xr[k]), g2);
+          const int colk = half * 64 + (k >> 5) * 128 + ((k & 31) << 1);  // column of the low element of pair k
+          if (eq & 0xffff0000u) first = colk + 1;
+          if (eq & 0x0000ffffu) first = colk;
+        }
+      }
+      float* ex_m = ex_m_all + (tcount & 1) * 256;
+      int* ex_i = ex_i_all + (tcount & 1) * 256;
+      ex_m[half * 128 + r] = lm;
+      ex_i[half * 128 + r] = first;
+      named_bar_sync(3, 256);
+      const float om = ex_m[(half ^ 1) * 128 + r];
+      const int oi = ex_i[(half ^ 1) * 128 + r];
+      const float gm = fmaxf(lm, om);
+      if (ce.amax && half == 0 && valid) {
+        int best = first;
+        if (om > lm || (om == lm && oi < first)) best = oi;
+        ce.amax[toff] = (uint8_t)best;
+      }
+      if (EPI == 1) {
+        // ---- pass 2: exp-sum (same fp32 formula as pixel_ce_kernel) and the target logit
+        const float moff = -gm * LOG2E;
+        float s = 0.f;
+        const int tq = t - half * 64;                     // position of the target inside my columns, if it is mine
+        const bool mine = ((t >> 6) & 1) == half;
+        const int tk = mine ? (((t >> 7) << 5) + ((tq & 63) >> 1)) : -1;  // pair index holding the target
+        float xt = 0.f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          const float x0f = __uint_as_float(xr[k] << 16), x1f = __uint_as_float(xr[k] & 0xffff0000u);
+          s += exp2f(fmaf(x0f, LOG2E, moff)) + exp2f(fmaf(x1f, LOG2E, moff));
+          if (k == tk) xt = (t & 1) ? x1f : x0f;
+        }
+        ex_s[half * 128 + r] = s;
+        if (mine) ex_t[r] = xt;
+        named_bar_sync(3, 256);
+        const float st = ex_s[r] + ex_s[128 + r];
+        xt = ex_t[r];
+        const float cev = gm + log2f(st) * LN2 - xt;
+        if (half == 0 && valid) loss_acc += fmaxf(cev, ce.clip);
+        const float scale = (valid && cev > ce.clip) ? ce.gscale : 0.f;
+        const float inv = scale / st;
+        // ---- pass 3: gradient tile -> bf16 -> swizzled staging -> TMA store (two 64-column chunks per thread)
+        const int sw = r & 7;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {  // (unrolled: `xr` must stay in registers)
+          const int c = half * 64 + cc * 128;
+          if (issuer) bulk_wait_read<1>();  // the store that used this staging buffer two chunks ago has drained
+          named_bar_sync(bar_id, 128);
+          uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOut2Bytes;
+          uint8_t* row = buf + r * 128;
+          if (r < p.rows) {
+#pragma unroll
+            for (int pc = 0; pc < 8; ++pc) {  // 16-byte pieces of 8 columns
+              uint32_t o[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t w = xr[cc * 32 + pc * 4 + u];
+                const float d0 = exp2f(fmaf(__uint_as_float(w << 16), LOG2E, moff)) * inv;
+                const float d1 = exp2f(fmaf(__uint_as_float(w & 0xffff0000u), LOG2E, moff)) * inv;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(d0, d1);
+                o[u] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(row + ((pc ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            if (mine && (t >> 7) == cc) {  // one-hot term: patch the target element (same thread: ordered after its vector store)
+              const int tl = t & 63;
+              const float et = exp2f(fmaf(xt, LOG2E, moff));
+              *reinterpret_cast<__nv_bfloat16*>(row + (((tl >> 3) ^ sw) << 4) + ((tl & 7) << 1)) =
+                  __float2bfloat16_rn(et * inv - scale);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            tma_store_4d(&tmO, buf, n0 + c, x0, y0, b0);
+            bulk_commit();
+          }
+          ++ochunk;
+        }
+      }
+    }
+    if (EPI == 1) {
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0 && half == 0 && loss_acc != 0.f) atomicAdd(ce.loss_sum, (double)loss_acc);
+      if (issuer) bulk_wait_all();
+    }
   } else {
     const int e = warp - 2;
     const int lg = warp & 3;
@@ -598,21 +769,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
   if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI = 0>
 static int launch_tap_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TapGemmDev& p,
-                            cudaStream_t stream) {
-  constexpr int smem = STAGES * (kATileBytes + (BN / 2) * 128) + kOutBufs * kStageOut2Bytes + (2 * STAGES + 4) * 8 + 16 + 1024;
+                            cudaStream_t stream, const CeParams* cep = nullptr) {
+  constexpr int smem = STAGES * (kATileBytes + (BN / 2) * 128) + kOutBufs * kStageOut2Bytes + (2 * STAGES + 4) * 8 + 16 +
+                       (EPI ? kCeExchangeBytes : 0) + 1024;
   static_assert(smem <= 232448, "tap_gemm2_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tap_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+    if (cudaFuncSetAttribute(tap_gemm2_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return SB_ERR_CUDA;
     configured = true;
   }
   const int total = ((p.m_tiles + 1) / 2) * p.n_tiles;
   const int pairs = total < 74 ? total : 74;
-  tap_gemm2_kernel<BN, STAGES><<<2 * pairs, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p);
+  CeParams ce{};
+  if (cep) ce = *cep;
+  tap_gemm2_kernel<BN, STAGES, EPI><<<2 * pairs, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p, ce);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -882,6 +1056,52 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
     case 128: return launch_tap_gemm<128, 6>(tmA, tmB, tmO, p, stream);
     default: return launch_tap_gemm<96, 6>(tmA, tmB, tmO, p, stream);
   }
+}
+
+// Logits layer fused with the per-pixel softmax cross-entropy (see the EPI = 1 / 2 epilogue of tap_gemm2_kernel).
+extern "C" int sb_logits_ce(const sb_tap_gemm_args* a, const uint8_t* target, float clip, float gscale,
+                            uint8_t* argmax_out, double* loss_sum, sb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !a->a || !a->w || !a->bias) return SB_ERR_ARG;
+  const bool train = a->out != nullptr;
+  if (train && (!target || !loss_sum || a->out_f32)) return SB_ERR_ARG;
+  if (!train && !argmax_out) return SB_ERR_ARG;
+  if (a->N != 768 || a->ntaps != 1 || a->tap_dy[0] != 0 || a->tap_dx[0] != 0 || a->C % 8 || a->ldw < a->C) return SB_ERR_ARG;
+  if (a->H != a->Ho || a->W != a->Wo || (train && (a->ldo != 768))) return SB_ERR_ARG;
+  const int rows = a->bw * a->bh * a->bb;
+  if (rows < 1 || rows > 128 || a->bw > 256 || a->bh > 256 || a->bb > 256) return SB_ERR_ARG;
+  if ((long long)a->B * a->Ho * a->Wo * 3 >= (1LL << 31)) return SB_ERR_ARG;
+  int rc = load_driver_entry();
+  if (rc) return rc;
+  TapGemmDev p;
+  p.B = a->B; p.Ho = a->Ho; p.Wo = a->Wo;
+  p.bw = a->bw; p.bh = a->bh; p.bb = a->bb; p.rows = rows;
+  p.tiles_x = (a->Wo + a->bw - 1) / a->bw;
+  p.tiles_y = (a->Ho + a->bh - 1) / a->bh;
+  const int tiles_b = (a->B + a->bb - 1) / a->bb;
+  p.C = a->C; p.kchunks = (a->C + 63) / 64; p.ntaps = 1;
+  for (int i = 0; i < SB_MAX_TAPS; ++i) p.tap_dy[i] = p.tap_dx[i] = 0;
+  p.N = 768; p.splits = 1;
+  p.out = a->out; p.out_f32 = 0; p.ldo = 768;
+  p.bias = a->bias; p.bias_mod = 768; p.relu = 0; p.atomic = 0; p.tma_out = 1;
+  p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+  p.n_tiles = 3;
+  CUtensorMap tmA, tmBh, tmO64;
+  rc = make_map_nhwc(&tmA, a->a, a->B, a->H, a->W, a->C, a->bw, a->bh, a->bb);
+  if (rc) return rc;
+  rc = make_map_2d(&tmBh, a->w, 768, a->C, a->ldw, 128);
+  if (rc) return rc;
+  if (train) {
+    rc = make_map_out64(&tmO64, a->out, a->B, a->Ho, a->Wo, 768, 768, a->bw, a->bh, a->bb);
+    if (rc) return rc;
+  } else {
+    tmO64 = tmA;  // unused
+  }
+  CeParams ce;
+  ce.target = target; ce.amax = argmax_out; ce.loss_sum = loss_sum; ce.clip = clip; ce.gscale = gscale;
+  ce.HW = a->Ho * a->Wo;
+  if (train) return launch_tap_gemm2<256, 4, 1>(tmA, tmBh, tmO64, p, stream, &ce);
+  return launch_tap_gemm2<256, 4, 2>(tmA, tmBh, tmO64, p, stream, &ce);
 }
 
 extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {

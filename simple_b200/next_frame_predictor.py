@@ -310,6 +310,7 @@ class NextFramePredictor(nn.Module):
         self._auto_repack = True
         self.parity_rand = None   # set to an InjectedRand to run with explicit randomness
         self._head_targets = None
+        self._logits_mode, self._ce_target, self._ce_clip = 'tensor', None, 0.0
         self._lp = None
         self.last_aux = {}
 
@@ -619,7 +620,15 @@ class NextFramePredictor(nn.Module):
             aux['loss_reward'], aux['loss_value'] = l_rew, l_val
         else:  # plain `model(x, a, target)` under autograd with the losses taken outside: differentiable library ops
             reward_pred = self.reward_estimator(torch.cat((x_mid, x_fin.unsqueeze(0).expand(B, -1)), dim=1))
-        logits = self._conv('logits', P['logits'], hf)  # bf16 [B,H,W,768], channel = colour*256 + value
+        if self._logits_mode == 'tensor':
+            logits = self._conv('logits', P['logits'], hf)  # bf16 [B,H,W,768], channel = colour*256 + value
+        else:  # logits GEMM fused with the softmax-CE / arg-max decode: the logits never reach HBM (ops.LogitsCE)
+            m, pw, logits = self._weights_cache['logits'], self._packed['logits'], None
+            if self._logits_mode == 'ce':
+                aux['loss_reconstruct'], aux['argmax'] = ops.LogitsCE.apply(P['logits'], hf, m.weight, m.bias, pw,
+                                                                             self._ce_target, self._ce_clip)
+            else:
+                aux['argmax'] = ops.logits_argmax(P['logits'], hf, m.bias, pw)
         return logits, reward_pred, value_pred
 
     def _posterior_features(self, ps, inj_s):
@@ -637,11 +646,16 @@ class NextFramePredictor(nn.Module):
         x2 = ops.mean_attention(c2, sm.mean_attentions[1])
         return torch.cat((x1, x2), dim=-1)
 
-    def forward_internal(self, x, action, target=None, epsilon=0, rewards=None, values=None):
+    def forward_internal(self, x, action, target=None, epsilon=0, rewards=None, values=None, logits_mode='tensor',
+                         ce_target=None, ce_clip=0.0):
         """Runs the network and returns the INTERNAL logits (bf16 [B,H,W,768], colour-major) + reward + value.
         `rewards` (long [B]) / `values` (f32 [B]): when given, the reward CE and value MSE of simple/trainer.py:138-141
-        are produced by the fused heads kernel and left in `last_aux['loss_reward' / 'loss_value']`."""
+        are produced by the fused heads kernel and left in `last_aux['loss_reward' / 'loss_value']`.
+        `logits_mode`: 'tensor' materialises the logits; 'ce' fuses the logits GEMM with the clipped pixel CE against
+        `ce_target` (u8 [B,3,H,W]) -> `last_aux['loss_reconstruct' / 'argmax']`, logits = None; 'argmax' (rollouts)
+        leaves only the decoded frame in `last_aux['argmax']`."""
         self._head_targets = (rewards, values) if rewards is not None else None
+        self._logits_mode, self._ce_target, self._ce_clip = logits_mode, ce_target, ce_clip
         dev = x.device
         if dev.type != 'cuda':
             raise RuntimeError('simple_b200.NextFramePredictor runs on CUDA (sm_100a) only; there is no CPU fallback')

@@ -382,47 +382,52 @@ class TapConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        spec, pw = ctx.spec, ctx.pw
         a, y = ctx.saved_tensors
         if y is not None:
             dy = dy * (y > 0)
-        dy = dy.contiguous().to(torch.bfloat16)
-        B = a.shape[0]
-        da = None
-        if spec.need_dgrad and ctx.needs_input_grad[1]:
-            w_op = pw.fwd if spec.transposed else pw.tr
-            splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
-            if splits > 1:
-                da = _bias_act(tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits,
-                                        tag=spec.name + '.dgrad', flops=spec.flops * B), None, False)
-            else:
-                da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
-                              flops=spec.flops * B)
-        T = len(spec.taps)
-        slot = pw.grad_slot if pw.defer_unpack else None
-        if spec.transposed:
-            # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
-            dwp = slot if slot is not None else zeros((spec.Ca, T * spec.N), a.device)
-            tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for one wave of CTAs
-                      tag=spec.name + '.wgrad', flops=spec.flops * B)
-        else:
-            dwp = slot if slot is not None else zeros((spec.N, T * spec.Ca), a.device)
-            tap_wgrad(a, dy, spec.taps, dwp, splits=0,
-                      tag=spec.name + '.wgrad', flops=spec.flops * B)
-        if pw.defer_unpack:
-            pw.gpacked, dweight = dwp, None
-            if pw.on_ready is not None:
-                pw.on_ready()
-        else:
-            dweight = pw.unpack_grad(dwp)
-        dbias = None
-        if ctx.has_bias:
-            ext = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
-            # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
-            dbias = ext if ext is not None else colsum(dy.reshape(-1, spec.N // spec.bias_tile))
-            if pw.operm is not None:
-                dbias = dbias[pw.operm_long]
+        da, dweight, dbias = _tap_conv_backward(ctx.spec, ctx.pw, a, dy, ctx.needs_input_grad[1], ctx.has_bias)
         return None, da, dweight, dbias, None
+
+
+def _tap_conv_backward(spec, pw, a, dy, need_da, has_bias):
+    """dgrad, wgrad (into the packed layout / the data-parallel arena slot) and bias gradient of one tap convolution."""
+    dy = dy.contiguous().to(torch.bfloat16)
+    B = a.shape[0]
+    da = None
+    if spec.need_dgrad and need_da:
+        w_op = pw.fwd if spec.transposed else pw.tr
+        splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
+        if splits > 1:
+            da = _bias_act(tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits,
+                                    tag=spec.name + '.dgrad', flops=spec.flops * B), None, False)
+        else:
+            da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
+                          flops=spec.flops * B)
+    T = len(spec.taps)
+    slot = pw.grad_slot if pw.defer_unpack else None
+    if spec.transposed:
+        # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
+        dwp = slot if slot is not None else zeros((spec.Ca, T * spec.N), a.device)
+        tap_wgrad(dy, a, spec.neg_taps, dwp, splits=0,  # 0: the launcher sizes the pixel split for one wave of CTAs
+                  tag=spec.name + '.wgrad', flops=spec.flops * B)
+    else:
+        dwp = slot if slot is not None else zeros((spec.N, T * spec.Ca), a.device)
+        tap_wgrad(a, dy, spec.taps, dwp, splits=0,
+                  tag=spec.name + '.wgrad', flops=spec.flops * B)
+    if pw.defer_unpack:
+        pw.gpacked, dweight = dwp, None
+        if pw.on_ready is not None:
+            pw.on_ready()
+    else:
+        dweight = pw.unpack_grad(dwp)
+    dbias = None
+    if has_bias:
+        ext = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
+        # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
+        dbias = ext if ext is not None else colsum(dy.reshape(-1, spec.N // spec.bias_tile))
+        if pw.operm is not None:
+            dbias = dbias[pw.operm_long]
+    return da, dweight, dbias
 
 
 def refresh_transposed_all(pws, cache):
@@ -593,6 +598,67 @@ def pixel_argmax(logits):
     amax = torch.empty(B, 3, H, W, device=logits.device, dtype=torch.uint8)
     _lib.check(_lib.lib().sb_pixel_ce(logits.data_ptr(), None, B, H * W, 0.0, 0.0, None, amax.data_ptr(), None, None,
                                       _lib.stream_ptr()), 'sb_pixel_ce')
+    return amax
+
+
+def _logits_args(spec, a, pw, bias_p, out):
+    from .gemm import _taps, choose_box
+    B, H, W, C = a.shape
+    bw, bh, bb = choose_box(spec.Wo, spec.Ho, B)
+    args = _lib.TapGemmArgs()
+    args.a = a.data_ptr(); args.B, args.H, args.W, args.C = B, H, W, C
+    args.Ho, args.Wo = spec.Ho, spec.Wo
+    args.bw, args.bh, args.bb = bw, bh, bb
+    _taps(args, spec.taps)
+    args.w = pw.fwd.data_ptr(); args.N = 768; args.ldw = pw.fwd.shape[1]
+    args.out = out.data_ptr() if out is not None else None
+    args.out_f32, args.ldo = 0, 768
+    args.bias = bias_p.data_ptr()
+    args.relu, args.splits, args.accumulate, args.bias_mod = 0, 1, 0, 0
+    return args
+
+
+class LogitsCE(torch.autograd.Function):
+    """Logits conv (next_frame_predictor.py:356-357) + clipped per-pixel CE + arg-max (trainer.py:130,134-137) in ONE
+    tcgen05 kernel (sb_logits_ce): the logits never reach HBM; the forward launch leaves the gradient w.r.t. the logits,
+    which the backward feeds to the ordinary dgrad / wgrad kernels.  The loss enters the total with weight 1."""
+
+    @staticmethod
+    def forward(ctx, spec, a, weight, bias, pw, target_u8, clip):
+        B, H, W, _ = a.shape
+        n = float(B * 3 * H * W)
+        bias_p = bias.detach().float().contiguous()[pw.operm_inv]
+        dl = torch.empty(B, H, W, 768, device=a.device, dtype=torch.bfloat16)
+        amax = torch.empty(B, 3, H, W, device=a.device, dtype=torch.uint8)
+        loss_sum = zeros((1,), a.device, torch.float64)
+        args = _logits_args(spec, a, pw, bias_p, dl)
+        rec = profiling.RECORDER
+        ev0 = rec.start() if rec is not None else None
+        _lib.check(_lib.lib().sb_logits_ce(ctypes.byref(args), target_u8.contiguous().data_ptr(), float(clip), 1.0 / n,
+                                           amax.data_ptr(), loss_sum.data_ptr(), _lib.stream_ptr()), 'sb_logits_ce')
+        if rec is not None:  # algorithmic work of the fused kernel: the GEMM flops, and hf in + dlogits out as bytes
+            rec.stop('logits_ce_kernel', 'train', B * H * W * (768 * 2 + a.shape[3] * 2 + 6), 'byte', ev0)
+            rec.add_work('tap_gemm_kernel', spec.name + '.fwd+ce', spec.flops * B, 'flop', rec.items[-1])
+        ctx.spec, ctx.pw = spec, pw
+        ctx.save_for_backward(a, dl)
+        ctx.mark_non_differentiable(amax)
+        return (loss_sum / n - clip).float().reshape(()), amax
+
+    @staticmethod
+    def backward(ctx, gloss, _):
+        a, dl = ctx.saved_tensors
+        da, dweight, dbias = _tap_conv_backward(ctx.spec, ctx.pw, a, dl, ctx.needs_input_grad[1], True)
+        return None, da, dweight, dbias, None, None, None
+
+
+def logits_argmax(spec, a, bias, pw):
+    """Rollout decode (subproc_vec_env.py:428): arg-max frame straight out of the logits GEMM's epilogue."""
+    B, H, W, _ = a.shape
+    bias_p = bias.detach().float().contiguous()[pw.operm_inv]
+    amax = torch.empty(B, 3, H, W, device=a.device, dtype=torch.uint8)
+    args = _logits_args(spec, a, pw, bias_p, None)
+    _lib.check(_lib.lib().sb_logits_ce(ctypes.byref(args), None, 0.0, 0.0, amax.data_ptr(), None, _lib.stream_ptr()),
+               'sb_logits_ce')
     return amax
 
 

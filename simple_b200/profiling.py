@@ -18,6 +18,11 @@ class Recorder:
         ev1.record()
         self.items.append((kernel, tag, work, unit, ev0, ev1))
 
+    def add_work(self, kernel, tag, work, unit, timed_item):
+        """Credit `work` of another kind (e.g. the GEMM flops of a fused GEMM + loss launch) to the events of an item
+        that was already recorded."""
+        self.items.append((kernel, tag, work, unit, timed_item[4], timed_item[5]))
+
     def summary(self):
         """Per kernel: total ms / work / launches, and per tag [ms, work, launches].  A tag's time is the MEDIAN of its
         samples times their count: one preempted or cold launch (seen: a single 1.8 ms outlier among 80 us launches)

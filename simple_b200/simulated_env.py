@@ -156,8 +156,8 @@ class SimulatedVecEnv:
             _, action, _ = self._policy.act(self._obs)
             self._act.copy_(action.reshape(A, 1))
         onehot = torch.zeros(A, 1, self.n_action, device=self.device).scatter_(2, self._act.unsqueeze(-1), 1.0)
-        logits, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot)
-        new = ops.pixel_argmax(logits)  # u8 [A,3,H,W]
+        _, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot, logits_mode='argmax')
+        new = model.last_aux['argmax']  # u8 [A,3,H,W]: decoded in the epilogue of the logits GEMM
         c = cfg.frame_shape[0]
         self.frames.copy_(torch.cat((self.frames[:, c:], new), dim=1))
         self._obs.copy_(self.frames)

@@ -21,14 +21,21 @@ def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsi
     bf16 logits (ops.PixelCE); `argmax` is the u8 frame the reference obtains with torch.argmax (trainer.py:130).
     """
     target = new_states_u8.float() / 255
-    logits, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon, rewards=rewards,
-                                                             values=values)
+    new_states_u8 = new_states_u8.contiguous()
+    clip = float(config.target_loss_clipping)
     out = {}
-    if keep_logits:  # tests only: the fused loss overwrites the logits with their gradient
+    if keep_logits:  # tests: materialised logits + the stand-alone fused loss kernel (which overwrites them with their gradient)
+        logits, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon, rewards=rewards,
+                                                                 values=values)
         B, H, W, _ = logits.shape
         out['logits_ref'] = logits.detach().reshape(B, H, W, 3, 256).permute(0, 4, 3, 1, 2).float().clone()
-    loss_reconstruct, argmax = ops.PixelCE.apply(logits, new_states_u8.contiguous(), float(config.target_loss_clipping),
-                                                 True, True, getattr(model, 'logits_dbias', None))
+        loss_reconstruct, argmax = ops.PixelCE.apply(logits, new_states_u8, clip, True, True,
+                                                     getattr(model, 'logits_dbias', None))
+    else:  # the logits GEMM carries the loss in its epilogue: the logits are never written to HBM
+        _, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon, rewards=rewards,
+                                                            values=values, logits_mode='ce', ce_target=new_states_u8,
+                                                            ce_clip=clip)
+        loss_reconstruct, argmax = model.last_aux['loss_reconstruct'], model.last_aux['argmax']
     # value MSE and reward CE (trainer.py:138-139) come out of the fused heads kernel together with their gradients
     loss_value, loss_reward = model.last_aux['loss_value'], model.last_aux['loss_reward']
     loss = loss_reconstruct + loss_value + loss_reward

@@ -62,8 +62,13 @@ for e in evs:
     a = agg.setdefault(k, [0, 0.0])
     a[0] += 1 / N
     a[1] += t
-for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+top = int(os.environ.get('SB_TOP', '40'))
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f'{t:8.3f} ms {n:6.1f}x  {k}')
+own = [(n, t) for k, (n, t) in agg.items() if 'sb::' in k]
+other = [(n, t) for k, (n, t) in agg.items() if 'sb::' not in k]
+print(f'--- kernels of this library (sb::): {sum(n for n, _ in own):.0f} launches, {sum(t for _, t in own):.3f} ms; '
+      f'library / ATen kernels: {sum(n for n, _ in other):.0f} launches, {sum(t for _, t in other):.3f} ms')
 # timeline of the last profiled step: idle gaps of the GPU (> 15 us) and where the NCCL kernels sit
 tl = sorted(((e.time_range.start, e.time_range.end, e.name.split('(')[0][:60]) for e in evs), key=lambda x: x[0])
 per = len(tl) // N
