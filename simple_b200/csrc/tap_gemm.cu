@@ -110,25 +110,6 @@ constexpr int kStageOutBytes = 128 * 64;  // epilogue staging buffer: 128 rows x
 constexpr int kOutBufs = 4;               // 2 column halves x double buffering
 constexpr int kStageOut2Bytes = 128 * 128;  // CTA-pair kernel: 128 rows x 64 bf16 (128-byte rows)
 
-__device__ __forceinline__ unsigned long long f2_as_u64(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-      : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)), "l"(f2_as_u64(c)));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d)) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
-  return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<unsigned long long*>(&d)) : "l"(f2_as_u64(a)), "l"(f2_as_u64(b)));
-  return d;
-}
-
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -435,11 +416,10 @@ struct CeParams {
   float clip, gscale;
   int HW;
 };
-constexpr int kCeExchangeBytes = 128 * 21 * 4;  // per row: max[2][4], argmax[2][4] (tile parity), sum[4], target logit
-constexpr int kCeThreads = 576;                // TMA warp, MMA warp, 16 epilogue warps
+constexpr int kCeExchangeBytes = 128 * 11 * 4;  // per row: max[2][2], argmax[2][2] (tile parity), sum[2], target logit
 
 template <int BN, int STAGES, int EPI = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI ? kCeThreads : kFwdThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
     tap_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TapGemmDev p,
                      const __grid_constant__ CeParams ce) {
@@ -472,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI ? kCeThreads : k
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], EPI ? 32 : 16);  // one arrival per epilogue warp of both CTAs
+      mbar_init(&tempty[s], 16);
     }
     fence_mbar_init();
   }
@@ -550,22 +530,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI ? kCeThreads : k
       }
     }
   } else if (EPI != 0) {
-    // ---------------- fused softmax-CE epilogue: 16 warps, thread = (row, 64-column quarter of the row's 256 logits) ----
+    // ---------------- fused softmax-CE epilogue ----------------
     constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     const int e = warp - 2;
-    const int lg = warp & 3;           // TMEM lane quarter this warp may access
-    const int qt = e >> 2;             // column quarter: columns [64 qt, 64 qt + 64) = one staged / TMA-stored chunk
+    const int lg = warp & 3;
+    const int half = e >> 2;           // half 0 owns columns [0,64) u [128,192), half 1 owns [64,128) u [192,256)
     const int r = lg * 32 + lane;      // row of the 128-row tile = TMEM lane
-    const bool issuer = ((e & 3) == 0) && lane == 0;  // one TMA-store issuing thread per quarter
-    const uint32_t bar_id = 1u + (uint32_t)qt;        // named barrier of the 4 warps of this quarter
-    // exchange area of the four quarters of a row; max / arg-max are double-buffered by tile parity because the rollout
-    // variant has a single barrier per tile (a fast thread may already write tile i+1 while a partner still reads tile i)
-    float* ex_m_all = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parity][4 quarters][128] row maxima
-    int* ex_i_all = reinterpret_cast<int*>(ex_m_all + 1024);    // [2][4][128] first arg-max columns
-    float* ex_s = reinterpret_cast<float*>(ex_i_all + 1024);    // [4][128] exp-sums
-    float* ex_t = ex_s + 512;                                   // [128] target logit
+    const bool issuer = ((e & 3) == 0) && lane == 0;
+    const uint32_t bar_id = 1u + (uint32_t)half;
+    // exchange area of the two column halves of a row; max / arg-max are double-buffered by tile parity because the
+    // rollout variant has a single barrier per tile (a fast thread may already write tile i+1 while its partner reads i)
+    float* ex_m_all = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parity][2 halves][128] row maxima
+    int* ex_i_all = reinterpret_cast<int*>(ex_m_all + 512);     // [2][2][128] first arg-max columns
+    float* ex_s = reinterpret_cast<float*>(ex_i_all + 512);     // [2][128] exp-sums
+    float* ex_t = ex_s + 256;                                   // [128] target logit
     const int xl = r % p.bw, yl = (r / p.bw) % p.bh, bl = r / (p.bw * p.bh);
-    uint8_t* buf = sO + qt * kStageOut2Bytes;  // this quarter's staging tile (128 rows x 64 bf16, 128B-swizzled rows)
+    uint32_t ochunk = 0;
     float loss_acc = 0.f;
     int tcount = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++tcount) {
@@ -582,24 +562,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI ? kCeThreads : k
       const uint32_t aph = (uint32_t)(tcount >> 1) & 1u;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      // ---- pass 1: my 64 logits -> +bias -> bf16 (the rounding of the materialised path), packed in 32 registers
-      uint32_t xr[32];
+      // ---- pass 1: my 128 logits -> +bias -> bf16 (the rounding of the materialised path), packed in 64 registers
+      uint32_t xr[64];
       __nv_bfloat162 m2 = __floats2bfloat162_rn(-INFINITY, -INFINITY);
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const int col = qt * 64 + sub * 32;
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int col = half * 64 + (q4 >> 1) * 128 + (q4 & 1) * 32;  // first column of this 32-column piece
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + col), v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + j));
-          const float2 s0 = fadd2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(bv.x, bv.y));
-          const float2 s1 = fadd2(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(bv.z, bv.w));
-          const __nv_bfloat162 a0 = __floats2bfloat162_rn(s0.x, s0.y);
-          const __nv_bfloat162 a1 = __floats2bfloat162_rn(s1.x, s1.y);
-          xr[sub * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&a0);
-          xr[sub * 16 + (j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&a1);
+          const __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(v[j]) + bv.x, __uint_as_float(v[j + 1]) + bv.y);
+          const __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(v[j + 2]) + bv.z, __uint_as_float(v[j + 3]) + bv.w);
+          xr[q4 * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&a0);
+          xr[q4 * 16 + (j >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&a1);
           m2 = __hmax2(m2, __hmax2(a0, a1));
         }
       }
@@ -612,104 +590,97 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI ? kCeThreads : k
       }
       const float2 mf = __bfloat1622float2(m2);
       const float lm = fmaxf(mf.x, mf.y);
-      // first of my 64 columns holding the local maximum: equality masks per bf16 pair, 16 columns per mask word
+      // first column (in this thread's ascending column order) holding the local maximum
       int first = 256;
       {
         const __nv_bfloat162 g2 = __float2bfloat162_rn(lm);
 #pragma unroll
-        for (int wd = 3; wd >= 0; --wd) {
-          uint32_t acc = 0;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t eq = __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xr[wd * 8 + k]), g2);
-            acc |= eq & ((1u << (2 * k)) | (1u << (17 + 2 * k)));
-          }
-          const uint32_t bits = (acc & 0xffffu) | (acc >> 16);  // bit i = column wd*16 + i holds the maximum
-          if (bits) first = qt * 64 + wd * 16 + __ffs(bits) - 1;
+        for (int k = 63; k >= 0; --k) {
+          const uint32_t eq = __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xr[k]), g2);
+          const int colk = half * 64 + (k >> 5) * 128 + ((k & 31) << 1);  // column of the low element of pair k
+          if (eq & 0xffff0000u) first = colk + 1;
+          if (eq & 0x0000ffffu) first = colk;
         }
       }
-      float* ex_m = ex_m_all + (tcount & 1) * 512;
-      int* ex_i = ex_i_all + (tcount & 1) * 512;
-      ex_m[qt * 128 + r] = lm;
-      ex_i[qt * 128 + r] = first;
-      named_bar_sync(5, 512);
-      float gm = lm;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) gm = fmaxf(gm, ex_m[o * 128 + r]);
-      if (ce.amax && qt == 0 && valid) {
-        int best = 256;
-#pragma unroll
-        for (int o = 3; o >= 0; --o)  // quarters hold ascending column ranges: the lowest quarter with the maximum wins
-          if (ex_m[o * 128 + r] == gm) best = ex_i[o * 128 + r];
+      float* ex_m = ex_m_all + (tcount & 1) * 256;
+      int* ex_i = ex_i_all + (tcount & 1) * 256;
+      ex_m[half * 128 + r] = lm;
+      ex_i[half * 128 + r] = first;
+      named_bar_sync(3, 256);
+      const float om = ex_m[(half ^ 1) * 128 + r];
+      const int oi = ex_i[(half ^ 1) * 128 + r];
+      const float gm = fmaxf(lm, om);
+      if (ce.amax && half == 0 && valid) {
+        int best = first;
+        if (om > lm || (om == lm && oi < first)) best = oi;
         ce.amax[toff] = (uint8_t)best;
       }
       if (EPI == 1) {
-        // ---- pass 2: exp-sum (same fp32 formula as pixel_ce_kernel, packed f32x2 pipes) and the target logit
+        // ---- pass 2: exp-sum (same fp32 formula as pixel_ce_kernel) and the target logit
         const float moff = -gm * LOG2E;
-        const float2 l2 = make_float2(LOG2E, LOG2E), mo2 = make_float2(moff, moff);
-        float2 sa = make_float2(0.f, 0.f), sb2 = make_float2(0.f, 0.f);
+        float s = 0.f;
+        const int tq = t - half * 64;                     // position of the target inside my columns, if it is mine
+        const bool mine = ((t >> 6) & 1) == half;
+        const int tk = mine ? (((t >> 7) << 5) + ((tq & 63) >> 1)) : -1;  // pair index holding the target
+        float xt = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const float2 a0 = ffma2(make_float2(__uint_as_float(xr[k] << 16), __uint_as_float(xr[k] & 0xffff0000u)), l2, mo2);
-          const float2 a1 = ffma2(make_float2(__uint_as_float(xr[k + 1] << 16), __uint_as_float(xr[k + 1] & 0xffff0000u)),
-                                  l2, mo2);
-          sa = fadd2(sa, make_float2(exp2f(a0.x), exp2f(a0.y)));
-          sb2 = fadd2(sb2, make_float2(exp2f(a1.x), exp2f(a1.y)));
+        for (int k = 0; k < 64; ++k) {
+          const float x0f = __uint_as_float(xr[k] << 16), x1f = __uint_as_float(xr[k] & 0xffff0000u);
+          s += exp2f(fmaf(x0f, LOG2E, moff)) + exp2f(fmaf(x1f, LOG2E, moff));
+          if (k == tk) xt = (t & 1) ? x1f : x0f;
         }
-        const bool mine = (t >> 6) == qt;
-        if (mine) {  // target logit: compare-select over the 32 packed registers (no dynamic register indexing)
-          const int tk = (t & 63) >> 1;
-          uint32_t w = 0;
-#pragma unroll
-          for (int k = 0; k < 32; ++k) w = (k == tk) ? xr[k] : w;
-          ex_t[r] = (t & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
-        }
-        ex_s[qt * 128 + r] = (sa.x + sa.y) + (sb2.x + sb2.y);
-        named_bar_sync(5, 512);
-        const float st = (ex_s[r] + ex_s[128 + r]) + (ex_s[256 + r] + ex_s[384 + r]);
-        const float xt = ex_t[r];
+        ex_s[half * 128 + r] = s;
+        if (mine) ex_t[r] = xt;
+        named_bar_sync(3, 256);
+        const float st = ex_s[r] + ex_s[128 + r];
+        xt = ex_t[r];
         const float cev = gm + log2f(st) * LN2 - xt;
-        if (qt == 0 && valid) loss_acc += fmaxf(cev, ce.clip);
+        if (half == 0 && valid) loss_acc += fmaxf(cev, ce.clip);
         const float scale = (valid && cev > ce.clip) ? ce.gscale : 0.f;
         const float inv = scale / st;
-        const float2 inv2 = make_float2(inv, inv);
-        // ---- pass 3: my 64-column gradient chunk -> bf16 -> swizzled staging -> TMA store
-        if (issuer) bulk_wait_read<0>();  // last tile's store of this staging tile has been read out (a whole tile ago)
-        named_bar_sync(bar_id, 128);
-        uint8_t* row = buf + r * 128;
+        // ---- pass 3: gradient tile -> bf16 -> swizzled staging -> TMA store (two 64-column chunks per thread)
         const int sw = r & 7;
-        if (r < p.rows) {
 #pragma unroll
-          for (int pc = 0; pc < 8; ++pc) {  // 16-byte pieces of 8 columns
-            uint32_t o[4];
+        for (int cc = 0; cc < 2; ++cc) {  // (unrolled: `xr` must stay in registers)
+          const int c = half * 64 + cc * 128;
+          if (issuer) bulk_wait_read<1>();  // the store that used this staging buffer two chunks ago has drained
+          named_bar_sync(bar_id, 128);
+          uint8_t* buf = sO + (half * 2 + (int)(ochunk & 1u)) * kStageOut2Bytes;
+          uint8_t* row = buf + r * 128;
+          if (r < p.rows) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t w = xr[pc * 4 + u];
-              const float2 a = ffma2(make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)), l2, mo2);
-              const float2 d = fmul2(make_float2(exp2f(a.x), exp2f(a.y)), inv2);
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(d.x, d.y);
-              o[u] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int pc = 0; pc < 8; ++pc) {  // 16-byte pieces of 8 columns
+              uint32_t o[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t w = xr[cc * 32 + pc * 4 + u];
+                const float d0 = exp2f(fmaf(__uint_as_float(w << 16), LOG2E, moff)) * inv;
+                const float d1 = exp2f(fmaf(__uint_as_float(w & 0xffff0000u), LOG2E, moff)) * inv;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(d0, d1);
+                o[u] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(row + ((pc ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<uint4*>(row + ((pc ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (mine && (t >> 7) == cc) {  // one-hot term: patch the target element (same thread: ordered after its vector store)
+              const int tl = t & 63;
+              const float et = exp2f(fmaf(xt, LOG2E, moff));
+              *reinterpret_cast<__nv_bfloat16*>(row + (((tl >> 3) ^ sw) << 4) + ((tl & 7) << 1)) =
+                  __float2bfloat16_rn(et * inv - scale);
+            }
           }
-          if (mine) {  // one-hot term: patch the target element (same thread: ordered after its vector stores)
-            const int tl = t & 63;
-            const float et = exp2f(fmaf(xt, LOG2E, moff));
-            *reinterpret_cast<__nv_bfloat16*>(row + (((tl >> 3) ^ sw) << 4) + ((tl & 7) << 1)) =
-                __float2bfloat16_rn(et * inv - scale);
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            tma_store_4d(&tmO, buf, n0 + c, x0, y0, b0);
+            bulk_commit();
           }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (issuer) {
-          tma_store_4d(&tmO, buf, n0 + qt * 64, x0, y0, b0);
-          bulk_commit();
+          ++ochunk;
         }
       }
     }
     if (EPI == 1) {
       loss_acc = warp_sum(loss_acc);
-      if (lane == 0 && qt == 0 && loss_acc != 0.f) atomicAdd(ce.loss_sum, (double)loss_acc);
+      if (lane == 0 && half == 0 && loss_acc != 0.f) atomicAdd(ce.loss_sum, (double)loss_acc);
       if (issuer) bulk_wait_all();
     }
   } else {
@@ -815,7 +786,7 @@ static int launch_tap_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   const int pairs = total < 74 ? total : 74;
   CeParams ce{};
   if (cep) ce = *cep;
-  tap_gemm2_kernel<BN, STAGES, EPI><<<2 * pairs, EPI ? kCeThreads : kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p, ce);
+  tap_gemm2_kernel<BN, STAGES, EPI><<<2 * pairs, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p, ce);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
