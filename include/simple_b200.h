@@ -85,7 +85,13 @@ typedef struct {
   float* dw;          /* fp32 [N, ldw] */
   int ldw;
   int splits;         /* pixel-tile split factor; 0 = automatic (one co-resident wave of CTAs) */
+  float* dbias;       /* optional fp32 [N] (caller zeroes): += sum over all pixels of dy[., n] -- the bias gradient, taken by
+                         the tensor core from the dy tiles the kernel stages anyway (an extra N = 16 MMA against a tile of
+                         ones).  Ignored (left untouched) when the launcher picks the swapped orientation: check
+                         sb_tap_wgrad_bias_ok() first. */
 } sb_tap_wgrad_args;
+/* 1 if sb_tap_wgrad would fill `dbias` for a gradient of N dy-channels x C a-channels (normal tile orientation). */
+int sb_tap_wgrad_bias_ok(int N, int C);
 int sb_tap_wgrad(const sb_tap_wgrad_args* args, sb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ class TapWgradArgs(ctypes.Structure):
         ('dy', ctypes.c_void_p), ('Ho', ctypes.c_int), ('Wo', ctypes.c_int), ('N', ctypes.c_int),
         ('bw', ctypes.c_int), ('bh', ctypes.c_int), ('bb', ctypes.c_int),
         ('ntaps', ctypes.c_int), ('tap_dy', ctypes.c_int * SB_MAX_TAPS), ('tap_dx', ctypes.c_int * SB_MAX_TAPS),
-        ('dw', ctypes.c_void_p), ('ldw', ctypes.c_int), ('splits', ctypes.c_int),
+        ('dw', ctypes.c_void_p), ('ldw', ctypes.c_int), ('splits', ctypes.c_int), ('dbias', ctypes.c_void_p),
     ]
 
 
@@ -107,6 +107,8 @@ def lib():
     L.sb_init.restype = ctypes.c_int
     L.sb_launch_count.restype = ctypes.c_longlong
     L.sb_version.restype = ctypes.c_char_p
+    L.sb_tap_wgrad_bias_ok.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.sb_tap_wgrad_bias_ok.restype = ctypes.c_int
     L.sb_set_pair_mode.argtypes = [ctypes.c_int]
     L.sb_set_pair_mode.restype = ctypes.c_int
     L.sb_set_wgrad_tap_groups.argtypes = [ctypes.c_int]
@@ -173,7 +175,7 @@ class _Sigs:
     sb_colsum_f32 = [_p, _i, _i, _i, _p, _p]
 
 
-EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_tap_wgrad_bias_ok', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
 
 
 def check(rc, what):

@@ -807,7 +807,12 @@ struct TapWgradDev {
   // gradient wastes 44 % of a 256 x 512 tiling but none of a 384 x 192 one).  `C`/`N` above always name the N-side / M-side
   // channel counts of the launch; Ctrue is the A-channel count that addresses dw.
   int swapped, Ctrue;
+  // Optional bias gradient (normal orientation only): dbias[m] += sum over pixels of dY[pixel, m].  It rides on the
+  // tensor core: one more MMA per K step multiplies the dY tile (already in shared memory) with a constant tile of ones
+  // into 16 spare TMEM columns, so the column sums cost no extra pass over dY (the logits gradient is 826 MB).
+  float* dbias;
 };
+constexpr int kWgOnesBytes = 2048;            // bf16 ones: 16 pixels x 128-byte rows, read as an MN-major N = 16 operand
 constexpr int kWgRows = 64;                   // pixels per stage (K of the contraction)
 constexpr int kWgChunkBytes = kWgRows * 128;  // 64 pixels x 64 channels bf16
 
@@ -821,14 +826,16 @@ __global__ void __launch_bounds__(kGemmThreads)
   constexpr int NCH = BN / 64;
   constexpr int DY_BYTES = 2 * kWgChunkBytes;
   constexpr int A_BYTES = NCH * kWgChunkBytes;  // per tap
-  constexpr int TMEM_COLS = TG * BN <= 64 ? 64 : TG * BN <= 128 ? 128 : TG * BN <= 256 ? 256 : 512;
+  constexpr int ACC_COLS = TG * BN + 16;  // + the bias-gradient accumulator
+  constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(BN % 64 == 0, "N-side tile = whole 64-channel chunks");
-  static_assert(TG * BN <= 512, "accumulators of one tap group must fit TMEM");
+  static_assert(ACC_COLS <= 512, "accumulators of one tap group must fit TMEM");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDY = smem;
   uint8_t* sA = smem + STAGES * DY_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + STAGES * TG * A_BYTES);
+  uint8_t* sOnes = sA + STAGES * TG * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOnes + kWgOnesBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -846,6 +853,11 @@ __global__ void __launch_bounds__(kGemmThreads)
   const int pt_begin = (int)((long long)PT * blockIdx.y / p.splits);
   const int pt_end = (int)((long long)PT * (blockIdx.y + 1) / p.splits);
   const int nk = pt_end - pt_begin;
+  const bool do_bias = p.dbias != nullptr && !p.swapped && ct == 0 && t == 0;
+  if (do_bias) {
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's shared-memory reads
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -916,6 +928,15 @@ __global__ void __launch_bounds__(kGemmThreads)
             umma_bf16(tmem_base + (uint32_t)(g * BN), ad, bd, idesc, (uint32_t)((i | k) != 0));
           }
         }
+        if (do_bias) {  // D[128 x 16] += dY^T (128 x 16 pixels) * ones (16 pixels x 16): every column = sum over the pixels
+          const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
+#pragma unroll
+          for (int k = 0; k < kWgRows / 16; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
+            const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), kWgChunkBytes, 1024);
+            umma_bf16(tmem_base + (uint32_t)(TG * BN), ad, od, idesc1, (uint32_t)((i | k) != 0));
+          }
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
@@ -926,6 +947,12 @@ __global__ void __launch_bounds__(kGemmThreads)
     const int lg = warp & 3;
     const int m = m0 + lg * 32 + lane;
     const bool valid = m < p.N;
+    if (do_bias) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(TG * BN), v);  // 16 identical sums (+ 16 idle columns)
+      tmem_ld_wait();
+      if (valid) atomicAdd(p.dbias + m, __uint_as_float(v[0]));
+    }
     // normal: dw[m][t*C + c]; swapped (row = A channel, column = dY channel): dw[column][t*Ctrue + row], the 32 lanes of a
     // warp still hit 32 consecutive floats
 #pragma unroll 1
@@ -959,7 +986,7 @@ __global__ void __launch_bounds__(kGemmThreads)
 template <int BN, int STAGES, int TG = 1>
 static int launch_tap_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmA, const TapWgradDev& p, dim3 grid,
                             cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 + TG * (BN / 64)) * kWgChunkBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (2 + TG * (BN / 64)) * kWgChunkBytes + kWgOnesBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "tap_wgrad_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
@@ -1104,6 +1131,34 @@ extern "C" int sb_logits_ce(const sb_tap_gemm_args* a, const uint8_t* target, fl
   return launch_tap_gemm2<256, 4, 2>(tmA, tmBh, tmO64, p, stream, &ce);
 }
 
+// Tile the [dY channels N] x [A channels C] gradient: least padded MMA work; ties: fewer tiles (fewer re-reads of the M
+// side), then the smaller tile.
+static int wgrad_pad_n(int ch, int* bn_out) {
+  int best = 1 << 30, best_tiles = 1 << 30, bn_best = 64;
+  const int opts[4] = {64, 128, 192, 256};
+  for (int bn : opts) {
+    const int full = ch / bn, rem = ch - full * bn;
+    const int cost = full * bn + ((rem + 15) / 16) * 16, tiles = full + (rem ? 1 : 0);
+    if (cost < best || (cost == best && tiles < best_tiles)) {
+      best = cost;
+      best_tiles = tiles;
+      bn_best = bn;
+    }
+  }
+  *bn_out = bn_best;
+  return best;
+}
+// 1: run with the A channels on the 128-row M side (the swapped epilogue issues scalar atomics: only for a clear win)
+static int wgrad_swapped(int N, int C, int* bn_norm, int* bn_swap) {
+  const long long cost_norm = (long long)((N + 127) / 128) * 128 * wgrad_pad_n(C, bn_norm);
+  const long long cost_swap = (long long)((C + 127) / 128) * 128 * wgrad_pad_n(N, bn_swap);
+  return (cost_swap * 100 < cost_norm * 85) ? 1 : 0;
+}
+extern "C" int sb_tap_wgrad_bias_ok(int N, int C) {
+  int a, b;
+  return wgrad_swapped(N, C, &a, &b) ? 0 : 1;
+}
+
 extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!a || !a->a || !a->dy || !a->dw) return SB_ERR_ARG;
@@ -1123,29 +1178,13 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
     p.tap_dx[i] = i < a->ntaps ? a->tap_dx[i] : 0;
   }
   p.dw = a->dw; p.ldw = a->ldw;
+  p.dbias = a->dbias;
   const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
   // Tile the [dY channels N] x [A channels C] gradient: M side in 128-row tiles, N side in BN-column tiles
   // (BN in {64,128,192,256}; the last tile runs the MMA at the 16-rounded remainder).  Pick the orientation and BN that
   // waste the fewest tensor-core cycles.
-  auto pad_n = [](int ch, int* bn_out) {
-    int best = 1 << 30, best_tiles = 1 << 30, bn_best = 64;
-    const int opts[4] = {64, 128, 192, 256};
-    for (int bn : opts) {  // least padded MMA work; ties: fewer tiles (fewer re-reads of the M side), then the smaller tile
-      const int full = ch / bn, rem = ch - full * bn;
-      const int cost = full * bn + ((rem + 15) / 16) * 16, tiles = full + (rem ? 1 : 0);
-      if (cost < best || (cost == best && tiles < best_tiles)) {
-        best = cost;
-        best_tiles = tiles;
-        bn_best = bn;
-      }
-    }
-    *bn_out = bn_best;
-    return best;
-  };
   int bn_norm, bn_swap;
-  const long long cost_norm = (long long)((a->N + 127) / 128) * 128 * pad_n(a->C, &bn_norm);
-  const long long cost_swap = (long long)((a->C + 127) / 128) * 128 * pad_n(a->N, &bn_swap);
-  p.swapped = (cost_swap * 100 < cost_norm * 85) ? 1 : 0;  // the swapped epilogue issues scalar atomics: only for a clear win
+  p.swapped = wgrad_swapped(a->N, a->C, &bn_norm, &bn_swap);
   p.Ctrue = a->C;
   int BN;
   const void *m_ptr, *n_ptr;

@@ -74,7 +74,7 @@ def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bia
     return out
 
 
-def tap_wgrad(a, dy, taps, dw, splits=1, box=None, tag=None, flops=0.0):
+def tap_wgrad(a, dy, taps, dw, splits=1, box=None, tag=None, flops=0.0, dbias=None):
     """dw[n, t*C+c] += sum_{b,y,x} dy[b,y,x,n] * a[b,y+dy_t,x+dx_t,c].  dw: fp32 [N, >=T*C] (accumulated)."""
     assert a.dtype == torch.bfloat16 and a.is_contiguous() and dy.dtype == torch.bfloat16 and dy.is_contiguous()
     assert dw.dtype == torch.float32 and dw.is_contiguous()
@@ -88,6 +88,7 @@ def tap_wgrad(a, dy, taps, dw, splits=1, box=None, tag=None, flops=0.0):
     args.bw, args.bh, args.bb = bw, bh, bb
     _taps(args, taps)
     args.dw = dw.data_ptr(); args.ldw = dw.shape[1]; args.splits = splits
+    args.dbias = dbias.data_ptr() if dbias is not None else None
     rec = profiling.RECORDER
     ev0 = rec.start() if rec is not None else None
     _lib.check(_lib.lib().sb_tap_wgrad(ctypes.byref(args), _lib.stream_ptr()), 'sb_tap_wgrad')

@@ -405,6 +405,14 @@ def _tap_conv_backward(spec, pw, a, dy, need_da, has_bias):
                           flops=spec.flops * B)
     T = len(spec.taps)
     slot = pw.grad_slot if pw.defer_unpack else None
+    # bias gradient: (1) handed over by the fused consumer of the output (prep stage / pixel CE), else (2) taken by the
+    # weight-gradient kernel from the dy tiles it stages anyway (an extra ones-MMA), else (3) a column-sum pass over dy
+    dbias = None
+    if has_bias:
+        dbias = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
+    mma_bias = None
+    if has_bias and dbias is None and not spec.transposed and _lib.lib().sb_tap_wgrad_bias_ok(spec.N, spec.Ca):
+        mma_bias = dbias = zeros((spec.N,), a.device)
     if spec.transposed:
         # dW[ci, t, (ph,co)] = sum_pix a[pix, ci] * dy[pix + tap, (ph,co)]
         dwp = slot if slot is not None else zeros((spec.Ca, T * spec.N), a.device)
@@ -412,19 +420,16 @@ def _tap_conv_backward(spec, pw, a, dy, need_da, has_bias):
                   tag=spec.name + '.wgrad', flops=spec.flops * B)
     else:
         dwp = slot if slot is not None else zeros((spec.N, T * spec.Ca), a.device)
-        tap_wgrad(a, dy, spec.taps, dwp, splits=0,
-                  tag=spec.name + '.wgrad', flops=spec.flops * B)
+        tap_wgrad(a, dy, spec.taps, dwp, splits=0, tag=spec.name + '.wgrad', flops=spec.flops * B, dbias=mma_bias)
     if pw.defer_unpack:
         pw.gpacked, dweight = dwp, None
         if pw.on_ready is not None:
             pw.on_ready()
     else:
         dweight = pw.unpack_grad(dwp)
-    dbias = None
     if has_bias:
-        ext = spec.dbias_src.pop('dbias', None) if spec.dbias_src is not None else None
-        # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
-        dbias = ext if ext is not None else colsum(dy.reshape(-1, spec.N // spec.bias_tile))
+        if dbias is None:  # N = (phase, channel) for transposed convs: folding the phases into rows sums them per channel
+            dbias = colsum(dy.reshape(-1, spec.N // spec.bias_tile))
         if pw.operm is not None:
             dbias = dbias[pw.operm_long]
     return da, dweight, dbias

@@ -71,7 +71,14 @@ def test_wgrad(C, N, splits):
     dy = torch.randn(B, H, W, N, device=_dev()).bfloat16()
     taps = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
     dw = torch.zeros(N, 9 * C, device=_dev())
-    tap_wgrad(x, dy, taps, dw, splits=splits)
+    # bias gradient by the extra ones-MMA of the weight-gradient kernel (normal tile orientation only)
+    from simple_b200 import _lib
+    dbias = torch.zeros(N, device=_dev()) if _lib.lib().sb_tap_wgrad_bias_ok(N, C) else None
+    tap_wgrad(x, dy, taps, dw, splits=splits, dbias=dbias)
+    if dbias is not None:
+        torch.cuda.synchronize()
+        ref_b = dy.float().sum(dim=(0, 1, 2))
+        assert float((dbias - ref_b).abs().max()) <= 1e-3 * float(ref_b.abs().max()) + 1e-3, (dbias[:4], ref_b[:4])
     xn = x.float().permute(0, 3, 1, 2).requires_grad_(False)
     wref = torch.zeros(N, C, 3, 3, device=_dev(), requires_grad=True)
     y = F.conv2d(xn, wref, padding=1)
@@ -197,11 +204,13 @@ def test_wgrad_tap_groups_match_single_tap_kernel_and_torch():
     L = _lib.lib()
     dw_g = torch.zeros(N, 9 * C, device=_dev())
     dw_1 = torch.zeros(N, 9 * C, device=_dev())
+    db_g = torch.zeros(N, device=_dev())
+    db_1 = torch.zeros(N, device=_dev())
     prev = L.sb_set_wgrad_tap_groups(1)
     try:
-        tap_wgrad(x, dy, taps, dw_g, splits=0)
+        tap_wgrad(x, dy, taps, dw_g, splits=0, dbias=db_g)
         L.sb_set_wgrad_tap_groups(0)
-        tap_wgrad(x, dy, taps, dw_1, splits=0)
+        tap_wgrad(x, dy, taps, dw_1, splits=0, dbias=db_1)
     finally:
         L.sb_set_wgrad_tap_groups(prev)
     wref = torch.zeros(N, C, 3, 3, device=_dev(), requires_grad=True)
@@ -212,3 +221,6 @@ def test_wgrad_tap_groups_match_single_tap_kernel_and_torch():
     scale = float(ref.abs().max())
     assert float((dw_g - dw_1).abs().max()) <= 2e-5 * scale
     assert float((dw_g - ref).abs().max()) <= 2e-3 * scale, float((dw_g - ref).abs().max()) / scale
+    ref_b = dy.float().sum(dim=(0, 1, 2))
+    for db in (db_g, db_1):  # bias gradient from the ones-MMA, in both kernel variants
+        assert float((db - ref_b).abs().max()) <= 1e-3 * float(ref_b.abs().max()) + 1e-3
