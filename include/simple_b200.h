@@ -33,6 +33,9 @@ int sb_set_pair_mode(int enabled);
 /* Same for sb_tap_wgrad's tap groups (3 taps of a 3x3 layer share one dY tile per pipeline stage; used for narrow
  * layers with many pixels: the gate conv).  0 = one tap per CTA everywhere. */
 int sb_set_wgrad_tap_groups(int enabled);
+/* Same for two 128-row M tiles per sb_tap_wgrad CTA (two dY tiles per pipeline stage against the same A chunks: 1.5x the
+ * flops per TMA-loaded row; used when the M side has >= 256 channels).  0 = one M tile per CTA everywhere. */
+int sb_set_wgrad_mt2(int enabled);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores ("tap GEMM").

@@ -111,6 +111,8 @@ def lib():
     L.sb_tap_wgrad_bias_ok.restype = ctypes.c_int
     L.sb_set_pair_mode.argtypes = [ctypes.c_int]
     L.sb_set_pair_mode.restype = ctypes.c_int
+    L.sb_set_wgrad_mt2.argtypes = [ctypes.c_int]
+    L.sb_set_wgrad_mt2.restype = ctypes.c_int
     L.sb_set_wgrad_tap_groups.argtypes = [ctypes.c_int]
     L.sb_set_wgrad_tap_groups.restype = ctypes.c_int
     L.sb_set_ce_tma.argtypes = [ctypes.c_int]
@@ -175,7 +177,7 @@ class _Sigs:
     sb_colsum_f32 = [_p, _i, _i, _i, _p, _p]
 
 
-EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_tap_wgrad_bias_ok', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_tap_wgrad_bias_ok', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_wgrad_mt2', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
 
 
 def check(rc, what):

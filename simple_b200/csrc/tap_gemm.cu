@@ -17,6 +17,7 @@ namespace sb {
 
 long long g_launches = 0;
 int g_wgrad_tap_groups = 1;  // 1: 3-tap groups in the weight-gradient kernel where eligible (A/B switch for tests)
+int g_wgrad_mt2 = 1;  // 1: two 128-row M tiles per weight-gradient CTA where the M side has >= 256 channels (A/B switch)
 int g_pair_mode = 1;  // 1: use the CTA-pair (cta_group::2) tap GEMM where eligible; 0: single-CTA kernel only
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -819,17 +820,24 @@ constexpr int kWgChunkBytes = kWgRows * 128;  // 64 pixels x 64 channels bf16
 // TG = taps per CTA: one dY tile per stage feeds TG shifted A tiles and TG accumulators (TMEM columns j*BN).  A 3x3
 // layer with few channels (the gate conv: 128 x 80 per tap) is bound by re-reading dY once per tap; TG = 3 reads it 3x
 // instead of 9x.  TG > 1 needs the normal orientation (the shift is on the N-side operand).
-template <int BN, int STAGES, int TG>
+// MT = 128-row M tiles per CTA.  The kernel is bound by the TMA unit's box-ROW rate (every loaded row is one pixel x 64
+// channels = 128 bytes, ~3.5 clk per row per SM), not by bytes: at MT = 1 a stage of (2 + BN/64) chunks x 64 rows feeds
+// 2*128*BN*64 flops, i.e. 10.9 kflop per row at BN = 256 -- 40 % of the tensor peak, which is what ncu shows (42.8 %
+// tensor-pipe active).  MT = 2 keeps TWO dY tiles per stage against the same A chunks (two TMEM accumulators): 16.4 kflop
+// per loaded row.
+template <int BN, int STAGES, int TG, int MT>
 __global__ void __launch_bounds__(kGemmThreads)
     tap_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ TapWgradDev p) {
   constexpr int NCH = BN / 64;
-  constexpr int DY_BYTES = 2 * kWgChunkBytes;
+  constexpr int DY_BYTES = MT * 2 * kWgChunkBytes;
   constexpr int A_BYTES = NCH * kWgChunkBytes;  // per tap
-  constexpr int ACC_COLS = TG * BN + 16;  // + the bias-gradient accumulator
+  constexpr bool BIAS_ROOM = MT * TG * BN + 16 * MT <= 512;  // 16 spare TMEM columns per M tile for the bias gradient
+  constexpr int ACC_COLS = MT * TG * BN + (BIAS_ROOM ? 16 * MT : 0);
   constexpr int TMEM_COLS = ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static_assert(BN % 64 == 0, "N-side tile = whole 64-channel chunks");
   static_assert(ACC_COLS <= 512, "accumulators of one tap group must fit TMEM");
+  static_assert(MT == 1 || TG == 1, "tap groups and multiple M tiles are not combined");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sDY = smem;
@@ -848,12 +856,12 @@ __global__ void __launch_bounds__(kGemmThreads)
   const int t = (w % groups) * TG;             // first tap of this CTA's group
   const int ntg = min(TG, p.ntaps - t);        // taps in the group
   const int mtile = w / groups;
-  const int m0 = mtile * 128, c0 = ct * BN;
+  const int m0 = mtile * 128 * MT, c0 = ct * BN;
   const int PT = p.tiles_x * p.tiles_y * p.tiles_b;
   const int pt_begin = (int)((long long)PT * blockIdx.y / p.splits);
   const int pt_end = (int)((long long)PT * (blockIdx.y + 1) / p.splits);
   const int nk = pt_end - pt_begin;
-  const bool do_bias = p.dbias != nullptr && !p.swapped && ct == 0 && t == 0;
+  const bool do_bias = BIAS_ROOM && p.dbias != nullptr && !p.swapped && ct == 0 && t == 0;
   if (do_bias) {
     for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's shared-memory reads
@@ -891,8 +899,9 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int b0 = (pt / (p.tiles_x * p.tiles_y)) * p.bb;
         mbar_expect_tx(&full[s], (uint32_t)(DY_BYTES + ntg * A_BYTES));
         const int mx = (TG == 1 && p.swapped) ? dx : 0, my = (TG == 1 && p.swapped) ? dy : 0;  // M-side pixel shift
-        tma_load_4d(sDY + s * DY_BYTES, &tmDY, &full[s], m0, x0 + mx, y0 + my, b0);
-        tma_load_4d(sDY + s * DY_BYTES + kWgChunkBytes, &tmDY, &full[s], m0 + 64, x0 + mx, y0 + my, b0);
+#pragma unroll
+        for (int j = 0; j < 2 * MT; ++j)  // (channels past the tensor are zero-filled: an odd last M tile costs nothing but time)
+          tma_load_4d(sDY + s * DY_BYTES + j * kWgChunkBytes, &tmDY, &full[s], m0 + j * 64, x0 + mx, y0 + my, b0);
 #pragma unroll
         for (int g = 0; g < TG; ++g) {
           if (g >= ntg) break;
@@ -921,20 +930,26 @@ __global__ void __launch_bounds__(kGemmThreads)
           if (g >= ntg) break;
           const uint32_t b_addr = smem_u32(sA + (s * TG + g) * A_BYTES);
 #pragma unroll
-          for (int k = 0; k < kWgRows / 16; ++k) {
-            // MN-major, SW128: LBO = byte stride between 64-channel chunks, SBO = byte stride between 8-pixel groups
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 16 * 128, kWgChunkBytes, 1024);
-            umma_bf16(tmem_base + (uint32_t)(g * BN), ad, bd, idesc, (uint32_t)((i | k) != 0));
+          for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+            for (int k = 0; k < kWgRows / 16; ++k) {
+              // MN-major, SW128: LBO = byte stride between 64-channel chunks, SBO = byte stride between 8-pixel groups
+              const uint64_t ad = make_smem_desc_sw128(a_addr + mi * 2 * kWgChunkBytes + k * 16 * 128, kWgChunkBytes, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 16 * 128, kWgChunkBytes, 1024);
+              umma_bf16(tmem_base + (uint32_t)((mi * TG + g) * BN), ad, bd, idesc, (uint32_t)((i | k) != 0));
+            }
           }
         }
         if (do_bias) {  // D[128 x 16] += dY^T (128 x 16 pixels) * ones (16 pixels x 16): every column = sum over the pixels
           const uint32_t idesc1 = make_idesc_bf16(128, 16, 1, 1);
 #pragma unroll
-          for (int k = 0; k < kWgRows / 16; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 16 * 128, kWgChunkBytes, 1024);
-            const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), kWgChunkBytes, 1024);
-            umma_bf16(tmem_base + (uint32_t)(TG * BN), ad, od, idesc1, (uint32_t)((i | k) != 0));
+          for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+            for (int k = 0; k < kWgRows / 16; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + mi * 2 * kWgChunkBytes + k * 16 * 128, kWgChunkBytes, 1024);
+              const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), kWgChunkBytes, 1024);
+              umma_bf16(tmem_base + (uint32_t)(MT * TG * BN + mi * 16), ad, od, idesc1, (uint32_t)((i | k) != 0));
+            }
           }
         }
         umma_commit(&empty[s]);
@@ -945,36 +960,39 @@ __global__ void __launch_bounds__(kGemmThreads)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int lg = warp & 3;
-    const int m = m0 + lg * 32 + lane;
-    const bool valid = m < p.N;
-    if (do_bias) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(TG * BN), v);  // 16 identical sums (+ 16 idle columns)
-      tmem_ld_wait();
-      if (valid) atomicAdd(p.dbias + m, __uint_as_float(v[0]));
-    }
-    // normal: dw[m][t*C + c]; swapped (row = A channel, column = dY channel): dw[column][t*Ctrue + row], the 32 lanes of a
-    // warp still hit 32 consecutive floats
 #pragma unroll 1
-    for (int gc = 0; gc < ntg * BN; gc += 32) {
-      const int g = gc / BN, c = gc - g * BN;  // tap of the group, column inside its accumulator
-      if (c0 + c >= p.C) continue;
-      float* orow = p.swapped ? p.dw + (long long)(t + g) * p.Ctrue + m
-                              : p.dw + (long long)m * p.ldw + (long long)(t + g) * p.C + c0;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)gc, v);
-      tmem_ld_wait();
-      if (!valid) continue;
-      if (p.swapped) {
+    for (int mi = 0; mi < MT; ++mi) {
+      const int m = m0 + mi * 128 + lg * 32 + lane;
+      const bool valid = m < p.N;
+      if (do_bias) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(MT * TG * BN), v);  // identical column sums
+        tmem_ld_wait();
+        if (valid) atomicAdd(p.dbias + m, __uint_as_float(v[mi * 16]));
+      }
+      // normal: dw[m][t*C + c]; swapped (row = A channel, column = dY channel): dw[column][t*Ctrue + row], the 32 lanes
+      // of a warp still hit 32 consecutive floats
+#pragma unroll 1
+      for (int gc = 0; gc < ntg * BN; gc += 32) {
+        const int g = gc / BN, c = gc - g * BN;  // tap of the group, column inside its accumulator
+        if (c0 + c >= p.C) continue;
+        float* orow = p.swapped ? p.dw + (long long)(t + g) * p.Ctrue + m
+                                : p.dw + (long long)m * p.ldw + (long long)(t + g) * p.C + c0;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mi * TG * BN + gc), v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        if (p.swapped) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + c + j < p.C) atomicAdd(orow + (long long)(c0 + c + j) * p.ldw, __uint_as_float(v[j]));
-      } else {
+          for (int j = 0; j < 32; ++j)
+            if (c0 + c + j < p.C) atomicAdd(orow + (long long)(c0 + c + j) * p.ldw, __uint_as_float(v[j]));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (c0 + c + j < p.C)
-            red_add_v4(orow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                       __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + c + j < p.C)
+              red_add_v4(orow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
+        }
       }
     }
   }
@@ -983,19 +1001,19 @@ __global__ void __launch_bounds__(kGemmThreads)
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES, int TG = 1>
+template <int BN, int STAGES, int TG = 1, int MT = 1>
 static int launch_tap_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmA, const TapWgradDev& p, dim3 grid,
                             cudaStream_t stream) {
-  constexpr int smem = STAGES * (2 + TG * (BN / 64)) * kWgChunkBytes + kWgOnesBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (2 * MT + TG * (BN / 64)) * kWgChunkBytes + kWgOnesBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "tap_wgrad_kernel: shared memory budget exceeded");
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tap_wgrad_kernel<BN, STAGES, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+    if (cudaFuncSetAttribute(tap_wgrad_kernel<BN, STAGES, TG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
         cudaSuccess)
       return SB_ERR_CUDA;
     configured = true;
   }
-  tap_wgrad_kernel<BN, STAGES, TG><<<grid, kGemmThreads, smem, stream>>>(tmDY, tmA, p);
+  tap_wgrad_kernel<BN, STAGES, TG, MT><<<grid, kGemmThreads, smem, stream>>>(tmDY, tmA, p);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;
@@ -1206,6 +1224,10 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   const bool grouped = g_wgrad_tap_groups != 0 && !p.swapped && BN == 128 && p.c_tiles == 1 && p.ntaps % 3 == 0 &&
                        PT >= 1024;
   const int groups = grouped ? p.ntaps / 3 : p.ntaps;
+  // two M tiles per CTA (see the kernel comment) when the M side has at least 256 channels; with a bias gradient
+  // requested the 16 extra TMEM columns must still fit (BN <= 192)
+  const bool mt2 = g_wgrad_mt2 != 0 && !grouped && p.m_tiles >= 2 && (p.dbias == nullptr || p.swapped || BN <= 192);
+  if (mt2) p.m_tiles = (p.m_tiles + 1) / 2;
   const int ctas = p.m_tiles * groups * p.c_tiles;
   int splits = a->splits;
   static int slots = 0;
@@ -1225,6 +1247,14 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   if (rc) return rc;
   dim3 grid(ctas, p.splits, 1);
   if (grouped) return launch_tap_wgrad<128, 3, 3>(tmDY, tmA, p, grid, stream);
+  if (mt2) {
+    switch (BN) {
+      case 256: return launch_tap_wgrad<256, 3, 1, 2>(tmDY, tmA, p, grid, stream);
+      case 192: return launch_tap_wgrad<192, 3, 1, 2>(tmDY, tmA, p, grid, stream);
+      case 128: return launch_tap_wgrad<128, 4, 1, 2>(tmDY, tmA, p, grid, stream);
+      default: return launch_tap_wgrad<64, 4, 1, 2>(tmDY, tmA, p, grid, stream);
+    }
+  }
   switch (BN) {
     case 256: return launch_tap_wgrad<256, 4>(tmDY, tmA, p, grid, stream);
     case 192: return launch_tap_wgrad<192, 4>(tmDY, tmA, p, grid, stream);
@@ -1243,6 +1273,11 @@ extern "C" long long sb_launch_count(void) { return sb::g_launches; }
 extern "C" int sb_set_wgrad_tap_groups(int enabled) {
   const int prev = sb::g_wgrad_tap_groups;
   sb::g_wgrad_tap_groups = enabled ? 1 : 0;
+  return prev;
+}
+extern "C" int sb_set_wgrad_mt2(int enabled) {
+  const int prev = sb::g_wgrad_mt2;
+  sb::g_wgrad_mt2 = enabled ? 1 : 0;
   return prev;
 }
 extern "C" int sb_set_pair_mode(int enabled) {

@@ -188,6 +188,44 @@ def test_wgrad_swapped_orientation_and_bn192():
     assert torch.allclose(dw, ref, rtol=1e-3, atol=5e-2), float((dw - ref).abs().max())
 
 
+@pytest.mark.parametrize('C,N,with_bias', [(256, 256, False), (768, 768, False), (96, 768, True), (128, 384, True), (384, 192, False)])
+def test_wgrad_two_m_tiles_per_cta_matches_one(C, N, with_bias):
+    """MT = 2 (two dY tiles per pipeline stage and CTA) against the one-M-tile kernel and torch, with and without the
+    ones-MMA bias gradient; (96, 768) is the logits layer's shape, (384, 192) runs in the swapped orientation."""
+    from simple_b200 import _lib
+    from simple_b200.gemm import tap_wgrad
+    torch.manual_seed(5)
+    B, H, W = 6, 13, 10
+    x = torch.randn(B, H, W, C, device=_dev()).bfloat16()
+    dy = torch.randn(B, H, W, N, device=_dev()).bfloat16()
+    taps = [(0, 0), (0, 1), (1, 0), (1, 1)]
+    L = _lib.lib()
+    res = []
+    prev = L.sb_set_wgrad_mt2(1)
+    try:
+        for mode in (1, 0):
+            L.sb_set_wgrad_mt2(mode)
+            dw = torch.zeros(N, 4 * C, device=_dev())
+            db = torch.zeros(N, device=_dev()) if with_bias and L.sb_tap_wgrad_bias_ok(N, C) else None
+            tap_wgrad(x, dy, taps, dw, splits=0, dbias=db)
+            res.append((dw, db))
+    finally:
+        L.sb_set_wgrad_mt2(prev)
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    xp = F.pad(xn, (0, 1, 0, 1))
+    wref = torch.zeros(N, C, 2, 2, device=_dev(), requires_grad=True)
+    (g,) = torch.autograd.grad(F.conv2d(xp, wref), wref, dy.float().permute(0, 3, 1, 2))
+    ref = g.permute(0, 2, 3, 1).reshape(N, 4 * C)
+    scale = float(ref.abs().max())
+    assert float((res[0][0] - res[1][0]).abs().max()) <= 2e-5 * scale
+    assert float((res[0][0] - ref).abs().max()) <= 2e-3 * scale
+    if res[0][1] is not None:
+        ref_b = dy.float().sum(dim=(0, 1, 2))
+        for _, db in res:
+            assert float((db - ref_b).abs().max()) <= 1e-3 * float(ref_b.abs().max()) + 1e-3
+
+
 def test_wgrad_tap_groups_match_single_tap_kernel_and_torch():
     """The gate conv's weight gradient (3x3 taps, 128 x 80 per tap, half a million pixels) runs with THREE taps per CTA:
     one dY tile per pipeline stage feeds three shifted A tiles and three TMEM accumulators.  Same result as the
