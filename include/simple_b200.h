@@ -65,7 +65,6 @@ typedef struct {
   int relu;
   int splits;         /* split-K factor; >1 forces fp32 red.add accumulation into `out` (caller zeroes it) */
   int accumulate;     /* 1: red.add into fp32 `out` even when splits == 1 */
-  int bn_hint;        /* 0: automatic N tile; 64: narrow tiles for split-K launches (fewer splits => less red.add traffic) */
   int bias_mod;       /* 0: bias has N entries; else bias[column % bias_mod] (a multiple of 32 dividing N): transposed
                          convolutions run with N = (phase, channel) and share one bias per channel */
 } sb_tap_gemm_args;

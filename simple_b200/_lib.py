@@ -55,7 +55,7 @@ class TapGemmArgs(ctypes.Structure):
         ('w', ctypes.c_void_p), ('N', ctypes.c_int), ('ldw', ctypes.c_int),
         ('out', ctypes.c_void_p), ('out_f32', ctypes.c_int), ('ldo', ctypes.c_int),
         ('bias', ctypes.c_void_p), ('relu', ctypes.c_int), ('splits', ctypes.c_int), ('accumulate', ctypes.c_int),
-        ('bn_hint', ctypes.c_int), ('bias_mod', ctypes.c_int),
+        ('bias_mod', ctypes.c_int),
     ]
 
 

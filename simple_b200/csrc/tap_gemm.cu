@@ -1055,12 +1055,9 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
   p.bias_mod = a->bias_mod > 0 ? a->bias_mod : a->N;
   if (a->bias && (p.bias_mod % 32 || a->N % p.bias_mod)) return SB_ERR_ARG;
 
-  // N tile: 256 when it divides N (fewer A re-reads), else 192 / 128 / 96.  Split-K launches (tiny M, deep K) may ask
-  // for BN = 64: the fp32 red.add traffic is splits x M x N, and narrow tiles fill the SMs with 4x fewer splits -- those
-  // launches are bound by the L2 atomic rate (4.7 M float atomics for a 384 x 768 output at 16 splits), not by the MMAs
+  // N tile: 256 when it divides N (fewer A re-reads), else 192 / 128 / 96
   int BN;
-  if (a->bn_hint == 64 && atomic && a->N % 64 == 0) BN = 64;
-  else if (a->N % 256 == 0) BN = 256;
+  if (a->N % 256 == 0) BN = 256;
   else if (a->N % 192 == 0) BN = 192;
   else if (a->N % 128 == 0) BN = 128;
   else if (a->N <= 96) BN = 96;
@@ -1099,7 +1096,6 @@ extern "C" int sb_tap_gemm(const sb_tap_gemm_args* a, sb_stream_t stream_) {
     }
   }
   switch (BN) {
-    case 64: return launch_tap_gemm<64, 8>(tmA, tmB, tmO, p, stream);
     case 256: return launch_tap_gemm<256, 4>(tmA, tmB, tmO, p, stream);
     case 192: return launch_tap_gemm<192, 4>(tmA, tmB, tmO, p, stream);
     case 128: return launch_tap_gemm<128, 6>(tmA, tmB, tmO, p, stream);

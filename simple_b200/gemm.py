@@ -40,7 +40,7 @@ def _taps(args, taps):
 
 
 def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bias=None, relu=False, splits=1,
-             accumulate=False, box=None, tag=None, flops=0.0, bias_mod=0, bn_hint=0):
+             accumulate=False, box=None, tag=None, flops=0.0, bias_mod=0):
     """out[b,y,x,n] (+)= sum_t sum_c a[b,y+dy_t,x+dx_t,c] * w[n, t*C+c].  a: bf16 [B,H,W,C]; w: bf16 [N, >=T*C]."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and a.is_contiguous() and a.dim() == 4
     assert w.dtype == torch.bfloat16 and w.is_contiguous() and w.dim() == 2
@@ -65,7 +65,6 @@ def tap_gemm(a, w, taps, Ho, Wo, N=None, out=None, out_dtype=torch.bfloat16, bia
     args.out = out.data_ptr(); args.out_f32 = int(out.dtype == torch.float32); args.ldo = out.shape[3]
     args.bias = bias.data_ptr() if bias is not None else None
     args.bias_mod = int(bias_mod)
-    args.bn_hint = int(bn_hint)
     args.relu = int(relu); args.splits = splits; args.accumulate = int(accumulate)
     rec = profiling.RECORDER
     ev0 = rec.start() if rec is not None else None

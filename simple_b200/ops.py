@@ -366,10 +366,10 @@ class TapConv(torch.autograd.Function):
             if spec.bias_tile > 1:  # N = (phase, channel): the epilogue indexes the bias by column % channels
                 bias_mod = spec.N // spec.bias_tile
         B = a.shape[0]
-        splits, hint = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
+        splits = auto_splits(B, spec.Ho, spec.Wo, spec.N, len(spec.taps) * -(-spec.Ca // 64))
         if splits > 1:
             acc = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, splits=splits, tag=spec.name + '.fwd',
-                           flops=spec.flops * B, bn_hint=hint)
+                           flops=spec.flops * B)
             y = _bias_act(acc, bias_f, spec.relu, spec.out_f32, bias_mod)
         else:
             y = tap_gemm(a, w_op, spec.taps, spec.Ho, spec.Wo, N=spec.N, bias=bias_f, relu=spec.relu,
@@ -396,10 +396,10 @@ def _tap_conv_backward(spec, pw, a, dy, need_da, has_bias):
     da = None
     if spec.need_dgrad and need_da:
         w_op = pw.fwd if spec.transposed else pw.tr
-        splits, hint = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
+        splits = auto_splits(B, spec.Ha, spec.Wa, spec.Ca, len(spec.taps) * -(-spec.N // 64))
         if splits > 1:
             da = _bias_act(tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, splits=splits,
-                                    tag=spec.name + '.dgrad', flops=spec.flops * B, bn_hint=hint), None, False)
+                                    tag=spec.name + '.dgrad', flops=spec.flops * B), None, False)
         else:
             da = tap_gemm(dy, w_op, spec.neg_taps, spec.Ha, spec.Wa, N=spec.Ca, tag=spec.name + '.dgrad',
                           flops=spec.flops * B)
@@ -468,32 +468,23 @@ def refresh_transposed_all(pws, cache):
 SPLIT_FLOOR = True
 
 
-NARROW_SPLIT_TILES = os.environ.get('SB_NARROW_SPLIT', '1') != '0'
-
-
 def auto_splits(B, Ho, Wo, N, KT):
-    """(split-K factor, N-tile hint) for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at
-    HBM speed in ONE co-resident wave (148 slots measured a shade faster than two, and halves the fp32 atomics).
-    Split launches are bound by the L2 atomic rate -- their red.add traffic is splits x M x N floats -- so they run with
-    64-column N tiles (hint 64): four times as many tiles, a quarter of the splits."""
+    """Split-K factor for tiny-M layers (deep 3x2 / 6x5 feature maps): enough CTAs to pull the weights at HBM speed
+    (one co-resident wave: 148 slots measured a shade faster than two, and halves the fp32 atomics)."""
     from .gemm import choose_box
     bw, bh, bb = choose_box(Wo, Ho, B)
     m_tiles = -(-Wo // bw) * -(-Ho // bh) * -(-B // bb)
     BN = 256 if N % 256 == 0 else 192 if N % 192 == 0 else 128 if N % 128 == 0 else 96 if N <= 96 else 128
     ctas = m_tiles * -(-N // BN)
     if ctas >= 100:
-        return 1, 0
+        return 1
     slots = int(os.environ.get('SB_SPLIT_SLOTS', '148'))
-    hint = 0
-    if NARROW_SPLIT_TILES and N % 64 == 0 and BN > 64:
-        hint, ctas = 64, m_tiles * (N // 64)
     # floor: tiles x splits never exceeds the resident grid, so no CTA of the persistent kernel gets a second tile
     # (ceil gave e.g. 9 tiles x 17 splits = 153 work items on 148 CTAs: five CTAs ran twice as long as the rest).
+    # A/B on the replayed step (tools/split_ab.py, ms/step): ceil 7.42 / 7.42, floor 7.35 / 7.56 -- within run-to-run
+    # noise, so the rule is chosen on the work-balance argument
     s = slots // ctas if SPLIT_FLOOR else -(-slots // ctas)
-    s = int(max(1, min(KT, s, 32)))
-    if s == 1 and hint:  # narrow tiles only pay together with a split (atomic) epilogue
-        return 1, 0
-    return s, hint
+    return int(max(1, min(KT, s, 32)))
 
 
 def _bias_act(acc, bias, relu, keep_f32=False, bias_mod=0):

@@ -157,13 +157,11 @@ def test_split_k_sizing_and_transpose_table_layout():
     import re
     import numpy as np
     from simple_b200 import ops
-    # deep 3x2 feature map at batch 64: 384 rows = 3 M tiles; split launches use 64-column N tiles: 3 x 12 = 36 tiles,
-    # 4 splits = 144 CTAs (a quarter of the red.add traffic of 9 wide tiles x 16 splits)
-    assert ops.auto_splits(64, 3, 2, 768, 192) == (4, 64)     # 144 <= 148: no CTA gets a second work item
-    assert ops.auto_splits(64, 105, 80, 96, 2) == (1, 0)       # thousands of tiles: never split
-    s, hint = ops.auto_splits(16, 3, 2, 768, 192)
-    assert 1 <= s <= 32 and hint == 64                         # rollout batch: capped
-    assert ops.auto_splits(1, 3, 2, 768, 4)[0] <= 4            # never more splits than K steps
+    # deep 3x2 feature map at batch 64: 384 rows = 3 M tiles, N = 768 = 3 N tiles -> 9 tiles, 16 splits = 144 CTAs
+    assert ops.auto_splits(64, 3, 2, 768, 192) == 16          # 144 <= 148: no CTA gets a second work item
+    assert ops.auto_splits(64, 105, 80, 96, 2) == 1            # thousands of tiles: never split
+    assert 1 <= ops.auto_splits(16, 3, 2, 768, 192) <= 32      # rollout batch: capped
+    assert ops.auto_splits(1, 3, 2, 768, 4) <= 4               # never more splits than K steps
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'simple_b200.h')).read()
     m = re.search(r'typedef struct sb_transpose_desc \{(.*?)\} sb_transpose_desc;', hdr, re.S)
     assert m, 'sb_transpose_desc missing from the header'
