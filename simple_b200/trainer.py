@@ -12,6 +12,8 @@ import torch
 from . import ops
 from .adafactor import Adafactor
 
+NVTX = os.environ.get('SB_NVTX', '0') == '1'  # NVTX ranges around forward+loss / backward / grad sync / optimiser
+
 
 def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsilon, keep_logits=False):
     """Forward + the losses of simple/trainer.py:134-144.  Returns a dict of device scalars (no host sync).
@@ -184,8 +186,14 @@ class Trainer:
         `after_backward(out)`: optional gradient-independent tail work of the caller (frame feedback); it is issued
         between the backward pass and the optimiser so that it overlaps the last gradient all-reduce."""
         self.model.train()
+        nvtx = torch.cuda.nvtx if NVTX else None  # ranges for Nsight timelines (host-side markers: graph-capture safe)
+        if nvtx:
+            nvtx.range_push('wm_step/forward+loss')
         ops.ARENA.begin(frames.device)  # one memset for all zero-initialised scratch of the step
         out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push('wm_step/backward')
         self.optimizer.zero_grad(set_to_none=True)
         packed = self.model.packed_weight_map(defer_unpack=self.packed_grads) if self.packed_grads else None
         if self.grad_sync is not None and hasattr(self.grad_sync, 'prepare'):
@@ -196,12 +204,20 @@ class Trainer:
             self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous operand
             if after_backward is not None:
                 after_backward(out)
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push('wm_step/grad_sync+feedback')
         if self.grad_sync is not None:
             grads = self.grad_sync(self.model, packed, tail)
         else:
             grads = None
             tail()
+        if nvtx:
+            nvtx.range_pop()
+            nvtx.range_push('wm_step/clip+adafactor')
         self.optimizer.step(max_grad_norm=self.config.clip_grad_norm, grads=grads, packed=packed)
+        if nvtx:
+            nvtx.range_pop()
         if packed:
             for pw in packed.values():
                 pw.gpacked = None
