@@ -366,6 +366,7 @@ def run_own(args):
         # ---- roofline pass: per-launch CUDA-event timing of the hot kernels over 3 extra steps.  Rank 0 only, so the
         # gradient all-reduce is switched off for it (a collective entered by one rank alone would never return).
         sync_saved, trainer.grad_sync = trainer.grad_sync, None
+        scale_saved, trainer.optimizer.grad_scale = trainer.optimizer.grad_scale, 1.0  # local gradients: no DP sum
         eager = StepRunner(trainer, replay, B, use_graph=False, resident=True)
         eager.begin(starts, 0)
         for j in range(2):
@@ -377,6 +378,7 @@ def run_own(args):
         summ = rec.summary()
         profiling.RECORDER = None
         trainer.grad_sync = sync_saved
+        trainer.optimizer.grad_scale = scale_saved
         gem = [summ[k] for k in ('tap_gemm_kernel', 'tap_wgrad_kernel') if k in summ]
         if gem:
             fl, tm, nl = sum(g['work'] for g in gem), sum(g['ms'] for g in gem), sum(g['launches'] for g in gem)

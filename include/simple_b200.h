@@ -36,6 +36,9 @@ int sb_set_wgrad_tap_groups(int enabled);
 /* Same for two 128-row M tiles per sb_tap_wgrad CTA (two dY tiles per pipeline stage against the same A chunks: 1.5x the
  * flops per TMA-loaded row; used when the M side has >= 256 channels).  0 = one M tile per CTA everywhere. */
 int sb_set_wgrad_mt2(int enabled);
+/* Leave n SMs out of every persistent / one-wave grid launched from now on (room for a concurrent NCCL kernel during
+   the data-parallel backward pass); returns the previous value. */
+int sb_set_sm_reserve(int n);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores ("tap GEMM").
@@ -235,6 +238,9 @@ int sb_unpack_conv_grad(const float* packed, int O, int I, int KH, int KW, int s
  * Descriptors and block maps live in DEVICE memory (built by the host wrapper each step; one small H2D copy).
  *   sb_grad_sumsq:      block_map[i] = (tensor, first 4096-element chunk); *total = sum g^2.  scratch: caller-owned fp32
  *                       [1 + SB_SUMSQ_MAX_CTAS], zeroed ONCE (word 0 is a ticket counter the kernel resets itself).
+ *                       sumsq_scale: *total = sumsq_scale * sum g^2 -- 1 normally; 1/world^2 when g holds the SUM of
+ *                       the data-parallel shards' gradients (Adafactor itself is invariant to a constant gradient
+ *                       scale, only the clip coefficient needs the true norm).
  *   sb_adafactor_conv:  4-D weights (O,I,KH,KW) of one kernel size; block_map[i] = (descriptor index, first patch), 128 patches
  *                       per block, the blocks of one tensor consecutive; pass 1 updates row/col states and writes
  *                       acc[0]=sum u^2, acc[1]=sum p^2, pass 2 applies the update.  g is scaled by
@@ -271,7 +277,7 @@ int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, sb_stream_t
 /* glen_dev: optional per-descriptor gradient length (a packed gradient buffer is longer than its parameter) */
 #define SB_SUMSQ_MAX_CTAS (148 * 8)
 int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev, int nblocks,
-                  float* total, float* scratch, sb_stream_t stream);
+                  float* total, float* scratch, float sumsq_scale, sb_stream_t stream);
 int sb_adafactor_conv(const sb_tensor_desc* descs_dev, const int* block_map_dev, int nblocks, int KH, int KW,
                       const float* total_sumsq, float max_norm, int pass, float* scratch, int ntensors,
                       sb_stream_t stream);

@@ -40,6 +40,29 @@ class Adafactor(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._cache = {}
         self.grad_norm_sq = None  # device scalar: squared global gradient norm of the last step (before clipping)
+        self._grad_scale = 1.0
+
+    @property
+    def grad_scale(self):
+        """The gradients handed to `step` are (true gradient) / grad_scale.  Data-parallel training sets 1 / world: the
+        shards' gradients are SUMMED (a plain sum is what the NVSwitch can reduce), the clip coefficient is computed from
+        the true norm (`sb_grad_sumsq` scales the sum of squares), and nothing else needs to know -- Adafactor's update
+        g / sqrt(EMA g^2) is invariant to a constant gradient scale (bit-exactly so for a power of two; eps1 = 1e-30
+        aside).  The second-moment states live in the same units; changing the scale re-scales them."""
+        return self._grad_scale
+
+    @grad_scale.setter
+    def grad_scale(self, s):
+        s = float(s)
+        if s <= 0:
+            raise ValueError('grad_scale must be positive')
+        if s != self._grad_scale:
+            f = (self._grad_scale / s) ** 2
+            for st in self.state.values():
+                for k in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
+                    if k in st:
+                        st[k].mul_(f)
+            self._grad_scale = s
 
     def _init_state(self, p):
         st = self.state[p]
@@ -165,7 +188,8 @@ class Adafactor(torch.optim.Optimizer):
         _lib.check(L.sb_adafactor_tick(descs_ptr, n, s), 'sb_adafactor_tick')
         mn = float(max_grad_norm) if max_grad_norm is not None else 0.0
         _lib.check(L.sb_grad_sumsq(descs_ptr, glen_ptr, maps['sumsq'].data_ptr(), maps['sumsq'].shape[0],
-                                   total.data_ptr(), rec['sumsq_scratch'].data_ptr(), s), 'sb_grad_sumsq')
+                                   total.data_ptr(), rec['sumsq_scratch'].data_ptr(), float(self.grad_scale) ** 2, s),
+                   'sb_grad_sumsq')
         cs = rec['conv_scratch'].data_ptr()
         for (kh, kw, is_packed), bm in maps['conv'].items():
             for pas in (1, 2):

@@ -48,7 +48,8 @@ __device__ __forceinline__ float warp_ordered_sum(const volatile float* v, int n
 // never drift apart (round 1 used one fp32 atomic per CTA and re-broadcast the weights every window).
 __global__ void __launch_bounds__(256)
     grad_sumsq_kernel(const sb_tensor_desc* __restrict__ descs, const long long* __restrict__ glen,
-                      const int2* __restrict__ block_map, int nblocks, float* total, float* scratch) {
+                      const int2* __restrict__ block_map, int nblocks, float* total, float* scratch,
+                      float sumsq_scale) {
   __shared__ float red[8];
   __shared__ unsigned s_ticket;
   float s = 0.f;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256)
     __threadfence();
     const float t = warp_ordered_sum(scratch + 1, (int)gridDim.x, (int)threadIdx.x);
     if (threadIdx.x == 0) {
-      *total = t;
+      *total = t * sumsq_scale;
       *reinterpret_cast<unsigned*>(scratch) = 0u;  // ready for the next launch / graph replay
     }
   }
@@ -484,11 +485,11 @@ extern "C" int sb_adafactor_tick(const sb_tensor_desc* descs_dev, int ntensors, 
 }
 
 extern "C" int sb_grad_sumsq(const sb_tensor_desc* descs_dev, const long long* glen_dev, const int* block_map_dev,
-                             int nblocks, float* total, float* scratch, sb_stream_t stream) {
+                             int nblocks, float* total, float* scratch, float sumsq_scale, sb_stream_t stream) {
   if (!descs_dev || !block_map_dev || nblocks < 1 || !total || !scratch) return SB_ERR_ARG;
   const int grid = nblocks < SB_SUMSQ_MAX_CTAS ? nblocks : SB_SUMSQ_MAX_CTAS;  // 8 CTAs of 256 threads per SM: one resident wave
   grad_sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs_dev, glen_dev, (const int2*)block_map_dev, nblocks,
-                                                            total, scratch);
+                                                            total, scratch, sumsq_scale);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

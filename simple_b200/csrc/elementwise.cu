@@ -15,6 +15,7 @@
 
 namespace sb {
 extern long long g_launches;
+extern int g_sm_reserve;
 
 struct __align__(16) BF8 {
   __nv_bfloat162 v[4];
@@ -1045,7 +1046,7 @@ static void reduce_cfg(const PrepParams& q, int nb, int cap, int* PL, int* slabs
     env_read = true;
   }
   if (cap < 1) cap = 2;
-  const int slots = cap * 148;
+  const int slots = cap * (148 - g_sm_reserve);
   int want = slots * (g_prep_waves > 0 ? g_prep_waves : 1) / nb;
   if (want < 1) want = 1;
   int per = (P + want - 1) / want;

@@ -16,6 +16,7 @@
 namespace sb {
 
 long long g_launches = 0;
+int g_sm_reserve = 0;  // SMs left to a concurrent collective (sb_set_sm_reserve): persistent grids use 148 - reserve
 int g_wgrad_tap_groups = 1;  // 1: 3-tap groups in the weight-gradient kernel where eligible (A/B switch for tests)
 int g_wgrad_mt2 = 1;  // 1: two 128-row M tiles per weight-gradient CTA where the M side has >= 256 channels (A/B switch)
 int g_pair_mode = 1;  // 1: use the CTA-pair (cta_group::2) tap GEMM where eligible; 0: single-CTA kernel only
@@ -383,7 +384,8 @@ static int launch_tap_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < 148 ? total : 148;
+  const int sms = 148 - g_sm_reserve;
+  const int grid = total < sms ? total : sms;
   tap_gemm_kernel<BN, STAGES><<<grid, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p);
   ++g_launches;
   SB_CHECK_LAUNCH();
@@ -784,7 +786,8 @@ static int launch_tap_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     configured = true;
   }
   const int total = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  const int pairs = total < 74 ? total : 74;
+  const int max_pairs = (148 - g_sm_reserve) / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
   CeParams ce{};
   if (cep) ce = *cep;
   tap_gemm2_kernel<BN, STAGES, EPI><<<2 * pairs, kFwdThreads, smem, stream>>>(tmA, tmB, tmO, p, ce);
@@ -1238,7 +1241,7 @@ extern "C" int sb_tap_wgrad(const sb_tap_wgrad_args* a, sb_stream_t stream_) {
   }
   // auto: ONE co-resident wave (one CTA per SM).  Measured over all 18 weight gradients of the training step: one wave
   // 1.17 ms, two waves 1.28 ms, four 1.53 ms -- longer K loops amortise the prologue and halve the fp32 atomics
-  if (splits < 1) splits = slots / ctas;
+  if (splits < 1) splits = (slots > g_sm_reserve ? slots - g_sm_reserve : 1) / ctas;
   p.splits = splits < 1 ? 1 : (splits > PT ? PT : splits);
   CUtensorMap tmDY, tmA;
   rc = make_map_nhwc(&tmDY, m_ptr, a->B, mH, mW, mC, a->bw, a->bh, a->bb);
@@ -1273,6 +1276,15 @@ extern "C" long long sb_launch_count(void) { return sb::g_launches; }
 extern "C" int sb_set_wgrad_tap_groups(int enabled) {
   const int prev = sb::g_wgrad_tap_groups;
   sb::g_wgrad_tap_groups = enabled ? 1 : 0;
+  return prev;
+}
+// Leave `n` SMs free in every persistent / one-wave grid launched from now on.  Data-parallel training sets it for the
+// backward pass: the gradient all-reduce of a finished bucket runs on a side stream meanwhile, and a CTA that finds its
+// SM taken by a collective's CTA would otherwise run as a second wave behind the other 140 (measured: +37 % on the
+// pair GEMMs that overlap an all-reduce).  Returns the previous value.
+extern "C" int sb_set_sm_reserve(int n) {
+  const int prev = sb::g_sm_reserve;
+  sb::g_sm_reserve = n < 0 ? 0 : (n > 64 ? 64 : n);
   return prev;
 }
 extern "C" int sb_set_wgrad_mt2(int enabled) {

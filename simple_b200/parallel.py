@@ -35,7 +35,7 @@ class FlatGradSync:
     (`pw.grad_slot`) INTO the arena, laid out in the order the backward pass finishes them (decoder first), split into
     buckets.  When the last layer of a bucket reports its gradient (`pw.on_ready`), the bucket's all-reduce is launched
     on a side stream and runs over NVLink while the rest of the backward pass keeps the SMs busy; only the last bucket
-    (shallow encoder layers + the 3 M non-conv parameters) is exposed.  Works under CUDA-graph capture (the side stream
+    (down1, down0, embed, gate + the 2.3 M non-conv parameters: 4 M of 68 M values) is exposed.  Works under CUDA-graph capture (the side stream
     is forked from / joined to the capturing stream with events).
 
     Parameters whose gradient is None on this step (gate.* on the first step of a window) are None
@@ -46,15 +46,23 @@ class FlatGradSync:
     ORDER = ['logits', 'up4', 'up3', 'up2', 'up1', 'up0', 'mid1', 'mid0', 's_conv2', 's_conv1', 's_embed',
              'down4', 'down3', 'down2', 'down1', 'down0', 'embed', 'gate']
 
-    def __init__(self, model, group=None, n_buckets=4):
+    # layers after which a bucket is sent (backward order): 25 M | 15 M | 10 M | 9 M | 5 M values, 4 M left for the end
+    BOUNDS_AFTER = ('up0', 's_conv2', 'down4', 'down3', 'down2')
+
+    def __init__(self, model, group=None, bounds_after=None):
         self.params = [p for p in model.parameters()]
         self.group = group
         self.flat = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.n_buckets = int(os.environ.get('SB_DP_BUCKETS', n_buckets))
+        env = os.environ.get('SB_DP_BOUNDS')
+        self.bounds_after = tuple(env.split(',')) if env else tuple(bounds_after or self.BOUNDS_AFTER)
         self._layout = None      # overlap mode: dict(name -> (offset, numel)), bucket boundaries, tail offset
         self._comm_stream = None
-        self._avg = dist.ReduceOp.AVG if hasattr(dist.ReduceOp, 'AVG') else None
+        self.last_scale = 1.0  # the gradients returned by the last call are (mean gradient) / last_scale
+        # SMs the compute kernels leave to the all-reduce CTAs while a bucket is in flight (sb_set_sm_reserve).  Measured at
+        # 2 GPUs (tools/dp_matrix.sh): 0 -> 7.19 ms, 4 -> 7.23, 8 -> 7.29, 16 -> 7.31 with NCCL's default CTA count, and no
+        # better than 7.18 with any NCCL_MAX_CTAS: the overlap cost is memory-system contention, not displaced CTAs -> off
+        self.sm_reserve = int(os.environ.get('SB_DP_SM_RESERVE', '0'))
 
     # ---- overlap mode ------------------------------------------------------------------------------------------
     def prepare(self, model, packed):
@@ -72,21 +80,23 @@ class FlatGradSync:
             conv_total = off
             conv_params = {id(p) for p in packed}
             tail = sum(p.numel() for p in self.params if id(p) not in conv_params)
-            self.flat = torch.zeros(conv_total + tail, device=dev, dtype=torch.float32)
-            # bucket i ends after the first layer that brings the running size past (i+1)/n of the conv total; the last
-            # bucket (whatever follows the final boundary, plus the non-conv tail) is reduced at the end of backward
+            self.flat = self._alloc_arena(conv_total + tail, dev)
+            # a bucket ends after each layer named in `bounds_after`: few large buckets while plenty of backward is left
+            # to hide them behind, then small ones, so that what is still in flight when the backward pass ends (the
+            # layers after the final boundary plus the non-conv tail: ~4 M of 68 M values) is as short as it can be
             bounds, members, cur = [], [], set()
-            target = [conv_total * (i + 1) / self.n_buckets for i in range(self.n_buckets)]
             for n in names:
                 cur.add(n)
-                end = slots[n][0] + slots[n][1]
-                if len(bounds) < self.n_buckets - 1 and end >= target[len(bounds)]:
-                    bounds.append(end)
+                if n in self.bounds_after:
+                    bounds.append(slots[n][0] + slots[n][1])
                     members.append(cur)
                     cur = set()
             self._layout = dict(names=names, slots=slots, conv_total=conv_total, bounds=bounds, members=members)
             self._comm_stream = torch.cuda.Stream(device=dev)
         L = self._layout
+        if self.sm_reserve:  # a step that raised between the first bucket and the end must not leave it set
+            from . import _lib
+            _lib.lib().sb_set_sm_reserve(0)
         self.flat[:L['conv_total']].zero_()  # wgrad accumulates with red.add
         self._launched = 0
         self._ready = set()
@@ -96,12 +106,29 @@ class FlatGradSync:
             pw.grad_slot = self.flat[o:o + k].view(pw.fwd.shape)
             pw.on_ready = (lambda name=n: self._on_ready(name))
 
+    def _alloc_arena(self, n, dev):
+        """The gradient arena comes from NCCL's own allocator and is registered with the communicator (user-buffer
+        registration): the NVLS all-reduce then reads and writes it in place instead of staging through its own buffers.
+        Measured at 8 GPUs: 7.55 -> 7.32 ms per step.  SB_DP_NCCL_POOL=0 falls back to a plain allocation."""
+        if os.environ.get('SB_DP_NCCL_POOL', '1') == '1' and dist.get_backend(self.group) == 'nccl':
+            try:
+                dist.all_reduce(torch.zeros(1, device=dev), group=self.group)  # the communicator must exist first
+                backend = (self.group or dist.group.WORLD)._get_backend(dev)
+                pool = torch.cuda.MemPool(backend.mem_allocator)
+                with torch.cuda.use_mem_pool(pool):
+                    flat = torch.zeros(n, device=dev, dtype=torch.float32)
+                backend.register_mem_pool(pool)
+                self._pool = pool
+                return flat
+            except (RuntimeError, AttributeError) as e:  # NCCL built without ncclMemAlloc / torch without MemPool
+                import warnings
+                warnings.warn(f'FlatGradSync: NCCL-registered gradient arena unavailable ({e}); using a plain allocation')
+        return torch.zeros(n, device=dev, dtype=torch.float32)
+
     def _all_reduce(self, buf):
-        if self._avg is not None:
-            dist.all_reduce(buf, op=self._avg, group=self.group)
-        else:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-            buf.mul_(1.0 / self.world)
+        # a plain SUM: that is what NCCL can hand to the NVSwitch (NVLS in-switch reduction; AVG is a pre-multiplied sum
+        # and falls back to the ring).  The 1 / world is folded into the clip coefficient (`last_scale`).
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
 
     def _on_ready(self, name):
         L = self._layout
@@ -112,6 +139,9 @@ class FlatGradSync:
             lo = L['bounds'][self._launched - 1] if self._launched else 0
             hi = L['bounds'][self._launched]
             cur = torch.cuda.current_stream()
+            if self.sm_reserve:
+                from . import _lib
+                _lib.lib().sb_set_sm_reserve(self.sm_reserve)
             self._comm_stream.wait_stream(cur)  # this bucket's gradients are complete on the compute stream
             with torch.cuda.stream(self._comm_stream):
                 self._all_reduce(self.flat[lo:hi])
@@ -137,10 +167,14 @@ class FlatGradSync:
         if overlap is not None:
             overlap()
         cur.wait_stream(self._comm_stream)
+        if self.sm_reserve:
+            from . import _lib
+            _lib.lib().sb_set_sm_reserve(0)
         for p, pw in packed.items():
             if pw.grad_slot is not None and pw.gpacked is not None:
                 views[p] = pw.grad_slot
             pw.on_ready = None
+        self.last_scale = 1.0 / self.world
         return views
 
     # ---- entry point -------------------------------------------------------------------------------------------
@@ -152,6 +186,7 @@ class FlatGradSync:
             return self._finish_overlapped(packed, overlap)
         if overlap is not None:
             overlap()
+        self.last_scale = 1.0
         active = []
         for p in self.params:
             pw = packed.get(p) if packed else None

@@ -149,6 +149,7 @@ class Trainer:
                               if k in ('step', 'exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq')})
         seed = self.model._seed_dev
         torch.save({'model': {k: v.detach().cpu() for k, v in self.model.state_dict().items()}, 'optimizer': opt_state,
+                    'grad_scale': self.optimizer.grad_scale,  # units of the second-moment states (1 / DP world size)
                     'model_step': self.model_step, 'reward_step': self.reward_step, 'epoch': int(epoch),
                     'dropout_seed': int(seed.item()) if seed is not None else None,
                     'torch_rng': torch.get_rng_state(),
@@ -161,6 +162,8 @@ class Trainer:
         dev = self.model.logits.weight.device
         self.optimizer.state.clear()
         self.optimizer._cache.clear()
+        current_scale = self.optimizer.grad_scale
+        self.optimizer._grad_scale = float(ck.get('grad_scale', 1.0))  # the stored states' units ...
         for p, saved in zip(self.model.parameters(), ck['optimizer']):
             if not saved:
                 continue
@@ -170,6 +173,7 @@ class Trainer:
             for k in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
                 if k in saved:
                     st[k].copy_(saved[k].to(dev))
+        self.optimizer.grad_scale = current_scale  # ... converted to this run's (another world size)
         self.model_step, self.reward_step = ck['model_step'], ck['reward_step']
         if ck.get('dropout_seed') is not None:
             if self.model._seed_dev is not None and self.model._seed_dev.device == dev:
@@ -209,6 +213,8 @@ class Trainer:
             nvtx.range_push('wm_step/grad_sync+feedback')
         if self.grad_sync is not None:
             grads = self.grad_sync(self.model, packed, tail)
+            # overlap mode hands back the SUM over the ranks (see Adafactor.grad_scale); set outside graph capture
+            self.optimizer.grad_scale = getattr(self.grad_sync, 'last_scale', 1.0)
         else:
             grads = None
             tail()
