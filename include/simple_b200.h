@@ -389,6 +389,17 @@ int sb_reward_value(const float* hid_pre, const float* w2, const float* b2, cons
                     float* dhid_pre, float* dw2, float* db2, float* dvalue, sb_stream_t stream);
 /* out[N] += column sums of x [M,N] (row stride ld): bias gradients of the dense layers. */
 int sb_colsum_f32(const float* x, int M, int N, int ld, float* out, sb_stream_t stream);
+/* ---- skinny fp32 GEMMs of the latent / heads block (dense.cu) ---------------------------------------------------
+ * C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).  a_trans: A stored [K,M]; b_trans: B stored [N,K] (an nn.Linear
+ * weight); lda / ldb / ldc: row pitches in elements (inner strides are 1).  accumulate = 0: stores C.  accumulate = 1:
+ * C must hold zeros or an addend; the K range is split over sb_dense_splits(M,N,K) CTAs per 64x64 tile, partial
+ * products are added with fp32 red.add.
+ * Replaces the nn.Linear forwards and autograd matmuls of simple/utils.py:98-105 (ActionInjector),
+ * simple/next_frame_predictor.py:11-24 (RewardEstimator), :43-52,:87-121 (BitsPredictor), :153-159,:176 (StochasticModel). */
+int sb_dense_splits(int M, int N, int K);
+int sb_dense(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, long long lda,
+             long long ldb, long long ldc, int a_trans, int b_trans, int accumulate, sb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

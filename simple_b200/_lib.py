@@ -114,6 +114,8 @@ def lib():
     L.sb_set_wgrad_mt2.argtypes = [ctypes.c_int]
     L.sb_set_wgrad_mt2.restype = ctypes.c_int
     L.sb_set_sm_reserve.argtypes = [ctypes.c_int]
+    L.sb_dense_splits.argtypes = [ctypes.c_int] * 3
+    L.sb_dense_splits.restype = ctypes.c_int
     L.sb_set_sm_reserve.restype = ctypes.c_int
     L.sb_set_wgrad_tap_groups.argtypes = [ctypes.c_int]
     L.sb_set_wgrad_tap_groups.restype = ctypes.c_int
@@ -154,6 +156,7 @@ class _Sigs:
     sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_grad_sumsq = [_p, _p, _p, _i, _p, _p, _f, _p]
+    sb_dense = [_p, _p, _p, _p, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _p]
     sb_adafactor_tick = [_p, _i, _p]
     sb_adafactor_conv = [_p, _p, _i, _i, _i, _p, _f, _i, _p, _i, _p]
     sb_adafactor_small = [_p, _p, _i, _i, _p, _f, _p]
@@ -179,7 +182,7 @@ class _Sigs:
     sb_colsum_f32 = [_p, _i, _i, _i, _p, _p]
 
 
-EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_tap_wgrad_bias_ok', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_wgrad_mt2', 'sb_set_sm_reserve', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
+EXPORTED = ['sb_init', 'sb_launch_count', 'sb_version', 'sb_tap_wgrad_bias_ok', 'sb_set_pair_mode', 'sb_set_wgrad_tap_groups', 'sb_set_wgrad_mt2', 'sb_set_sm_reserve', 'sb_dense_splits', 'sb_set_prep_specialize', 'sb_set_ce_tma'] + [n for n in dir(_Sigs) if n.startswith('sb_')]
 
 
 def check(rc, what):

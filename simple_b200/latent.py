@@ -18,7 +18,7 @@ import ctypes
 import torch
 
 from . import _lib
-from .ops import zeros as _zeros
+from .ops import dense, zeros as _zeros
 
 INJ_WIDTHS = (768, 768, 768, 768, 384, 192, 96)  # action_injectors.0-5, stochastic_model.action_injector
 INJ_S = sum(INJ_WIDTHS)
@@ -110,7 +110,7 @@ class HeadsIn(torch.autograd.Function):
         B, dev = x5.shape[0], x5.device
         assert x5.dtype == torch.bfloat16 and x5.is_contiguous() and x5.numel() == B * 4608
         a = action.reshape(B, -1).float()
-        bank = torch.addmm(lp.inj_b.flat, a, lp.inj_w.flat.t())  # [B, 2S]: dense1 pre-activations | dense2 outputs
+        bank = dense(a, lp.inj_w.flat, b_trans=True, bias=lp.inj_b.flat)  # [B, 2S]: dense1 pre-activations | dense2 outputs
         ve = lp.model.value_estimator.dense
         scsh = torch.empty(2, B * INJ_S, device=dev)
         h_flat = torch.empty(B, 4608, device=dev)
@@ -160,7 +160,7 @@ class HeadsIn(torch.autograd.Function):
         _lib.check(L.sb_heads_bwd(x5.data_ptr(), bank.data_ptr(), lp.widths, len(INJ_WIDTHS), ctypes.byref(g),
                                   ve.weight.data_ptr(), _ptr(dvalue), _ptr(dh), B, dx5.data_ptr(), dbank.data_ptr(),
                                   dwv.data_ptr(), dbv.data_ptr(), dbank_b.data_ptr(), st), 'sb_heads_bwd')
-        lp.inj_w.split_grad(dbank.t() @ a)
+        lp.inj_w.split_grad(dense(dbank, a, a_trans=True))
         lp.inj_b.split_grad(dbank_b)
         if dvalue is not None:
             _acc_grad(ve.weight, dwv.view(1, 4608))
@@ -179,13 +179,13 @@ def _sampler_operands(bp, bsum, L, st):
     _lib.check(L.sb_sampler_tables(bp.lstm.weight_hh.data_ptr(), bp.lstm.weight_ih.data_ptr(), bp.dense5.weight.data_ptr(),
                                    bp.dense4.weight.data_ptr(), bp.dense4.bias.data_ptr(), whhT.data_ptr(),
                                    wihT.data_ptr(), w5T.data_ptr(), emb.data_ptr(), st), 'sb_sampler_tables')
-    E = torch.addmm(bsum, emb, wihT)  # [256,512]: input-gate pre-activations of every symbol
+    E = dense(emb, wihT, bias=bsum)  # [256,512]: input-gate pre-activations of every symbol
     return whhT, wihT, w5T, E
 
 
 def _sample_bits(first, h0, c0, hc_ld, bsum, wihT, whhT, w5T, E, b5, noise, seed_ptr, B, L, st):
     dev = first.device
-    G0 = torch.addmm(bsum, first, wihT)  # [B,512]
+    G0 = dense(first, wihT, bias=bsum)  # [B,512]
     bits = torch.empty(B, 128, device=dev)
     ints = torch.empty(B, 16, device=dev, dtype=torch.int32)
     _lib.check(L.sb_lstm_sample2(G0.data_ptr(), h0.data_ptr(), c0.data_ptr(), E.data_ptr(), whhT.data_ptr(),
@@ -208,7 +208,7 @@ class LatentTrain(torch.autograd.Function):
         eps_ptr, eps_val = _eps(epsilon)
         f32 = dict(device=dev, dtype=torch.float32)
         # ---- posterior bits (draw order of the reference: truncnorm, flip noise, first mix)
-        pre = torch.addmm(sm.dense1.bias, x12, sm.dense1.weight.t())  # [B,128]
+        pre = dense(x12, sm.dense1.weight, b_trans=True, bias=sm.dense1.bias)  # [B,128]
         tn, u_flip, u1 = rand.truncnorm(pre.shape), rand.uniform(pre.shape), rand.uniform(pre.shape)
         x = torch.empty(B, 128, **f32)
         bits2 = torch.empty(B, 128, **f32)
@@ -220,7 +220,7 @@ class LatentTrain(torch.autograd.Function):
                                            bits2.data_ptr(), bits_clean.data_ptr(), flags.data_ptr(), tints.data_ptr(),
                                            st), 'sb_posterior_bits_fwd')
         # ---- BitsPredictor, teacher-forced pass on the clean bits (:87-107)
-        proj = torch.addmm(lp.b123.flat, h_flat, lp.w123.flat.t())  # [B,384] = first | h0 | c0
+        proj = dense(h_flat, lp.w123.flat, b_trans=True, bias=lp.b123.flat)  # [B,384] = first | h0 | c0
         keep1, keep2 = rand.keep_mask((B, 16, 128), 0.1), rand.keep_mask((B, 16, 128), 0.1)
         bsum = torch.empty(512, **f32)
         tin = torch.empty(B, 16, 128, **f32)
@@ -229,7 +229,7 @@ class LatentTrain(torch.autograd.Function):
                                           bp.lstm.bias_ih.data_ptr(), bp.lstm.bias_hh.data_ptr(), bsum.data_ptr(), B,
                                           tin.data_ptr(), st), 'sb_teacher_embed_fwd')
         whhT, wihT, w5T, E = _sampler_operands(bp, bsum, L, st)
-        xw = torch.addmm(bsum, tin.view(B * 16, 128), wihT)  # [16B,512] input-gate pre-activations of all steps
+        xw = dense(tin.view(B * 16, 128), wihT, bias=bsum)  # [16B,512] input-gate pre-activations of all steps
         hs = torch.empty(B, 16, 128, **f32)
         act = torch.empty(B, 16, 512, **f32)
         cs = torch.empty(B, 16, 128, **f32)
@@ -239,7 +239,7 @@ class LatentTrain(torch.autograd.Function):
         outs_d = torch.empty(B * 16, 128, **f32)
         _lib.check(L.sb_drop_scale(hs.data_ptr(), _ptr(keep2), 0.1, seed_ptr, seed_val, 107, outs_d.data_ptr(),
                                    B * 16 * 128, st), 'sb_drop_scale')
-        pred = torch.addmm(bp.dense5.bias, outs_d, w5T)  # [16B,256]
+        pred = dense(outs_d, w5T, bias=bp.dense5.bias)  # [16B,256]
         zbuf = _zeros((1 + 256 + 128 + 1536 + 128 * 256 + 128,), dev)  # loss | db5 | db1 | db23 | dw4 | db4
         loss_sum, db5, db1 = zbuf[0:1], zbuf[1:257], zbuf[257:385]
         dpred = torch.empty(B * 16, 256, **f32)
@@ -256,7 +256,7 @@ class LatentTrain(torch.autograd.Function):
                                  float(cfg.latent_rnn_max_sampling), seed_ptr, seed_val, B, bits3.data_ptr(),
                                  flags.data_ptr(), st), 'sb_mix_bits')
         # ---- add_bits (:153-159) and the third mix
-        zz = torch.addmm(lp.b23.flat, bits3, lp.w23.flat.t())  # [B,1536]
+        zz = dense(bits3, lp.w23.flat, b_trans=True, bias=lp.b23.flat)  # [B,1536]
         u3 = rand.uniform((B, 768, 3, 2))
         hm = torch.empty(B, 3, 2, 768, device=dev, dtype=torch.bfloat16)
         x_mid = torch.empty(B, 768, **f32)
@@ -298,20 +298,20 @@ class LatentTrain(torch.autograd.Function):
         dzz = torch.empty(B, 1536, **f32)
         _lib.check(L.sb_latent_out_bwd(_ptr(dhm), _ptr(dx_mid), dxm_ld, h_flat.data_ptr(), zz.data_ptr(), m3.data_ptr(),
                                        B, dh_a.data_ptr(), dzz.data_ptr(), db23.data_ptr(), st), 'sb_latent_out_bwd')
-        lp.w23.split_grad(dzz.t() @ bits3)
+        lp.w23.split_grad(dense(dzz, bits3, a_trans=True))
         lp.b23.split_grad(db23)
-        dbits3 = dzz @ lp.w23.flat  # [B,128]
+        dbits3 = dense(dzz, lp.w23.flat)  # [B,128]
         # ---- posterior bits -> dense1 of the stochastic model
         dpre = torch.empty(B, 128, **f32)
         _lib.check(L.sb_posterior_bits_bwd(dbits3.data_ptr(), x.data_ptr(), flags.data_ptr(), B, dpre.data_ptr(),
                                            db1.data_ptr(), st), 'sb_posterior_bits_bwd')
-        _acc_grad(sm.dense1.weight, dpre.t() @ x12)
+        _acc_grad(sm.dense1.weight, dense(dpre, x12, a_trans=True))
         _acc_grad(sm.dense1.bias, db1)
-        dx12 = dpre @ sm.dense1.weight
+        dx12 = dense(dpre, sm.dense1.weight)
         # ---- teacher-forced LSTM loss (its gradient w.r.t. the logits was produced by the forward CE launch)
-        _acc_grad(bp.dense5.weight, dpred.t() @ outs_d)
+        _acc_grad(bp.dense5.weight, dense(dpred, outs_d, a_trans=True))
         _acc_grad(bp.dense5.bias, db5)
-        douts_d = dpred @ bp.dense5.weight  # [16B,128]
+        douts_d = dense(dpred, bp.dense5.weight)  # [16B,128]
         dhs = torch.empty(B * 16, 128, **f32)
         _lib.check(L.sb_drop_scale(douts_d.data_ptr(), _ptr(keep2), 0.1, seed_ptr, seed_val, 107, dhs.data_ptr(),
                                    B * 16 * 128, st), 'sb_drop_scale')
@@ -322,23 +322,23 @@ class LatentTrain(torch.autograd.Function):
                                          dproj[:, 128:256].data_ptr(), dproj[:, 256:384].data_ptr(), st),
                    'sb_lstm_teacher_bwd')
         h_prev = torch.cat((proj[:, 128:256].unsqueeze(1), hs[:, :-1]), dim=1).reshape(B * 16, 128)
-        _acc_grad(bp.lstm.weight_hh, dxw.t() @ h_prev)
-        _acc_grad(bp.lstm.weight_ih, dxw.t() @ tin.view(B * 16, 128))
+        _acc_grad(bp.lstm.weight_hh, dense(dxw, h_prev, a_trans=True))
+        _acc_grad(bp.lstm.weight_ih, dense(dxw, tin.view(B * 16, 128), a_trans=True))
         dbg = _zeros((512 + 384,), dev)
         _lib.check(L.sb_colsum_f32(dxw.data_ptr(), B * 16, 512, 512, dbg.data_ptr(), st), 'sb_colsum_f32')
         _acc_grad(bp.lstm.bias_ih, dbg[:512])
         _acc_grad(bp.lstm.bias_hh, dbg[:512])
-        dtin = dxw @ bp.lstm.weight_ih  # [16B,128]
+        dtin = dense(dxw, bp.lstm.weight_ih)  # [16B,128]
         _lib.check(L.sb_teacher_embed_bwd(dtin.data_ptr(), tints.data_ptr(), _ptr(keep1), 0.1, seed_ptr, seed_val, B,
                                           dproj.data_ptr(), 384, dw4.data_ptr(), db4.data_ptr(), st),
                    'sb_teacher_embed_bwd')
         _acc_grad(bp.dense4.weight, dw4)
         _acc_grad(bp.dense4.bias, db4)
         # ---- dense1 | dense2 | dense3 of the BitsPredictor
-        lp.w123.split_grad(dproj.t() @ h_flat)
+        lp.w123.split_grad(dense(dproj, h_flat, a_trans=True))
         _lib.check(L.sb_colsum_f32(dproj.data_ptr(), B, 384, 384, dbg[512:].data_ptr(), st), 'sb_colsum_f32')
         lp.b123.split_grad(dbg[512:])
-        dh = torch.addmm(dh_a, dproj, lp.w123.flat)
+        dh = dense(dproj, lp.w123.flat, out=dh_a)
         return dh, dx12, None, None, None, None, None
 
 
@@ -350,7 +350,7 @@ def latent_eval(h_flat, lp, rand, aux):
     sm = lp.model.stochastic_model
     bp = sm.bits_predictor
     seed_ptr, seed_val = _seed(rand)
-    proj = torch.addmm(lp.b123.flat, h_flat, lp.w123.flat.t())
+    proj = dense(h_flat, lp.w123.flat, b_trans=True, bias=lp.b123.flat)
     tb = bp._sampler_tables if (bp.cache_sampler_tables and bp._sampler_tables is not None) else None
     if tb is None:
         from . import ops
@@ -363,7 +363,7 @@ def latent_eval(h_flat, lp, rand, aux):
         f = force['sampled_bits'].to(dev)
         rand.mismatch['sampled_bits'] = float((f != bits).float().mean())
         bits = f.contiguous()
-    zz = torch.addmm(lp.b23.flat, bits, lp.w23.flat.t())
+    zz = dense(bits, lp.w23.flat, b_trans=True, bias=lp.b23.flat)
     hm = torch.empty(B, 3, 2, 768, device=dev, dtype=torch.bfloat16)
     x_mid = torch.empty(B, 768, device=dev)
     _lib.check(L.sb_latent_out_fwd(h_flat.data_ptr(), zz.data_ptr(), None, 0, None, 0.0, 0.0, seed_ptr, seed_val, B,
@@ -385,7 +385,7 @@ class HeadsOut(torch.autograd.Function):
         B, dev = x_mid.shape[0], x_mid.device
         re = model.reward_estimator
         r_in = torch.cat((x_mid, x_fin.unsqueeze(0).expand(B, -1)), dim=1)  # [B,864]
-        hid = torch.addmm(re.dense1.bias, r_in, re.dense1.weight.t())       # [B,128]
+        hid = dense(r_in, re.dense1.weight, b_trans=True, bias=re.dense1.bias)       # [B,128]
         reward_pred = torch.empty(B, 3, device=dev)
         if rewards is None:
             _lib.check(L.sb_reward_value(hid.data_ptr(), re.dense2.weight.data_ptr(), re.dense2.bias.data_ptr(), None,
@@ -416,10 +416,10 @@ class HeadsOut(torch.autograd.Function):
         dw2, db2, db1 = z[2:386].view(3, 128), z[386:389], z[389:517]
         _acc_grad(re.dense2.weight, dw2)
         _acc_grad(re.dense2.bias, db2)
-        _acc_grad(re.dense1.weight, dhid.t() @ r_in)
+        _acc_grad(re.dense1.weight, dense(dhid, r_in, a_trans=True))
         _lib.check(L.sb_colsum_f32(dhid.data_ptr(), B, 128, 128, db1.data_ptr(), st), 'sb_colsum_f32')
         _acc_grad(re.dense1.bias, db1)
-        dr_in = dhid @ re.dense1.weight  # [B,864]
+        dr_in = dense(dhid, re.dense1.weight)  # [B,864]
         dx_fin = _zeros((96,), r_in.device)
         _lib.check(L.sb_colsum_f32(dr_in[:, 768:].data_ptr(), B, 96, 864, dx_fin.data_ptr(), st), 'sb_colsum_f32')
         return dr_in[:, :768], dx_fin, dvalue, None, None, None

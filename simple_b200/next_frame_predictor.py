@@ -104,7 +104,7 @@ class BitsPredictor(nn.Module):  # :66-121
         B = x.shape[0]
         w123 = torch.cat((self.dense1.weight, self.dense2.weight, self.dense3.weight), dim=0)
         b123 = torch.cat((self.dense1.bias, self.dense2.bias, self.dense3.bias), dim=0)
-        first, h, c = F.linear(x, w123, b123).chunk(3, dim=1)
+        first, h, c = ops.dense(x.float(), w123, b_trans=True, bias=b123).chunk(3, dim=1)
         noise = rand.sample_noise(B, n) if hasattr(rand, 'sample_noise') else None
         # weight-only operands.  While the weights are static (rollouts) they live in PERSISTENT tensors that
         # `refresh_sampler_tables` rewrites in place: a captured rollout graph keeps reading valid, current memory

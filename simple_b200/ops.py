@@ -109,6 +109,35 @@ def zeros(shape, device, dtype=torch.float32):
     return ARENA.zeros(shape, dtype, device)
 
 
+def dense(a, b, a_trans=False, b_trans=False, bias=None, out=None):
+    """fp32 `op(a) @ op(b) (+ bias)`, or `out += ...` when `out` is given (sb_dense: the skinny GEMMs of the latent /
+    heads block).  a: [M,K] ([K,M] with a_trans); b: [K,N] ([N,K] with b_trans, i.e. an nn.Linear weight); unit inner
+    strides, any row pitch (views into the flat parameter banks).  Small outputs are split along K across the chip and
+    summed with red.add into zero-initialised memory (the step's zero arena)."""
+    for t in (a, b):
+        if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError('sb_dense: operands must be 2-D fp32 with a unit inner stride')
+    K, M = a.shape if a_trans else (a.shape[1], a.shape[0])
+    N = b.shape[0] if b_trans else b.shape[1]
+    if (b.shape[1] if b_trans else b.shape[0]) != K:
+        raise ValueError(f'sb_dense: inner dimensions differ ({tuple(a.shape)} x {tuple(b.shape)})')
+    L = _lib.lib()
+    if out is not None:
+        if out.dtype != torch.float32 or out.shape != (M, N) or out.stride(1) != 1:
+            raise ValueError('sb_dense: bad accumulator')
+        acc = 1
+    elif L.sb_dense_splits(M, N, K) > 1:
+        out, acc = zeros((M, N), a.device), 1
+    else:
+        out, acc = torch.empty(M, N, device=a.device), 0
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError('sb_dense: bad bias')
+    _lib.check(L.sb_dense(a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+                          M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_trans), int(b_trans), acc,
+                          _lib.stream_ptr()), 'sb_dense')
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # raw kernel wrappers
 # ---------------------------------------------------------------------------------------------------------------
@@ -704,7 +733,7 @@ class MeanAttentionFn(torch.autograd.Function):
                                            B, HW, C, O, dx.data_ptr(), dwe.data_ptr(), dbe.data_ptr(), 1,
                                            _lib.stream_ptr()), 'sb_mean_attention_bwd')
         _lib.check(L.sb_colsum_f32(dy.data_ptr(), B, O, O, dbd.data_ptr(), _lib.stream_ptr()), 'sb_colsum_f32')
-        return dx, dwe.reshape(ctx.we_shape), dbe, dy.t() @ l_save, dbd
+        return dx, dwe.reshape(ctx.we_shape), dbe, dense(dy, l_save, a_trans=True), dbd
 
 
 def mean_attention(x_nhwc_bf16, module):
@@ -722,7 +751,7 @@ def lstm_sampler_tables(lstm, dense5, dense4, out=None):
         bias = (lstm.bias_ih + lstm.bias_hh).float()
         emb = dense4.weight.t().float() + dense4.bias.float()  # [256,128]: dense4(one_hot(s)) for every symbol s
         new = dict(whhT=lstm.weight_hh.t().contiguous().float(), w5T=dense5.weight.t().contiguous().float(),
-                   E=torch.addmm(bias, emb, lstm.weight_ih.t().float()).contiguous(), bias=bias,
+                   E=dense(emb.contiguous(), lstm.weight_ih.detach().float(), b_trans=True, bias=bias), bias=bias,
                    b5=dense5.bias.detach().float().contiguous(), wihT=lstm.weight_ih.t().contiguous().float())
         if out is None or any(out[k].device != v.device for k, v in new.items()):
             return new
@@ -738,7 +767,7 @@ def lstm_sample(x0, h0, c0, lstm, dense5, dense4, noise=None, seed=None, tables=
     f = lambda t: t.detach().float().contiguous()
     tb = tables if tables is not None else lstm_sampler_tables(lstm, dense5, dense4)
     with torch.no_grad():
-        G0 = torch.addmm(tb['bias'], f(x0), tb['wihT'])  # [B,512]
+        G0 = dense(f(x0), tb['wihT'], bias=tb['bias'])  # [B,512]
     h0, c0 = f(h0), f(c0)
     bits = torch.empty(B, 128, device=x0.device, dtype=torch.float32)
     ints = torch.empty(B, 16, device=x0.device, dtype=torch.int32)
@@ -782,5 +811,5 @@ class LstmTeacher(torch.autograd.Function):
                                                   whh.data_ptr(), B, 128, dpre.data_ptr(), dh0.data_ptr(), dc0.data_ptr(),
                                                   _lib.stream_ptr()), 'sb_lstm_teacher_bwd')
         h_prev = torch.cat((h0.unsqueeze(1), hs[:, :-1]), dim=1).reshape(-1, 128)
-        dw_hh = dpre.reshape(-1, 512).t() @ h_prev  # [512,128]
+        dw_hh = dense(dpre.reshape(-1, 512), h_prev, a_trans=True)  # [512,128]
         return dpre, dh0, dc0, dw_hh

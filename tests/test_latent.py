@@ -198,7 +198,10 @@ def test_fused_latent_block_in_kernel_randomness_is_regenerated_by_backward_and_
     hm_a, bits_a, bp_a, h_flat = run(11)
     hm_b, bits_b, _, _ = run(11)
     hm_c, bits_c, _, _ = run(12)
-    assert torch.equal(hm_a, hm_b) and torch.equal(bits_a, bits_b)
+    # same seed -> same draws and decisions; the values agree to fp32 summation order (the dense layers split K across
+    # CTAs and add with red.add), which shows up as isolated 1-ulp differences after the bf16 rounding of hm
+    assert torch.equal(bits_a.sign(), bits_b.sign()) and torch.allclose(bits_a, bits_b, atol=1e-5)
+    assert float((hm_a != hm_b).float().mean()) < 1e-3 and torch.allclose(hm_a, hm_b, atol=2e-2)
     assert not torch.equal(bits_a, bits_c)
     # third mix keeps the layer with probability 1 - (1 - eps) * 0.8 = 0.44
     h_nhwc = h_flat.reshape(B, 768, 6).permute(0, 2, 1).reshape(B, 3, 2, 768)

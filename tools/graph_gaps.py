@@ -92,7 +92,7 @@ other = [(n, t) for k, (n, t) in agg.items() if 'sb::' not in k]
 print(f'--- kernels of this library (sb::): {sum(n for n, _ in own):.0f} launches, {sum(t for _, t in own):.3f} ms; '
       f'library / ATen kernels: {sum(n for n, _ in other):.0f} launches, {sum(t for _, t in other):.3f} ms')
 # timeline of the last profiled step: idle gaps of the GPU (> 15 us) and where the NCCL kernels sit
-tl = sorted(((e.time_range.start, e.time_range.end, e.name.split('(')[0][:60]) for e in evs), key=lambda x: x[0])
+tl = sorted(((e.time_range.start, e.time_range.end, e.name.split('(')[0][:110]) for e in evs), key=lambda x: x[0])
 per = len(tl) // N
 last = tl[-per:]
 t0 = last[0][0]
@@ -112,6 +112,10 @@ for key in ('pixel_ce_kernel', 'adafactor_tick', 'grad_sumsq', 'frame_feedback')
         if key in n:
             print(f'  mark {key} +{(a - t0) / 1e3:6.3f} ms')
             break
+if os.environ.get('SB_DUMP'):  # every kernel of the last replayed step, in order: start (us), duration (us), name
+    with open(os.environ['SB_DUMP'], 'w') as f:
+        for a, b, n in last:
+            f.write(f'{a - t0:9.1f} {b - a:7.1f}  {n}\n')
 if world > 1:
     sys.stdout.flush()
     os._exit(0)
