@@ -389,6 +389,18 @@ int sb_reward_value(const float* hid_pre, const float* w2, const float* b2, cons
                     float* dhid_pre, float* dw2, float* db2, float* dvalue, sb_stream_t stream);
 /* out[N] += column sums of x [M,N] (row stride ld): bias gradients of the dense layers. */
 int sb_colsum_f32(const float* x, int M, int N, int ld, float* out, sb_stream_t stream);
+/* ---- step bookkeeping (latent.cu) ------------------------------------------------------------------------------
+ * sb_loss_total: out5 = (total, reconstruct, value, reward, lstm) with reconstruct = rec_sum / n - clip (the logits
+ *   kernel sums max(ce, clip); simple/trainer.py:134-144), total = ((rec + value) + reward) + lstm; running5 (or NULL)
+ *   += out5 (the per-window loss log, trainer.py:150-154).
+ * sb_gather_step: this step's batch out of the device-resident replay (trainer.py:108-121): record idx[b] of
+ *   obs_src u8 [nrec, frame_bytes], act_src f32 [nrec, n_action], rew_src i64 [nrec], val_src f32 [nrec]. */
+int sb_loss_total(const double* rec_sum, double n, float clip, const float* l_value, const float* l_reward,
+                  const float* l_lstm, float* out5, float* running5, sb_stream_t stream);
+int sb_gather_step(const long long* idx, int B, long long nrec, const uint8_t* obs_src, long long frame_bytes,
+                   const float* act_src, int n_action, const long long* rew_src, const float* val_src, uint8_t* obs,
+                   float* act, long long* rew, float* val, sb_stream_t stream);
+
 /* ---- skinny fp32 GEMMs of the latent / heads block (dense.cu) ---------------------------------------------------
  * C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]).  a_trans: A stored [K,M]; b_trans: B stored [N,K] (an nn.Linear
  * weight); lda / ldb / ldc: row pitches in elements (inner strides are 1).  accumulate = 0: stores C.  accumulate = 1:

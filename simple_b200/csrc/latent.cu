@@ -443,6 +443,47 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
   if (r1 > r0) atomicAdd(out + c, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// step bookkeeping: the losses of simple/trainer.py:134-144 from the kernels' raw sums, and the batch gather of
+// trainer.py:108-121 (replay[idx + j] -> static step inputs).  Two tiny launches instead of ~15 ATen kernels.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void loss_total_kernel(const double* __restrict__ rec_sum, double inv_n, float clip,
+                                  const float* __restrict__ l_value, const float* __restrict__ l_reward,
+                                  const float* __restrict__ l_lstm, float* __restrict__ out5, float* running5) {
+  if (threadIdx.x != 0) return;
+  // max(ce, clip) summed by the logits kernel; trainer.py:136-137 subtracts the clip constant again after the mean
+  const float rec = (float)(*rec_sum * inv_n - (double)clip);
+  const float v = *l_value, r = *l_reward, l = l_lstm ? *l_lstm : 0.f;
+  const float total = ((rec + v) + r) + l;  // the order of trainer.py:141-143
+  const float o[5] = {total, rec, v, r, l};
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    out5[i] = o[i];
+    if (running5) running5[i] += o[i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gather_step_kernel(const long long* __restrict__ idx, long long nrec, const uint8_t* __restrict__ obs_src,
+                       long long frame_bytes, const float* __restrict__ act_src, int n_action,
+                       const long long* __restrict__ rew_src, const float* __restrict__ val_src,
+                       uint8_t* __restrict__ obs, float* __restrict__ act, long long* __restrict__ rew,
+                       float* __restrict__ val) {
+  const int b = blockIdx.y;
+  long long r = idx[b];
+  r = r < 0 ? 0 : (r >= nrec ? nrec - 1 : r);  // (the trainer only samples valid starts; never read out of bounds)
+  const uint4* src = reinterpret_cast<const uint4*>(obs_src + r * frame_bytes);
+  uint4* dst = reinterpret_cast<uint4*>(obs + (long long)b * frame_bytes);
+  const long long nv = frame_bytes >> 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nv; i += (long long)gridDim.x * 256)
+    dst[i] = __ldg(src + i);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < n_action) act[(long long)b * n_action + threadIdx.x] = act_src[r * n_action + threadIdx.x];
+    if (threadIdx.x == 32) rew[b] = rew_src[r];
+    if (threadIdx.x == 33) val[b] = val_src[r];
+  }
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -614,6 +655,30 @@ extern "C" int sb_colsum_f32(const float* x, int M, int N, int ld, float* out, s
   if (!x || M < 1 || N < 1 || ld < N || !out) return SB_ERR_ARG;
   const int ysplit = M >= 256 ? 8 : (M >= 32 ? 4 : 1);
   colsum_f32_kernel<<<dim3((N + 255) / 256, ysplit), 256, 0, (cudaStream_t)stream>>>(x, M, N, ld, out);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_loss_total(const double* rec_sum, double n, float clip, const float* l_value, const float* l_reward,
+                             const float* l_lstm, float* out5, float* running5, sb_stream_t stream) {
+  if (!rec_sum || n <= 0 || !l_value || !l_reward || !out5) return SB_ERR_ARG;
+  loss_total_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rec_sum, 1.0 / n, clip, l_value, l_reward, l_lstm, out5, running5);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_gather_step(const long long* idx, int B, long long nrec, const uint8_t* obs_src, long long frame_bytes,
+                              const float* act_src, int n_action, const long long* rew_src, const float* val_src,
+                              uint8_t* obs, float* act, long long* rew, float* val, sb_stream_t stream) {
+  if (!idx || B < 1 || nrec < 1 || !obs_src || frame_bytes < 16 || (frame_bytes & 15) || !act_src || n_action < 1 ||
+      n_action > 32 || !rew_src || !val_src || !obs || !act || !rew || !val)
+    return SB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(obs_src) | reinterpret_cast<uintptr_t>(obs)) & 15) return SB_ERR_ARG;
+  const int chunks = (int)((frame_bytes / 16 + 255) / 256);
+  gather_step_kernel<<<dim3(chunks < 8 ? chunks : 8, B), 256, 0, (cudaStream_t)stream>>>(
+      idx, nrec, obs_src, frame_bytes, act_src, n_action, rew_src, val_src, obs, act, rew, val);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

@@ -627,6 +627,10 @@ class NextFramePredictor(nn.Module):
             if self._logits_mode == 'ce':
                 aux['loss_reconstruct'], aux['argmax'] = ops.LogitsCE.apply(P['logits'], hf, m.weight, m.bias, pw,
                                                                              self._ce_target, self._ce_clip)
+            elif self._logits_mode == 'ce_raw':  # the raw f64 sum; trainer.TotalLoss finishes all losses in one launch
+                aux['rec_sum'], aux['argmax'] = ops.LogitsCE.apply(P['logits'], hf, m.weight, m.bias, pw,
+                                                                   self._ce_target, self._ce_clip, True)
+                aux['rec_n'] = float(B * 3 * hf.shape[1] * hf.shape[2])
             else:
                 aux['argmax'] = ops.logits_argmax(P['logits'], hf, m.bias, pw)
         return logits, reward_pred, value_pred

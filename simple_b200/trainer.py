@@ -15,14 +15,50 @@ from .adafactor import Adafactor
 NVTX = os.environ.get('SB_NVTX', '0') == '1'  # NVTX ranges around forward+loss / backward / grad sync / optimiser
 
 
-def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsilon, keep_logits=False):
+_ONES = {}
+
+
+def _one(device, dtype):
+    """Persistent constant 1 (gradient seeds: no fill kernel per step, valid under CUDA-graph capture)."""
+    key = (torch.device(device), dtype)
+    if key not in _ONES:
+        _ONES[key] = torch.ones((1,) if dtype == torch.float64 else (), device=device, dtype=dtype)
+    return _ONES[key]
+
+
+class TotalLoss(torch.autograd.Function):
+    """loss = loss_reconstruct + loss_value + loss_reward (+ loss_lstm) (simple/trainer.py:134-144) from the kernels' raw
+    results in ONE launch (sb_loss_total), optionally added to a running [5] log accumulator.  Every summand enters with
+    weight 1: the backward pass hands the incoming gradient through (the producers computed their gradients for weight 1
+    in their forward launches)."""
+
+    @staticmethod
+    def forward(ctx, rec_sum, n, clip, l_value, l_reward, l_lstm, running):
+        from . import _lib
+        out = torch.empty(5, device=rec_sum.device, dtype=torch.float32)
+        _lib.check(_lib.lib().sb_loss_total(rec_sum.data_ptr(), float(n), float(clip), l_value.data_ptr(),
+                                            l_reward.data_ptr(), l_lstm.data_ptr() if l_lstm is not None else None,
+                                            out.data_ptr(), running.data_ptr() if running is not None else None,
+                                            _lib.stream_ptr()), 'sb_loss_total')
+        ctx.has_lstm = l_lstm is not None
+        ctx.dev = rec_sum.device
+        parts = tuple(out[i] for i in range(5))
+        ctx.mark_non_differentiable(*parts[1:])
+        return parts
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        return _one(ctx.dev, torch.float64), None, None, g, g, (g if ctx.has_lstm else None), None
+
+
+def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsilon, keep_logits=False, loss_acc=None):
     """Forward + the losses of simple/trainer.py:134-144.  Returns a dict of device scalars (no host sync).
 
     frames f32 [B,12,H,W] in [0,1]; actions f32 [B,n] one-hot; new_states_u8 u8 [B,3,H,W]; rewards long [B];
     values f32 [B].  The pixel cross-entropy, its gradient and the argmax decode are ONE fused kernel pass over the
     bf16 logits (ops.PixelCE); `argmax` is the u8 frame the reference obtains with torch.argmax (trainer.py:130).
     """
-    target = new_states_u8.float() / 255
+    target = new_states_u8 / 255  # (true division of the u8 frame: float32, same values as .float() / 255)
     new_states_u8 = new_states_u8.contiguous()
     clip = float(config.target_loss_clipping)
     out = {}
@@ -35,9 +71,17 @@ def wm_loss(model, config, frames, actions, new_states_u8, rewards, values, epsi
                                                      getattr(model, 'logits_dbias', None))
     else:  # the logits GEMM carries the loss in its epilogue: the logits are never written to HBM
         _, reward_pred, value_pred = model.forward_internal(frames, actions, target, epsilon, rewards=rewards,
-                                                            values=values, logits_mode='ce', ce_target=new_states_u8,
+                                                            values=values, logits_mode='ce_raw', ce_target=new_states_u8,
                                                             ce_clip=clip)
-        loss_reconstruct, argmax = model.last_aux['loss_reconstruct'], model.last_aux['argmax']
+        aux = model.last_aux
+        l_lstm = model.stochastic_model.get_lstm_loss() if config.use_stochastic_model else None
+        loss, l_rec, l_val, l_rew, l_lstm_out = TotalLoss.apply(aux['rec_sum'], aux['rec_n'], clip, aux['loss_value'],
+                                                                aux['loss_reward'], l_lstm, loss_acc)
+        if config.use_stochastic_model:
+            out['loss_lstm'] = l_lstm_out
+        out.update(loss=loss, loss_reconstruct=l_rec, loss_value=l_val, loss_reward=l_rew, argmax=aux['argmax'],
+                   reward_pred=reward_pred, value_pred=value_pred)
+        return out
     # value MSE and reward CE (trainer.py:138-139) come out of the fused heads kernel together with their gradients
     loss_value, loss_reward = model.last_aux['loss_value'], model.last_aux['loss_reward']
     loss = loss_reconstruct + loss_value + loss_reward
@@ -185,7 +229,7 @@ class Trainer:
         self._runner = None  # captured graphs refer to the old optimiser records
         return ck['epoch']
 
-    def train_step(self, frames, actions, new_states_u8, rewards, values, epsilon, after_backward=None):
+    def train_step(self, frames, actions, new_states_u8, rewards, values, epsilon, after_backward=None, loss_acc=None):
         """One optimiser step (trainer.py:122-149).  Returns the loss dict of `wm_loss` (device scalars).
         `after_backward(out)`: optional gradient-independent tail work of the caller (frame feedback); it is issued
         between the backward pass and the optimiser so that it overlaps the last gradient all-reduce."""
@@ -194,7 +238,8 @@ class Trainer:
         if nvtx:
             nvtx.range_push('wm_step/forward+loss')
         ops.ARENA.begin(frames.device)  # one memset for all zero-initialised scratch of the step
-        out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon)
+        out = wm_loss(self.model, self.config, frames, actions, new_states_u8, rewards, values, epsilon,
+                      loss_acc=loss_acc)
         if nvtx:
             nvtx.range_pop()
             nvtx.range_push('wm_step/backward')
@@ -202,7 +247,7 @@ class Trainer:
         packed = self.model.packed_weight_map(defer_unpack=self.packed_grads) if self.packed_grads else None
         if self.grad_sync is not None and hasattr(self.grad_sync, 'prepare'):
             self.grad_sync.prepare(self.model, packed)  # gradient arena + bucketed all-reduce overlapped with backward
-        out['loss'].backward()
+        out['loss'].backward(gradient=_one(out['loss'].device, torch.float32))
 
         def tail():
             self.model.commit_state()  # after backward: the gate's weight gradient still needed the previous operand
@@ -337,12 +382,20 @@ class StepRunner:
 
     def _body(self):
         tr, rp, B = self.trainer, self.replay, self.B
-        if self.resident:
-            idx = self.idx
-            new_states, action, reward, value = rp['new_obs'][idx], rp['action'][idx], rp['reward'][idx], rp['value'][idx]
-        else:
-            new_states, action, reward, value = (self.inp['new_obs'], self.inp['action'], self.inp['reward'],
-                                                 self.inp['value'])
+        if self.resident:  # this step's batch out of the device-resident replay: one gather launch into static buffers
+            from . import _lib
+            no, ac, rw, va = rp['new_obs'], rp['action'], rp['reward'], rp['value']
+            ok = (no.dtype == torch.uint8 and ac.dtype == torch.float32 and rw.dtype == torch.int64
+                  and va.dtype == torch.float32 and all(t.is_contiguous() for t in (no, ac, rw, va)))
+            if not ok:
+                raise TypeError('StepRunner: replay tensors must be contiguous u8 / f32 / i64 / f32 (DeviceReplay)')
+            _lib.check(_lib.lib().sb_gather_step(self.idx.data_ptr(), B, no.shape[0], no.data_ptr(),
+                                                 no[0].numel(), ac.data_ptr(), ac.shape[1], rw.data_ptr(), va.data_ptr(),
+                                                 self.inp['new_obs'].data_ptr(), self.inp['action'].data_ptr(),
+                                                 self.inp['reward'].data_ptr(), self.inp['value'].data_ptr(),
+                                                 _lib.stream_ptr()), 'sb_gather_step')
+        new_states, action, reward, value = (self.inp['new_obs'], self.inp['action'], self.inp['reward'],
+                                             self.inp['value'])
         # scheduled sampling (trainer.py:125-132): ground truth w.p. epsilon, else own argmax decode; input noise with
         # the per-frame median; frame-stack shift -- one kernel, in place on the static frame buffer.  Issued right
         # after the backward pass (nothing later reads the frames): under data parallelism it hides behind the last
@@ -350,8 +403,11 @@ class StepRunner:
         def feedback(out):
             ops.frame_feedback(self.frames, new_states, out['argmax'], self.eps, float(tr.config.input_noise),
                                tr.model._seed_dev)
-        out = tr.train_step(self.frames, action, new_states, reward, value, self.eps, after_backward=feedback)
-        self.losses += torch.stack([out[k].detach().float() for k in self.names])
+        fused_log = len(self.names) == 5  # sb_loss_total adds (total, reconstruct, value, reward, lstm) to the log itself
+        out = tr.train_step(self.frames, action, new_states, reward, value, self.eps, after_backward=feedback,
+                            loss_acc=self.losses if fused_log else None)
+        if not fused_log:
+            self.losses += torch.stack([out[k].detach().float() for k in self.names])
         self.idx += 1
         self.last = {k: v.detach() for k, v in out.items()}  # no reference to this step's autograd graph survives
 

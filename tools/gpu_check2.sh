@@ -7,6 +7,6 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench rc=$?"
 tail -c 600 gpurun_out/bench.json
-SB_TOP=70 timeout 300 python tools/graph_gaps.py > gpurun_out/graph_gaps.txt 2>&1
+SB_TOP=70 SB_DUMP=gpurun_out/step_kernels.txt timeout 300 python tools/graph_gaps.py > gpurun_out/graph_gaps.txt 2>&1
 echo "gaps rc=$?"
 head -90 gpurun_out/graph_gaps.txt
