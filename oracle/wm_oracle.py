@@ -259,7 +259,7 @@ def lstm_cell(p, prefix, x, h, c):
 # ----------------------------------------------------------------------------------
 # BitsPredictor / StochasticModel (simple/next_frame_predictor.py:66-206)
 # ----------------------------------------------------------------------------------
-def bits_predictor(p, cfg, x, rand, target_bits=None, prefix='stochastic_model.bits_predictor'):
+def bits_predictor(p, cfg, x, rand, target_bits=None, prefix='stochastic_model.bits_predictor', aux=None):
     nsteps = cfg.bottleneck_bits // 8
     x = torch.flatten(x, start_dim=1)
     first = F.linear(x, p[prefix + '.dense1.weight'], p[prefix + '.dense1.bias'])
@@ -287,10 +287,16 @@ def bits_predictor(p, cfg, x, rand, target_bits=None, prefix='stochastic_model.b
         h, c = lstm_cell(p, prefix + '.lstm', inp, h, c)
         logits = F.linear(h, p[prefix + '.dense5.weight'], p[prefix + '.dense5.bias'])
         w = torch.exp(logits / 1.0)  # atari_utils/atari_utils/utils.py:95-101
-        sample = torch.argmax(w / rand.exponential(w.shape), dim=-1)
+        noisy = w / rand.exponential(w.shape)
+        sample = torch.argmax(noisy, dim=-1)
+        if aux is not None:  # log-domain scores of the categorical draw: how close a decision was (tests: near-ties)
+            aux.setdefault('sample_scores', []).append(torch.log(noisy).detach())
         outs.append(sample)
         inp = F.linear(F.one_hot(sample, 256).float(), p[prefix + '.dense4.weight'], p[prefix + '.dense4.bias'])
     outs = torch.stack(outs, dim=1)
+    if aux is not None:
+        aux['sample_scores'] = torch.stack(aux['sample_scores'], dim=1)  # [B, 16, 256]
+        aux['samples'] = outs
     bits = int_to_bit(outs).reshape(-1, cfg.bottleneck_bits)
     return 2 * bits - 1, 0.0
 
@@ -328,14 +334,14 @@ def stochastic_model(p, cfg, layer, inputs, action, target, epsilon, rand, train
         bits = bits * noise
         bits = mix(bits, x, 1 - epsilon, rand)
         _, lstm_loss = bits_predictor(p, cfg, layer, rand, bits_clean)
-        bits_pred, _ = bits_predictor(p, cfg, layer, rand)
+        bits_pred, _ = bits_predictor(p, cfg, layer, rand, aux=aux)
         aux['bits_pred'] = bits_pred
         bits_pred = bits_clean + (bits_pred - bits_clean).detach()
         bits = mix(bits_pred, bits, 1 - (1 - epsilon) * cfg.latent_rnn_max_sampling, rand)
         aux['bits'] = bits
         res = add_bits(p, layer, bits)
         return mix(res, layer, 1 - (1 - epsilon) * cfg.latent_use_max_probability, rand), lstm_loss
-    bits, _ = bits_predictor(p, cfg, layer, rand)
+    bits, _ = bits_predictor(p, cfg, layer, rand, aux=aux)
     aux['bits'] = bits
     return add_bits(p, layer, bits), 0.0
 

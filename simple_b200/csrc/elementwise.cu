@@ -565,39 +565,43 @@ __global__ void __launch_bounds__(256, 2)
 // out[b,c] = (mean, biased variance).  No atomics: run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) stats_small_kernel(const __grid_constant__ PrepParams q, float* out, int nb) {
+  // one WARP per (sample, 8 channels): the lanes own the <= 64 pixels (two each at most), read once and kept in
+  // registers for both passes; fixed-order butterfly sums (round 2b: one THREAD per group took 13-29 us per launch on
+  // these 6- and 30-pixel planes -- a serial chain of dependent loads; now ~3 us)
   const int CV = q.C / 8;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nb * CV) return;
-  const int b = i / CV + q.b_base, c = (i % CV) * 8;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nb * CV) return;
+  const int b = w / CV + q.b_base, c = (w % CV) * 8;
   const int P = q.H * q.W;
-  float mean[8], m2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) mean[j] = m2[j] = 0.f;
+  float z[2][8];
   RawZ raw;
-  for (int pix = 0; pix < P; ++pix) {
-    const int y = pix / q.W, x = pix - y * q.W;
-    float z[8], mainv[8];
-    finish_z<true, kRT>(q, raw, b, y, x, c, z, mainv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mean[j] += z[j];
-  }
-  const float invP = 1.0f / (float)P;
+  for (int h = 0; h < 2; ++h) {
+    const int pix = lane + 32 * h;
+    if (pix < P) {
+      const int y = pix / q.W, x = pix - y * q.W;
+      float mainv[8];
+      finish_z<true, kRT>(q, raw, b, y, x, c, z[h], mainv);
+    } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) mean[j] *= invP;
-  for (int pix = 0; pix < P; ++pix) {
-    const int y = pix / q.W, x = pix - y * q.W;
-    float z[8], mainv[8];
-    finish_z<true, kRT>(q, raw, b, y, x, c, z, mainv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = z[j] - mean[j];
-      m2[j] += d * d;
+      for (int j = 0; j < 8; ++j) z[h][j] = 0.f;
     }
   }
+  const float invP = 1.0f / (float)P;
+  float mean[8], var[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mean[j] = warp_sum(z[0][j] + z[1][j]) * invP;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    out[((long long)b * q.C + c + j) * 2] = mean[j];
-    out[((long long)b * q.C + c + j) * 2 + 1] = m2[j] * invP;
+    const float d0 = (lane < P) ? z[0][j] - mean[j] : 0.f, d1 = (lane + 32 < P) ? z[1][j] - mean[j] : 0.f;
+    var[j] = warp_sum(d0 * d0 + d1 * d1) * invP;
+  }
+  if (lane < 8) {
+    float m = mean[0], v = var[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (lane == j) { m = mean[j]; v = var[j]; }
+    *reinterpret_cast<float2*>(out + ((long long)b * q.C + c + lane) * 2) = make_float2(m, v);
   }
 }
 
@@ -1088,8 +1092,8 @@ extern "C" int sb_stats(const sb_prep_args* a, float* sums, sb_stream_t stream) 
   const int nb = launch_samples(a);
   cudaStream_t st = (cudaStream_t)stream;
   if (q.moments) {
-    const int total = nb * (q.C / 8);
-    stats_small_kernel<<<(total + 127) / 128, 128, 0, st>>>(q, sums, nb);
+    const int total = nb * (q.C / 8);  // one warp each
+    stats_small_kernel<<<(total + 3) / 4, 128, 0, st>>>(q, sums, nb);
     ++g_launches;
     SB_CHECK_LAUNCH();
     return SB_OK;

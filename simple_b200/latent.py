@@ -391,7 +391,7 @@ class HeadsOut(torch.autograd.Function):
             _lib.check(L.sb_reward_value(hid.data_ptr(), re.dense2.weight.data_ptr(), re.dense2.bias.data_ptr(), None,
                                          None, None, B, reward_pred.data_ptr(), None, None, None, None, None, st),
                        'sb_reward_value')
-            z = torch.zeros(2, device=dev)
+            z = _zeros((2,), dev)
             return reward_pred, z[0], z[1]
         z = torch.zeros(2 + 3 * 128 + 3 + 128, device=dev)  # losses | dw2 | db2 | db1 (own buffer: the losses are returned)
         losses, dw2, db2 = z[:2], z[2:386].view(3, 128), z[386:389]

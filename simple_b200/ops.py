@@ -109,6 +109,24 @@ def zeros(shape, device, dtype=torch.float32):
     return ARENA.zeros(shape, dtype, device)
 
 
+class use_arena:
+    """`with use_arena(a):` serves `zeros()` from another arena (the simulated env keeps its own: a buffer baked into its
+    captured step must not be re-allocated when the trainer's demand grows)."""
+
+    def __init__(self, arena):
+        self.arena = arena
+
+    def __enter__(self):
+        global ARENA
+        self.prev, ARENA = ARENA, self.arena
+        return self.arena
+
+    def __exit__(self, *exc):
+        global ARENA
+        ARENA = self.prev
+        return False
+
+
 def dense(a, b, a_trans=False, b_trans=False, bias=None, out=None):
     """fp32 `op(a) @ op(b) (+ bias)`, or `out += ...` when `out` is given (sb_dense: the skinny GEMMs of the latent /
     heads block).  a: [M,K] ([K,M] with a_trans); b: [K,N] ([N,K] with b_trans, i.e. an nn.Linear weight); unit inner

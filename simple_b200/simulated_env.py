@@ -146,6 +146,7 @@ class SimulatedVecEnv:
         self._graph = None
         self._graph_key = None
         self._warm = 0
+        self._arena = ops.ZeroArena()  # zero-initialised scratch of one env step (its address is part of the graph key)
         self._policy = None
 
     def _core(self):
@@ -155,8 +156,12 @@ class SimulatedVecEnv:
         if self._policy is not None:
             _, action, _ = self._policy.act(self._obs)
             self._act.copy_(action.reshape(A, 1))
-        onehot = torch.zeros(A, 1, self.n_action, device=self.device).scatter_(2, self._act.unsqueeze(-1), 1.0)
-        _, reward_pred, value_pred = model.forward_internal(self.frames.float() / 255, onehot, logits_mode='argmax')
+        # all zero-initialised scratch of the step (split-K accumulators, statistics, the one-hot) out of ONE memset
+        with ops.use_arena(self._arena):
+            self._arena.begin(self.device)
+            onehot = ops.zeros((A, 1, self.n_action), self.device).scatter_(2, self._act.unsqueeze(-1), 1.0)
+            _, reward_pred, value_pred = model.forward_internal(self.frames / 255, onehot, logits_mode='argmax')
+            self._arena.end()
         new = model.last_aux['argmax']  # u8 [A,3,H,W]: decoded in the epilogue of the logits GEMM
         c = cfg.frame_shape[0]
         self.frames.copy_(torch.cat((self.frames[:, c:], new), dim=1))
@@ -164,6 +169,10 @@ class SimulatedVecEnv:
         self._rew.copy_((torch.argmax(reward_pred, dim=1) - 1).to(torch.float32))
         self._val.copy_(value_pred.float())
         model.commit_state()
+
+    def _capture_key(self):
+        buf = self._arena.buf
+        return (self.model.capture_key(rollout=True), buf.data_ptr() if buf is not None else 0)
 
     @torch.no_grad()
     def _advance(self):
@@ -175,7 +184,7 @@ class SimulatedVecEnv:
         model._auto_repack = False
         try:
             first = not model._has_prev
-            if self._graph is not None and self._graph_key != model.capture_key(rollout=True):
+            if self._graph is not None and self._graph_key != self._capture_key():
                 self._graph, self._warm = None, 0  # a buffer the graph baked in was re-allocated: capture again
             if first or not self.use_graph:
                 self._core()
@@ -187,7 +196,7 @@ class SimulatedVecEnv:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._core()
-                self._graph, self._graph_key = g, model.capture_key(rollout=True)
+                self._graph, self._graph_key = g, self._capture_key()
                 g.replay()
             else:
                 self._graph.replay()
