@@ -1,12 +1,12 @@
+#!/bin/bash
+# Round-end evidence, part A (no profiler): GPU test suite, smoke(), bench.py (own arm + reference arm), timelines.
 set -x
 mkdir -p gpurun_out/final
-timeout 600 python -m pytest tests -x -q -m gpu --timeout 120 --timeout-method=thread > gpurun_out/final/pytest_gpu.log 2>&1; echo pytest rc=$?
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final/smoke.log 2>&1; echo smoke rc=$?
-timeout 400 python bench.py > gpurun_out/final/bench.json 2> gpurun_out/final/bench.err; echo bench rc=$?
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final/bench_ref.json 2> gpurun_out/final/bench_ref.err; echo ref rc=$?
-timeout 200 python tools/graph_gaps.py > gpurun_out/final/graph_gaps.txt 2>&1; echo gaps rc=$?
-timeout 200 python tools/ncu_step.py > gpurun_out/final/step.log 2>&1; echo step rc=$?
-timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/final/launches.csv python tools/ncu_step.py > gpurun_out/final/ncu1.log 2>&1; echo ncu1 rc=$?
-timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"tap_gemm2_kernel|pixel_ce_kernel|tap_wgrad_kernel" -c 8 -f -o gpurun_out/final/full_hot python tools/ncu_step.py > gpurun_out/final/ncu2.log 2>&1; echo ncu2 rc=$?
-ls -la gpurun_out/final
-tail -2 gpurun_out/final/pytest_gpu.log; tail -1 gpurun_out/final/smoke.log; head -c 600 gpurun_out/final/bench.json; echo; cat gpurun_out/final/bench_ref.json | head -c 400
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 --timeout-method=thread -p no:cacheprovider > gpurun_out/final/pytest_gpu.log 2>&1; echo pytest rc=$?
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final/smoke.log 2>&1; echo smoke rc=$?
+timeout 600 python bench.py > gpurun_out/final/bench.json 2> gpurun_out/final/bench.err; echo bench rc=$?
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final/bench_ref.json 2> gpurun_out/final/bench_ref.err; echo ref rc=$?
+timeout 600 python bench.py --agents 32 --n-action 9 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/final/bench_a32_n9.json 2> gpurun_out/final/bench_a32_n9.err; echo cfg4 rc=$?
+SB_TOP=80 SB_DUMP=gpurun_out/final/step_kernels.txt timeout 300 python tools/graph_gaps.py > gpurun_out/final/graph_gaps.txt 2>&1; echo gaps rc=$?
+SB_DUMP=gpurun_out/final/rollout_kernels.txt timeout 300 python tools/rollout_gaps.py 16 > gpurun_out/final/rollout_gaps.txt 2>&1; echo rollout rc=$?
+tail -2 gpurun_out/final/pytest_gpu.log; tail -1 gpurun_out/final/smoke.log; head -c 400 gpurun_out/final/bench.json; echo; head -c 300 gpurun_out/final/bench_ref.json; echo; head -c 300 gpurun_out/final/bench_a32_n9.json
