@@ -25,6 +25,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 CE_DRAM_BYTES_B64 = 1599.7e6  # dram__bytes_read+write of one pixel_ce_kernel launch at B=64 (ncu, profiles/)
+FUSED_CE_DRAM_BYTES_B64 = 872.2e6  # tap_gemm2_kernel<256,4,1> (logits GEMM + CE epilogue), same source, round 2
 ALG_GFLOP_PER_FRAME_TRAIN = 36.80  # conv/deconv fwd+bwd per sample (algorithmic)
 
 
@@ -408,8 +409,10 @@ def run_own(args):
                 'kernel': ('tap_gemm2_kernel<256,4,1>: logits GEMM + softmax-CE epilogue (the logits never reach HBM)'
                            if fused else 'pixel_ce_kernel'),
                 'achieved': ach, 'peak': hbm, 'unit': 'GB/s', 'frac': ach / hbm,
-                'traffic': None if fused else (CE_DRAM_BYTES_B64 if B == 64 else None),
-                'traffic_source': None if fused else 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
+                'traffic': (FUSED_CE_DRAM_BYTES_B64 if fused else CE_DRAM_BYTES_B64) if B == 64 else None,
+                'traffic_source': ('ncu dram__bytes_read.sum + dram__bytes_write.sum of the launch, '
+                                   'profiles/r2_ncu_launches_train_b64_v8.csv (B=64)') if fused
+                else 'ncu --set full, profiles/r1_ncu_full_v13.summary.txt (B=64)',
                 'peak_source': how, 'ms_per_launch': c['ms'] / c['launches'],
                 'alg_bytes_per_launch': c['work'] / c['launches'],
                 'alg_bytes_definition': ('read hf (bf16 x 96) + write dlogits (bf16 x 768) + targets + arg-max per pixel; '
