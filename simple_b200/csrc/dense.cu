@@ -33,43 +33,55 @@ struct DenseDev {
   int a_trans, b_trans, accumulate, kchunk;
 };
 
-// one operand tile -> shared memory as [k][row]; `contig_k`: global memory is contiguous along k (else along row)
+// one operand tile, global -> registers (4 values per thread); `CONTIG_K`: global memory is contiguous along k (else along
+// the row dimension).  Split from the shared-memory store so that the NEXT tile's loads are in flight while the current
+// one is multiplied (these kernels run 2-6 K tiles per CTA: un-pipelined, every tile paid a full global-load latency).
 template <bool CONTIG_K>
-__device__ __forceinline__ void load_tile(float (*dst)[kDM + kDPad], const float* __restrict__ src, long long ld, int row0,
-                                          int rows, int k0, int kend, bool vec_ok) {
+__device__ __forceinline__ float4 fetch_tile(const float* __restrict__ src, long long ld, int row0, int rows, int k0,
+                                             int kend, bool vec_ok) {
   const int t = threadIdx.x;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   if (CONTIG_K) {
     const int r = t >> 2, kq = (t & 3) * 4;  // 64 rows x 4 quads of k
     const int gr = row0 + r, gk = k0 + kq;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gr < rows) {
+    if (gr < rows && gk < kend) {
       const float* p = src + (long long)gr * ld + gk;
       if (vec_ok && gk + 3 < kend) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        q = __ldg(reinterpret_cast<const float4*>(p));
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (gk + i < kend) v[i] = __ldg(p + i);
+        q.x = __ldg(p);
+        if (gk + 1 < kend) q.y = __ldg(p + 1);
+        if (gk + 2 < kend) q.z = __ldg(p + 2);
+        if (gk + 3 < kend) q.w = __ldg(p + 3);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[kq + i][r] = v[i];
   } else {
     const int k = t >> 4, rq = (t & 15) * 4;  // 16 k x 16 quads of rows
     const int gk = k0 + k, gr = row0 + rq;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gk < kend) {
+    if (gk < kend && gr < rows) {
       const float* p = src + (long long)gk * ld + gr;
       if (vec_ok && gr + 3 < rows) {
         q = __ldg(reinterpret_cast<const float4*>(p));
       } else {
-        if (gr < rows) q.x = __ldg(p);
+        q.x = __ldg(p);
         if (gr + 1 < rows) q.y = __ldg(p + 1);
         if (gr + 2 < rows) q.z = __ldg(p + 2);
         if (gr + 3 < rows) q.w = __ldg(p + 3);
       }
     }
+  }
+  return q;
+}
+
+// registers -> shared memory as [k][row]
+template <bool CONTIG_K>
+__device__ __forceinline__ void stash_tile(float (*dst)[kDM + kDPad], const float4 q) {
+  const int t = threadIdx.x;
+  if (CONTIG_K) {
+    const int r = t >> 2, kq = (t & 3) * 4;
+    dst[kq][r] = q.x; dst[kq + 1][r] = q.y; dst[kq + 2][r] = q.z; dst[kq + 3][r] = q.w;
+  } else {
+    const int k = t >> 4, rq = (t & 15) * 4;
     *reinterpret_cast<float4*>(&dst[k][rq]) = q;
   }
 }
@@ -82,7 +94,7 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseDev p) {
   const int kbeg = blockIdx.z * p.kchunk;
   const int kend = min(p.K, kbeg + p.kchunk);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  // 16-byte loads need the base and the row pitch aligned; with A^T / B (row-contiguous) also the tile origin
+  // 16-byte loads need the base and the row pitch aligned (tile origins are multiples of 4 elements)
   const bool a_vec = ((reinterpret_cast<uintptr_t>(p.A) | (uintptr_t)(p.lda * 4)) & 15) == 0;
   const bool b_vec = ((reinterpret_cast<uintptr_t>(p.B) | (uintptr_t)(p.ldb * 4)) & 15) == 0;
   float acc[4][4];
@@ -90,21 +102,27 @@ __global__ void __launch_bounds__(256) dense_kernel(DenseDev p) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // A tile as [k][m]: stored [M,K] -> contiguous along k; stored [K,M] -> contiguous along m
+  // B tile as [k][n]: stored [N,K] (b_trans) -> contiguous along k; stored [K,N] -> contiguous along n
+  float4 qa = fetch_tile<!A_T>(p.A, p.lda, m0, p.M, kbeg, kend, a_vec);
+  float4 qb = fetch_tile<B_T>(p.B, p.ldb, n0, p.N, kbeg, kend, b_vec);
   for (int k0 = kbeg; k0 < kend; k0 += kDK) {
-    // A tile as [k][m]: stored [M,K] -> contiguous along k; stored [K,M] -> contiguous along m
-    load_tile<!A_T>(As, p.A, p.lda, m0, p.M, k0, kend, a_vec);
-    // B tile as [k][n]: stored [N,K] (b_trans) -> contiguous along k; stored [K,N] -> contiguous along n
-    load_tile<B_T>(Bs, p.B, p.ldb, n0, p.N, k0, kend, b_vec);
+    stash_tile<!A_T>(As, qa);
+    stash_tile<B_T>(Bs, qb);
     __syncthreads();
+    if (k0 + kDK < kend) {  // next tile: in flight underneath the FMAs below
+      qa = fetch_tile<!A_T>(p.A, p.lda, m0, p.M, k0 + kDK, kend, a_vec);
+      qb = fetch_tile<B_T>(p.B, p.ldb, n0, p.N, k0 + kDK, kend, b_vec);
+    }
 #pragma unroll
     for (int kk = 0; kk < kDK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float av[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
     }
     __syncthreads();
   }
