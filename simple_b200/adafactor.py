@@ -6,8 +6,6 @@ Same constructor / `zero_grad()` / `step()` surface and the same per-parameter s
 (csrc/adafactor.cu) with no host synchronisation.  Only the defaults the reference uses are implemented; any other
 hyper-parameter raises (there is no slow path).
 """
-import ctypes
-import math
 
 import numpy as np
 import torch

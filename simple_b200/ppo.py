@@ -10,7 +10,6 @@ agents) so that the replicas stay identical.
 """
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 
 class DevicePPO:

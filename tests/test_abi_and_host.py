@@ -1,7 +1,6 @@
 """CPU-side checks: the C-ABI library builds for sm_100a, loads, and exports every symbol include/simple_b200.h
 declares (no compute calls without a GPU); host-side logic of the reference-facing surface."""
 import ctypes
-import math
 import os
 import re
 
@@ -170,3 +169,46 @@ def test_split_k_sizing_and_transpose_table_layout():
     dt = np.dtype([('fwd', np.uint64), ('tr', np.uint64), ('Opad', np.int32), ('PHI', np.int32), ('T', np.int32),
                    ('first_tile', np.int32)])
     assert dt.itemsize == 32
+
+
+def test_host_side_launch_sizing_entry_points():
+    """Pure host logic behind the C ABI (no GPU): K-split sizing of sb_dense, the SM-reserve switch."""
+    from simple_b200 import _lib
+    L = _lib.lib()
+    # big outputs: one CTA per 64x64 tile, no split; small outputs: ~2 CTAs per SM, at least two 16-wide K tiles each
+    assert L.sb_dense_splits(384, 4608, 64) == 1          # 6 x 72 tiles
+    assert L.sb_dense_splits(64, 14976, 3) == 1           # 234 tiles
+    s = L.sb_dense_splits(64, 384, 4608)                   # BitsPredictor dense1|2|3: 6 tiles
+    assert s == 50 and 6 * s >= 148 * 2
+    assert L.sb_dense_splits(64, 128, 60) == 2            # K = 60: two K tiles of 32 at most
+    assert L.sb_dense_splits(1, 1, 1) == 1
+    prev = L.sb_set_sm_reserve(8)
+    try:
+        assert L.sb_set_sm_reserve(1000) == 8             # returns the previous value; clamps
+        assert L.sb_set_sm_reserve(-3) == 64
+        assert L.sb_set_sm_reserve(0) == 0
+    finally:
+        L.sb_set_sm_reserve(prev)
+
+
+def test_adafactor_grad_scale_rescales_second_moment_states():
+    """Data parallel hands the optimiser SUMMED gradients (grad_scale = 1 / world): the states live in those units and
+    are converted when the scale changes (a checkpoint moving between world sizes)."""
+    from simple_b200.adafactor import Adafactor
+    w = torch.nn.Parameter(torch.ones(4, 6))
+    b = torch.nn.Parameter(torch.ones(6))
+    opt = Adafactor([w, b])
+    for p in (w, b):
+        st = opt._init_state(p)
+        for k in ('exp_avg_sq_row', 'exp_avg_sq_col', 'exp_avg_sq'):
+            if k in st:
+                st[k].fill_(2.0)
+    assert opt.grad_scale == 1.0
+    opt.grad_scale = 0.125                                   # gradients now arrive 8 x larger -> g^2 states 64 x
+    assert float(opt.state[w]['exp_avg_sq_row'][0]) == 128.0 and float(opt.state[b]['exp_avg_sq'][0]) == 128.0
+    opt.grad_scale = 0.5
+    assert float(opt.state[w]['exp_avg_sq_col'][0]) == 8.0
+    opt.grad_scale = 1.0
+    assert float(opt.state[w]['exp_avg_sq_row'][0]) == 2.0
+    with pytest.raises(ValueError):
+        opt.grad_scale = 0.0
