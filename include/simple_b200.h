@@ -389,6 +389,14 @@ int sb_reward_value(const float* hid_pre, const float* w2, const float* b2, cons
                     float* dhid_pre, float* dw2, float* db2, float* dvalue, sb_stream_t stream);
 /* out[N] += column sums of x [M,N] (row stride ld): bias gradients of the dense layers. */
 int sb_colsum_f32(const float* x, int M, int N, int ld, float* out, sb_stream_t stream);
+/* Simulated-env step tail (simple/subproc_vec_env.py:428-441), one launch: frames u8 [A, stack_channels, HW] shifted by c
+ * channels in place with `fresh` u8 [A, c, HW] appended; obs f32 (same shape, values 0..255) or NULL;
+ * rew_out[a] = argmax_r reward_pred[a, r] - 1 (first maximum), val_out = value_pred (either pair may be NULL).
+ * HW must be a multiple of 16, the image pointers 16-byte aligned. */
+int sb_env_post(uint8_t* frames, const uint8_t* fresh, float* obs, int A, int stack_channels, int c, int HW,
+                const float* reward_pred, int R, const float* value_pred, float* rew_out, float* val_out,
+                sb_stream_t stream);
+
 /* ---- step bookkeeping (latent.cu) ------------------------------------------------------------------------------
  * sb_loss_total: out5 = (total, reconstruct, value, reward, lstm) with reconstruct = rec_sum / n - clip (the logits
  *   kernel sums max(ce, clip); simple/trainer.py:134-144), total = ((rec + value) + reward) + lstm; running5 (or NULL)

@@ -156,6 +156,7 @@ class _Sigs:
     sb_lstm_teacher_fwd = [_p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_lstm_teacher_bwd = [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]
     sb_grad_sumsq = [_p, _p, _p, _i, _p, _p, _f, _p]
+    sb_env_post = [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]
     sb_loss_total = [_p, ctypes.c_double, _f, _p, _p, _p, _p, _p, _p]
     sb_gather_step = [_p, _i, _ll, _p, _ll, _p, _i, _p, _p, _p, _p, _p, _p, _p]
     sb_dense = [_p, _p, _p, _p, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _p]

@@ -112,6 +112,50 @@ __global__ void __cluster_dims__(kFfCluster, 1, 1) __launch_bounds__(256)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Simulated-env step tail (simple/subproc_vec_env.py:428-441): u8 frame stack shifted by one frame with the decoded
+// frame appended (in place), the float observation the policy reads, reward = argmax(reward logits) - 1 and the value
+// estimate -- one launch instead of cat / copy / argmax / sub / cast kernels.  One thread owns 16 pixels of one agent
+// across all channels (reads channel k + c before it overwrites channel k: in place is safe).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    env_post_kernel(uint8_t* __restrict__ frames, const uint8_t* __restrict__ fresh, float* __restrict__ obs, int SC, int c,
+                    int HW, const float* __restrict__ reward_pred, int R, const float* __restrict__ value_pred,
+                    float* __restrict__ rew_out, float* __restrict__ val_out, int A) {
+  const int a = blockIdx.y;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;  // 16-pixel group
+  if (v * 16 < HW) {
+    for (int k = 0; k < SC; ++k) {
+      const uint8_t* src = (k + c < SC) ? frames + ((size_t)a * SC + k + c) * HW : fresh + ((size_t)a * c + (k + c - SC)) * HW;
+      const uint4 q = *reinterpret_cast<const uint4*>(src + (size_t)v * 16);
+      *reinterpret_cast<uint4*>(frames + ((size_t)a * SC + k) * HW + (size_t)v * 16) = q;
+      if (obs) {
+        float4* o = reinterpret_cast<float4*>(obs + ((size_t)a * SC + k) * HW + (size_t)v * 16);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o[j] = make_float4((float)(w[j] & 255u), (float)((w[j] >> 8) & 255u), (float)((w[j] >> 16) & 255u),
+                             (float)(w[j] >> 24));
+      }
+    }
+  }
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < A; i += blockDim.x) {
+      if (reward_pred) {
+        int best = 0;
+        float bv = reward_pred[(size_t)i * R];
+        for (int r = 1; r < R; ++r) {
+          const float x = reward_pred[(size_t)i * R + r];
+          if (x > bv) { bv = x; best = r; }  // first maximum, like torch.argmax
+        }
+        rew_out[i] = (float)(best - 1);
+      }
+      if (value_pred) val_out[i] = value_pred[i];
+    }
+  }
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -122,6 +166,21 @@ extern "C" int sb_frame_feedback(float* stack, const uint8_t* gt, const uint8_t*
   if (!stack || !gt || !pred || B < 1 || C_new < 1 || C_new > 8 || C_stack <= C_new || HW < 1) return SB_ERR_ARG;
   frame_feedback_kernel<<<dim3(kFfCluster, B), 256, 0, (cudaStream_t)stream>>>(stack, gt, pred, eps_ptr, p_noise, seed_ptr,
                                                                                seed, C_stack, C_new, HW);
+  ++g_launches;
+  SB_CHECK_LAUNCH();
+  return SB_OK;
+}
+
+extern "C" int sb_env_post(uint8_t* frames, const uint8_t* fresh, float* obs, int A, int stack_channels, int c, int HW,
+                           const float* reward_pred, int R, const float* value_pred, float* rew_out, float* val_out,
+                           sb_stream_t stream) {
+  if (!frames || !fresh || A < 1 || c < 1 || stack_channels <= c || HW < 16 || (HW & 15)) return SB_ERR_ARG;
+  if ((reward_pred && (R < 1 || !rew_out)) || (value_pred && !val_out)) return SB_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(fresh) | reinterpret_cast<uintptr_t>(obs)) & 15)
+    return SB_ERR_ARG;
+  const int groups = HW / 16;
+  env_post_kernel<<<dim3((groups + 255) / 256, A), 256, 0, (cudaStream_t)stream>>>(
+      frames, fresh, obs, stack_channels, c, HW, reward_pred, R, value_pred, rew_out, val_out, A);
   ++g_launches;
   SB_CHECK_LAUNCH();
   return SB_OK;

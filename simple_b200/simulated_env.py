@@ -13,7 +13,7 @@ last step of a rollout; observations are the u8 round trip of the frame stack, r
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class Box:
@@ -163,11 +163,18 @@ class SimulatedVecEnv:
             _, reward_pred, value_pred = model.forward_internal(self.frames / 255, onehot, logits_mode='argmax')
             self._arena.end()
         new = model.last_aux['argmax']  # u8 [A,3,H,W]: decoded in the epilogue of the logits GEMM
-        c = cfg.frame_shape[0]
-        self.frames.copy_(torch.cat((self.frames[:, c:], new), dim=1))
-        self._obs.copy_(self.frames)
-        self._rew.copy_((torch.argmax(reward_pred, dim=1) - 1).to(torch.float32))
-        self._val.copy_(value_pred.float())
+        c, h, w = cfg.frame_shape
+        rp, vp = reward_pred.float().contiguous(), value_pred.float().contiguous().reshape(-1)
+        if (h * w) % 16 == 0:  # frame-stack shift, float observation, reward decode and value copy in ONE launch
+            _lib.check(_lib.lib().sb_env_post(self.frames.data_ptr(), new.contiguous().data_ptr(), self._obs.data_ptr(), A,
+                                              self.stack_channels, c, h * w, rp.data_ptr(), rp.shape[1], vp.data_ptr(),
+                                              self._rew.data_ptr(), self._val.data_ptr(), _lib.stream_ptr()),
+                       'sb_env_post')
+        else:
+            self.frames.copy_(torch.cat((self.frames[:, c:], new), dim=1))
+            self._obs.copy_(self.frames)
+            self._rew.copy_((torch.argmax(rp, dim=1) - 1).to(torch.float32))
+            self._val.copy_(vp)
         model.commit_state()
 
     def _capture_key(self):

@@ -248,3 +248,32 @@ def test_device_ppo_learns_in_the_simulated_env():
     assert set(metrics) == {'ppo_value_loss', 'ppo_action_loss', 'ppo_entropy'}
     assert all(np.isfinite(x) for x in metrics.values()) and 0 < metrics['ppo_entropy'] <= np.log(3) + 1e-4
     assert any(not torch.equal(a, b) for a, b in zip(before, policy.parameters()))
+
+
+@pytest.mark.gpu
+def test_env_post_kernel_matches_torch_ops():
+    """sb_env_post (frame-stack shift in place + float observation + reward decode + value copy) vs the torch ops of
+    simple/subproc_vec_env.py:428-441 it replaces."""
+    from simple_b200 import _lib
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    for A, SC, c, H, W in ((16, 12, 3, 105, 80), (3, 8, 2, 4, 8)):
+        frames = torch.randint(0, 256, (A, SC, H, W), generator=g, dtype=torch.uint8).to(dev)
+        fresh = torch.randint(0, 256, (A, c, H, W), generator=g, dtype=torch.uint8).to(dev)
+        rp = torch.randn(A, 3, generator=g).to(dev)
+        rp[0] = 0.5  # a three-way tie decodes to the first maximum
+        vp = torch.randn(A, generator=g).to(dev)
+        want_frames = torch.cat((frames[:, c:], fresh), dim=1)
+        obs = torch.full((A, SC, H, W), -1.0, device=dev)
+        rew, val = torch.empty(A, device=dev), torch.empty(A, device=dev)
+        _lib.check(_lib.lib().sb_env_post(frames.data_ptr(), fresh.data_ptr(), obs.data_ptr(), A, SC, c, H * W,
+                                          rp.data_ptr(), 3, vp.data_ptr(), rew.data_ptr(), val.data_ptr(),
+                                          _lib.stream_ptr()), 'sb_env_post')
+        torch.cuda.synchronize()
+        assert torch.equal(frames, want_frames)
+        assert torch.equal(obs, want_frames.float())
+        assert torch.equal(rew, (torch.argmax(rp, dim=1) - 1).float()) and float(rew[0]) == -1.0
+        assert torch.equal(val, vp)
+    # unsupported geometry is refused, not mis-handled
+    assert _lib.lib().sb_env_post(frames.data_ptr(), fresh.data_ptr(), None, 1, 8, 2, 24, None, 0, None, None, None,
+                                  _lib.stream_ptr()) != 0
