@@ -321,7 +321,7 @@ int sb_lstm_teacher_bwd(const float* dhs, const float* act, const float* cs, con
 
 /* ---------------------------------------------------------------------------------------------------------
  * Latent / heads block (csrc/latent.cu): every elementwise, reduction, gather and scatter piece between the bottleneck
- * and the middle network, forward and backward; the dense layers between them are plain library GEMMs issued by the
+ * and the middle network, forward and backward; the dense layers between them are sb_dense launches issued by the
  * caller.  "flat" = the reference's flatten order of the [768,3,2] bottleneck (index c*6 + h*2 + w).  Optional explicit
  * randomness pointers (NULL = drawn in-kernel from a counter hash of seed + *seed_ptr; the backward regenerates it).
  * Replaces: simple/next_frame_predictor.py:328 (value head), simple/utils.py:98-105 (ActionInjector scale/shift, all

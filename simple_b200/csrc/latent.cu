@@ -11,7 +11,7 @@
 //                                               lookup, dropout 0.1, (LSTM: lstm.cu), dropout 0.1, CE over 256 symbols
 //   simple/next_frame_predictor.py:153-159      add_bits
 //   simple/next_frame_predictor.py:11-24,339,352-354 + simple/trainer.py:138-141   reward MLP tail, reward CE, value MSE
-// The dense layers between these stages are plain [B,K]x[K,N] library GEMMs issued by the host wrapper (ops.py); every
+// The dense layers between these stages are [B,K]x[K,N] sb_dense launches (dense.cu) issued by the host wrapper; every
 // elementwise / reduction / gather / scatter piece around them, forward AND backward, lives here, so that one training
 // step launches ~45 kernels for this block instead of ~300 ATen kernels.
 // All tensors fp32 unless stated.  "flat" = the reference's flatten order of [768,3,2]: index c*6 + p, p = h*2 + w.

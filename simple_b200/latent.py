@@ -1,5 +1,5 @@
 """Latent / heads block of the world model: everything between the bottleneck and the middle network, the reward and
-value heads and their losses, as fused CUDA kernels (csrc/latent.cu) around plain library GEMMs.
+value heads and their losses, as fused CUDA kernels (csrc/latent.cu) around the skinny fp32 GEMMs of `sb_dense` (csrc/dense.cu).
 
 Reference: simple/next_frame_predictor.py:153-200 (StochasticModel), :66-121 (BitsPredictor), :11-34 (heads), :328-339,
 :352-354; simple/utils.py:91-105 (ActionInjector), :157-163 (mix); simple/trainer.py:138-141 (value / reward losses).
