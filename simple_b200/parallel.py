@@ -65,6 +65,27 @@ class FlatGradSync:
         self.sm_reserve = int(os.environ.get('SB_DP_SM_RESERVE', '0'))
 
     # ---- overlap mode ------------------------------------------------------------------------------------------
+    @classmethod
+    def bucket_layout(cls, sizes, bounds_after):
+        """Arena layout of the conv gradients: `sizes` {layer name: packed gradient length} -> slots in backward
+        completion order (`ORDER`, unknown layers last) and the buckets.  A bucket ends after each layer named in
+        `bounds_after`: few large buckets while plenty of backward is left to hide them behind, then small ones, so that
+        what is still in flight when the backward pass ends (the layers after the final boundary plus the non-conv tail:
+        ~4 M of 68 M values) is as short as it can be."""
+        names = [n for n in cls.ORDER if n in sizes] + [n for n in sizes if n not in cls.ORDER]
+        off, slots = 0, {}
+        for n in names:
+            slots[n] = (off, sizes[n])
+            off += sizes[n]
+        bounds, members, cur = [], [], set()
+        for n in names:
+            cur.add(n)
+            if n in bounds_after:
+                bounds.append(slots[n][0] + slots[n][1])
+                members.append(cur)
+                cur = set()
+        return dict(names=names, slots=slots, conv_total=off, bounds=bounds, members=members)
+
     def prepare(self, model, packed):
         """Call after the forward pass and before backward (packed-gradient mode only)."""
         if not packed or self.world < 2 or not torch.cuda.is_available():
@@ -72,26 +93,10 @@ class FlatGradSync:
         pws = model._packed
         dev = next(iter(pws.values())).fwd.device
         if self._layout is None:
-            names = [n for n in self.ORDER if n in pws] + [n for n in pws if n not in self.ORDER]
-            off, slots = 0, {}
-            for n in names:
-                slots[n] = (off, pws[n].fwd.numel())
-                off += pws[n].fwd.numel()
-            conv_total = off
+            self._layout = self.bucket_layout({n: pw.fwd.numel() for n, pw in pws.items()}, self.bounds_after)
             conv_params = {id(p) for p in packed}
             tail = sum(p.numel() for p in self.params if id(p) not in conv_params)
-            self.flat = self._alloc_arena(conv_total + tail, dev)
-            # a bucket ends after each layer named in `bounds_after`: few large buckets while plenty of backward is left
-            # to hide them behind, then small ones, so that what is still in flight when the backward pass ends (the
-            # layers after the final boundary plus the non-conv tail: ~4 M of 68 M values) is as short as it can be
-            bounds, members, cur = [], [], set()
-            for n in names:
-                cur.add(n)
-                if n in self.bounds_after:
-                    bounds.append(slots[n][0] + slots[n][1])
-                    members.append(cur)
-                    cur = set()
-            self._layout = dict(names=names, slots=slots, conv_total=conv_total, bounds=bounds, members=members)
+            self.flat = self._alloc_arena(self._layout['conv_total'] + tail, dev)
             self._comm_stream = torch.cuda.Stream(device=dev)
         L = self._layout
         if self.sm_reserve:  # a step that raised between the first bucket and the end must not leave it set

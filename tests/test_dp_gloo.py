@@ -96,3 +96,25 @@ def test_global_batch_median_by_histogram_all_reduce():
     for rank, med, want, local in got:
         assert med == want, (rank, med, want)
     assert {local for *_, local in got} != {got[0][2]}  # (the shards' own medians are not the global one)
+
+
+def test_gradient_arena_bucket_layout():
+    """Host logic of the overlapped all-reduce: slots follow the backward completion order, a bucket closes after each
+    boundary layer, and only the small shallow-encoder layers are left for the exposed last all-reduce."""
+    from simple_b200.parallel import FlatGradSync
+    sizes = {'down0': 3, 'down1': 12, 'down2': 47, 'down3': 94, 'down4': 94, 'mid0': 53, 'mid1': 53, 'up0': 94, 'up1': 94,
+             'up2': 47, 'up3': 12, 'up4': 3, 'logits': 1, 'embed': 1, 'gate': 1, 's_embed': 1, 's_conv1': 8, 's_conv2': 42,
+             'extra': 5}
+    L = FlatGradSync.bucket_layout(sizes, FlatGradSync.BOUNDS_AFTER)
+    assert L['names'][:6] == ['logits', 'up4', 'up3', 'up2', 'up1', 'up0'] and L['names'][-2:] == ['gate', 'extra']
+    assert L['conv_total'] == sum(sizes.values())
+    off = 0
+    for n in L['names']:  # contiguous, non-overlapping slots
+        assert L['slots'][n] == (off, sizes[n])
+        off += sizes[n]
+    assert [sorted(m) for m in L['members']] == [sorted(['logits', 'up4', 'up3', 'up2', 'up1', 'up0']),
+                                                 sorted(['mid1', 'mid0', 's_conv2']), sorted(['s_conv1', 's_embed', 'down4']),
+                                                 ['down3'], ['down2']]
+    assert L['bounds'] == [251, 399, 502, 596, 643]
+    left = L['conv_total'] - L['bounds'][-1]   # down1, down0, embed, gate (+ unknown layers): the exposed remainder
+    assert left == 12 + 3 + 1 + 1 + 5 and left < 0.05 * L['conv_total']
